@@ -1,0 +1,4 @@
+"""juqbox_b200: B200-native objective + adjoint-gradient path of Juqbox."""
+from .params import (objparams, lsolver_object, wmatsetup, orig_wmatsetup, setup_rotmatrices, initial_cond,
+                     calculate_timestep, estimate_Neumann, assign_thresholds, assign_thresholds_freq,
+                     change_target, tikhonov_pen, tikhonov_grad, NEUMANN_SOLVER, Stormer_Verlet)

@@ -1,0 +1,292 @@
+"""Host-side problem description: the Python mirror of Juqbox's `objparams` and its setup helpers.
+
+Everything in this file runs once per problem on the host (it builds the *inputs* of the
+hot path); nothing here is on the per-evaluation path. Names, argument meaning and error
+behaviour follow the reference so that a Juqbox setup script translates line by line:
+
+  objparams            /root/reference/src/evalobjgrad.jl:152-343
+  lsolver_object       /root/reference/src/linear_solvers.jl:28-65   (Neumann only)
+  wmatsetup            /root/reference/src/evalobjgrad.jl:1544-1669
+  orig_wmatsetup       /root/reference/src/evalobjgrad.jl:1683-1808
+  setup_rotmatrices    /root/reference/src/evalobjgrad.jl:1822-1886
+  initial_cond         /root/reference/src/evalobjgrad.jl:3155-3203
+  calculate_timestep   /root/reference/src/evalobjgrad.jl:2944-2965
+  estimate_Neumann     /root/reference/src/evalobjgrad.jl:2891-2928
+  assign_thresholds    /root/reference/src/evalobjgrad.jl:1917-1958 (bounds only; used by configs)
+  tikhonov_pen/grad    /root/reference/src/evalobjgrad.jl:2291-2351
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+NEUMANN_SOLVER = 1
+Stormer_Verlet = 1
+
+
+class lsolver_object:
+    """Linear-solver selection (reference: src/linear_solvers.jl:28-65).
+
+    Only the truncated Neumann series is on the hot path (every named config uses it);
+    asking for another solver raises, exactly like the reference's `error("Please specify a
+    supported linear solver")` does for unknown ids.
+    """
+
+    def __init__(self, tol: float = 1e-10, max_iter: int = 3, nrhs: int = 1, solver: int = NEUMANN_SOLVER):
+        if solver != NEUMANN_SOLVER:
+            raise ValueError("Please specify a supported linear solver (only NEUMANN_SOLVER is built for B200)")
+        self.tol = float(tol)
+        self.max_iter = int(max_iter)
+        self.solver_id = solver
+        self.solver_name = "Neumann"
+
+    def print_info(self):
+        print("*** Using linear solver: ", self.solver_name, " with max_iter = ", self.max_iter)
+
+
+def _diag_weights(Ne, Ng, orig: bool) -> np.ndarray:
+    Ne = np.asarray(Ne, dtype=np.int64)
+    Ng = np.asarray(Ng, dtype=np.int64)
+    Nt = Ne + Ng
+    Ndim = len(Ne)
+    assert Ndim in (1, 2, 3)
+    Ntot = int(np.prod(Nt))
+    w = np.zeros(Ntot)
+    coeff = 1.0
+    if Ng.sum() > 0:
+        nForb = 0
+        if Ndim == 1:
+            fact = 0.1
+            for q in range(int(Ng[0])):
+                w[Ntot - 1 - q] = fact ** q
+            coeff = 1.0
+        elif Ndim == 2:
+            fact = 1e-3
+            q = 0
+            for i2 in range(1, Nt[1] + 1):
+                for i1 in range(1, Nt[0] + 1):
+                    if not (i1 <= Ne[0] and i2 <= Ne[1]):
+                        t1 = fact ** int(Nt[0] - i1) if i1 > Ne[0] else 0.0
+                        t2 = fact ** int(Nt[1] - i2) if i2 > Ne[1] else 0.0
+                        if i1 == Nt[0] or i2 == Nt[1]:
+                            nForb += 1
+                        w[q] = max(t1, t2)
+                    q += 1
+            coeff = (10.0 if orig else 1.0) / nForb
+        else:
+            fact = 1e-3
+            q = 0
+            for i3 in range(1, Nt[2] + 1):
+                for i2 in range(1, Nt[1] + 1):
+                    for i1 in range(1, Nt[0] + 1):
+                        if not (i1 <= Ne[0] and i2 <= Ne[1] and i3 <= Ne[2]):
+                            t1 = fact ** int(Nt[0] - i1) if i1 > Ne[0] else 0.0
+                            t2 = fact ** int(Nt[1] - i2) if i2 > Ne[1] else 0.0
+                            t3 = fact ** int(Nt[2] - i3) if i3 > Ne[2] else 0.0
+                            forbFact = 1.0
+                            if orig and i3 == Nt[2] and i1 <= Ne[0] and i2 <= Ne[1]:
+                                forbFact = 100.0
+                            w[q] = forbFact * max(t1, t2, t3)
+                            if i1 == Nt[0] or i2 == Nt[1] or i3 == Nt[2]:
+                                nForb += 1
+                        q += 1
+            coeff = 10.0 / nForb
+    return coeff * w
+
+
+def wmatsetup(Ne, Ng) -> np.ndarray:
+    """Diagonal of the default guard-level weight matrix W (reference returns Diagonal(w))."""
+    return _diag_weights(Ne, Ng, orig=False)
+
+
+def orig_wmatsetup(Ne, Ng) -> np.ndarray:
+    """Alternative weights used by the cnot2/cnot3 test cases (reference :1683-1808)."""
+    return _diag_weights(Ne, Ng, orig=True)
+
+
+def setup_rotmatrices(Ne, Ng, fund_freq):
+    """Diagonal rotating-frame frequencies per subsystem (reference :1822-1886)."""
+    Nt = [int(a + b) for a, b in zip(Ne, Ng)]
+    Nosc = len(Nt)
+    assert 1 <= Nosc <= 3
+    if Nosc == 1:
+        return 2 * np.pi * fund_freq[0] * np.arange(Nt[0], dtype=float)
+    out = []
+    for k in range(Nosc):
+        # index of subsystem k varies with stride prod(Nt[:k]) (subsystem 1 fastest)
+        idx = (np.arange(int(np.prod(Nt))) // int(np.prod(Nt[:k]))) % Nt[k]
+        out.append(2 * np.pi * fund_freq[k] * idx.astype(float))
+    return tuple(out)
+
+
+def initial_cond(Ne, Ng) -> np.ndarray:
+    """Canonical unit vectors spanning the essential subspace, Ntot x N (reference :3155-3203)."""
+    Ne = [int(x) for x in Ne]
+    Nt = [int(a + b) for a, b in zip(Ne, Ng)]
+    Ntot, N = int(np.prod(Nt)), int(np.prod(Ne))
+    U0 = np.zeros((Ntot, N))
+    col = 0
+    for mrow in range(Ntot):
+        rem, guard = mrow, False
+        for k in range(len(Nt)):
+            if rem % Nt[k] >= Ne[k]:
+                guard = True
+            rem //= Nt[k]
+        if not guard:
+            U0[mrow, col] = 1.0
+            col += 1
+    assert col == N
+    return U0
+
+
+def calculate_timestep(T, H0, Hsym_ops, Hanti_ops, maxpar, Pmin: int = 40) -> int:
+    """nsteps = ceil(T * max|eig(H0 + sum maxpar_i (Hsym_i + i Hanti_i))| * Pmin / 2pi)."""
+    K1 = np.array(H0, dtype=complex)
+    for i in range(len(Hsym_ops)):
+        K1 = K1 + maxpar[i] * np.asarray(Hsym_ops[i]) + 1j * maxpar[i] * np.asarray(Hanti_ops[i])
+    lamb = np.linalg.eigvalsh(K1) if np.allclose(K1, K1.conj().T) else np.linalg.eigvals(K1)
+    maxeig = np.max(np.abs(lamb))
+    return int(math.ceil(T * maxeig * Pmin / (2 * np.pi)))
+
+
+def assign_thresholds(params, D1, maxpar):
+    """Frequency-independent box bounds per control (reference :2004-2016); minCoeff = -maxCoeff."""
+    Nfreq, Nc = params.Nfreq, params.Ncoupled
+    maxCoeff = np.zeros(2 * Nc * Nfreq * D1)
+    for c in range(Nc):
+        off = c * 2 * D1 * Nfreq
+        maxCoeff[off:off + 2 * D1 * Nfreq] = maxpar[c]
+    return -maxCoeff, maxCoeff
+
+
+def assign_thresholds_freq(maxamp, Ncoupled, Nfreq, D1):
+    """Frequency-dependent box bounds (reference :1975-1988)."""
+    maxCoeff = np.zeros(2 * Ncoupled * Nfreq * D1)
+    for c in range(Ncoupled):
+        for f in range(Nfreq):
+            off = 2 * c * Nfreq * D1 + f * 2 * D1
+            maxCoeff[off:off + 2 * D1] = maxamp[f]
+    return -maxCoeff, maxCoeff
+
+
+@dataclass
+class objparams:
+    """Problem definition; field names as in the reference struct (src/evalobjgrad.jl:53-149)."""
+    Ne: Sequence[int]
+    Ng: Sequence[int]
+    T: float
+    nsteps: int
+    Uinit: np.ndarray = None
+    Utarget: np.ndarray = None
+    Cfreq: np.ndarray = None
+    Rfreq: Sequence[float] = ()
+    Hconst: np.ndarray = None
+    Hsym_ops: List[np.ndarray] = field(default_factory=list)
+    Hanti_ops: List[np.ndarray] = field(default_factory=list)
+    Hunc_ops: List[np.ndarray] = field(default_factory=list)
+    objFuncType: int = 1
+    leak_ubound: float = 1.0e-3
+    wmatScale: float = 1.0
+    use_sparse: bool = False
+    use_custom_forbidden: bool = False
+    linear_solver: Optional[lsolver_object] = None
+    Integrator: int = Stormer_Verlet
+
+    def __post_init__(self):
+        self.Ne = [int(x) for x in self.Ne]
+        self.Ng = [int(x) for x in self.Ng]
+        self.Nt = [a + b for a, b in zip(self.Ne, self.Ng)]
+        self.Nosc = len(self.Ne)
+        self.N = int(np.prod(self.Ne))
+        Ntot = int(np.prod(self.Nt))
+        self.Nguard = Ntot - self.N
+        self.T = float(self.T)
+        self.nsteps = int(self.nsteps)
+        self.Cfreq = np.atleast_2d(np.asarray(self.Cfreq, dtype=float))
+        self.Nfreq = self.Cfreq.shape[1]
+        self.Ncoupled = len(self.Hsym_ops)
+        self.Nunc = len(self.Hunc_ops)
+        if self.Nunc != 0:
+            # uncoupled controls are outside the B200 hot path
+            raise NotImplementedError("uncoupled controls (Hunc_ops) are not on the B200 hot path")
+        if self.use_custom_forbidden:
+            raise NotImplementedError("custom (dense) forbidden-state weights are not on the B200 hot path")
+        if self.Integrator != Stormer_Verlet:
+            raise NotImplementedError("only Integrator = Stormer_Verlet is built for B200")
+        assert len(self.Hanti_ops) == self.Ncoupled
+        assert len(self.Rfreq) >= self.Ncoupled
+        assert self.Cfreq.shape[0] >= self.Ncoupled
+        self.Uinit = np.asarray(self.Uinit, dtype=float)
+        Ut = np.asarray(self.Utarget, dtype=complex)
+        assert self.Uinit.shape == (Ntot, self.N)
+        assert Ut.shape == (Ntot, self.N)
+        self.Utarget_r = np.ascontiguousarray(Ut.real)
+        self.Utarget_i = np.ascontiguousarray(Ut.imag)
+        self.Hconst = np.asarray(self.Hconst, dtype=float)
+        self.Hsym_ops = [np.asarray(h, dtype=float) for h in self.Hsym_ops]
+        self.Hanti_ops = [np.asarray(h, dtype=float) for h in self.Hanti_ops]
+        for h in [self.Hconst] + self.Hsym_ops + self.Hanti_ops:
+            assert h.shape == (Ntot, Ntot)
+        if self.linear_solver is None:
+            self.linear_solver = lsolver_object(nrhs=self.N)
+        self.pFidType = 2          # hard-wired in the reference constructor (:164)
+        self.tik0 = 0.01           # default Tikhonov coefficient (:202)
+        self.use_bcarrier = True   # (:208)
+        self.wmat_real = self.wmatScale * wmatsetup(self.Ne, self.Ng)  # diagonal, stored as a vector
+        self.quiet = False
+        self.usingPriorCoeffs = False
+        self.priorCoeffs = np.zeros(0)
+        self.objThreshold = 0.0
+        self.traceInfidelityThreshold = 0.0
+        self.saveConvHist = True
+        self.objHist, self.primaryHist, self.secondaryHist, self.dualInfidelityHist = [], [], [], []
+        # last-evaluation cache used by the Ipopt callbacks (src/ipopt_interface.jl:27-31)
+        self.last_pcof = np.zeros(0)
+        self.last_infidelity = 0.0
+        self.last_leak = 0.0
+        self.last_infidelity_grad = np.zeros(0)
+        self.last_leak_grad = np.zeros(0)
+        self.lastTraceInfidelity = 0.0
+        self.lastLeakIntegral = 0.0
+        self.save_pcof_hist = False
+        self.pcof_hist = []
+
+    @property
+    def Ntot(self) -> int:
+        return self.N + self.Nguard
+
+
+def change_target(params: objparams, new_Utarget: np.ndarray) -> None:
+    """Reference: change_target! (src/evalobjgrad.jl:1492-1505). Call Working_Arrays.update_target after."""
+    new_Utarget = np.asarray(new_Utarget, dtype=complex)
+    assert new_Utarget.shape == (params.Ntot, params.N)
+    params.Utarget_r = np.ascontiguousarray(new_Utarget.real)
+    params.Utarget_i = np.ascontiguousarray(new_Utarget.imag)
+
+
+def estimate_Neumann(tol: float, params: objparams, maxpar) -> None:
+    """Set the number of Neumann terms J (reference estimate_Neumann!, :2891-2928)."""
+    k = params.T / params.nsteps
+    assert len(maxpar) >= params.Ncoupled
+    S = 0.5 * k * maxpar[0] * params.Hanti_ops[0]
+    for j in range(1, params.Ncoupled):
+        S = S + 0.5 * k * maxpar[j] * params.Hanti_ops[j]
+    normS = np.linalg.norm(S, 2)
+    nterms = int(math.ceil(math.log(tol) / math.log(normS))) - 1
+    if nterms > 0:
+        params.linear_solver.max_iter = nterms
+
+
+def tikhonov_pen(pcof: np.ndarray, params: objparams) -> float:
+    Npar = len(pcof)
+    d = pcof - params.priorCoeffs if params.usingPriorCoeffs else pcof
+    return params.tik0 * float(np.dot(d, d)) / Npar
+
+
+def tikhonov_grad(pcof: np.ndarray, params: objparams) -> np.ndarray:
+    Npar = len(pcof)
+    d = pcof - params.priorCoeffs if params.usingPriorCoeffs else pcof
+    return (2.0 * params.tik0 / Npar) * d

@@ -1,0 +1,2 @@
+"""ORACLE — test infrastructure only (see oracle/traceobjgrad_oracle.c header). Never imported by juqbox_b200."""
+from .jq_oracle import oracle_traceobjgrad, build, max_threads  # noqa: F401

@@ -1,0 +1,116 @@
+"""ctypes loader for the CPU oracle (oracle/traceobjgrad_oracle.c).
+
+ORACLE — TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs;
+never by the product package.  Takes a juqbox_b200 `objparams`-like object (duck-typed: only plain attributes
+are read) so that the oracle and the CUDA path see byte-identical inputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class _Problem(C.Structure):
+    _fields_ = [("n", C.c_int), ("m", C.c_int), ("Nc", C.c_int), ("Nfreq", C.c_int), ("J", C.c_int),
+                ("objFuncType", C.c_int), ("sparse", C.c_int), ("nsteps", C.c_int64), ("T", C.c_double),
+                ("Uinit", C.c_void_p), ("Vtr", C.c_void_p), ("Vti", C.c_void_p), ("wdiag", C.c_void_p),
+                ("Cfreq", C.c_void_p), ("H0", C.c_void_p), ("Hsym", C.c_void_p), ("Hanti", C.c_void_p),
+                ("colptr", C.c_void_p), ("rowval", C.c_void_p), ("nzval", C.c_void_p)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libjq_oracle.so")
+    src = os.path.join(_HERE, "traceobjgrad_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.jqo_traceobjgrad_batch.restype = C.c_int
+        _LIB.jqo_max_threads.restype = C.c_int
+    return _LIB
+
+
+def max_threads() -> int:
+    return int(_lib().jqo_max_threads())
+
+
+def _f(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _csc(a):
+    """Dense -> CSC (0-based), dropping exact zeros like Julia's sparse()."""
+    a = np.asarray(a, dtype=np.float64)
+    n = a.shape[0]
+    colptr, rowval, nzval = [0], [], []
+    for c in range(n):
+        rows = np.nonzero(a[:, c])[0]
+        rowval.extend(rows.tolist())
+        nzval.extend(a[rows, c].tolist())
+        colptr.append(len(rowval))
+    return np.array(colptr, dtype=np.int64), np.array(rowval, dtype=np.int64), np.array(nzval, dtype=np.float64)
+
+
+def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nthreads: int = 1):
+    """Run the oracle on a batch: pcof [nbatch, Npar] (or [Npar]), shifts [nsamples, n] or None.
+
+    Returns dict with objf, infid, leak, trace_infid  [nbatch, nsamples] and grad, infidgrad, leakgrad
+    [nbatch, nsamples, Npar] (infidgrad == grad and leakgrad == 0 for objFuncType 1, as in the reference).
+    """
+    lib = _lib()
+    pcof = np.ascontiguousarray(np.atleast_2d(np.asarray(pcof, dtype=np.float64)))
+    nbatch, Npar = pcof.shape
+    n, m, Nc = params.Ntot, params.N, params.Ncoupled
+    keep = []
+
+    def ptr(a):
+        keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+
+    P = _Problem()
+    P.n, P.m, P.Nc, P.Nfreq = n, m, Nc, params.Nfreq
+    P.J, P.objFuncType, P.sparse = params.linear_solver.max_iter, params.objFuncType, int(bool(params.use_sparse))
+    P.nsteps, P.T = params.nsteps, params.T
+    P.Uinit, P.Vtr, P.Vti = ptr(_f(params.Uinit)), ptr(_f(params.Utarget_r)), ptr(_f(params.Utarget_i))
+    P.wdiag = ptr(np.ascontiguousarray(params.wmat_real, dtype=np.float64))
+    P.Cfreq = ptr(_f(params.Cfreq[:Nc, :]))
+    if params.use_sparse:
+        parts = [_csc(h) for h in [params.Hconst] + list(params.Hsym_ops) + list(params.Hanti_ops)]
+        P.colptr = ptr(np.concatenate([p[0] for p in parts]))
+        P.rowval = ptr(np.concatenate([p[1] for p in parts] + [np.zeros(1, np.int64)]))
+        P.nzval = ptr(np.concatenate([p[2] for p in parts] + [np.zeros(1)]))
+    else:
+        P.H0 = ptr(_f(params.Hconst))
+        P.Hsym = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hsym_ops]))
+        P.Hanti = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hanti_ops]))
+    if shifts is not None:
+        shifts = np.ascontiguousarray(np.atleast_2d(np.asarray(shifts, dtype=np.float64)))
+        assert shifts.shape[1] == n
+        nsamples = shifts.shape[0]
+    else:
+        nsamples = 1
+    ntraj = nbatch * nsamples
+    out = np.zeros((ntraj, 4))
+    grad = np.zeros((ntraj, Npar))
+    infidgrad = np.zeros((ntraj, Npar))
+    leakgrad = np.zeros((ntraj, Npar))
+    rc = lib.jqo_traceobjgrad_batch(C.byref(P), C.c_int(Npar), C.c_int(nbatch), ptr(pcof), C.c_int(nsamples),
+                                    ptr(shifts) if shifts is not None else None, C.c_int(int(evaladjoint)),
+                                    C.c_int(nthreads), ptr(out), ptr(grad), ptr(infidgrad), ptr(leakgrad))
+    if rc != 0:
+        raise ValueError("pcof must have an even number of elements >= %d, not %d" % (3 * 2 * Nc, Npar))
+    shp = (nbatch, nsamples)
+    return {"objf": out[:, 0].reshape(shp), "infid": out[:, 1].reshape(shp), "leak": out[:, 2].reshape(shp),
+            "trace_infid": out[:, 3].reshape(shp), "grad": grad.reshape(shp + (Npar,)),
+            "infidgrad": infidgrad.reshape(shp + (Npar,)), "leakgrad": leakgrad.reshape(shp + (Npar,))}

@@ -1,0 +1,64 @@
+"""CPU tests: pin the oracle (oracle/traceobjgrad_oracle.c) against every golden the reference holds for the
+Stormer-Verlet traceobjgrad path (test/runtests.jl:30-54), with the reference's own acceptance rule."""
+import numpy as np
+import pytest
+
+from helpers import golden_config, ref_pass, with_tikhonov
+from oracle import oracle_traceobjgrad
+
+FAST = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq"]
+
+
+@pytest.mark.parametrize("case", FAST + ["cnot3"])
+def test_oracle_matches_reference_golden(case):
+    cfg, g = golden_config(case)
+    res = oracle_traceobjgrad(cfg.params, cfg.pcof0)
+    objv, grad = with_tikhonov(cfg, res)
+    ok, dobj, dgrad = ref_pass(objv, grad, g["obj0"], g["grad0"])
+    print(case, "objDiff", dobj, "relGradErr", dgrad)
+    assert ok, (case, dobj, dgrad)
+
+
+def test_oracle_objective_only_matches_full():
+    cfg, _ = golden_config("swap02")
+    a = oracle_traceobjgrad(cfg.params, cfg.pcof0, evaladjoint=False)
+    b = oracle_traceobjgrad(cfg.params, cfg.pcof0, evaladjoint=True)
+    assert a["objf"][0, 0] == b["objf"][0, 0] and a["leak"][0, 0] == b["leak"][0, 0]
+
+
+def test_oracle_rejects_bad_pcof_length():
+    cfg, _ = golden_config("rabi")          # reference: evalobjgrad.jl:604-606
+    with pytest.raises(ValueError):
+        oracle_traceobjgrad(cfg.params, np.zeros(5))
+
+
+def test_oracle_gradient_is_the_derivative():
+    """Independent of the goldens: central finite difference of the oracle's own objective
+    (the check left commented in test/cases/cnot2-setup.jl:284-296)."""
+    cfg, _ = golden_config("swap02")
+    p0 = cfg.pcof0.copy()
+    base = oracle_traceobjgrad(cfg.params, p0)
+    h = 1e-6
+    for k in (0, 7, 23, 39):
+        pp, pm = p0.copy(), p0.copy()
+        pp[k] += h
+        pm[k] -= h
+        fd = (oracle_traceobjgrad(cfg.params, pp, evaladjoint=False)["objf"][0, 0]
+              - oracle_traceobjgrad(cfg.params, pm, evaladjoint=False)["objf"][0, 0]) / (2 * h)
+        assert abs(fd - base["grad"][0, 0, k]) < 1e-7 * max(1.0, abs(fd)), (k, fd, base["grad"][0, 0, k])
+
+
+def test_oracle_threads_and_samples_are_independent():
+    from juqbox_b200.configs import noise_shift
+    cfg, _ = golden_config("swap02")
+    rng = np.random.default_rng(1)
+    pc = cfg.pcof0[None, :] * (1 + 0.1 * rng.standard_normal((3, 1)))
+    sh = noise_shift(cfg.params.Ntot, [-0.05, 0.0, 0.07])
+    a = oracle_traceobjgrad(cfg.params, pc, sh, nthreads=1)
+    b = oracle_traceobjgrad(cfg.params, pc, sh, nthreads=4)
+    assert np.array_equal(a["grad"], b["grad"]) and np.array_equal(a["objf"], b["objf"])
+    single = oracle_traceobjgrad(cfg.params, pc[1], sh[2:3])
+    assert np.array_equal(single["grad"][0, 0], a["grad"][1, 2])
+    # zero shift == no shift
+    ns = oracle_traceobjgrad(cfg.params, pc[0])
+    assert np.allclose(ns["grad"][0, 0], a["grad"][0, 1], rtol=0, atol=1e-15)
