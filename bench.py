@@ -1,0 +1,310 @@
+#!/usr/bin/env python3
+"""bench.py — objective+gradient evaluations/sec of the traceobjgrad hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cnot2] [--batch B] [--impl reference]
+
+One "step" = one batched obj+grad evaluation (`jq_traceobjgrad_batch`) of B synthetic pcof candidates per GPU on the
+named BASELINE configuration (default: cnot2, "batched random pcof evaluations").  Ranks shard the candidates
+(weak scaling, no data-path collective); the risk-neutral leg in `extra` shards noise samples and does the one
+NCCL all-reduce per evaluation that the path really has.  Prints ONE JSON line on rank 0.
+
+  value     device-resident throughput: inputs already in HBM, CUDA events on the launching stream, max over ranks
+  e2e       same metric through the host-pointer C-ABI call (pinned host buffers, H2D + D2H inside the timed region)
+  roofline  algorithmic FP64 flops (SURVEY.md 8d formula) / kernel time, against the FP64 FMA peak measured in-run
+  cpu_baseline   the CPU oracle (a port: the Julia reference cannot run in this image) on a bounded sample
+  --impl reference   the same oracle with every host thread, as the reference arm
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def alg_flops_per_eval(p, npar):
+    """algorithmic flops of one obj+grad evaluation (structural nonzeros, FMA = 2)."""
+    n, m, J, Nc, Nf = p.Ntot, p.N, p.linear_solver.max_iter, p.Ncoupled, p.Nfreq
+    h0 = np.asarray(p.Hconst)
+    nnzK = n + int(np.count_nonzero(h0 - np.diag(np.diag(h0)))) + sum(int(np.count_nonzero(h)) for h in p.Hsym_ops)
+    nnzS = sum(int(np.count_nonzero(h)) for h in p.Hanti_ops)
+    nnzq = [int(np.count_nonzero(h)) for h in p.Hsym_ops]
+    f_state = 2 * m * (4 * nnzK + (4 + 2 * J) * nnzS) + (9 + 4 * J) * n * m
+    f_adj = 2 * m * (4 * nnzK + (4 + 2 * J) * nnzS) + (16 + 4 * J) * n * m
+    f_pen = 6 * n * m
+    f_grad = sum(12 * m * z for z in nnzq) + 16 * n * m + 96 * Nc * Nf
+    f_ctrl = 160 * Nc * Nf + 8 * sum(nnzq)
+    return p.nsteps * ((f_state + f_pen + f_ctrl) + (f_state + f_adj + f_grad + f_ctrl))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_run(cfg, pcof, shifts, nthreads, budget_s):
+    """Time the oracle on a bounded sample of the same workload; returns (evals_per_sec, n_evals, seconds)."""
+    from oracle import oracle_traceobjgrad
+    nsamp = 1 if shifts is None else len(shifts)
+    t0 = time.perf_counter()
+    oracle_traceobjgrad(cfg.params, pcof[:1], None if shifts is None else shifts[:1], nthreads=1)
+    t_one = time.perf_counter() - t0
+    ncand = int(max(1, min(len(pcof), (budget_s / max(t_one, 1e-6)) * nthreads / nsamp)))
+    ncand = max(ncand, min(len(pcof), -(-nthreads // nsamp)))      # at least one trajectory per thread
+    t0 = time.perf_counter()
+    oracle_traceobjgrad(cfg.params, pcof[:ncand], shifts, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return ncand * nsamp / dt, ncand * nsamp, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cnot2", choices=["rabi", "cnot1", "cnot2", "cnot3", "risk_neutral"])
+    ap.add_argument("--batch", type=int, default=0, help="pcof candidates per GPU per step (0 = per-workload default)")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 warp-slot")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from juqbox_b200 import configs
+    cfg = configs.example(args.workload)
+    default_batch = {"rabi": 262144, "cnot1": 32768, "cnot2": 16384, "cnot3": 1024, "risk_neutral": 4096}[args.workload]
+    B = args.batch or default_batch
+    shifts_h = configs.noise_shift(cfg.params.Ntot, cfg.nodes) if args.workload == "risk_neutral" else None
+    nsamp = 1 if shifts_h is None else len(shifts_h)
+    npar = cfg.nCoeff
+    workload = {"workload": f"{args.workload} (examples/{'Risk_Neutral/swap-02-risk-neutral' if args.workload == 'risk_neutral' else args.workload + '-setup'}.jl, Stormer-Verlet)",
+                "n": cfg.params.Ntot, "m": cfg.params.N, "nsteps": cfg.params.nsteps, "neumann_terms": cfg.params.linear_solver.max_iter,
+                "npar": npar, "candidates_per_gpu": B, "noise_samples": nsamp, "state_steps_per_eval": 3 * cfg.params.nsteps,
+                "l2": "flushed (256 MiB write) between timed steps"}
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle, all host threads
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import max_threads
+        nthr = max_threads()
+        pc = configs.synthetic_pcof(cfg, B)
+        vals, sample = [], None
+        budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+        for it in range(args.warmup + args.steps):
+            v, ne, dt = cpu_baseline_run(cfg, pc, shifts_h, nthr, budget)
+            sample = f"{ne} obj+grad evaluations of the {B}-candidate batch per step, {nthr} threads"
+            if it >= args.warmup:
+                vals.append((ne, dt))
+        tot_e, tot_t = sum(v[0] for v in vals), sum(v[1] for v in vals)
+        val = tot_e / tot_t
+        print(json.dumps({"impl": "reference", "metric": "objective+gradient evals/sec (traceobjgrad)", "value": val, "unit": "evals/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": workload,
+                          "cpu_baseline": {"value": val, "unit": "evals/s", "cores": nthr, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    import juqbox_b200 as jq
+    from juqbox_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wa = jq.Working_Arrays(cfg.params, npar, device=local_rank)
+    wa.set_kernel(args.kernel)
+    pc_h = configs.synthetic_pcof(cfg, B, seed_offset=rank)
+    pc_d = torch.from_numpy(pc_h).to(dev)
+    sh_d = torch.from_numpy(shifts_h).to(dev) if shifts_h is not None else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    out = None
+
+    def step():
+        nonlocal out
+        out = wa.evaluate_device(pc_d, sh_d, None, True, out=out, stream=stream)
+
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kernel_ms = []
+    barrier()
+    for e0, e1 in evs:
+        flush.fill_(1)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        kernel_ms.append(wa.last_kernel_ms)      # library's own events around the trajectory kernel (synchronises)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs))
+    evals_per_step = world * B * nsamp
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+    kern_ms = float(np.mean(kernel_ms))
+    used_kernel = wa.last_kernel
+
+    # ---- end to end through the host-pointer C ABI, pinned host buffers
+    pin_in = torch.from_numpy(pc_h).pin_memory()
+    pc_pin = pin_in.numpy()
+    for _ in range(1):
+        wa.evaluate(pc_pin, shifts_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = wa.evaluate(pc_pin, shifts_h)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_val = evals_per_step * args.steps / e2e_s
+    h2d = pc_pin.nbytes + (shifts_h.nbytes if shifts_h is not None else 0)
+    d2h = sum(r[k].nbytes for k in ("infid", "leak", "trace_infid", "grad", "infidgrad"))
+
+    # ---- roofline of the dominant (trajectory) kernel
+    flops_eval = alg_flops_per_eval(cfg.params, npar)
+    peak = _lib.fp64_peak_tflops(local_rank)
+    achieved = flops_eval * B * nsamp / (kern_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": None, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": {1: "jq_generic_kernel", 2: "jq_slot_kernel"}[used_kernel],
+                "hbm_alg_bytes_per_launch": 8 * (B * npar + nsamp * cfg.params.Ntot + B * nsamp * (4 + npar))}
+
+    # ---- CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1:
+        from oracle import max_threads
+        v1, ne1, dt1 = cpu_baseline_run(cfg, pc_h, shifts_h, 1, args.cpu_budget * 0.4)
+        nthr = max_threads()
+        vN, neN, dtN = cpu_baseline_run(cfg, pc_h, shifts_h, nthr, args.cpu_budget)
+        cpu = {"value": vN, "unit": "evals/s", "cores": nthr, "kind": "port",
+               "sample": f"{neN} obj+grad evaluations from the same batch in {dtN:.1f}s on {nthr} threads (pthread pool over trajectories)",
+               "single_thread": {"value": v1, "cores": 1, "sample": f"{ne1} evaluations in {dt1:.1f}s"}}
+
+    # ---- extra: risk-neutral evaluation with the sample shard + NCCL all-reduce (the path's one exchange step)
+    extra = {}
+    if not args.no_extra:
+        rn = configs.example("risk_neutral")
+        S = 1024                                             # noise samples per GPU (weak scaling)
+        nodes, weights = np.polynomial.legendre.leggauss(S * world)
+        nodes, weights = nodes * 0.5 * (2 * np.pi * 2e-2), weights * 0.5
+        sl = slice(rank * S, (rank + 1) * S)
+        wr = jq.Working_Arrays(rn.params, rn.nCoeff, device=local_rank)
+        pcr = torch.from_numpy(configs.synthetic_pcof(rn, 1)).to(dev)
+        shr = torch.from_numpy(configs.noise_shift(rn.params.Ntot, nodes[sl])).to(dev)
+        wtr = torch.from_numpy(np.ascontiguousarray(weights[sl])).to(dev)
+        packed = torch.empty(2 + rn.nCoeff, dtype=torch.float64, device=dev)
+        o = None
+
+        def rn_step():
+            nonlocal o
+            o = wr.evaluate_device(pcr, shr, wtr, True, out=o, stream=stream)
+            packed[0:1].copy_(o["infid"]); packed[1:2].copy_(o["leak"]); packed[2:].copy_(o["grad"][0])
+            if world > 1:
+                dist.all_reduce(packed)                      # one NCCL all-reduce of 2 + Npar doubles per evaluation
+        for _ in range(3):
+            rn_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            rn_step()
+        b.record(stream)
+        barrier()
+        ms = max_over_ranks(a.elapsed_time(b))
+        extra["risk_neutral_sample_sharded"] = {
+            "samples_per_gpu": S, "evals_per_sec": world * S * args.steps / (ms * 1e-3), "ms_per_risk_neutral_evaluation": ms / args.steps,
+            "allreduce_doubles": 2 + rn.nCoeff, "collective": "nccl all_reduce(sum)" if world > 1 else "none (1 GPU)",
+            "objective": float(packed[0].item() + packed[1].item())}
+        wr.close()
+
+    if rank == 0:
+        line = {"metric": "objective+gradient evals/sec (traceobjgrad)", "value": value, "unit": "evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
+                "state_steps_per_sec": value * 3 * cfg.params.nsteps,
+                "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": int(2 * args.steps), "roofline": roofline, "clocks": clocks, "extra": extra}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    wa.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,122 @@
+/*
+ * juqbox_b200.h — C ABI of the B200-native objective + adjoint-gradient path of Juqbox.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its boundary is the Julia
+ * method  traceobjgrad(pcof0, params::objparams, wa::Working_Arrays, verbose, evaladjoint)
+ * (/root/reference/src/evalobjgrad.jl:504) and its only production caller, the risk-neutral sample loop
+ * eval_f_g_grad! (/root/reference/src/ipopt_interface.jl:24-70).  A Julia maintainer binds the entry points
+ * below with `ccall` (see INTEGRATION.md and julia/JuqboxB200.jl); this repo's own host mirror binds them
+ * with ctypes (juqbox_b200/_lib.py).
+ *
+ * Conventions: plain C, FP64 only, column-major matrices (Julia layout), 0-based CSC, host pointers unless the
+ * name says `_device`.  Every function returns 0 on success or a negative jq_status; jq_last_error() gives the
+ * text.  A handle is bound to one GPU and is not thread-safe (the reference is single-threaded, synchronous).
+ * There is no CPU fallback: without a CUDA device jq_create fails with JQ_ERR_CUDA.
+ */
+#ifndef JUQBOX_B200_H
+#define JUQBOX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jq_handle jq_handle;
+
+typedef enum jq_status {
+    JQ_OK = 0,
+    JQ_ERR_ARG = -1,         /* bad argument / unsupported option (message says which) */
+    JQ_ERR_PCOF_LENGTH = -2, /* mirrors error() at src/evalobjgrad.jl:604-606 and DimensionMismatch at src/bsplines.jl:178-181 */
+    JQ_ERR_CUDA = -3,        /* CUDA runtime error, or no device */
+    JQ_ERR_ALLOC = -4
+} jq_status;
+
+enum { JQ_DENSE = 0, JQ_CSC = 1 };
+
+/* One real n x n operator: Hconst, Hsym_ops[q] or Hanti_ops[q] of objparams (src/evalobjgrad.jl:85-90).
+ * JQ_DENSE: nzval = n*n values, column-major (Array{Float64,2}); colptr/rowval ignored.
+ * JQ_CSC:   SparseMatrixCSC{Float64,Int64} converted to 0-based indices. */
+typedef struct jq_operator {
+    int32_t format;
+    int64_t nnz;
+    const int64_t *colptr; /* n+1 */
+    const int64_t *rowval; /* nnz */
+    const double *nzval;
+} jq_operator;
+
+/* The fields of `objparams` that the Stormer-Verlet path reads. */
+typedef struct jq_problem {
+    int32_t n;             /* Ntot = N + Nguard                         (evalobjgrad.jl:522) */
+    int32_t m;             /* N, number of propagated columns           (:508)               */
+    int32_t ncoupled;      /* length(Hsym_ops) == length(Hanti_ops)     (:170,:243)          */
+    int32_t nfreq;         /* size(Cfreq, 2)                            (:169)               */
+    int32_t neumann_terms; /* linear_solver.max_iter (Neumann solver)   (linear_solvers.jl:46) */
+    int32_t obj_func_type; /* objFuncType: 1 = infidelity+leak, 2/3 = also return infidelity-only gradient (:848-855) */
+    int32_t pfid_type;     /* pFidType; only 2 is built (hard-wired by the reference constructor, :164) */
+    int32_t reserved;
+    int64_t nsteps;
+    double T;
+    const double *uinit;     /* n*m, params.Uinit */
+    const double *vtarget_r; /* n*m, params.Utarget_r */
+    const double *vtarget_i; /* n*m, params.Utarget_i */
+    const double *wdiag;     /* n, diagonal of params.wmat_real (Diagonal weights only) */
+    const double *cfreq;     /* ncoupled*nfreq, params.Cfreq column-major: (c,f) at c + ncoupled*f */
+    jq_operator h0;          /* params.Hconst */
+    const jq_operator *hsym; /* ncoupled */
+    const jq_operator *hanti;/* ncoupled */
+} jq_problem;
+
+/* Replaces Working_Arrays(params, nCoeff) (src/evalobjgrad.jl:405): copies the problem to the GPU `device`,
+ * builds the row-wise operator tables and picks the kernel.  Create once, reuse for every evaluation. */
+int jq_create(const jq_problem *problem, int device, jq_handle **out);
+int jq_destroy(jq_handle *h);
+
+/* change_target! (src/evalobjgrad.jl:1492-1505): new n*m target, real and imaginary parts. */
+int jq_update_target(jq_handle *h, const double *vtarget_r, const double *vtarget_i);
+
+/* Batched traceobjgrad(pcof, params, wa, false, evaladjoint) — replaces the body of the `for i = 1:nquad` loop of
+ * eval_f_g_grad! (src/ipopt_interface.jl:38-65) and the epsilon sweep of examples/Risk_Neutral/run_all.jl:9-28.
+ *
+ * Trajectory (b, s) evaluates candidate pcof[b*npar .. ] with Hconst + Diagonal(h0_diag_shift[s*n .. ]);
+ * h0_diag_shift == NULL means nsamples must be 1 and no shift.  (The reference's noise model is
+ * shift[j] = 0.01*ep*10^(j-2) for j = 2..n, 1-based, src/ipopt_interface.jl:41-44; any diagonal is accepted.)
+ *
+ * weights == NULL: per-trajectory outputs, index t = b*nsamples + s:  infid[t] (primaryobjf), leak[t]
+ *   (secondaryobjf), trace_infid[t], grad[t*npar ..] (totalgrad) and, if obj_func_type != 1, infidgrad / leakgrad.
+ * weights != NULL ([nsamples]): outputs are the weighted sums over s that eval_f_g_grad! accumulates
+ *   (src/ipopt_interface.jl:48-59), one per candidate b.
+ * Any output pointer may be NULL.  evaladjoint == 0 skips the backward sweep (gradients are not written).
+ * For obj_func_type == 1 infidgrad receives a copy of grad (reference :951) and leakgrad is left untouched.
+ * Blocking: returns after the results are in the host buffers. */
+int jq_traceobjgrad_batch(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
+                          const double *h0_diag_shift, const double *weights, int32_t evaladjoint,
+                          double *infid, double *leak, double *trace_infid, double *grad, double *infidgrad,
+                          double *leakgrad);
+
+/* Same, with every array already in device memory of the handle's GPU and the work enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = the handle's own stream).  Asynchronous: no host synchronisation. */
+int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
+                                 const double *h0_diag_shift, const double *weights, int32_t evaladjoint,
+                                 double *infid, double *leak, double *trace_infid, double *grad,
+                                 double *infidgrad, double *leakgrad, void *cuda_stream);
+
+/* Kernel selection, for tests and profiling: 0 = automatic, 1 = generic (one CTA per trajectory, any operators),
+ * 2 = register-resident warp-slot kernel (fails with JQ_ERR_ARG if the problem shape has no instantiation). */
+int jq_set_kernel(jq_handle *h, int32_t kernel);
+/* what: 0 = kernel actually used by the last evaluation (1/2), 1 = CUDA-event time of the last evaluation's
+ * trajectory kernel in ms (synchronises), 2 = number of kernels launched by the last evaluation,
+ * 3 = trajectories resident per CTA, 4 = CTAs launched, 5 = registers per thread, 6 = dynamic smem bytes per CTA. */
+int jq_query(jq_handle *h, int32_t what, double *value);
+
+/* Measured FP64 FMA throughput of `device` in TFLOP/s (8 independent DFMA chains per thread on every SM, best of
+ * 5 CUDA-event timed launches) — the roofline denominator for this path; MEASURED_PEAKS.json has no FP64 entry. */
+int jq_fp64_peak(int device, double *tflops);
+
+const char *jq_last_error(void);
+const char *jq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JUQBOX_B200_H */

@@ -1,0 +1,267 @@
+"""Host-side mirror of the reference's evaluation API, calling the CUDA library through the C ABI.
+
+  Working_Arrays(params, nCoeff)                      src/evalobjgrad.jl:405   -> owns the device handle
+  traceobjgrad(pcof0, params, wa, verbose, evaladjoint)  src/evalobjgrad.jl:504
+  eval_f_g_grad!(pcof, params, wa, nodes, weights, compute_adjoint)   src/ipopt_interface.jl:24-70
+  eval_f_par / eval_grad_f_par / eval_g_par / eval_jac_g_par           src/ipopt_interface.jl:77-179
+plus the batched forms the reference only has as serial loops (traceobjgrad_batch, ep_sweep).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .configs import noise_shift
+from .params import objparams, tikhonov_grad, tikhonov_pen
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _csc(a):
+    a = np.asarray(a, dtype=np.float64)
+    n = a.shape[0]
+    colptr, rowval, nzval = [0], [], []
+    for c in range(n):
+        rows = np.nonzero(a[:, c])[0]          # sparse() drops exact zeros (src/evalobjgrad.jl:265-288)
+        rowval.extend(rows.tolist())
+        nzval.extend(a[rows, c].tolist())
+        colptr.append(len(rowval))
+    return (np.array(colptr, dtype=np.int64), np.array(rowval + [0], dtype=np.int64)[:max(len(rowval), 1)],
+            np.array(nzval + [0.0], dtype=np.float64)[:max(len(nzval), 1)], len(nzval))
+
+
+class Working_Arrays:
+    """Device-resident replacement of the reference's Working_Arrays: one handle per (params, nCoeff) and GPU."""
+
+    def __init__(self, params: objparams, nCoeff: int, device: Optional[int] = None):
+        lib = _lib.load()
+        self._lib = lib
+        self.params = params
+        self.nCoeff = int(nCoeff)
+        nsig = 2 * params.Ncoupled
+        if nCoeff % (nsig * params.Nfreq) != 0 or nCoeff < 3 * nsig:
+            raise ValueError(f"pcof must have an even number of elements >= {3 * nsig}, not {nCoeff}")
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0")) if "JUQBOX_B200_USE_LOCAL_RANK" in os.environ else 0
+        self.device = device
+        self._keep = []
+        self._handle = C.c_void_p()
+        pb = self._describe(params)
+        _lib.check(lib.jq_create(C.byref(pb), C.c_int(device), C.byref(self._handle)))
+
+    # -- problem descriptor -------------------------------------------------------------------
+    def _ptr(self, a):
+        self._keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+
+    def _op(self, mat, sparse):
+        op = _lib.jq_operator()
+        if sparse:
+            cp, rv, nz, nnz = _csc(mat)
+            op.format, op.nnz = _lib.JQ_CSC, nnz
+            op.colptr, op.rowval, op.nzval = self._ptr(cp), self._ptr(rv), self._ptr(nz)
+        else:
+            a = np.asfortranarray(mat, dtype=np.float64)
+            op.format, op.nnz = _lib.JQ_DENSE, a.size
+            op.nzval = self._ptr(a)
+        return op
+
+    def _describe(self, p: objparams):
+        pb = _lib.jq_problem()
+        pb.n, pb.m, pb.ncoupled, pb.nfreq = p.Ntot, p.N, p.Ncoupled, p.Nfreq
+        pb.neumann_terms = p.linear_solver.max_iter
+        pb.obj_func_type, pb.pfid_type = p.objFuncType, p.pFidType
+        pb.nsteps, pb.T = p.nsteps, p.T
+        pb.uinit = self._ptr(np.asfortranarray(p.Uinit, dtype=np.float64))
+        pb.vtarget_r = self._ptr(np.asfortranarray(p.Utarget_r, dtype=np.float64))
+        pb.vtarget_i = self._ptr(np.asfortranarray(p.Utarget_i, dtype=np.float64))
+        pb.wdiag = self._ptr(_f64(p.wmat_real))
+        pb.cfreq = self._ptr(np.asfortranarray(p.Cfreq[:p.Ncoupled, :], dtype=np.float64))
+        pb.h0 = self._op(p.Hconst, p.use_sparse)
+        OpArr = _lib.jq_operator * p.Ncoupled
+        hs = OpArr(*[self._op(h, p.use_sparse) for h in p.Hsym_ops])
+        ha = OpArr(*[self._op(h, p.use_sparse) for h in p.Hanti_ops])
+        self._keep += [hs, ha]
+        pb.hsym, pb.hanti = hs, ha
+        return pb
+
+    # -- lifecycle ----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self._lib.jq_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update_target(self):
+        """Push params.Utarget_r/i to the device after change_target (src/evalobjgrad.jl:1492)."""
+        p = self.params
+        vr, vi = np.asfortranarray(p.Utarget_r, dtype=np.float64), np.asfortranarray(p.Utarget_i, dtype=np.float64)
+        _lib.check(self._lib.jq_update_target(self._handle, vr.ctypes.data_as(C.c_void_p), vi.ctypes.data_as(C.c_void_p)))
+
+    def set_kernel(self, kernel: int):
+        """0 = automatic, 1 = generic kernel, 2 = warp-slot kernel."""
+        _lib.check(self._lib.jq_set_kernel(self._handle, int(kernel)))
+
+    def query(self, what: int) -> float:
+        v = C.c_double()
+        _lib.check(self._lib.jq_query(self._handle, int(what), C.byref(v)))
+        return v.value
+
+    @property
+    def last_kernel(self) -> int:
+        return int(self.query(0))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return self.query(1)
+
+    # -- evaluation ---------------------------------------------------------------------------
+    def evaluate(self, pcof, shifts=None, weights=None, evaladjoint=True):
+        """Batched evaluation with host arrays (copies inside): see jq_traceobjgrad_batch."""
+        p = self.params
+        pcof = _f64(np.atleast_2d(pcof))
+        nbatch, npar = pcof.shape
+        nsamples = 1
+        sp = wp = None
+        if shifts is not None:
+            shifts = _f64(np.atleast_2d(shifts))
+            if shifts.shape[1] != p.Ntot:
+                raise ValueError("shifts must be [nsamples, Ntot]")
+            nsamples = shifts.shape[0]
+            sp = shifts.ctypes.data_as(C.c_void_p)
+        if weights is not None:
+            weights = _f64(np.atleast_1d(weights))
+            if len(weights) != nsamples:
+                raise ValueError("weights must have one entry per sample")
+            wp = weights.ctypes.data_as(C.c_void_p)
+        shape = (nbatch,) if weights is not None else (nbatch, nsamples)
+        out = {k: np.zeros(shape) for k in ("infid", "leak", "trace_infid")}
+        gptr = [None, None, None]
+        if evaladjoint:
+            out["grad"] = np.zeros(shape + (npar,))
+            out["infidgrad"] = np.zeros(shape + (npar,))
+            out["leakgrad"] = np.zeros(shape + (npar,))
+            gptr = [out[k].ctypes.data_as(C.c_void_p) for k in ("grad", "infidgrad", "leakgrad")]
+        _lib.check(self._lib.jq_traceobjgrad_batch(
+            self._handle, nbatch, pcof.ctypes.data_as(C.c_void_p), npar, nsamples, sp, wp, int(bool(evaladjoint)),
+            out["infid"].ctypes.data_as(C.c_void_p), out["leak"].ctypes.data_as(C.c_void_p),
+            out["trace_infid"].ctypes.data_as(C.c_void_p), *gptr))
+        out["objf"] = out["infid"] + out["leak"]
+        return out
+
+    def evaluate_device(self, pcof, shifts=None, weights=None, evaladjoint=True, out=None, stream=None):
+        """Batched evaluation on torch CUDA tensors (no host copies, asynchronous on `stream` or torch's current
+        stream).  pcof [nbatch, npar], shifts [nsamples, n], weights [nsamples]; returns dict of CUDA tensors."""
+        import torch
+        assert pcof.is_cuda and pcof.dtype == torch.float64 and pcof.is_contiguous()
+        nbatch, npar = pcof.shape
+        nsamples = 1 if shifts is None else shifts.shape[0]
+        shape = (nbatch,) if weights is not None else (nbatch, nsamples)
+        if out is None:
+            out = {k: torch.empty(shape, dtype=torch.float64, device=pcof.device) for k in ("infid", "leak", "trace_infid")}
+            if evaladjoint:
+                out["grad"] = torch.empty(shape + (npar,), dtype=torch.float64, device=pcof.device)
+                if self.params.objFuncType != 1:
+                    out["infidgrad"] = torch.empty_like(out["grad"])
+                    out["leakgrad"] = torch.empty_like(out["grad"])
+        st = stream if stream is not None else torch.cuda.current_stream(pcof.device)
+
+        def dp(t):
+            return C.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(self._lib.jq_traceobjgrad_batch_device(
+            self._handle, nbatch, dp(pcof), npar, nsamples, dp(shifts), dp(weights), int(bool(evaladjoint)),
+            dp(out["infid"]), dp(out["leak"]), dp(out["trace_infid"]), dp(out.get("grad")), dp(out.get("infidgrad")),
+            dp(out.get("leakgrad")), C.c_void_p(st.cuda_stream)))
+        return out
+
+
+def traceobjgrad(pcof0, params: objparams, wa: Working_Arrays, verbose: bool = False, evaladjoint: bool = True):
+    """Drop-in for the reference method (src/evalobjgrad.jl:504): same return tuples (:1032-1035)."""
+    if verbose:
+        raise NotImplementedError("verbose=true (state history / forward-sensitivity check) stays on the reference's "
+                                  "CPU path (SURVEY.md rows 14 and 8f-4)")
+    pcof0 = np.asarray(pcof0, dtype=np.float64)
+    r = wa.evaluate(pcof0[None, :], evaladjoint=evaladjoint)
+    objfv, primary, secondary = r["objf"][0, 0], r["infid"][0, 0], r["leak"][0, 0]
+    if not evaladjoint:
+        return objfv, primary, secondary
+    totalgrad = r["grad"][0, 0]
+    if params.objFuncType != 1:
+        infidelgrad, leakgrad = r["infidgrad"][0, 0], r["leakgrad"][0, 0]
+    else:
+        infidelgrad, leakgrad = totalgrad, np.zeros(0)
+    return objfv, totalgrad, primary, secondary, r["trace_infid"][0, 0], infidelgrad, leakgrad
+
+
+def traceobjgrad_batch(pcofs, params: objparams, wa: Working_Arrays, nodes=None, weights=None, evaladjoint=True):
+    """All (candidate, noise sample) trajectories in one call; nodes are the epsilons of the risk-neutral model."""
+    shifts = None if nodes is None else noise_shift(params.Ntot, nodes)
+    return wa.evaluate(pcofs, shifts, weights, evaladjoint)
+
+
+def eval_f_g_grad(pcof, params: objparams, wa: Working_Arrays, nodes=(0.0,), weights=(1.0,), compute_adjoint=True):
+    """eval_f_g_grad! (src/ipopt_interface.jl:24-70): the nquad-sample loop becomes one batched call."""
+    pcof = np.asarray(pcof, dtype=np.float64)
+    nodes, weights = np.atleast_1d(np.asarray(nodes, float)), np.atleast_1d(np.asarray(weights, float))
+    r = wa.evaluate(pcof[None, :], noise_shift(params.Ntot, nodes), weights, compute_adjoint)
+    params.last_pcof = pcof.copy()
+    params.last_infidelity = float(r["infid"][0])
+    params.last_leak = float(r["leak"][0])
+    if compute_adjoint:
+        params.last_infidelity_grad = r["infidgrad"][0].copy()
+        params.last_leak_grad = r["leakgrad"][0].copy() if params.objFuncType != 1 else np.zeros(len(pcof))
+    params.lastTraceInfidelity = params.last_infidelity
+    params.lastLeakIntegral = params.last_leak
+
+
+def _stale(pcof, params):
+    return len(params.last_pcof) != len(pcof) or np.linalg.norm(pcof - params.last_pcof) > 1.0e-15
+
+
+def eval_f_par(pcof, params, wa, nodes=(0.0,), weights=(1.0,)):
+    pcof = np.asarray(pcof, dtype=np.float64)
+    if _stale(pcof, params):
+        eval_f_g_grad(pcof, params, wa, nodes, weights, True)
+    f = params.last_infidelity + params.last_leak if params.objFuncType == 1 else params.last_infidelity
+    return f + tikhonov_pen(pcof, params)
+
+
+def eval_g_par(pcof, g, params, wa, nodes=(0.0,), weights=(1.0,)):
+    pcof = np.asarray(pcof, dtype=np.float64)
+    if _stale(pcof, params):
+        eval_f_g_grad(pcof, params, wa, nodes, weights, True)
+    g[0] = params.last_leak
+    return g[0]
+
+
+def eval_grad_f_par(pcof, grad_f, params, wa, nodes=(0.0,), weights=(1.0,)):
+    pcof = np.asarray(pcof, dtype=np.float64)
+    if _stale(pcof, params):
+        eval_f_g_grad(pcof, params, wa, nodes, weights, True)
+    grad_f[:] = params.last_infidelity_grad + tikhonov_grad(pcof, params)
+    if params.save_pcof_hist:
+        params.pcof_hist.append(pcof.copy())
+
+
+def eval_jac_g_par(pcof, rows, cols, jac_g, params, wa, nodes=(0.0,), weights=(1.0,)):
+    pcof = np.asarray(pcof, dtype=np.float64)
+    if jac_g is None:
+        if len(rows) > 0:
+            rows[:] = 1
+            cols[:] = np.arange(1, len(pcof) + 1)
+        return
+    if _stale(pcof, params):
+        eval_f_g_grad(pcof, params, wa, nodes, weights, True)
+        return                      # the reference returns without filling jac_g in this branch (:169-173)
+    jac_g[:] = params.last_leak_grad

@@ -1,0 +1,361 @@
+// C-ABI layer (include/juqbox_b200.h): problem upload, operator tables, kernel selection, launches and the
+// per-candidate weighted reduction.  No torch types, no CPU fallback.
+#include "jq_common.h"
+#include "../../include/juqbox_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(JQ_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct jq_handle {
+    int device = 0;
+    DevProblem P{};
+    int n = 0, m = 0, Nc = 0, Nfreq = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> owned;          // device allocations freed at destroy
+    double *d_vtr = nullptr, *d_vti = nullptr;
+    // host copies of the row-wise operators (for the planners)
+    std::vector<int> rowptr, col;
+    std::vector<double> val;
+    SlotPlan *slot = nullptr;
+    char slot_reason[256] = "";
+    int kernel_pref = 0;
+    // growable scratch
+    double *d_scal = nullptr, *d_grad = nullptr, *d_igrad = nullptr;
+    size_t cap_traj = 0, cap_grad = 0, cap_igrad = 0;
+    double *d_in = nullptr;  size_t cap_in = 0;    // staged host inputs
+    double *d_out = nullptr; size_t cap_out = 0;   // staged host outputs
+    // last-evaluation facts
+    int last_kernel = 0, last_launches = 0, last_ctas = 0, last_regs = 0, last_tpc = 1;
+    size_t last_smem = 0;
+    bool timed = false;
+};
+
+template <class T>
+static int upload(jq_handle *h, const T *src, size_t count, T **dst) {
+    void *p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    h->owned.push_back(p);
+    if (count) CU(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (T *)p;
+    return 0;
+}
+
+static int grow(double **buf, size_t *cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    CU(cudaMalloc((void **)buf, need * sizeof(double)));
+    *cap = need;
+    return 0;
+}
+
+// operator -> sorted CSR rows appended to (rowptr, col, val); `force_diag` inserts missing diagonal entries.
+static int append_rows(const jq_operator &op, int n, bool force_diag, std::vector<int> &rowptr, std::vector<int> &col,
+                       std::vector<double> &val, const char *name) {
+    std::vector<std::vector<std::pair<int, double>>> rows(n);
+    if (op.format == JQ_DENSE) {
+        if (!op.nzval) return fail(JQ_ERR_ARG, "%s: dense operator without values", name);
+        for (int c = 0; c < n; ++c)
+            for (int r = 0; r < n; ++r) {
+                const double v = op.nzval[(size_t)c * n + r];
+                if (v != 0.0) rows[r].push_back({c, v});
+            }
+    } else if (op.format == JQ_CSC) {
+        if (!op.colptr || (op.nnz > 0 && (!op.rowval || !op.nzval))) return fail(JQ_ERR_ARG, "%s: CSC operator with null arrays", name);
+        if (op.colptr[0] != 0 || op.colptr[n] != op.nnz) return fail(JQ_ERR_ARG, "%s: CSC colptr must be 0-based and end at nnz", name);
+        for (int c = 0; c < n; ++c)
+            for (int64_t p = op.colptr[c]; p < op.colptr[c + 1]; ++p) {
+                const int64_t r = op.rowval[p];
+                if (r < 0 || r >= n) return fail(JQ_ERR_ARG, "%s: CSC row index %lld out of range", name, (long long)r);
+                rows[r].push_back({c, op.nzval[p]});
+            }
+    } else {
+        return fail(JQ_ERR_ARG, "%s: unknown operator format %d", name, op.format);
+    }
+    for (int r = 0; r < n; ++r) {
+        auto &row = rows[r];
+        std::sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+        if (force_diag) {
+            bool has = false;
+            for (auto &e : row) has |= (e.first == r);
+            if (!has) {
+                row.push_back({r, 0.0});
+                std::sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.first < b.first; });
+            }
+        }
+        rowptr.push_back((int)col.size());
+        for (auto &e : row) { col.push_back(e.first); val.push_back(e.second); }
+    }
+    rowptr.push_back((int)col.size());
+    return 0;
+}
+
+extern "C" const char *jq_last_error(void) { return g_err; }
+extern "C" const char *jq_version(void) { return "juqbox_b200 0.1 (sm_100a)"; }
+
+extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
+    if (!pb || !out) return fail(JQ_ERR_ARG, "jq_create: null argument");
+    *out = nullptr;
+    if (pb->n < 1 || pb->m < 1 || pb->m > pb->n) return fail(JQ_ERR_ARG, "jq_create: need 1 <= m <= n (n=%d, m=%d)", pb->n, pb->m);
+    if (pb->ncoupled < 1) return fail(JQ_ERR_ARG, "jq_create: ncoupled must be >= 1 (uncoupled-only controls are not on this path)");
+    if (pb->nfreq < 1 || pb->nsteps < 1 || !(pb->T > 0.0) || pb->neumann_terms < 0)
+        return fail(JQ_ERR_ARG, "jq_create: need nfreq >= 1, nsteps >= 1, T > 0, neumann_terms >= 0");
+    if (pb->pfid_type != 2) return fail(JQ_ERR_ARG, "jq_create: only pFidType == 2 is built (got %d)", pb->pfid_type);
+    if (pb->obj_func_type < 1 || pb->obj_func_type > 3) return fail(JQ_ERR_ARG, "jq_create: objFuncType must be 1, 2 or 3");
+    if (!pb->uinit || !pb->vtarget_r || !pb->vtarget_i || !pb->wdiag || !pb->cfreq || !pb->hsym || !pb->hanti)
+        return fail(JQ_ERR_ARG, "jq_create: null problem array");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(JQ_ERR_CUDA, "jq_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(JQ_ERR_ARG, "jq_create: device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    jq_handle *h = new jq_handle();
+    h->device = device;
+    const int n = pb->n, m = pb->m, Nc = pb->ncoupled;
+    h->n = n; h->m = m; h->Nc = Nc; h->Nfreq = pb->nfreq;
+    int rc = append_rows(pb->h0, n, true, h->rowptr, h->col, h->val, "Hconst");
+    for (int q = 0; q < Nc && rc == 0; ++q) rc = append_rows(pb->hsym[q], n, false, h->rowptr, h->col, h->val, "Hsym_ops");
+    for (int q = 0; q < Nc && rc == 0; ++q) rc = append_rows(pb->hanti[q], n, false, h->rowptr, h->col, h->val, "Hanti_ops");
+    if (rc) { delete h; return rc; }
+    std::vector<int> h0diag(n);
+    for (int r = 0; r < n; ++r)
+        for (int p = h->rowptr[r]; p < h->rowptr[r + 1]; ++p)
+            if (h->col[p] == r) h0diag[r] = p;
+
+    DevProblem &P = h->P;
+    P.n = n; P.m = m; P.Nc = Nc; P.Nfreq = pb->nfreq; P.J = pb->neumann_terms; P.objFuncType = pb->obj_func_type;
+    P.nsteps = pb->nsteps; P.T = pb->T;
+    double *tmp = nullptr;
+    int *itmp = nullptr;
+#define UP(src, cnt, field)                                                        \
+    do {                                                                           \
+        if ((rc = upload(h, src, (size_t)(cnt), &tmp)) != 0) { jq_destroy(h); return rc; } \
+        field = tmp;                                                               \
+    } while (0)
+#define UPI(src, cnt, field)                                                        \
+    do {                                                                            \
+        if ((rc = upload(h, src, (size_t)(cnt), &itmp)) != 0) { jq_destroy(h); return rc; } \
+        field = itmp;                                                               \
+    } while (0)
+    UP(pb->uinit, n * m, P.uinit);
+    UP(pb->vtarget_r, n * m, h->d_vtr);
+    UP(pb->vtarget_i, n * m, h->d_vti);
+    P.vtr = h->d_vtr; P.vti = h->d_vti;
+    UP(pb->wdiag, n, P.wdiag);
+    UP(pb->cfreq, Nc * pb->nfreq, P.cfreq);
+    UP(h->val.data(), h->val.size(), P.val);
+    UPI(h->rowptr.data(), h->rowptr.size(), P.rowptr);
+    UPI(h->col.data(), h->col.size(), P.col);
+    UPI(h0diag.data(), n, P.h0diag);
+#undef UP
+#undef UPI
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
+        cudaEventCreate(&h->ev1) != cudaSuccess) {
+        jq_destroy(h);
+        return fail(JQ_ERR_CUDA, "jq_create: stream/event creation failed");
+    }
+    HostOps H{n, m, Nc, pb->nfreq, h->rowptr.data(), h->col.data(), h->val.data()};
+    h->slot = jq_slot_plan_create(P, H, h->slot_reason, sizeof(h->slot_reason));
+    *out = h;
+    return 0;
+}
+
+extern "C" int jq_destroy(jq_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *p : h->owned) cudaFree(p);
+    for (double *p : {h->d_scal, h->d_grad, h->d_igrad, h->d_in, h->d_out}) if (p) cudaFree(p);
+    if (h->slot) jq_slot_plan_destroy(h->slot);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int jq_update_target(jq_handle *h, const double *vr, const double *vi) {
+    if (!h || !vr || !vi) return fail(JQ_ERR_ARG, "jq_update_target: null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(h->d_vtr, vr, sizeof(double) * h->n * h->m, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_vti, vi, sizeof(double) * h->n * h->m, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
+    if (!h || kernel < 0 || kernel > 2) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0, 1 or 2");
+    if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no warp-slot instantiation for this problem (%s)", h->slot_reason);
+    h->kernel_pref = kernel;
+    return 0;
+}
+
+extern "C" int jq_query(jq_handle *h, int32_t what, double *value) {
+    if (!h || !value) return fail(JQ_ERR_ARG, "jq_query: null argument");
+    switch (what) {
+    case 0: *value = h->last_kernel; break;
+    case 1: {
+        if (!h->timed) return fail(JQ_ERR_ARG, "jq_query: no evaluation has run yet");
+        CU(cudaEventSynchronize(h->ev1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *value = ms;
+        break;
+    }
+    case 2: *value = h->last_launches; break;
+    case 3: *value = h->last_tpc; break;
+    case 4: *value = h->last_ctas; break;
+    case 5: *value = h->last_regs; break;
+    case 6: *value = (double)h->last_smem; break;
+    default: return fail(JQ_ERR_ARG, "jq_query: unknown item %d", what);
+    }
+    return 0;
+}
+
+// Per-candidate outputs: copies (weights == nullptr) or weighted sums over the samples of each candidate
+// (src/ipopt_interface.jl:48-59), always in sample order -> deterministic.
+__global__ void jq_finalize_kernel(int nbatch, int nsamples, int Npar, int objFuncType, int evaladjoint, const double *w,
+                                   const double *scal, const double *gt, const double *igt, double *infid, double *leak,
+                                   double *tinfid, double *grad, double *infidgrad, double *leakgrad) {
+    const int nout = w ? nbatch : nbatch * nsamples;
+    const long long total = (long long)nout * (Npar + 1);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(idx / (Npar + 1)), k = (int)(idx % (Npar + 1));
+        const int t0 = w ? o * nsamples : o, cnt = w ? nsamples : 1;
+        if (k == Npar) {
+            double a = 0.0, b = 0.0, c = 0.0;
+            for (int s = 0; s < cnt; ++s) {
+                const double ws = w ? w[s] : 1.0;
+                const double *sc = scal + (size_t)(t0 + s) * 4;
+                a += ws * sc[0]; b += ws * sc[1]; c += ws * sc[2];
+            }
+            if (infid) infid[o] = a;
+            if (leak) leak[o] = b;
+            if (tinfid) tinfid[o] = c;
+        } else if (evaladjoint) {
+            double g = 0.0, ig = 0.0;
+            for (int s = 0; s < cnt; ++s) {
+                const double ws = w ? w[s] : 1.0;
+                g += ws * gt[(size_t)(t0 + s) * Npar + k];
+                if (objFuncType != 1) ig += ws * igt[(size_t)(t0 + s) * Npar + k];
+            }
+            if (grad) grad[(size_t)o * Npar + k] = g;
+            if (objFuncType != 1) {
+                if (infidgrad) infidgrad[(size_t)o * Npar + k] = ig;
+                if (leakgrad) leakgrad[(size_t)o * Npar + k] = g - ig;   // src/evalobjgrad.jl:947
+            } else if (infidgrad) {
+                infidgrad[(size_t)o * Npar + k] = g;                      // infidelgrad = totalgrad, :951
+            }
+        }
+    }
+}
+
+static int check_batch_args(jq_handle *h, int nbatch, const double *pcof, int npar, int nsamples, const double *shift) {
+    if (!h) return fail(JQ_ERR_ARG, "null handle");
+    if (nbatch < 1 || !pcof) return fail(JQ_ERR_ARG, "need nbatch >= 1 and a pcof array");
+    const int nsig = 2 * h->Nc;
+    if (npar % nsig != 0 || npar < 3 * nsig)   // src/evalobjgrad.jl:604-606
+        return fail(JQ_ERR_PCOF_LENGTH, "pcof must have an even number of elements >= %d, not %d", 3 * nsig, npar);
+    if (npar % (nsig * h->Nfreq) != 0 || npar / (nsig * h->Nfreq) < 3)   // src/bsplines.jl:177-181 (and k >= 3 needs D1 >= 3)
+        return fail(JQ_ERR_PCOF_LENGTH, "Inconsistent number of coefficients and size of parameter vector (nCoeff = %d, Nfreq = %d, Ncoupled = %d)", npar, h->Nfreq, h->Nc);
+    if (nsamples < 1) return fail(JQ_ERR_ARG, "nsamples must be >= 1");
+    if (!shift && nsamples != 1) return fail(JQ_ERR_ARG, "nsamples > 1 needs h0_diag_shift");
+    return 0;
+}
+
+extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
+                                            const double *shift, const double *weights, int32_t evaladjoint, double *infid,
+                                            double *leak, double *trace_infid, double *grad, double *infidgrad, double *leakgrad,
+                                            void *cuda_stream) {
+    int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const size_t ntraj = (size_t)nbatch * nsamples;
+    if ((rc = grow(&h->d_scal, &h->cap_traj, ntraj * 4)) != 0) return rc;
+    if (evaladjoint && (rc = grow(&h->d_grad, &h->cap_grad, ntraj * npar)) != 0) return rc;
+    if (evaladjoint && h->P.objFuncType != 1 && (rc = grow(&h->d_igrad, &h->cap_igrad, ntraj * npar)) != 0) return rc;
+
+    LaunchArgs A{};
+    A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = evaladjoint ? 1 : 0;
+    A.pcof = pcof; A.shift = shift; A.scal = h->d_scal; A.grad = h->d_grad; A.infidgrad = h->P.objFuncType != 1 ? h->d_igrad : nullptr;
+
+    const bool use_slot = h->slot && h->kernel_pref != 1;
+    int ctas = 0, regs = 0, tpc = 1;
+    size_t smem = 0;
+    CU(cudaEventRecord(h->ev0, st));
+    if (use_slot) {
+        CU(jq_slot_launch(h->slot, h->P, A, st, &ctas, &regs, &smem, &tpc));
+    } else {
+        if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024)
+            return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory (n*m = %d)", h->n * h->m);
+        CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
+    }
+    CU(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    h->last_kernel = use_slot ? 2 : 1;
+    h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = tpc;
+    const int nout = weights ? nbatch : (int)ntraj;
+    const long long total = (long long)nout * (npar + 1);
+    const int fb = 256, fg = (int)std::min<long long>((total + fb - 1) / fb, 148 * 8);
+    jq_finalize_kernel<<<fg, fb, 0, st>>>(nbatch, nsamples, npar, h->P.objFuncType, A.evaladjoint, weights, h->d_scal, h->d_grad,
+                                          h->d_igrad, infid, leak, trace_infid, grad, infidgrad, leakgrad);
+    CU(cudaGetLastError());
+    h->last_launches = 2;
+    return 0;
+}
+
+extern "C" int jq_traceobjgrad_batch(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
+                                     const double *shift, const double *weights, int32_t evaladjoint, double *infid, double *leak,
+                                     double *trace_infid, double *grad, double *infidgrad, double *leakgrad) {
+    int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    const size_t ntraj = (size_t)nbatch * nsamples, nout = weights ? (size_t)nbatch : ntraj;
+    const size_t n_pcof = (size_t)nbatch * npar, n_shift = shift ? (size_t)nsamples * h->n : 0, n_w = weights ? (size_t)nsamples : 0;
+    if ((rc = grow(&h->d_in, &h->cap_in, n_pcof + n_shift + n_w)) != 0) return rc;
+    const bool want_g = evaladjoint && grad, want_ig = evaladjoint && infidgrad, want_lg = evaladjoint && leakgrad && h->P.objFuncType != 1;
+    const size_t n_outs = 3 * nout + (size_t)(want_g + want_ig + want_lg) * nout * npar;
+    if ((rc = grow(&h->d_out, &h->cap_out, n_outs)) != 0) return rc;
+    cudaStream_t st = h->stream;
+    double *d_pcof = h->d_in, *d_shift = shift ? h->d_in + n_pcof : nullptr, *d_w = weights ? h->d_in + n_pcof + n_shift : nullptr;
+    CU(cudaMemcpyAsync(d_pcof, pcof, n_pcof * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (shift) CU(cudaMemcpyAsync(d_shift, shift, n_shift * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (weights) CU(cudaMemcpyAsync(d_w, weights, n_w * sizeof(double), cudaMemcpyHostToDevice, st));
+    double *o_infid = h->d_out, *o_leak = o_infid + nout, *o_tinf = o_leak + nout, *cur = o_tinf + nout;
+    double *o_g = nullptr, *o_ig = nullptr, *o_lg = nullptr;
+    if (want_g) { o_g = cur; cur += nout * npar; }
+    if (want_ig) { o_ig = cur; cur += nout * npar; }
+    if (want_lg) { o_lg = cur; cur += nout * npar; }
+    rc = jq_traceobjgrad_batch_device(h, nbatch, d_pcof, npar, nsamples, d_shift, d_w, evaladjoint, o_infid, o_leak, o_tinf, o_g, o_ig,
+                                      o_lg, st);
+    if (rc) return rc;
+    if (infid) CU(cudaMemcpyAsync(infid, o_infid, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (leak) CU(cudaMemcpyAsync(leak, o_leak, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (trace_infid) CU(cudaMemcpyAsync(trace_infid, o_tinf, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_g) CU(cudaMemcpyAsync(grad, o_g, nout * npar * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_ig) CU(cudaMemcpyAsync(infidgrad, o_ig, nout * npar * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_lg) CU(cudaMemcpyAsync(leakgrad, o_lg, nout * npar * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}

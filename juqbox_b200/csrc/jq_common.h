@@ -1,0 +1,46 @@
+// Internal declarations shared by the C-ABI layer (jq_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// Problem data as the kernels see it (device pointers).  Operators are row-wise CSR, one per
+// o in {0: Hconst (diagonal included even if zero), 1..Nc: Hsym_q, Nc+1..2Nc: Hanti_q}.
+struct DevProblem {
+    int n, m, Nc, Nfreq, J, objFuncType;
+    long long nsteps;
+    double T;
+    const double *uinit, *vtr, *vti, *wdiag, *cfreq;  // n*m, n*m, n*m, n, Nc*Nfreq
+    const int *rowptr;     // (1+2Nc)*(n+1), positions absolute into col/val
+    const int *col;
+    const double *val;
+    const int *h0diag;     // n: position of H0[i,i] inside col/val (always present)
+};
+
+// Per-launch arguments common to both kernels.
+struct LaunchArgs {
+    int ntraj, nsamples, Npar, D1, evaladjoint;
+    const double *pcof;    // [nbatch][Npar]
+    const double *shift;   // [nsamples][n] or nullptr
+    double *scal;          // [ntraj][4]: infid, leak, trace_infid, spare
+    double *grad;          // [ntraj][Npar] total gradient
+    double *infidgrad;     // [ntraj][Npar] (objFuncType != 1) or nullptr
+};
+
+// ---- generic kernel (jq_generic.cu): one CTA per trajectory, blocks in shared memory ----
+size_t jq_generic_smem_bytes(const DevProblem &P, int Npar);
+cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem);
+
+// ---- warp-slot kernel (jq_slot.cu): state columns in registers, operators in registers ----
+struct SlotPlan;   // opaque, built at jq_create
+SlotPlan *jq_slot_plan_create(const DevProblem &Pdev, const struct HostOps &H, char *err, size_t errlen);
+void jq_slot_plan_destroy(SlotPlan *);
+cudaError_t jq_slot_launch(SlotPlan *plan, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
+                           size_t *smem, int *traj_per_cta);
+
+// Host copy of the operators in row-wise form, used by the planners.
+struct HostOps {
+    int n, m, Nc, Nfreq;
+    const int *rowptr;
+    const int *col;
+    const double *val;
+};

@@ -1,0 +1,333 @@
+// Generic trajectory kernel: one CTA per trajectory, all n x m blocks in shared memory, operators as CSR rows
+// read through L1/L2.  Handles any operator sparsity (dense input is just CSR with full rows), any n*m that fits in
+// shared memory, and objFuncType 1/2/3.  It is the fallback for shapes the warp-slot kernel (jq_slot.cu) has no
+// instantiation for, and its independent cross-check in the tests.  The whole forward + backward time loop runs
+// inside the kernel; HBM is touched only for the launch inputs and the final outputs.
+//
+// Algorithm (reference lines): forward loop src/evalobjgrad.jl:698-753, infidelity :755-766, adjoint terminal
+// condition :810-844 / :2026-2042, backward loop :859-921, steppers src/StormerVerlet.jl:255-303,:365-406,:461-504,
+// Neumann src/linear_solvers.jl:94-106, controls src/bsplines.jl:211-304,:321-381, gradient :2567-2619.
+// K(t) and S(t) are never assembled: K(t)x = H0 x + sum_q p_q(t) Hsym_q x,  S(t)x = sum_q q_q(t) Hanti_q x.
+#include "jq_common.h"
+
+#define GEN_THREADS 128
+
+namespace {
+
+struct Ctx {
+    const DevProblem *P;
+    int n, m, len, Nc, Nfreq, D1, Npar, J;
+    double *vr, *vi, *vi05, *vr0;
+    double *lr, *li, *lr05, *li0;
+    double *lrn, *lin, *lr05n, *li0n;
+    double *rhs, *scr, *k1, *k2, *l1, *l2;
+    double *pcof, *grad, *igrad, *ctrl, *shift, *red;
+    double dtknot;
+};
+
+__device__ __forceinline__ double op_apply(const Ctx &c, int o, const double *x, int i, int j) {
+    const int *rp = c.P->rowptr + o * (c.n + 1);
+    const double *xc = x + j * c.n;
+    double s = 0.0;
+    for (int p = rp[i]; p < rp[i + 1]; ++p) s += c.P->val[p] * xc[c.P->col[p]];
+    return s;
+}
+__device__ __forceinline__ double applyK(const Ctx &c, int level, const double *x, int i, int j) {
+    double s = op_apply(c, 0, x, i, j) + c.shift[i] * x[i + j * c.n];
+    const double *ct = c.ctrl + level * 2 * c.Nc;
+    for (int q = 0; q < c.Nc; ++q) s += ct[2 * q] * op_apply(c, 1 + q, x, i, j);
+    return s;
+}
+__device__ __forceinline__ double applyS(const Ctx &c, int level, const double *x, int i, int j) {
+    const double *ct = c.ctrl + level * 2 * c.Nc;
+    double s = 0.0;
+    for (int q = 0; q < c.Nc; ++q) s += ct[2 * q + 1] * op_apply(c, 1 + c.Nc + q, x, i, j);
+    return s;
+}
+
+// src/bsplines.jl:211-304 (0-based indices)
+__device__ double bcarrier2(const Ctx &c, double t, int func) {
+    const int osc = func >> 1, qf = func & 1;
+    const double width = 3.0 * c.dtknot;
+    long long k = (long long)ceil(t / c.dtknot + 2.0);
+    k = k < 3 ? 3 : (k > c.D1 ? c.D1 : k);
+    double f = 0.0;
+    for (int fr = 0; fr < c.Nfreq; ++fr) {
+        const int off1 = 2 * osc * c.Nfreq * c.D1 + fr * 2 * c.D1 - 1, off2 = off1 + c.D1;
+        double fbs1 = 0.0, fbs2 = 0.0;
+        double tau = (t - c.dtknot * ((double)k - 1.5)) / width;
+        double b = 9.0 / 8 + 4.5 * tau + 4.5 * tau * tau;
+        fbs1 += c.pcof[off1 + k] * b;
+        fbs2 += c.pcof[off2 + k] * b;
+        tau = (t - c.dtknot * ((double)(k - 1) - 1.5)) / width;
+        b = 0.75 - 9.0 * tau * tau;
+        fbs1 += c.pcof[off1 + k - 1] * b;
+        fbs2 += c.pcof[off2 + k - 1] * b;
+        tau = (t - c.dtknot * ((double)(k - 2) - 1.5)) / width;
+        b = 9.0 / 8 - 4.5 * tau + 4.5 * tau * tau;
+        fbs1 += c.pcof[off1 + k - 2] * b;
+        fbs2 += c.pcof[off2 + k - 2] * b;
+        double sn, cs;
+        sincos(c.P->cfreq[osc + c.Nc * fr] * t, &sn, &cs);
+        f += qf ? fbs1 * sn + fbs2 * cs : fbs1 * cs - fbs2 * sn;
+    }
+    return f;
+}
+
+__device__ void eval_controls(const Ctx &c, double t, double dt) {
+    const int nf = 2 * c.Nc;
+    for (int idx = threadIdx.x; idx < 3 * nf; idx += GEN_THREADS) {
+        const int level = idx / nf, func = idx % nf;
+        const double tt = level == 0 ? t : (level == 1 ? t + 0.5 * dt : t + dt);
+        c.ctrl[idx] = bcarrier2(c, tt, func);
+    }
+    __syncthreads();
+}
+
+#define FOR_E for (int e = threadIdx.x, i = e % c.n, j = e / c.n; e < c.len; e += GEN_THREADS, i = e % c.n, j = e / c.n)
+
+// X = sum_{j<=J} (h/2)^j S^j B ; B destroyed, T scratch (src/linear_solvers.jl:94-106)
+__device__ void neumann(const Ctx &c, int level, double h, double *B, double *T, double *X) {
+    FOR_E X[e] = B[e];
+    double coeff = 1.0;
+    for (int it = 0; it < c.J; ++it) {
+        coeff *= 0.5 * h;
+        FOR_E { double tv = applyS(c, level, B, i, j); T[e] = tv; X[e] += coeff * tv; }
+        __syncthreads();
+        double *sw = B; B = T; T = sw;
+    }
+}
+
+// src/StormerVerlet.jl:461-504
+__device__ void state_step(const Ctx &c, double h) {
+    double *u = c.vr, *v = c.vi, *v05 = c.vi05;
+    FOR_E c.rhs[e] = applyK(c, 1, u, i, j) + applyS(c, 1, v, i, j);
+    __syncthreads();
+    neumann(c, 1, h, c.rhs, c.scr, c.l1);
+    FOR_E v05[e] = v[e] + 0.5 * h * c.l1[e];
+    __syncthreads();
+    FOR_E c.k1[e] = applyS(c, 0, u, i, j) - applyK(c, 0, v05, i, j);
+    __syncthreads();
+    FOR_E c.rhs[e] = applyS(c, 2, u, i, j) + 0.5 * h * applyS(c, 2, c.k1, i, j) - applyK(c, 2, v05, i, j);
+    __syncthreads();
+    FOR_E u[e] += 0.5 * h * c.k1[e];
+    neumann(c, 2, h, c.rhs, c.scr, c.k2);
+    FOR_E u[e] += 0.5 * h * c.k2[e];
+    __syncthreads();
+    FOR_E { c.l2[e] = applyK(c, 1, u, i, j) + applyS(c, 1, v05, i, j); v[e] += 0.5 * h * (c.l1[e] + c.l2[e]); }
+    __syncthreads();
+}
+
+// src/StormerVerlet.jl:255-303 (forcing) / :365-406 (no forcing).  Forcing with diagonal W:
+// hr0 = W vr0 / T, hi0 = hi1 = W vi05 / T, hr1 = W vr / T  (src/evalobjgrad.jl:862,882-888).
+__device__ void adjoint_step(const Ctx &c, double *mu, double *nu, double *X, double h, bool forcing, double tinv) {
+    FOR_E {
+        double f = forcing ? tinv * c.P->wdiag[i] * c.vr0[e] : 0.0;
+        c.rhs[e] = applyS(c, 0, mu, i, j) - applyK(c, 1, nu, i, j) + f;
+    }
+    __syncthreads();
+    neumann(c, 0, h, c.rhs, c.scr, c.k2);
+    FOR_E { mu[e] += 0.5 * h * c.k2[e]; X[e] = mu[e]; }
+    __syncthreads();
+    FOR_E {
+        double f = forcing ? tinv * c.P->wdiag[i] * c.vi05[e] : 0.0;
+        c.l2[e] = applyK(c, 0, X, i, j) + applyS(c, 1, nu, i, j) + f;
+    }
+    __syncthreads();
+    FOR_E {
+        double f = forcing ? tinv * c.P->wdiag[i] * c.vi05[e] : 0.0;
+        c.rhs[e] = applyS(c, 1, nu, i, j) + 0.5 * h * applyS(c, 1, c.l2, i, j) + applyK(c, 2, X, i, j) + f;
+    }
+    __syncthreads();
+    neumann(c, 1, h, c.rhs, c.scr, c.l1);
+    FOR_E nu[e] += 0.5 * h * (c.l2[e] + c.l1[e]);
+    __syncthreads();
+    FOR_E {
+        double f = forcing ? tinv * c.P->wdiag[i] * c.vr[e] : 0.0;
+        c.k1[e] = applyS(c, 2, X, i, j) - applyK(c, 1, nu, i, j) + f;
+    }
+    __syncthreads();
+    FOR_E mu[e] += 0.5 * h * c.k1[e];
+    __syncthreads();
+}
+
+// Sum `cnt` (<= 8) per-thread values over the CTA; result broadcast to every thread.
+__device__ void block_sum(const Ctx &c, double *v, int cnt) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = 0; k < cnt; ++k) {
+        double x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) c.red[w * 8 + k] = x;
+    }
+    __syncthreads();
+    for (int k = 0; k < cnt; ++k) {
+        double x = 0.0;
+        for (int ww = 0; ww < GEN_THREADS / 32; ++ww) x += c.red[ww * 8 + k];
+        v[k] = x;
+    }
+    __syncthreads();
+}
+
+// One step's contribution to the gradient (src/evalobjgrad.jl:2567-2619), scaled by dt at the end of the sweep.
+// tr(A,H,C) := sum_ij A_ij (H C)_ij.
+__device__ void grad_step(const Ctx &c, const double *lr05, const double *li, const double *li0, double t0, double dt,
+                          double *g) {
+    for (int q = 0; q < c.Nc; ++q) {
+        double T[5] = {0, 0, 0, 0, 0};
+        const int os = 1 + q, oa = 1 + c.Nc + q;
+        FOR_E {
+            const double aX = op_apply(c, oa, lr05, i, j), sX = op_apply(c, os, lr05, i, j);
+            T[0] += c.vr0[e] * aX;                                                              // tr(vr0, Ha, lr05)
+            T[1] += c.vi05[e] * sX;                                                             // tr(vi05, Hs, lr05)
+            T[2] += c.vr[e] * aX;                                                               // tr(vr, Ha, lr05)
+            T[3] += c.vr[e] * op_apply(c, os, li, i, j) + c.vr0[e] * op_apply(c, os, li0, i, j); // tr(vr,Hs,li)+tr(vr0,Hs,li0)
+            T[4] += c.vi05[e] * (op_apply(c, oa, li, i, j) + op_apply(c, oa, li0, i, j));        // tr(vi05,Ha,li)+tr(vi05,Ha,li0)
+        }
+        block_sum(c, T, 5);
+        // threads (f, alpha) scatter into the 3 knots of each of the 3 time points; deterministic order
+        for (int idx = threadIdx.x; idx < 2 * c.Nfreq; idx += GEN_THREADS) {
+            const int fr = idx >> 1, alpha = idx & 1;
+            const int base = 2 * q * c.Nfreq * c.D1 + fr * 2 * c.D1 + alpha * c.D1 - 1;
+            const double om = c.P->cfreq[q + c.Nc * fr];
+            for (int tp = 0; tp < 3; ++tp) {
+                const double tt = tp == 0 ? t0 : (tp == 1 ? t0 + dt : t0 + 0.5 * dt);
+                const double Pc = tp == 2 ? T[3] : -T[1];                       // multiplies grad p
+                const double Qc = tp == 0 ? -T[0] : (tp == 1 ? -T[2] : -T[4]);  // multiplies grad q
+                double sn, cs;
+                sincos(om * tt, &sn, &cs);
+                const double X = alpha == 0 ? Pc * cs + Qc * sn : Qc * cs - Pc * sn;
+                long long k = (long long)ceil(tt / c.dtknot + 2.0);
+                k = k < 3 ? 3 : (k > c.D1 ? c.D1 : k);
+                const double width = 3.0 * c.dtknot;
+                double tau = (tt - c.dtknot * ((double)k - 1.5)) / width;
+                g[base + k] += X * (9.0 / 8 + 4.5 * tau + 4.5 * tau * tau);
+                tau = (tt - c.dtknot * ((double)(k - 1) - 1.5)) / width;
+                g[base + k - 1] += X * (0.75 - 9.0 * tau * tau);
+                tau = (tt - c.dtknot * ((double)(k - 2) - 1.5)) / width;
+                g[base + k - 2] += X * (9.0 / 8 - 4.5 * tau + 4.5 * tau * tau);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ void trace_fid(const Ctx &c, double *re, double *im) {
+    double v[2] = {0.0, 0.0};
+    FOR_E {
+        v[0] += c.vr[e] * c.P->vtr[e] - c.vi[e] * c.P->vti[e];  // tr(ur'vtr + ui'vti), ui = -vi
+        v[1] += c.vr[e] * c.P->vti[e] + c.vi[e] * c.P->vtr[e];  // tr(ur'vti - ui'vtr)
+    }
+    block_sum(c, v, 2);
+    *re = v[0] / c.m;
+    *im = v[1] / c.m;
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, LaunchArgs A) {
+    extern __shared__ double sm[];
+    Ctx c;
+    c.P = &P;
+    c.n = P.n; c.m = P.m; c.len = P.n * P.m; c.Nc = P.Nc; c.Nfreq = P.Nfreq; c.J = P.J;
+    c.Npar = A.Npar; c.D1 = A.D1;
+    c.dtknot = P.T / (A.D1 - 2);
+    double *p = sm;
+    double **blk[] = {&c.vr, &c.vi, &c.vi05, &c.vr0, &c.lr, &c.li, &c.lr05, &c.li0, &c.lrn, &c.lin, &c.lr05n, &c.li0n,
+                      &c.rhs, &c.scr, &c.k1, &c.k2, &c.l1, &c.l2};
+    for (int b = 0; b < 18; ++b) {
+        if (b >= 8 && b < 12 && P.objFuncType == 1) { *blk[b] = nullptr; continue; }
+        *blk[b] = p; p += c.len;
+    }
+    c.pcof = p; p += c.Npar;
+    c.grad = p; p += c.Npar;
+    c.igrad = p; p += (P.objFuncType != 1 ? c.Npar : 0);
+    c.ctrl = p; p += 6 * c.Nc;
+    c.shift = p; p += c.n;
+    c.red = p;
+
+    const double tinv = 1.0 / P.T;
+    for (int traj = blockIdx.x; traj < A.ntraj; traj += gridDim.x) {
+        const int b = traj / A.nsamples, s = traj % A.nsamples;
+        for (int k = threadIdx.x; k < c.Npar; k += GEN_THREADS) { c.pcof[k] = A.pcof[(size_t)b * c.Npar + k]; c.grad[k] = 0.0; if (P.objFuncType != 1) c.igrad[k] = 0.0; }
+        for (int k = threadIdx.x; k < c.n; k += GEN_THREADS) c.shift[k] = A.shift ? A.shift[(size_t)s * c.n + k] : 0.0;
+        FOR_E { c.vr[e] = P.uinit[e]; c.vi[e] = 0.0; c.vi05[e] = 0.0; }
+        __syncthreads();
+
+        // ---------------- forward sweep ----------------
+        double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
+        for (long long step = 0; step < P.nsteps; ++step) {
+            FOR_E pen += P.wdiag[i] * c.vr[e] * c.vr[e];                           // penalf2aTrap(vr)
+            eval_controls(c, t, dt);
+            state_step(c, dt);
+            t = t + dt;
+            FOR_E pen += P.wdiag[i] * (c.vr[e] * c.vr[e] + 2.0 * c.vi05[e] * c.vi05[e]);  // penalf2a(vr, vi05)
+        }
+        double re, im, pv[1] = {pen};
+        block_sum(c, pv, 1);
+        trace_fid(c, &re, &im);
+        const double infid = 1.0 - (re * re + im * im);
+        const double leak = 0.5 * dt * tinv * pv[0];
+        if (threadIdx.x == 0) {
+            double *o = A.scal + (size_t)traj * 4;
+            o[0] = infid; o[1] = leak; o[2] = infid; o[3] = 0.0;
+        }
+        if (!A.evaladjoint) { __syncthreads(); continue; }
+
+        // ---------------- backward sweep ----------------
+        FOR_E {
+            const double lr = (re * P.vtr[e] + im * P.vti[e]) / c.m, li = (im * P.vtr[e] - re * P.vti[e]) / c.m;
+            c.lr[e] = lr; c.lr05[e] = lr; c.li[e] = li; c.li0[e] = li;
+            if (P.objFuncType != 1) { c.lrn[e] = lr; c.lr05n[e] = lr; c.lin[e] = li; c.li0n[e] = li; }
+        }
+        t = P.T;
+        dt = -dt;
+        __syncthreads();
+        for (long long step = P.nsteps - 1; step >= 0; --step) {
+            const double t0 = t;
+            FOR_E c.vr0[e] = c.vr[e];
+            eval_controls(c, t, dt);
+            state_step(c, dt);
+            t = t + dt;
+            adjoint_step(c, c.lr, c.li, c.lr05, dt, true, tinv);
+            grad_step(c, c.lr05, c.li, c.li0, t0, dt, c.grad);
+            FOR_E c.li0[e] = c.li[e];
+            if (P.objFuncType != 1) {
+                adjoint_step(c, c.lrn, c.lin, c.lr05n, dt, false, tinv);
+                grad_step(c, c.lr05n, c.lin, c.li0n, t0, dt, c.igrad);
+                FOR_E c.li0n[e] = c.lin[e];
+            }
+            __syncthreads();
+        }
+        for (int k = threadIdx.x; k < c.Npar; k += GEN_THREADS) {
+            A.grad[(size_t)traj * c.Npar + k] = dt * c.grad[k];
+            if (P.objFuncType != 1 && A.infidgrad) A.infidgrad[(size_t)traj * c.Npar + k] = dt * c.igrad[k];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+size_t jq_generic_smem_bytes(const DevProblem &P, int Npar) {
+    const size_t len = (size_t)P.n * P.m;
+    const size_t nblk = P.objFuncType == 1 ? 14 : 18;
+    return sizeof(double) * (nblk * len + Npar * (P.objFuncType == 1 ? 2 : 3) + 6 * P.Nc + P.n + (GEN_THREADS / 32) * 8);
+}
+
+cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem) {
+    const size_t bytes = jq_generic_smem_bytes(P, A.Npar);
+    cudaError_t e = cudaFuncSetAttribute(jq_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, jq_generic_kernel);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jq_generic_kernel, GEN_THREADS, bytes);
+    if (occ < 1) occ = 1;
+    int grid = A.ntraj < sms * occ ? A.ntraj : sms * occ;   // persistent: CTAs loop over trajectories
+    jq_generic_kernel<<<grid, GEN_THREADS, bytes, st>>>(P, A);
+    if (nctas) *nctas = grid;
+    if (regs) *regs = fa.numRegs;
+    if (smem) *smem = bytes;
+    return cudaGetLastError();
+}

@@ -1,0 +1,45 @@
+// FP64 roofline denominator: MEASURED_PEAKS.json has no FP64 entry, so the library measures
+// the DFMA issue rate itself — 8 independent FMA chains per thread, all SMs full, CUDA-event timed.
+#include "jq_common.h"
+#include "../../include/juqbox_b200.h"
+
+__global__ void __launch_bounds__(256) jq_dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int jq_fp64_peak(int device, double *tflops) {
+    if (!tflops) return JQ_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return JQ_ERR_CUDA;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double *buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return JQ_ERR_ALLOC;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        jq_dfma_peak_kernel<<<blocks, threads>>>(buf, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(buf); return JQ_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;   // 64 FMAs per loop trip per thread
+        if (rep > 0 && ms > 0.f) best = best > flops / (ms * 1e9) ? best : flops / (ms * 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *tflops = best;
+    return 0;
+}

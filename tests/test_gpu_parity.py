@@ -1,0 +1,155 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against
+(1) the reference's golden files with the reference's own acceptance rule (test/evalGrad.jl:43-69) and
+(2) the CPU oracle on seeded inputs, at the 1e-10 relative tolerance BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+
+from helpers import golden_config, ref_pass, with_tikhonov
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10   # north_star: "within 1e-10 relative in objective and gradient"
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+
+
+def _wa(cfg, kernel):
+    import juqbox_b200 as jq
+    wa = jq.Working_Arrays(cfg.params, len(cfg.pcof0) if cfg.pcof0 is not None else cfg.nCoeff)
+    try:
+        wa.set_kernel(kernel)
+    except Exception as e:
+        wa.close()
+        pytest.skip(f"kernel {kernel} unavailable for {cfg.name}: {e}")
+    return wa
+
+
+KERNELS = [1, 2]
+GOLDEN_CASES = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq", "cnot3"]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_cuda_matches_reference_golden(case, kernel):
+    cfg, g = golden_config(case)
+    wa = _wa(cfg, kernel)
+    res = wa.evaluate(cfg.pcof0)
+    assert wa.last_kernel == kernel
+    objv, grad = with_tikhonov(cfg, res)
+    ok, dobj, dgrad = ref_pass(objv, grad, g["obj0"], g["grad0"])
+    print(case, "kernel", kernel, "objDiff", dobj, "relGradErr", dgrad, "ms", wa.last_kernel_ms)
+    wa.close()
+    assert ok, (case, kernel, dobj, dgrad)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_traceobjgrad_dropin_tuple(kernel):
+    """The reference-shaped call returns the reference-shaped tuples (src/evalobjgrad.jl:1032-1035)."""
+    import juqbox_b200 as jq
+    from oracle import oracle_traceobjgrad
+    cfg, _ = golden_config("swap02")
+    wa = _wa(cfg, kernel)
+    o = oracle_traceobjgrad(cfg.params, cfg.pcof0)
+    objfv, totalgrad, primary, secondary, traceInfid, infidelgrad, leakgrad = jq.traceobjgrad(cfg.pcof0, cfg.params, wa, False, True)
+    assert abs(objfv - o["objf"][0, 0]) <= TOL * abs(o["objf"][0, 0])
+    assert abs(primary - o["infid"][0, 0]) <= TOL and abs(secondary - o["leak"][0, 0]) <= TOL * max(o["leak"][0, 0], 1e-3)
+    assert traceInfid == primary and infidelgrad is totalgrad and len(leakgrad) == 0
+    assert _rel(totalgrad, o["grad"][0, 0]) < TOL
+    f3 = jq.traceobjgrad(cfg.pcof0, cfg.params, wa, False, False)
+    assert len(f3) == 3 and abs(f3[0] - objfv) < 1e-14
+    with pytest.raises(ValueError):           # reference: error() at src/evalobjgrad.jl:604-606
+        jq.traceobjgrad(np.zeros(7), cfg.params, wa)
+    wa.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", ["rabi", "cnot1", "cnot2", "risk_neutral"])
+def test_example_configs_batch_vs_oracle(name, kernel):
+    """BASELINE configs on seeded synthetic pcof batches (no reference golden exists for these: oracle is the pin)."""
+    from juqbox_b200 import configs
+    from oracle import oracle_traceobjgrad
+    cfg = configs.example(name)
+    nb = 5
+    pc = configs.synthetic_pcof(cfg, nb)
+    pc[-1] = np.random.default_rng(7).uniform(-1, 1, cfg.nCoeff) * cfg.maxpar[0]     # full-amplitude stress vector
+    shifts = configs.noise_shift(cfg.params.Ntot, cfg.nodes) if name == "risk_neutral" else None
+    o = oracle_traceobjgrad(cfg.params, pc, shifts, nthreads=8)
+    wa = _wa(cfg, kernel)
+    r = wa.evaluate(pc, shifts)
+    wa.close()
+    for k in ("infid", "leak"):
+        assert np.all(np.abs(r[k] - o[k]) <= TOL * np.maximum(np.abs(o[k]), 1e-6)), (k, r[k], o[k])
+    for b in range(nb):
+        for s in range(r["grad"].shape[1]):
+            assert _rel(r["grad"][b, s], o["grad"][b, s]) < TOL, (b, s, _rel(r["grad"][b, s], o["grad"][b, s]))
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_risk_neutral_weighted_sum(kernel):
+    """eval_f_g_grad! semantics (src/ipopt_interface.jl:38-65): weighted sums over the quadrature nodes."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    from oracle import oracle_traceobjgrad
+    cfg = configs.example("risk_neutral")
+    pc = configs.synthetic_pcof(cfg, 2)
+    shifts = configs.noise_shift(cfg.params.Ntot, cfg.nodes)
+    o = oracle_traceobjgrad(cfg.params, pc, shifts, nthreads=8)
+    wa = _wa(cfg, kernel)
+    r = wa.evaluate(pc, shifts, cfg.weights)
+    w = cfg.weights
+    assert np.allclose(r["infid"], (o["infid"] * w).sum(1), rtol=TOL, atol=1e-14)
+    assert np.allclose(r["leak"], (o["leak"] * w).sum(1), rtol=TOL, atol=1e-14)
+    for b in range(2):
+        assert _rel(r["grad"][b], (o["grad"][b] * w[:, None]).sum(0)) < TOL
+    # Ipopt-callback layer on top (host): cache + Tikhonov
+    p = cfg.params
+    f = jq.eval_f_par(pc[0], p, wa, cfg.nodes, cfg.weights)
+    g = np.zeros(cfg.nCoeff)
+    jq.eval_grad_f_par(pc[0], g, p, wa, cfg.nodes, cfg.weights)
+    assert abs(f - (r["infid"][0] + r["leak"][0] + jq.tikhonov_pen(pc[0], p))) < 1e-14
+    assert _rel(g, r["grad"][0] + jq.tikhonov_grad(pc[0], p)) < 1e-14
+    wa.close()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_ragged_batches_and_determinism(kernel):
+    """Batch sizes that do not fill a CTA / a wave give the same per-trajectory results, bit for bit."""
+    from juqbox_b200 import configs
+    cfg = configs.example("rabi")
+    wa = _wa(cfg, kernel)
+    pc = configs.synthetic_pcof(cfg, 333)
+    full = wa.evaluate(pc)
+    again = wa.evaluate(pc)
+    assert np.array_equal(full["grad"], again["grad"]) and np.array_equal(full["infid"], again["infid"])
+    for nb in (1, 2, 31, 33, 150):
+        part = wa.evaluate(pc[:nb])
+        assert np.array_equal(part["grad"], full["grad"][:nb]), nb
+        assert np.array_equal(part["leak"], full["leak"][:nb]), nb
+    wa.close()
+
+
+def test_full_size_properties_cnot2():
+    """BASELINE size (cnot2 example, 4472 steps) through properties that need no oracle:
+    (a) the gradient is the derivative of the objective (central differences on the GPU objective),
+    (b) zero noise shift == no shift, (c) evaladjoint=False returns the same objective."""
+    from juqbox_b200 import configs
+    cfg = configs.example("cnot2")
+    import juqbox_b200 as jq
+    wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
+    rng = np.random.default_rng(11)
+    p0 = rng.uniform(-1, 1, cfg.nCoeff) * 0.5 * cfg.maxpar[0]
+    base = wa.evaluate(p0)
+    h = 1e-6
+    ks = [0, 13, 41, 79]
+    pert = np.stack([p0 + h * np.eye(cfg.nCoeff)[k] for k in ks] + [p0 - h * np.eye(cfg.nCoeff)[k] for k in ks])
+    f = wa.evaluate(pert, evaladjoint=False)["objf"][:, 0]
+    for a, k in enumerate(ks):
+        fd = (f[a] - f[a + len(ks)]) / (2 * h)
+        assert abs(fd - base["grad"][0, 0, k]) < 2e-7 * max(1.0, abs(fd)), (k, fd, base["grad"][0, 0, k])
+    z = wa.evaluate(p0, np.zeros((1, cfg.params.Ntot)))
+    assert np.array_equal(z["grad"], base["grad"])
+    assert wa.evaluate(p0, evaladjoint=False)["objf"][0, 0] == base["objf"][0, 0]
+    wa.close()

@@ -1,0 +1,86 @@
+"""CPU tests of the host logic and of the C-ABI library surface (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import golden_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from juqbox_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "juqbox_b200.h")).read()
+    declared = set(re.findall(r"\b(jq_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.jq_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product path must fail loudly without a device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import juqbox_b200 as jq
+    cfg, _ = golden_config("rabi")
+    with pytest.raises(Exception) as ei:
+        jq.Working_Arrays(cfg.params, 6)
+    assert "no CUDA device" in str(ei.value)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "juqbox_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "jq_oracle" not in src, f
+
+
+def test_named_config_shapes_match_survey_table():
+    """nsteps and J are computed, not stored; a wrong integer would break golden parity."""
+    from juqbox_b200 import configs
+    want = {"rabi": (2, 2, 57, 3, 6), "cnot1": (6, 4, 8796, 3, 60), "cnot2": (16, 4, 4472, 4, 80),
+            "cnot3": (64, 4, 31325, 3, 180), "risk_neutral": (4, 3, 7937, 5, 48)}
+    for name, (n, m, nsteps, J, npar) in want.items():
+        c = configs.example(name)
+        p = c.params
+        assert (p.Ntot, p.N, p.nsteps, p.linear_solver.max_iter, c.nCoeff) == (n, m, nsteps, J, npar), name
+    tw = {"rabi": (2, 2, 57, 10, 6), "swap02": (4, 3, 7915, 4, 40), "cnot2": (12, 4, 5985, 5, 80),
+          "cnot3": (96, 4, 32386, 6, 270)}
+    for name, (n, m, nsteps, J, npar) in tw.items():
+        c, _ = golden_config(name)
+        p = c.params
+        assert (p.Ntot, p.N, p.nsteps, p.linear_solver.max_iter, len(c.pcof0)) == (n, m, nsteps, J, npar), name
+
+
+def test_setup_helpers():
+    import juqbox_b200 as jq
+    assert np.allclose(jq.wmatsetup([3], [1]), [0, 0, 0, 1.0])
+    assert np.allclose(jq.wmatsetup([4], [2]), [0, 0, 0, 0, 0.1, 1.0])
+    w = jq.orig_wmatsetup([2, 2], [1, 2])
+    assert w.shape == (12,) and w[0] == 0 and w.max() == pytest.approx(10.0 / 6)   # nForb = 3 + 4 - 1 = 6
+    U0 = jq.initial_cond([2, 2], [1, 2])
+    assert U0.shape == (12, 4) and np.array_equal(np.nonzero(U0.T)[1], [0, 1, 3, 4])
+    o1, o2 = jq.setup_rotmatrices([2, 2], [1, 2], [1.0, 2.0])
+    assert np.allclose(o1[:4], 2 * np.pi * np.array([0, 1, 2, 0])) and np.allclose(o2[:4], [0, 0, 0, 4 * np.pi])
+
+
+def test_noise_shift_matches_reference_model():
+    from juqbox_b200.configs import noise_shift
+    s = noise_shift(4, [0.5])[0]          # H0[j,j] += 0.01*ep*10^(j-2), j = 2..n (1-based)
+    assert np.allclose(s, [0.0, 0.005, 0.05, 0.5])
+
+
+def test_tikhonov():
+    import juqbox_b200 as jq
+    cfg, _ = golden_config("swap02")
+    pc = cfg.pcof0
+    assert jq.tikhonov_pen(pc, cfg.params) == pytest.approx(0.01 * pc @ pc / len(pc))
+    assert np.allclose(jq.tikhonov_grad(pc, cfg.params), 2 * 0.01 * pc / len(pc))
