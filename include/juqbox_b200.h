@@ -95,7 +95,7 @@ int jq_traceobjgrad_batch(jq_handle *h, int32_t nbatch, const double *pcof, int3
                           double *leakgrad);
 
 /* Same, with every array already in device memory of the handle's GPU and the work enqueued on `cuda_stream`
- * (a cudaStream_t; NULL = the handle's own stream).  Asynchronous: no host synchronisation. */
+ * (a cudaStream_t, used as given: NULL is CUDA's legacy default stream).  Asynchronous: no host synchronisation. */
 int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
                                  const double *h0_diag_shift, const double *weights, int32_t evaladjoint,
                                  double *infid, double *leak, double *trace_infid, double *grad,

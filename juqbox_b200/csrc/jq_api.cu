@@ -290,7 +290,7 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift);
     if (rc) return rc;
     CU(cudaSetDevice(h->device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t ntraj = (size_t)nbatch * nsamples;
     if ((rc = grow(&h->d_scal, &h->cap_traj, ntraj * 4)) != 0) return rc;
     if (evaladjoint && (rc = grow(&h->d_grad, &h->cap_grad, ntraj * npar)) != 0) return rc;
