@@ -110,7 +110,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cnot2", choices=["rabi", "cnot1", "cnot2", "cnot3", "risk_neutral"])
     ap.add_argument("--batch", type=int, default=0, help="pcof candidates per GPU per step (0 = per-workload default)")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 warp-slot")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 slot layout, 3 fibre layout")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
@@ -239,7 +239,7 @@ def main():
     achieved = flops_eval * B * nsamp / (kern_ms * 1e-3) / 1e12
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": None, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": {1: "jq_generic_kernel", 2: "jq_slot_kernel"}[used_kernel],
+                "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>"}[used_kernel],
                 "hbm_alg_bytes_per_launch": 8 * (B * npar + nsamp * cfg.params.Ntot + B * nsamp * (4 + npar))}
 
     # ---- CPU baseline (rank 0, N = 1 only)

@@ -101,10 +101,12 @@ int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pco
                                  double *infid, double *leak, double *trace_infid, double *grad,
                                  double *infidgrad, double *leakgrad, void *cuda_stream);
 
-/* Kernel selection, for tests and profiling: 0 = automatic, 1 = generic (one CTA per trajectory, any operators),
- * 2 = register-resident warp-slot kernel (fails with JQ_ERR_ARG if the problem shape has no instantiation). */
+/* Kernel selection, for tests and profiling: 0 = automatic (3, else 2, else 1), 1 = generic (one CTA per trajectory,
+ * any operators), 2 = register-resident kernel, slot layout (sparse rows with <= 2 entries per row and control),
+ * 3 = register-resident kernel, fibre layout (Kronecker ladder structure).  2 and 3 fail with JQ_ERR_ARG if the
+ * problem has no instantiation. */
 int jq_set_kernel(jq_handle *h, int32_t kernel);
-/* what: 0 = kernel actually used by the last evaluation (1/2), 1 = CUDA-event time of the last evaluation's
+/* what: 0 = kernel actually used by the last evaluation (1/2/3), 1 = CUDA-event time of the last evaluation's
  * trajectory kernel in ms (synchronises), 2 = number of kernels launched by the last evaluation,
  * 3 = trajectories resident per CTA, 4 = CTAs launched, 5 = registers per thread, 6 = dynamic smem bytes per CTA. */
 int jq_query(jq_handle *h, int32_t what, double *value);

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libjuqbox_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "0", "-diag-suppress=550"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "0", "-diag-suppress=550,177"]
 
 
 def _nvcc() -> str:

@@ -35,8 +35,8 @@ struct jq_handle {
     // host copies of the row-wise operators (for the planners)
     std::vector<int> rowptr, col;
     std::vector<double> val;
-    SlotPlan *slot = nullptr;
-    char slot_reason[256] = "";
+    TrajPlan *slot = nullptr, *fiber = nullptr;
+    char slot_reason[256] = "", fiber_reason[256] = "";
     int kernel_pref = 0;
     // growable scratch
     double *d_scal = nullptr, *d_grad = nullptr, *d_igrad = nullptr;
@@ -175,7 +175,8 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
         return fail(JQ_ERR_CUDA, "jq_create: stream/event creation failed");
     }
     HostOps H{n, m, Nc, pb->nfreq, h->rowptr.data(), h->col.data(), h->val.data()};
-    h->slot = jq_slot_plan_create(P, H, h->slot_reason, sizeof(h->slot_reason));
+    h->slot = jq_slot_plan_create(P, H, pb->wdiag, h->slot_reason, sizeof(h->slot_reason));
+    h->fiber = jq_fiber_plan_create(P, H, pb->wdiag, h->fiber_reason, sizeof(h->fiber_reason));
     *out = h;
     return 0;
 }
@@ -186,7 +187,8 @@ extern "C" int jq_destroy(jq_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *p : h->owned) cudaFree(p);
     for (double *p : {h->d_scal, h->d_grad, h->d_igrad, h->d_in, h->d_out}) if (p) cudaFree(p);
-    if (h->slot) jq_slot_plan_destroy(h->slot);
+    if (h->slot) jq_traj_plan_destroy(h->slot);
+    if (h->fiber) jq_traj_plan_destroy(h->fiber);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -204,8 +206,9 @@ extern "C" int jq_update_target(jq_handle *h, const double *vr, const double *vi
 }
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
-    if (!h || kernel < 0 || kernel > 2) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0, 1 or 2");
-    if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no warp-slot instantiation for this problem (%s)", h->slot_reason);
+    if (!h || kernel < 0 || kernel > 3) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0, 1, 2 or 3");
+    if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no slot-layout instantiation for this problem (%s)", h->slot_reason);
+    if (kernel == 3 && !h->fiber) return fail(JQ_ERR_ARG, "jq_set_kernel: no fibre-layout instantiation for this problem (%s)", h->fiber_reason);
     h->kernel_pref = kernel;
     return 0;
 }
@@ -300,12 +303,15 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = evaladjoint ? 1 : 0;
     A.pcof = pcof; A.shift = shift; A.scal = h->d_scal; A.grad = h->d_grad; A.infidgrad = h->P.objFuncType != 1 ? h->d_igrad : nullptr;
 
-    const bool use_slot = h->slot && h->kernel_pref != 1;
+    TrajPlan *plan = nullptr;
+    if (h->kernel_pref == 3 || (h->kernel_pref == 0 && h->fiber)) plan = h->fiber;
+    else if (h->kernel_pref == 2 || (h->kernel_pref == 0 && h->slot)) plan = h->slot;
+    const bool use_slot = plan != nullptr;
     int ctas = 0, regs = 0, tpc = 1;
     size_t smem = 0;
     CU(cudaEventRecord(h->ev0, st));
     if (use_slot) {
-        CU(jq_slot_launch(h->slot, h->P, A, st, &ctas, &regs, &smem, &tpc));
+        CU(jq_traj_launch(plan, h->P, A, st, &ctas, &regs, &smem, &tpc));
     } else {
         if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024)
             return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory (n*m = %d)", h->n * h->m);
@@ -313,7 +319,7 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     }
     CU(cudaEventRecord(h->ev1, st));
     h->timed = true;
-    h->last_kernel = use_slot ? 2 : 1;
+    h->last_kernel = use_slot ? jq_traj_plan_kind(plan) : 1;
     h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = tpc;
     const int nout = weights ? nbatch : (int)ntraj;
     const long long total = (long long)nout * (npar + 1);

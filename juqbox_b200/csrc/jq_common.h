@@ -30,13 +30,6 @@ struct LaunchArgs {
 size_t jq_generic_smem_bytes(const DevProblem &P, int Npar);
 cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem);
 
-// ---- warp-slot kernel (jq_slot.cu): state columns in registers, operators in registers ----
-struct SlotPlan;   // opaque, built at jq_create
-SlotPlan *jq_slot_plan_create(const DevProblem &Pdev, const struct HostOps &H, char *err, size_t errlen);
-void jq_slot_plan_destroy(SlotPlan *);
-cudaError_t jq_slot_launch(SlotPlan *plan, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
-                           size_t *smem, int *traj_per_cta);
-
 // Host copy of the operators in row-wise form, used by the planners.
 struct HostOps {
     int n, m, Nc, Nfreq;
@@ -44,3 +37,12 @@ struct HostOps {
     const int *col;
     const double *val;
 };
+
+// ---- register-resident trajectory kernels (jq_traj.cu): slot layout (kind 2) and fibre layout (kind 3) ----
+struct TrajPlan;   // opaque, built at jq_create; nullptr + reason when the problem shape has no instantiation
+TrajPlan *jq_slot_plan_create(const DevProblem &Pdev, const HostOps &H, const double *wdiag_host, char *err, size_t errlen);
+TrajPlan *jq_fiber_plan_create(const DevProblem &Pdev, const HostOps &H, const double *wdiag_host, char *err, size_t errlen);
+void jq_traj_plan_destroy(TrajPlan *);
+int jq_traj_plan_kind(const TrajPlan *);
+cudaError_t jq_traj_launch(TrajPlan *plan, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
+                           size_t *smem, int *traj_per_cta);

@@ -1,0 +1,861 @@
+// Register-resident trajectory kernels: the state of a trajectory lives in REGISTERS for the whole forward and
+// backward time loops; shared memory is only the exchange medium of the sparse operator products.
+//
+// One kernel template, two lane layouts ("how the n x m block is cut into per-lane register elements"):
+//
+//  SlotLane<R,C,NC,WQ>  (kernel id 2) generic sparse rows.  A group = NL lanes; lane l owns rows l, l+NL, .. (R rows)
+//      and C columns.  Every row keeps per control <= WQ entries (neighbour position, Hsym value, Hanti value); one
+//      product pass stores the lane's elements to the group's exchange buffer and loads every neighbour.
+//  FiberLane<R,NC,LMASK> (kernel id 3) Kronecker ladder structure.  A lane owns a whole fibre of R consecutive rows
+//      (the levels of the fastest subsystem) of ONE column.  Controls in LMASK couple only rows inside a fibre
+//      (tridiagonal, coefficients in registers, no memory traffic at all); the other controls couple whole fibres
+//      with a fibre-uniform coefficient, so a pass exchanges one R-vector per neighbour fibre instead of one load
+//      per nonzero.  Single-subsystem problems (n = R) never touch shared memory inside the time loops.
+//
+// Common structure.  4 warps per CTA; a group of GL lanes (power of two <= 32) covers (part of) one trajectory,
+// GPT groups per trajectory, TPC trajectories per CTA.  Columns never couple inside the time loops, so products
+// only need __syncwarp; groups meet through shared memory + __syncthreads once per CH-step chunk (control table),
+// at the infidelity between the sweeps and at the final gradient sum.
+//   pass(x):  A_q = Hsym_q x and/or D_q = Hanti_q x ;  K(t)x = h0.*x + sum_q p_q(t) A_q ;  S(t)x = sum_q q_q(t) D_q
+// The A_q, D_q of the adjoint passes are exactly what the gradient traces need (tr(A'HC) = sum A.*(HC)), so the
+// gradient costs no extra products.  Control table: every CH steps all threads fill knot index, the three B-spline
+// values and cos/sin of every carrier at the 2CH+1 time points, then p_q, q_q for every resident trajectory.
+//
+// Reference lines: forward loop src/evalobjgrad.jl:698-753, infidelity :755-766, adjoint init :810-844/:2026-2042,
+// backward loop :859-921, steppers src/StormerVerlet.jl:255-303,:461-504, Neumann src/linear_solvers.jl:94-106,
+// controls src/bsplines.jl:211-304,:321-381, gradient src/evalobjgrad.jl:2567-2619.  The only algebraic regrouping
+// is S1*u + (h/2) S1*k1 = S1*(u + (h/2) k1)  (src/StormerVerlet.jl:483-484).
+#include "jq_common.h"
+
+#include <cstdio>
+#include <vector>
+
+#define TRAJ_WARPS 4
+#define TRAJ_THREADS (TRAJ_WARPS * 32)
+#define TRAJ_CH 16   // steps per control-table chunk
+
+struct TrajParams {
+    DevProblem P;
+    LaunchArgs A;
+    int NL;                                  // lanes per column block (slot: lanes per slot; fibre: fibres per column)
+    int GL, GPT, TPC, ngroups;               // lanes per group, groups per trajectory, trajectories / groups per CTA
+    int CPG;                                 // fibre layout: columns per group
+    int NLR;                                 // slot layout: NL * R (rows incl. padding)
+    const int *plan_i;                       // layout-specific integer table
+    const double *plan_d;                    // layout-specific coefficient table
+    const double *plan_d0, *plan_w;          // per (padded) row: H0 diagonal, guard weight
+    int o_exch, o_pcof, o_gsm, o_times, o_tabb, o_tabph, o_tabpq, o_red, o_tabk;   // shared-memory offsets in doubles
+    int exch_per_unit;                       // doubles of exchange buffer per group (slot) / per warp (fibre)
+};
+
+struct TrajPlan {
+    int kind;                                // 2 slot, 3 fibre
+    int R, C, NC, WQ, LMASK, UPL;
+    int NL, GL, GPT, TPC, ngroups, CPG, NLR, exch_per_unit;
+    int *d_i = nullptr;
+    double *d_d = nullptr, *d_d0 = nullptr, *d_w = nullptr;
+};
+
+namespace {
+
+#define UNROLL _Pragma("unroll")
+
+// ------------------------------------------------------------------------------------------------ exchange access
+// V doubles per position, laid out in planes of `stride` positions so that consecutive lanes hit consecutive banks.
+template <int V> struct Xch;
+template <> struct Xch<1> {
+    static __device__ __forceinline__ void st(double *b, int pos, int, const double *x) { b[pos] = x[0]; }
+    static __device__ __forceinline__ void ld(const double *b, int pos, int, double *x) { x[0] = b[pos]; }
+};
+template <> struct Xch<2> {
+    static __device__ __forceinline__ void st(double *b, int pos, int, const double *x) { reinterpret_cast<double2 *>(b)[pos] = make_double2(x[0], x[1]); }
+    static __device__ __forceinline__ void ld(const double *b, int pos, int, double *x) { double2 v = reinterpret_cast<const double2 *>(b)[pos]; x[0] = v.x; x[1] = v.y; }
+};
+template <> struct Xch<3> {
+    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) { b[pos] = x[0]; b[s + pos] = x[1]; b[2 * s + pos] = x[2]; }
+    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) { x[0] = b[pos]; x[1] = b[s + pos]; x[2] = b[2 * s + pos]; }
+};
+template <> struct Xch<4> {
+    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) {
+        reinterpret_cast<double2 *>(b)[pos] = make_double2(x[0], x[1]);
+        reinterpret_cast<double2 *>(b)[s + pos] = make_double2(x[2], x[3]);
+    }
+    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) {
+        double2 v = reinterpret_cast<const double2 *>(b)[pos], w = reinterpret_cast<const double2 *>(b)[s + pos];
+        x[0] = v.x; x[1] = v.y; x[2] = w.x; x[3] = w.y;
+    }
+};
+template <> struct Xch<6> {
+    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) {
+        UNROLL for (int p = 0; p < 3; ++p) reinterpret_cast<double2 *>(b)[p * s + pos] = make_double2(x[2 * p], x[2 * p + 1]);
+    }
+    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) {
+        UNROLL for (int p = 0; p < 3; ++p) { double2 v = reinterpret_cast<const double2 *>(b)[p * s + pos]; x[2 * p] = v.x; x[2 * p + 1] = v.y; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ lane layouts
+// Geometry of this thread inside the CTA, common to both layouts.
+struct Geo {
+    int lane, warp, lg, group, tloc, gi;     // lane in warp, warp, lane in group, group in CTA, trajectory in CTA, group in trajectory
+};
+
+template <int R_, int C_, int NC_, int WQ_>
+struct SlotLane {
+    static constexpr int R = R_, C = C_, NC = NC_, WQ = WQ_, E = R_ * C_;
+    int pos[R][NC][WQ], own[R];
+    double hs[R][NC][WQ], ha[R][NC][WQ];
+    double d0[E], w[E];
+    double p[3][NC], q[3][NC];
+    double *buf;
+    int nlr, parity, c0;
+
+    __device__ __forceinline__ void setup(const TrajParams &S, double *sm, const Geo &g) {
+        nlr = S.NLR; parity = 0; c0 = g.gi * C;
+        buf = sm + S.o_exch + g.group * S.exch_per_unit;
+        UNROLL for (int k = 0; k < R; ++k) {
+            const int r = k * S.NL + g.lg;
+            own[k] = r;
+            UNROLL for (int qq = 0; qq < NC; ++qq)
+                UNROLL for (int e = 0; e < WQ; ++e) {
+                    const int ix = (r * NC + qq) * WQ + e;
+                    pos[k][qq][e] = S.plan_i[ix];
+                    hs[k][qq][e] = S.plan_d[2 * ix];
+                    ha[k][qq][e] = S.plan_d[2 * ix + 1];
+                }
+        }
+    }
+    // (padded) row and column of element e
+    __device__ __forceinline__ int row(int e) const { return own[e / C]; }
+    __device__ __forceinline__ int col(int e) const { return c0 + e % C; }
+
+    template <bool WA, bool WD>
+    __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
+        double *b = buf + parity * (nlr * C);
+        parity ^= 1;
+        UNROLL for (int k = 0; k < R; ++k) Xch<C>::st(b, own[k], nlr, &x[k * C]);
+        __syncwarp();
+        UNROLL for (int k = 0; k < R; ++k)
+            UNROLL for (int qq = 0; qq < NC; ++qq) {
+                UNROLL for (int c = 0; c < C; ++c) { if (WA) A[k * C + c][qq] = 0.0; if (WD) D[k * C + c][qq] = 0.0; }
+                UNROLL for (int e = 0; e < WQ; ++e) {
+                    double xv[C];
+                    Xch<C>::ld(b, pos[k][qq][e], nlr, xv);
+                    UNROLL for (int c = 0; c < C; ++c) {
+                        if (WA) A[k * C + c][qq] = fma(hs[k][qq][e], xv[c], A[k * C + c][qq]);
+                        if (WD) D[k * C + c][qq] = fma(ha[k][qq][e], xv[c], D[k * C + c][qq]);
+                    }
+                }
+            }
+    }
+};
+
+template <int R_, int NC_, int LMASK_>
+struct FiberLane {
+    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, C = 1;
+    static constexpr bool REMOTE = (LMASK_ != (1 << NC_) - 1);
+    // local (inside the fibre) tridiagonal coefficients: x_{k+1} -> row k ("u"), x_k -> row k+1 ("l")
+    double lsu[NC][R > 1 ? R - 1 : 1], lsl[NC][R > 1 ? R - 1 : 1], lau[NC][R > 1 ? R - 1 : 1], lal[NC][R > 1 ? R - 1 : 1];
+    // remote: two neighbour fibres per control (lane position inside the warp) with fibre-uniform coefficients
+    int rpos[NC][2];
+    double rhs[NC][2], rha[NC][2];
+    double d0[E], w[E];
+    double p[3][NC], q[3][NC];
+    double *buf;
+    int parity, lane, row0, colj;
+
+    __device__ __forceinline__ void setup(const TrajParams &S, double *sm, const Geo &g) {
+        parity = 0; lane = g.lane;
+        const int rho = g.lg % S.NL, cj = g.lg / S.NL;
+        row0 = rho * R;
+        colj = g.gi * S.CPG + cj;
+        buf = sm + S.o_exch + g.warp * S.exch_per_unit;
+        const int *pi = S.plan_i + rho * (NC * 2);
+        const double *pd = S.plan_d + rho * (NC * (4 * (R - 1) + 4));
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            const double *c = pd + qq * (4 * (R - 1) + 4);
+            UNROLL for (int k = 0; k < R - 1; ++k) { lsu[qq][k] = c[4 * k]; lsl[qq][k] = c[4 * k + 1]; lau[qq][k] = c[4 * k + 2]; lal[qq][k] = c[4 * k + 3]; }
+            UNROLL for (int e = 0; e < 2; ++e) {
+                rpos[qq][e] = g.lane + pi[qq * 2 + e];          // plan stores the fibre offset (0 = padding -> own lane)
+                rhs[qq][e] = c[4 * (R - 1) + 2 * e];
+                rha[qq][e] = c[4 * (R - 1) + 2 * e + 1];
+            }
+        }
+    }
+    __device__ __forceinline__ int row(int e) const { return row0 + e; }
+    __device__ __forceinline__ int col(int) const { return colj; }
+
+    template <bool WA, bool WD>
+    __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
+        double *b = buf;
+        if (REMOTE) {
+            b = buf + parity * (R * 32);
+            parity ^= 1;
+            Xch<R>::st(b, lane, 32, x);
+            __syncwarp();
+        }
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            if ((LMASK >> qq) & 1) {
+                UNROLL for (int k = 0; k < R; ++k) {
+                    double a = 0.0, d = 0.0;
+                    if (k + 1 < R) { if (WA) a = lsu[qq][k] * x[k + 1]; if (WD) d = lau[qq][k] * x[k + 1]; }
+                    if (k > 0) { if (WA) a = fma(lsl[qq][k - 1], x[k - 1], a); if (WD) d = fma(lal[qq][k - 1], x[k - 1], d); }
+                    if (WA) A[k][qq] = a;
+                    if (WD) D[k][qq] = d;
+                }
+            } else {
+                double x0[R], x1[R];
+                Xch<R>::ld(b, rpos[qq][0], 32, x0);
+                Xch<R>::ld(b, rpos[qq][1], 32, x1);
+                UNROLL for (int k = 0; k < R; ++k) {
+                    if (WA) A[k][qq] = fma(rhs[qq][1], x1[k], rhs[qq][0] * x0[k]);
+                    if (WD) D[k][qq] = fma(rha[qq][1], x1[k], rha[qq][0] * x0[k]);
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ steppers
+// X = sum_{j<=J} (h/2)^j S_level^j B   (src/linear_solvers.jl:94-106); B is consumed.
+template <class LaneT>
+__device__ __forceinline__ void neumann(LaneT &L, int J, double h, int level, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
+    constexpr int E = LaneT::E, NC = LaneT::NC;
+    double dummy[E][NC], D[E][NC];
+    UNROLL for (int e = 0; e < E; ++e) X[e] = B[e];
+    double coeff = 1.0;
+    for (int it = 0; it < J; ++it) {
+        L.template pass<false, true>(B, dummy, D);
+        coeff *= 0.5 * h;
+        UNROLL for (int e = 0; e < E; ++e) {
+            double t = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq) t = fma(L.q[level][qq], D[e][qq], t);
+            B[e] = t;
+            X[e] = fma(coeff, t, X[e]);
+        }
+    }
+}
+
+// src/StormerVerlet.jl:461-504.  u, v updated in place; v05 returned.
+template <class LaneT>
+__device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E], double (&v05)[LaneT::E]) {
+    constexpr int E = LaneT::E, NC = LaneT::NC;
+    double A[E][NC], D[E][NC], rhs[E], l1[E], s0u[E];
+    L.template pass<true, true>(u, A, D);
+    UNROLL for (int e = 0; e < E; ++e) {
+        double r = L.d0[e] * u[e], s = 0.0;
+        UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], A[e][qq], r); s = fma(L.q[0][qq], D[e][qq], s); }
+        rhs[e] = r;            // K05 u
+        s0u[e] = s;            // S0 u
+    }
+    L.template pass<false, true>(v, A, D);
+    UNROLL for (int e = 0; e < E; ++e) UNROLL for (int qq = 0; qq < NC; ++qq) rhs[e] = fma(L.q[1][qq], D[e][qq], rhs[e]);   // + S05 v
+    neumann(L, J, h, 1, rhs, l1);
+    UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
+    L.template pass<true, true>(v05, A, D);
+    double k1v[E], s05v[E];
+    UNROLL for (int e = 0; e < E; ++e) {
+        double k0 = L.d0[e] * v05[e], k1 = k0, s = 0.0;
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            k0 = fma(L.p[0][qq], A[e][qq], k0);
+            k1 = fma(L.p[2][qq], A[e][qq], k1);
+            s = fma(L.q[1][qq], D[e][qq], s);
+        }
+        k1v[e] = k1;                                   // K1 v05
+        s05v[e] = s;                                   // S05 v05
+        u[e] = fma(0.5 * h, s0u[e] - k0, u[e]);        // u + (h/2) kappa1,  kappa1 = S0 u - K0 v05
+    }
+    L.template pass<false, true>(u, A, D);
+    UNROLL for (int e = 0; e < E; ++e) {
+        double s = -k1v[e];
+        UNROLL for (int qq = 0; qq < NC; ++qq) s = fma(L.q[2][qq], D[e][qq], s);
+        rhs[e] = s;                                    // S1 (u + (h/2) kappa1) - K1 v05
+    }
+    double k2[E];
+    neumann(L, J, h, 2, rhs, k2);
+    UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
+    L.template pass<true, false>(u, A, D);
+    UNROLL for (int e = 0; e < E; ++e) {
+        double l2 = fma(L.d0[e], u[e], s05v[e]);
+        UNROLL for (int qq = 0; qq < NC; ++qq) l2 = fma(L.p[1][qq], A[e][qq], l2);
+        v[e] = fma(0.5 * h, l1[e] + l2, v[e]);
+    }
+}
+
+// src/StormerVerlet.jl:255-303 with the diagonal-W forcing of src/evalobjgrad.jl:862,882-888, fused with the five
+// traces per control of adjoint_grad_calc! (src/evalobjgrad.jl:2578-2618):
+//   T[q][0] = tr(vr0,Ha,lr05)  T[q][1] = tr(vi05,Hs,lr05)  T[q][2] = tr(vr,Ha,lr05)
+//   T[q][3] = tr(vr,Hs,li)+tr(vr0,Hs,li0)                   T[q][4] = tr(vi05,Ha,li)+tr(vi05,Ha,li0)
+template <class LaneT>
+__device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (&mu)[LaneT::E], double (&nu)[LaneT::E],
+                                             const double (&vr0)[LaneT::E], const double (&vi05)[LaneT::E],
+                                             const double (&vr)[LaneT::E], double (&T)[LaneT::NC][5]) {
+    constexpr int E = LaneT::E, NC = LaneT::NC;
+    double A[E][NC], D[E][NC], rhs[E], s05n[E];
+    L.template pass<false, true>(mu, A, D);
+    UNROLL for (int e = 0; e < E; ++e) {
+        double s = L.w[e] * vr0[e];                    // hr0
+        UNROLL for (int qq = 0; qq < NC; ++qq) s = fma(L.q[0][qq], D[e][qq], s);
+        rhs[e] = s;                                    // S0 mu + hr0
+    }
+    L.template pass<true, true>(nu, A, D);
+    UNROLL for (int e = 0; e < E; ++e) {
+        double kk = L.d0[e] * nu[e], s = 0.0;
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            kk = fma(L.p[1][qq], A[e][qq], kk);
+            s = fma(L.q[1][qq], D[e][qq], s);
+            T[qq][3] = fma(vr0[e], A[e][qq], T[qq][3]);
+            T[qq][4] = fma(vi05[e], D[e][qq], T[qq][4]);
+        }
+        rhs[e] -= kk;                                  // - K05 nu
+        s05n[e] = s;                                   // S05 nu
+    }
+    double k2[E];
+    neumann(L, J, h, 0, rhs, k2);
+    UNROLL for (int e = 0; e < E; ++e) mu[e] = fma(0.5 * h, k2[e], mu[e]);   // X = mu
+    L.template pass<true, true>(mu, A, D);
+    double l2[E], k1x[E], s1x[E];
+    UNROLL for (int e = 0; e < E; ++e) {
+        double k0 = L.d0[e] * mu[e], k1 = k0, s = 0.0;
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            k0 = fma(L.p[0][qq], A[e][qq], k0);
+            k1 = fma(L.p[2][qq], A[e][qq], k1);
+            s = fma(L.q[2][qq], D[e][qq], s);
+            T[qq][0] = fma(vr0[e], D[e][qq], T[qq][0]);
+            T[qq][1] = fma(vi05[e], A[e][qq], T[qq][1]);
+            T[qq][2] = fma(vr[e], D[e][qq], T[qq][2]);
+        }
+        const double hi0 = L.w[e] * vi05[e];
+        l2[e] = k0 + s05n[e] + hi0;                    // K0 X + S05 nu + hi0
+        k1x[e] = k1 + hi0;                             // K1 X + hi1
+        s1x[e] = s;                                    // S1 X
+    }
+    L.template pass<false, true>(l2, A, D);
+    UNROLL for (int e = 0; e < E; ++e) {
+        double s = 0.0;
+        UNROLL for (int qq = 0; qq < NC; ++qq) s = fma(L.q[1][qq], D[e][qq], s);
+        rhs[e] = s05n[e] + 0.5 * h * s + k1x[e];        // S05 nu + (h/2) S05 l2 + K1 X + hi1
+    }
+    double l1[E];
+    neumann(L, J, h, 1, rhs, l1);
+    UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
+    L.template pass<true, true>(nu, A, D);
+    UNROLL for (int e = 0; e < E; ++e) {
+        double kk = L.d0[e] * nu[e];
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            kk = fma(L.p[1][qq], A[e][qq], kk);
+            T[qq][3] = fma(vr[e], A[e][qq], T[qq][3]);
+            T[qq][4] = fma(vi05[e], D[e][qq], T[qq][4]);
+        }
+        mu[e] = fma(0.5 * h, s1x[e] - kk + L.w[e] * vr[e], mu[e]);   // kappa1 = S1 X - K05 nu + hr1
+    }
+}
+
+__device__ __forceinline__ double group_sum(double x, int GL) {
+    for (int o = 1; o < GL; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// Fill the control table for `nst` steps starting at time t (all threads of the CTA).
+template <int NC>
+__device__ void fill_table(const TrajParams &S, double *sm, double t, double dt, int nst, double dtknot) {
+    double *times = sm + S.o_times, *tabb = sm + S.o_tabb, *tabph = sm + S.o_tabph, *tabpq = sm + S.o_tabpq;
+    int *tabk = reinterpret_cast<int *>(sm + S.o_tabk);
+    const int npts = 2 * nst + 1, Nfreq = S.P.Nfreq, D1 = S.A.D1;
+    __syncthreads();                       // the previous chunk's table is no longer in use
+    if (threadIdx.x == 0) {
+        double tt = t;
+        times[0] = tt;
+        for (int i = 0; i < nst; ++i) {    // same recurrence as the reference: t + 0.5 dt, then t = t + dt
+            times[2 * i + 1] = tt + 0.5 * dt;
+            tt = tt + dt;
+            times[2 * i + 2] = tt;
+        }
+    }
+    __syncthreads();
+    const double width = 3.0 * dtknot;
+    for (int idx = threadIdx.x; idx < npts * (NC * Nfreq + 1); idx += TRAJ_THREADS) {
+        const int i = idx / (NC * Nfreq + 1), j = idx % (NC * Nfreq + 1);
+        const double tt = times[i];
+        if (j == NC * Nfreq) {             // src/bsplines.jl:224-253
+            long long k = (long long)ceil(tt / dtknot + 2.0);
+            k = k < 3 ? 3 : (k > D1 ? D1 : k);
+            tabk[i] = (int)k;
+            double tau = (tt - dtknot * ((double)k - 1.5)) / width;
+            tabb[3 * i + 0] = 9.0 / 8 + 4.5 * tau + 4.5 * tau * tau;
+            tau = (tt - dtknot * ((double)(k - 1) - 1.5)) / width;
+            tabb[3 * i + 1] = 0.75 - 9.0 * tau * tau;
+            tau = (tt - dtknot * ((double)(k - 2) - 1.5)) / width;
+            tabb[3 * i + 2] = 9.0 / 8 - 4.5 * tau + 4.5 * tau * tau;
+        } else {
+            const int qq = j / Nfreq, fr = j % Nfreq;
+            double sn, cs;
+            sincos(S.P.cfreq[qq + NC * fr] * tt, &sn, &cs);
+            tabph[2 * (i * NC * Nfreq + j)] = cs;
+            tabph[2 * (i * NC * Nfreq + j) + 1] = sn;
+        }
+    }
+    __syncthreads();
+    const double *pcof = sm + S.o_pcof;
+    for (int idx = threadIdx.x; idx < npts * S.TPC * NC; idx += TRAJ_THREADS) {
+        const int i = idx / (S.TPC * NC), rem = idx % (S.TPC * NC), tr = rem / NC, qq = rem % NC;
+        const int k = tabk[i];
+        const double b0 = tabb[3 * i], b1 = tabb[3 * i + 1], b2 = tabb[3 * i + 2];
+        const double *pc = pcof + tr * S.A.Npar;
+        double pv = 0.0, qv = 0.0;
+        for (int fr = 0; fr < Nfreq; ++fr) {   // src/bsplines.jl:229-261
+            const int off1 = 2 * qq * Nfreq * D1 + fr * 2 * D1 - 1, off2 = off1 + D1;
+            const double fbs1 = pc[off1 + k] * b0 + pc[off1 + k - 1] * b1 + pc[off1 + k - 2] * b2;
+            const double fbs2 = pc[off2 + k] * b0 + pc[off2 + k - 1] * b1 + pc[off2 + k - 2] * b2;
+            const double cs = tabph[2 * (i * NC * Nfreq + qq * Nfreq + fr)], sn = tabph[2 * (i * NC * Nfreq + qq * Nfreq + fr) + 1];
+            pv += fbs1 * cs - fbs2 * sn;
+            qv += fbs1 * sn + fbs2 * cs;
+        }
+        tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq] = pv;
+        tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq + 1] = qv;
+    }
+    __syncthreads();
+}
+
+// Gradient scatter role: (control, frequency, alpha) with a 3-knot register window.
+struct Updater {
+    bool on;
+    int uq, uf, ua, gbase, kw;
+    double acc0, acc1, acc2;
+};
+
+template <class LaneT, int UPL>
+__global__ void __launch_bounds__(TRAJ_THREADS) jq_traj_kernel(const __grid_constant__ TrajParams S) {
+    constexpr int E = LaneT::E, NC = LaneT::NC;
+    extern __shared__ double sm[];
+    const DevProblem &P = S.P;
+    const LaunchArgs &A = S.A;
+    Geo g;
+    g.lane = threadIdx.x & 31; g.warp = threadIdx.x >> 5;
+    g.lg = g.lane & (S.GL - 1);
+    g.group = g.warp * (32 / S.GL) + g.lane / S.GL;
+    g.tloc = g.group / S.GPT; g.gi = g.group % S.GPT;
+    const int GL = S.GL;
+    const int traj = blockIdx.x * S.TPC + g.tloc;
+    const bool live_t = g.tloc < S.TPC && traj < A.ntraj;    // dead groups compute on zeros and write nothing
+    const int s = live_t ? traj % A.nsamples : 0;
+    const int n = P.n, m = P.m, Npar = A.Npar, D1 = A.D1, Nfreq = P.Nfreq, J = P.J;
+    const double tinv = 1.0 / P.T, dtknot = P.T / (D1 - 2);
+    const int tl = g.tloc < S.TPC ? g.tloc : 0;              // table row used by this group
+
+    LaneT L;
+    L.setup(S, sm, g);
+    bool ok[E];
+    UNROLL for (int e = 0; e < E; ++e) {
+        const int r = L.row(e);
+        ok[e] = live_t && r < n && L.col(e) < m;
+        L.d0[e] = ok[e] ? S.plan_d0[r] + (A.shift ? A.shift[(size_t)s * n + r] : 0.0) : 0.0;
+        L.w[e] = ok[e] ? S.plan_w[r] * tinv : 0.0;
+    }
+    // stage this CTA's pcof vectors and zero the per-group gradient accumulators
+    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += TRAJ_THREADS) {
+        const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
+        sm[S.o_pcof + idx] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * Npar + k] : 0.0;
+    }
+    for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += TRAJ_THREADS) sm[S.o_gsm + idx] = 0.0;
+
+    double vr[E], vi[E], vi05[E];
+    UNROLL for (int e = 0; e < E; ++e) {
+        vr[e] = ok[e] ? P.uinit[L.row(e) + (size_t)n * L.col(e)] : 0.0;
+        vi[e] = 0.0;
+        vi05[e] = 0.0;
+    }
+    const double *tabpq = sm + S.o_tabpq;
+
+#define LOAD_LEVELS(ls)                                                                                              \
+    UNROLL for (int qq = 0; qq < NC; ++qq) {                                                                         \
+        L.p[0][qq] = L.p[2][qq]; L.q[0][qq] = L.q[2][qq];                                                            \
+        const double *r1 = tabpq + ((2 * (ls) + 1) * S.TPC + tl) * 2 * NC, *r2 = tabpq + ((2 * (ls) + 2) * S.TPC + tl) * 2 * NC; \
+        L.p[1][qq] = r1[2 * qq]; L.q[1][qq] = r1[2 * qq + 1];                                                        \
+        L.p[2][qq] = r2[2 * qq]; L.q[2][qq] = r2[2 * qq + 1];                                                        \
+    }
+#define LOAD_LEVEL0()                                                                                                \
+    UNROLL for (int qq = 0; qq < NC; ++qq) { L.p[2][qq] = tabpq[tl * 2 * NC + 2 * qq]; L.q[2][qq] = tabpq[tl * 2 * NC + 2 * qq + 1]; }
+
+    // ------------------------------------------------------------ forward sweep (src/evalobjgrad.jl:698-753)
+    double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
+    for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
+        const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+        fill_table<NC>(S, sm, t, dt, nst, dtknot);
+        LOAD_LEVEL0();
+        for (int ls = 0; ls < nst; ++ls) {
+            LOAD_LEVELS(ls);
+            UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e], pen);                              // penalf2aTrap
+            state_step(L, J, dt, vr, vi, vi05);
+            UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e] + 2.0 * vi05[e] * vi05[e], pen);   // penalf2a
+            t = t + dt;
+        }
+    }
+    // infidelity (pFidType 2) and leak: group partials -> shared -> per-trajectory sums in group order
+    double *red = sm + S.o_red;
+    {
+        double re = 0.0, im = 0.0;
+        UNROLL for (int e = 0; e < E; ++e) {
+            const size_t ix = L.row(e) + (size_t)n * L.col(e);
+            const double tr_ = ok[e] ? P.vtr[ix] : 0.0, ti_ = ok[e] ? P.vti[ix] : 0.0;
+            re += vr[e] * tr_ - vi[e] * ti_;
+            im += vr[e] * ti_ + vi[e] * tr_;
+        }
+        re = group_sum(re, GL); im = group_sum(im, GL); pen = group_sum(pen, GL);
+        __syncthreads();
+        if (g.lg == 0) { red[g.group * 4] = re; red[g.group * 4 + 1] = im; red[g.group * 4 + 2] = pen; }
+        __syncthreads();
+    }
+    double rs = 0.0, is = 0.0, pens = 0.0;
+    for (int j = 0; j < S.GPT; ++j) {
+        const int gg = tl * S.GPT + j;
+        rs += red[gg * 4]; is += red[gg * 4 + 1]; pens += red[gg * 4 + 2];
+    }
+    rs /= m; is /= m;
+    const double infid = 1.0 - (rs * rs + is * is);
+    if (live_t && g.gi == 0 && g.lg == 0) {
+        double *o = A.scal + (size_t)traj * 4;
+        o[0] = infid; o[1] = 0.5 * dt * pens; o[2] = infid; o[3] = 0.0;   // w already carries 1/T
+    }
+    if (!A.evaladjoint) return;
+
+    // ------------------------------------------------------------ backward sweep (src/evalobjgrad.jl:810-921)
+    double lr[E], li[E], vr0[E];
+    UNROLL for (int e = 0; e < E; ++e) {
+        const size_t ix = L.row(e) + (size_t)n * L.col(e);
+        const double tr_ = ok[e] ? P.vtr[ix] : 0.0, ti_ = ok[e] ? P.vti[ix] : 0.0;
+        lr[e] = (rs * tr_ + is * ti_) / m;     // init_adjoint!, src/evalobjgrad.jl:2029-2042
+        li[e] = (is * tr_ - rs * ti_) / m;
+    }
+    // gradient scatter roles: role u = lg + j*GL < NU owns (control, frequency, alpha)
+    const int NU = NC * Nfreq * 2;
+    Updater U[UPL];
+    UNROLL for (int j = 0; j < UPL; ++j) {
+        const int u = g.lg + j * GL;
+        U[j].on = u < NU;
+        U[j].uq = U[j].on ? u / (2 * Nfreq) : 0;
+        U[j].uf = U[j].on ? (u >> 1) % Nfreq : 0;
+        U[j].ua = u & 1;
+        U[j].gbase = 2 * U[j].uq * Nfreq * D1 + U[j].uf * 2 * D1 + U[j].ua * D1 - 1;
+        U[j].kw = D1; U[j].acc0 = 0.0; U[j].acc1 = 0.0; U[j].acc2 = 0.0;
+    }
+    double *gsm = sm + S.o_gsm + g.group * Npar;
+    const double *tabb = sm + S.o_tabb, *tabph = sm + S.o_tabph;
+    const int *tabk = reinterpret_cast<const int *>(sm + S.o_tabk);
+
+    t = P.T;
+    dt = -dt;
+    for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
+        const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+        fill_table<NC>(S, sm, t, dt, nst, dtknot);
+        LOAD_LEVEL0();
+        for (int ls = 0; ls < nst; ++ls) {
+            LOAD_LEVELS(ls);
+            UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
+            state_step(L, J, dt, vr, vi, vi05);
+            double T[NC][5];
+            UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = 0.0;
+            adjoint_step(L, J, dt, lr, li, vr0, vi05, vr, T);
+            UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = group_sum(T[qq][j], GL);
+            UNROLL for (int j = 0; j < UPL; ++j) {
+                if (U[j].on) {
+                    double Tq[5];
+                    UNROLL for (int a = 0; a < 5; ++a) {
+                        Tq[a] = T[0][a];
+                        UNROLL for (int qq = 1; qq < NC; ++qq) Tq[a] = (U[j].uq == qq) ? T[qq][a] : Tq[a];
+                    }
+                    // time points in decreasing order: t0 (row 2ls), t0 + dt/2 (2ls+1), t0 + dt (2ls+2)
+                    UNROLL for (int tp = 0; tp < 3; ++tp) {
+                        const int i = 2 * ls + tp;
+                        const double Pc = tp == 1 ? Tq[3] : -Tq[1];
+                        const double Qc = tp == 0 ? -Tq[0] : (tp == 1 ? -Tq[4] : -Tq[2]);
+                        const int ph = 2 * (i * NC * Nfreq + U[j].uq * Nfreq + U[j].uf);
+                        const double cs = tabph[ph], sn = tabph[ph + 1];
+                        const double X = U[j].ua == 0 ? Pc * cs + Qc * sn : Qc * cs - Pc * sn;
+                        const int k = tabk[i];
+                        while (U[j].kw > k) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; U[j].acc0 = U[j].acc1; U[j].acc1 = U[j].acc2; U[j].acc2 = 0.0; --U[j].kw; }
+                        U[j].acc0 = fma(tabb[3 * i], X, U[j].acc0);
+                        U[j].acc1 = fma(tabb[3 * i + 1], X, U[j].acc1);
+                        U[j].acc2 = fma(tabb[3 * i + 2], X, U[j].acc2);
+                    }
+                }
+            }
+            t = t + dt;
+        }
+    }
+    UNROLL for (int j = 0; j < UPL; ++j)
+        if (U[j].on) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; gsm[U[j].gbase + U[j].kw - 1] += U[j].acc1; gsm[U[j].gbase + U[j].kw - 2] += U[j].acc2; }
+    __syncthreads();
+    // total gradient of each resident trajectory = dt * sum of its groups' partial gradients, in group order
+    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += TRAJ_THREADS) {
+        const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
+        if (tg >= A.ntraj) continue;
+        double gs = 0.0;
+        for (int j = 0; j < S.GPT; ++j) gs += sm[S.o_gsm + (tr * S.GPT + j) * Npar + k];
+        A.grad[(size_t)tg * Npar + k] = dt * gs;
+    }
+}
+
+typedef void (*traj_kernel_t)(const TrajParams);
+struct Inst { int kind, R, C, NC, WQ, LMASK, UPL; traj_kernel_t fn; };
+#define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
+#define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL>}
+const Inst kInst[] = {
+    SLOT(1, 2, 1, 2), SLOT(1, 3, 1, 2), SLOT(1, 4, 1, 2), SLOT(1, 4, 2, 2), SLOT(1, 2, 2, 2),
+    SLOT(2, 2, 3, 2), SLOT(3, 1, 3, 2), SLOT(1, 1, 1, 2), SLOT(1, 1, 2, 2),
+    FIBER(2, 1, 1, 1), FIBER(4, 1, 1, 1), FIBER(4, 1, 1, 2), FIBER(6, 1, 1, 2), FIBER(3, 1, 1, 1), FIBER(3, 1, 1, 2),
+    FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
+};
+
+const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL) {
+    for (const Inst &i : kInst)
+        if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL) return &i;
+    return nullptr;
+}
+
+double value_at(const HostOps &H, int o, int r, int c) {
+    const int *rp = H.rowptr + o * (H.n + 1);
+    double v = 0.0;
+    for (int p = rp[r]; p < rp[r + 1]; ++p) if (H.col[p] == c) v += H.val[p];
+    return v;
+}
+
+bool upload_plan(TrajPlan *pl, const std::vector<int> &pi, const std::vector<double> &pd, const std::vector<double> &d0,
+                 const std::vector<double> &w) {
+    bool ok = cudaMalloc(&pl->d_i, (pi.size() + 1) * sizeof(int)) == cudaSuccess && cudaMalloc(&pl->d_d, (pd.size() + 1) * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&pl->d_d0, d0.size() * sizeof(double)) == cudaSuccess && cudaMalloc(&pl->d_w, w.size() * sizeof(double)) == cudaSuccess;
+    if (!ok) return false;
+    cudaMemcpy(pl->d_i, pi.data(), pi.size() * sizeof(int), cudaMemcpyHostToDevice);
+    cudaMemcpy(pl->d_d, pd.data(), pd.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(pl->d_d0, d0.data(), d0.size() * sizeof(double), cudaMemcpyHostToDevice);
+    cudaMemcpy(pl->d_w, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice);
+    return true;
+}
+
+// H0 must be diagonal for both register layouts; returns false otherwise.
+bool h0_diagonal(const HostOps &H, std::vector<double> &d0) {
+    d0.assign(H.n, 0.0);
+    for (int r = 0; r < H.n; ++r)
+        for (int p = H.rowptr[r]; p < H.rowptr[r + 1]; ++p) {
+            if (H.col[p] == r) d0[r] = H.val[p];
+            else if (H.val[p] != 0.0) return false;
+        }
+    return true;
+}
+
+int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ planners
+TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
+    const int n = H.n, m = H.m, Nc = H.Nc;
+    auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.objFuncType != 1) return no("objFuncType != 1 uses the generic kernel (second adjoint set)");
+    if (n > 128) return no("n > 128");
+    std::vector<double> d0;
+    if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
+    int WQ = 0;
+    std::vector<std::vector<std::vector<int>>> cols(n, std::vector<std::vector<int>>(Nc));
+    for (int q = 0; q < Nc; ++q)
+        for (int r = 0; r < n; ++r) {
+            std::vector<int> &cc = cols[r][q];
+            for (int o : {1 + q, 1 + Nc + q}) {
+                const int *rp = H.rowptr + o * (n + 1);
+                for (int p = rp[r]; p < rp[r + 1]; ++p) {
+                    bool have = false;
+                    for (int x : cc) have |= (x == H.col[p]);
+                    if (!have) cc.push_back(H.col[p]);
+                }
+            }
+            WQ = (int)cc.size() > WQ ? (int)cc.size() : WQ;
+        }
+    if (WQ > 2) return no("more than 2 entries per row and control (not a ladder-type control Hamiltonian)");
+    WQ = 2;
+    int NL = 2;
+    while (NL < 32 && NL < n) NL <<= 1;
+    while (NL < 32 && NL < Nc * H.Nfreq * 2) NL <<= 1;
+    if (NL < Nc * H.Nfreq * 2) return no("more (control, frequency) pairs than lanes");
+    const int R = (n + NL - 1) / NL;
+    int C = 1;
+    for (int c = 1; c <= 4; ++c) if (m % c == 0 && R * c <= 4) C = c;
+    const Inst *inst = find_inst(2, R, C, Nc, WQ, 0, 1);
+    if (!inst && C > 1) { for (int c = C - 1; c >= 1 && !inst; --c) if (m % c == 0) { inst = find_inst(2, R, c, Nc, WQ, 0, 1); if (inst) C = c; } }
+    if (!inst) return no("no slot instantiation for this (rows per lane, columns per lane, controls)");
+
+    TrajPlan *pl = new TrajPlan();
+    pl->kind = 2; pl->R = R; pl->C = C; pl->NC = Nc; pl->WQ = WQ; pl->LMASK = 0; pl->UPL = 1;
+    pl->NL = NL; pl->NLR = NL * R; pl->GL = NL; pl->GPT = m / C; pl->CPG = C;
+    pl->ngroups = TRAJ_WARPS * (32 / NL);
+    pl->TPC = pl->ngroups / pl->GPT;
+    pl->exch_per_unit = 2 * pl->NLR * C;
+    if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
+    const int NLR = pl->NLR;
+    std::vector<int> pos((size_t)NLR * Nc * WQ);
+    std::vector<double> hv((size_t)NLR * Nc * WQ * 2, 0.0), d0p(NLR, 0.0), wp(NLR, 0.0);
+    for (int r = 0; r < NLR; ++r) {
+        if (r < n) { d0p[r] = d0[r]; wp[r] = wdiag[r]; }
+        for (int q = 0; q < Nc; ++q)
+            for (int e = 0; e < WQ; ++e) {
+                const size_t ix = ((size_t)r * Nc + q) * WQ + e;
+                pos[ix] = r;                                     // padding: own position, zero coefficients
+                if (r < n && e < (int)cols[r][q].size()) {
+                    const int c = cols[r][q][e];
+                    pos[ix] = c;
+                    hv[2 * ix] = value_at(H, 1 + q, r, c);
+                    hv[2 * ix + 1] = value_at(H, 1 + Nc + q, r, c);
+                }
+            }
+    }
+    if (!upload_plan(pl, pos, hv, d0p, wp)) { jq_traj_plan_destroy(pl); return no("cudaMalloc failed for the slot plan"); }
+    err[0] = 0;
+    return pl;
+}
+
+// Fibre layout: find R such that control q is either "local" (couples only rows r, r+-1 inside a block of R
+// consecutive rows) or "remote" (couples row k of fibre rho only to row k of <= 2 other fibres, with a coefficient
+// that does not depend on k).  True for Kronecker ladder operators with the first subsystem of size R.
+TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
+    const int n = H.n, m = H.m, Nc = H.Nc;
+    auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.objFuncType != 1) return no("objFuncType != 1 uses the generic kernel (second adjoint set)");
+    std::vector<double> d0;
+    if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
+    // block size: first break of control 0's first off-diagonals
+    int R = n;
+    for (int r = 0; r + 1 < n; ++r) {
+        bool any = false;
+        for (int o : {1, 1 + Nc}) any |= value_at(H, o, r, r + 1) != 0.0 || value_at(H, o, r + 1, r) != 0.0;
+        if (!any) { R = r + 1; break; }
+    }
+    if (n % R != 0) return no("rows do not split into equal fibres");
+    if (R < 2 || R > 6 || R == 5) return no("fibre length not instantiated");
+    const int nfib = n / R;
+    int LMASK = 0;
+    struct Rem { int off[2]; double hs[2], ha[2]; };
+    std::vector<std::vector<Rem>> rem(nfib, std::vector<Rem>(Nc));
+    for (int q = 0; q < Nc; ++q) {
+        bool local = false, remote = false;
+        for (int o : {1 + q, 1 + Nc + q}) {
+            const int *rp = H.rowptr + o * (n + 1);
+            for (int r = 0; r < n; ++r)
+                for (int p = rp[r]; p < rp[r + 1]; ++p) {
+                    if (H.val[p] == 0.0) continue;
+                    const int c = H.col[p];
+                    if (r / R == c / R) { if (c != r + 1 && c != r - 1) return no("control couples inside a fibre beyond nearest neighbours"); local = true; }
+                    else { if (r % R != c % R) return no("control couples different levels of different fibres"); remote = true; }
+                }
+        }
+        if (local && remote) return no("control is neither purely local nor purely remote");
+        if (local || !remote) LMASK |= 1 << q;       // an all-zero control is trivially local
+        if (remote) {
+            for (int f = 0; f < nfib; ++f) {
+                Rem &x = rem[f][q];
+                x.off[0] = x.off[1] = 0; x.hs[0] = x.hs[1] = x.ha[0] = x.ha[1] = 0.0;
+                int cnt = 0;
+                for (int f2 = 0; f2 < nfib; ++f2) {
+                    if (f2 == f) continue;
+                    const double s0 = value_at(H, 1 + q, f * R, f2 * R), a0 = value_at(H, 1 + Nc + q, f * R, f2 * R);
+                    bool nz = s0 != 0.0 || a0 != 0.0;
+                    for (int k = 1; k < R; ++k) {
+                        const double sk = value_at(H, 1 + q, f * R + k, f2 * R + k), ak = value_at(H, 1 + Nc + q, f * R + k, f2 * R + k);
+                        if (sk != s0 || ak != a0) return no("remote coupling is not uniform along the fibre");
+                    }
+                    if (!nz) continue;
+                    if (cnt == 2) return no("more than 2 neighbour fibres per control");
+                    x.off[cnt] = f2 - f; x.hs[cnt] = s0; x.ha[cnt] = a0; ++cnt;
+                }
+            }
+        }
+    }
+    if (LMASK != 1 && LMASK != (1 << Nc) - 1) return no("only control 1 local (or all local) is instantiated");
+    if (Nc > 1 && LMASK == (1 << Nc) - 1) return no("several local controls are not instantiated");
+    const int NL = pow2ceil(nfib);
+    if (NL > 32) return no("more than 32 fibres per column");
+    const int GL = pow2ceil(NL * m) > 32 ? 32 : pow2ceil(NL * m);
+    const int CPG = GL / NL, GPT = (m + CPG - 1) / CPG;
+    const int NU = Nc * H.Nfreq * 2, UPL = (NU + GL - 1) / GL;
+    if (UPL > 2) return no("too many (control, frequency) pairs for the group size");
+    const Inst *inst = find_inst(3, R, 1, Nc, 2, LMASK, UPL);
+    if (!inst) return no("no fibre instantiation for this (fibre length, controls, updaters per lane)");
+    // lane offsets of remote neighbours must stay inside the column block of NL lanes
+    TrajPlan *pl = new TrajPlan();
+    pl->kind = 3; pl->R = R; pl->C = 1; pl->NC = Nc; pl->WQ = 2; pl->LMASK = LMASK; pl->UPL = UPL;
+    pl->NL = NL; pl->NLR = NL * R; pl->GL = GL; pl->GPT = GPT; pl->CPG = CPG;
+    pl->ngroups = TRAJ_WARPS * (32 / GL);
+    pl->TPC = pl->ngroups / GPT;
+    pl->exch_per_unit = 2 * R * 32;
+    if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
+    const int per = Nc * (4 * (R - 1) + 4);
+    std::vector<int> pi((size_t)NL * Nc * 2, 0);
+    std::vector<double> pd((size_t)NL * per, 0.0), d0p((size_t)NL * R, 0.0), wp((size_t)NL * R, 0.0);
+    for (int f = 0; f < NL; ++f) {
+        if (f >= nfib) continue;                       // padding fibres: zero coefficients, own lane
+        for (int k = 0; k < R; ++k) { d0p[f * R + k] = d0[f * R + k]; wp[f * R + k] = wdiag[f * R + k]; }
+        for (int q = 0; q < Nc; ++q) {
+            double *c = pd.data() + (size_t)f * per + q * (4 * (R - 1) + 4);
+            if ((LMASK >> q) & 1) {
+                for (int k = 0; k < R - 1; ++k) {
+                    const int r = f * R + k;
+                    c[4 * k] = value_at(H, 1 + q, r, r + 1);        // Hs[r, r+1]: x_{k+1} -> row k
+                    c[4 * k + 1] = value_at(H, 1 + q, r + 1, r);    // Hs[r+1, r]: x_k -> row k+1
+                    c[4 * k + 2] = value_at(H, 1 + Nc + q, r, r + 1);
+                    c[4 * k + 3] = value_at(H, 1 + Nc + q, r + 1, r);
+                }
+            } else {
+                for (int e = 0; e < 2; ++e) {
+                    pi[((size_t)f * Nc + q) * 2 + e] = rem[f][q].off[e];
+                    c[4 * (R - 1) + 2 * e] = rem[f][q].hs[e];
+                    c[4 * (R - 1) + 2 * e + 1] = rem[f][q].ha[e];
+                }
+            }
+        }
+    }
+    if (!upload_plan(pl, pi, pd, d0p, wp)) { jq_traj_plan_destroy(pl); return no("cudaMalloc failed for the fibre plan"); }
+    err[0] = 0;
+    return pl;
+}
+
+void jq_traj_plan_destroy(TrajPlan *pl) {
+    if (!pl) return;
+    for (void *p : {(void *)pl->d_i, (void *)pl->d_d, (void *)pl->d_d0, (void *)pl->d_w}) if (p) cudaFree(p);
+    delete pl;
+}
+
+int jq_traj_plan_kind(const TrajPlan *pl) { return pl ? pl->kind : 0; }
+
+cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
+                           size_t *smem, int *traj_per_cta) {
+    const Inst *inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL);
+    if (!inst) return cudaErrorNotSupported;
+    TrajParams S{};
+    S.P = P; S.A = A;
+    S.NL = pl->NL; S.NLR = pl->NLR; S.GL = pl->GL; S.GPT = pl->GPT; S.TPC = pl->TPC; S.ngroups = pl->ngroups; S.CPG = pl->CPG;
+    S.plan_i = pl->d_i; S.plan_d = pl->d_d; S.plan_d0 = pl->d_d0; S.plan_w = pl->d_w;
+    S.exch_per_unit = pl->exch_per_unit;
+    const int npts = 2 * TRAJ_CH + 1, NC = pl->NC;
+    int o = 0;
+    auto take = [&](int cnt) { int at = o; o += (cnt + 1) & ~1; return at; };   // keep 16-byte alignment
+    S.o_exch = take(pl->exch_per_unit * (pl->kind == 2 ? pl->ngroups : TRAJ_WARPS));
+    S.o_pcof = take(pl->TPC * A.Npar);
+    S.o_gsm = take(pl->ngroups * A.Npar);
+    S.o_times = take(npts);
+    S.o_tabb = take(3 * npts);
+    S.o_tabph = take(2 * npts * NC * P.Nfreq);
+    S.o_tabpq = take(npts * pl->TPC * 2 * NC);
+    S.o_red = take(pl->ngroups * 4);
+    S.o_tabk = take((npts + 1) / 2);
+    const size_t bytes = (size_t)o * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, inst->fn);
+    if (e != cudaSuccess) return e;
+    const int grid = (A.ntraj + pl->TPC - 1) / pl->TPC;
+    inst->fn<<<grid, TRAJ_THREADS, bytes, st>>>(S);
+    if (nctas) *nctas = grid;
+    if (regs) *regs = fa.numRegs;
+    if (smem) *smem = bytes;
+    if (traj_per_cta) *traj_per_cta = pl->TPC;
+    return cudaGetLastError();
+}
