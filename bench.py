@@ -237,8 +237,15 @@ def main():
     flops_eval = alg_flops_per_eval(cfg.params, npar)
     peak = _lib.fp64_peak_tflops(local_rank)
     achieved = flops_eval * B * nsamp / (kern_ms * 1e-3) / 1e12
+    traffic = None                                  # DRAM bytes per launch from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json"))).get(args.workload)
+        if tj and tj["evals_per_launch"] == B * nsamp and used_kernel == 3:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": None, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "traffic": traffic, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>"}[used_kernel],
                 "hbm_alg_bytes_per_launch": 8 * (B * npar + nsamp * cfg.params.Ntot + B * nsamp * (4 + npar))}
 

@@ -28,6 +28,7 @@
 #include "jq_common.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #define TRAJ_WARPS 4
@@ -46,6 +47,8 @@ struct TrajParams {
     const double *plan_d0, *plan_w;          // per (padded) row: H0 diagonal, guard weight
     int o_exch, o_pcof, o_gsm, o_times, o_tabb, o_tabph, o_tabpq, o_red, o_tabk;   // shared-memory offsets in doubles
     int exch_per_unit;                       // doubles of exchange buffer per group (slot) / per warp (fibre)
+    int NparS;                               // shared-memory row stride of the staged pcof vectors (odd: no bank conflicts)
+    int GPW;                                 // groups per warp (32 / GL, rounded down: GL need not be a power of two)
 };
 
 struct TrajPlan {
@@ -150,9 +153,9 @@ struct SlotLane {
     }
 };
 
-template <int R_, int NC_, int LMASK_>
+template <int R_, int NC_, int LMASK_, int XM_ = 0>
 struct FiberLane {
-    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, C = 1;
+    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, C = 1, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles
     static constexpr bool REMOTE = (LMASK_ != (1 << NC_) - 1);
     // local (inside the fibre) tridiagonal coefficients: x_{k+1} -> row k ("u"), x_k -> row k+1 ("l")
     double lsu[NC][R > 1 ? R - 1 : 1], lsl[NC][R > 1 ? R - 1 : 1], lau[NC][R > 1 ? R - 1 : 1], lal[NC][R > 1 ? R - 1 : 1];
@@ -188,7 +191,7 @@ struct FiberLane {
     template <bool WA, bool WD>
     __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
         double *b = buf;
-        if (REMOTE) {
+        if (REMOTE && (XM == 0 || XM == 3)) {
             b = buf + parity * (R * 32);
             parity ^= 1;
             Xch<R>::st(b, lane, 32, x);
@@ -205,8 +208,20 @@ struct FiberLane {
                 }
             } else {
                 double x0[R], x1[R];
-                Xch<R>::ld(b, rpos[qq][0], 32, x0);
-                Xch<R>::ld(b, rpos[qq][1], 32, x1);
+                if (XM == 0) {
+                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
+                    Xch<R>::ld(b, rpos[qq][1], 32, x1);
+                } else if (XM == 2) {          // EXPERIMENT ONLY (wrong results): exchange is free
+                    UNROLL for (int k = 0; k < R; ++k) { x0[k] = x[k]; x1[k] = x[R - 1 - k]; }
+                } else if (XM == 3) {          // hybrid: one neighbour through shared memory, the other by shuffle
+                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
+                    UNROLL for (int k = 0; k < R; ++k) x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
+                } else {
+                    UNROLL for (int k = 0; k < R; ++k) {
+                        x0[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
+                        x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
+                    }
+                }
                 UNROLL for (int k = 0; k < R; ++k) {
                     if (WA) A[k][qq] = fma(rhs[qq][1], x1[k], rhs[qq][0] * x0[k]);
                     if (WD) D[k][qq] = fma(rha[qq][1], x1[k], rha[qq][0] * x0[k]);
@@ -351,9 +366,16 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     }
 }
 
-__device__ __forceinline__ double group_sum(double x, int GL) {
-    for (int o = 1; o < GL; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
+// Sum over the GL lanes of a group, result on every lane.  Power-of-two groups use the xor butterfly; other sizes
+// (single-fibre columns with m = 3) gather the GL values in lane order.
+__device__ __forceinline__ double group_sum(double x, int GL, int base) {
+    if ((GL & (GL - 1)) == 0) {
+        for (int o = 1; o < GL; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        return x;
+    }
+    double s = 0.0;
+    for (int j = 0; j < GL; ++j) s += __shfl_sync(0xffffffffu, x, base + j);
+    return s;
 }
 
 // Fill the control table for `nst` steps starting at time t (all threads of the CTA).
@@ -401,7 +423,7 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
         const int i = idx / (S.TPC * NC), rem = idx % (S.TPC * NC), tr = rem / NC, qq = rem % NC;
         const int k = tabk[i];
         const double b0 = tabb[3 * i], b1 = tabb[3 * i + 1], b2 = tabb[3 * i + 2];
-        const double *pc = pcof + tr * S.A.Npar;
+        const double *pc = pcof + tr * S.NparS;
         double pv = 0.0, qv = 0.0;
         for (int fr = 0; fr < Nfreq; ++fr) {   // src/bsplines.jl:229-261
             const int off1 = 2 * qq * Nfreq * D1 + fr * 2 * D1 - 1, off2 = off1 + D1;
@@ -424,20 +446,23 @@ struct Updater {
     double acc0, acc1, acc2;
 };
 
-template <class LaneT, int UPL>
-__global__ void __launch_bounds__(TRAJ_THREADS) jq_traj_kernel(const __grid_constant__ TrajParams S) {
+template <class LaneT, int UPL, int MINB = 1>
+__global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     extern __shared__ double sm[];
     const DevProblem &P = S.P;
     const LaunchArgs &A = S.A;
     Geo g;
     g.lane = threadIdx.x & 31; g.warp = threadIdx.x >> 5;
-    g.lg = g.lane & (S.GL - 1);
-    g.group = g.warp * (32 / S.GL) + g.lane / S.GL;
-    g.tloc = g.group / S.GPT; g.gi = g.group % S.GPT;
     const int GL = S.GL;
+    g.lg = g.lane % GL;
+    const int gw = g.lane / GL;                              // group inside the warp; lanes past GPW*GL are idle
+    const bool lane_on = gw < S.GPW;
+    g.group = g.warp * S.GPW + (lane_on ? gw : 0);
+    g.tloc = g.group / S.GPT; g.gi = g.group % S.GPT;
+    const int gbase_lane = (lane_on ? gw : 0) * GL;          // first lane of this group
     const int traj = blockIdx.x * S.TPC + g.tloc;
-    const bool live_t = g.tloc < S.TPC && traj < A.ntraj;    // dead groups compute on zeros and write nothing
+    const bool live_t = lane_on && g.tloc < S.TPC && traj < A.ntraj;    // dead groups compute on zeros and write nothing
     const int s = live_t ? traj % A.nsamples : 0;
     const int n = P.n, m = P.m, Npar = A.Npar, D1 = A.D1, Nfreq = P.Nfreq, J = P.J;
     const double tinv = 1.0 / P.T, dtknot = P.T / (D1 - 2);
@@ -455,7 +480,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) jq_traj_kernel(const __grid_cons
     // stage this CTA's pcof vectors and zero the per-group gradient accumulators
     for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += TRAJ_THREADS) {
         const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
-        sm[S.o_pcof + idx] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * Npar + k] : 0.0;
+        sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * Npar + k] : 0.0;
     }
     for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += TRAJ_THREADS) sm[S.o_gsm + idx] = 0.0;
 
@@ -501,9 +526,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS) jq_traj_kernel(const __grid_cons
             re += vr[e] * tr_ - vi[e] * ti_;
             im += vr[e] * ti_ + vi[e] * tr_;
         }
-        re = group_sum(re, GL); im = group_sum(im, GL); pen = group_sum(pen, GL);
+        re = group_sum(re, GL, gbase_lane); im = group_sum(im, GL, gbase_lane); pen = group_sum(pen, GL, gbase_lane);
         __syncthreads();
-        if (g.lg == 0) { red[g.group * 4] = re; red[g.group * 4 + 1] = im; red[g.group * 4 + 2] = pen; }
+        if (lane_on && g.lg == 0) { red[g.group * 4] = re; red[g.group * 4 + 1] = im; red[g.group * 4 + 2] = pen; }
         __syncthreads();
     }
     double rs = 0.0, is = 0.0, pens = 0.0;
@@ -532,7 +557,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) jq_traj_kernel(const __grid_cons
     Updater U[UPL];
     UNROLL for (int j = 0; j < UPL; ++j) {
         const int u = g.lg + j * GL;
-        U[j].on = u < NU;
+        U[j].on = lane_on && u < NU;
         U[j].uq = U[j].on ? u / (2 * Nfreq) : 0;
         U[j].uf = U[j].on ? (u >> 1) % Nfreq : 0;
         U[j].ua = u & 1;
@@ -556,7 +581,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) jq_traj_kernel(const __grid_cons
             double T[NC][5];
             UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = 0.0;
             adjoint_step(L, J, dt, lr, li, vr0, vi05, vr, T);
-            UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = group_sum(T[qq][j], GL);
+            UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = group_sum(T[qq][j], GL, gbase_lane);
             UNROLL for (int j = 0; j < UPL; ++j) {
                 if (U[j].on) {
                     double Tq[5];
@@ -597,19 +622,25 @@ __global__ void __launch_bounds__(TRAJ_THREADS) jq_traj_kernel(const __grid_cons
 }
 
 typedef void (*traj_kernel_t)(const TrajParams);
-struct Inst { int kind, R, C, NC, WQ, LMASK, UPL; traj_kernel_t fn; };
-#define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
-#define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL>}
+// variant (experiments, env JQ_TRAJ_VARIANT): bit 0 = warp-shuffle exchange, bit 1 = 3 CTAs/SM register cap
+struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
+#define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
+#define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL>}
+#define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL, MINB>}
+#define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, ((XM) == 1 ? 1 : (XM) == 2 ? 4 : (XM) == 3 ? 8 : 0) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, XM>, UPL, MINB>}
 const Inst kInst[] = {
     SLOT(1, 2, 1, 2), SLOT(1, 3, 1, 2), SLOT(1, 4, 1, 2), SLOT(1, 4, 2, 2), SLOT(1, 2, 2, 2),
     SLOT(2, 2, 3, 2), SLOT(3, 1, 3, 2), SLOT(1, 1, 1, 2), SLOT(1, 1, 2, 2),
-    FIBER(2, 1, 1, 1), FIBER(4, 1, 1, 1), FIBER(4, 1, 1, 2), FIBER(6, 1, 1, 2), FIBER(3, 1, 1, 1), FIBER(3, 1, 1, 2),
+    FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
+    FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3), FIBERV(4, 2, 1, 1, 1, 3), FIBERV(4, 2, 1, 1, 2, 1), FIBERV(4, 2, 1, 1, 3, 1),
+    FIBERV(4, 3, 1, 1, 1, 1), FIBERV(4, 3, 1, 1, 0, 3), FIBERV(4, 3, 1, 1, 1, 3),
+    FIBERV(6, 1, 1, 2, 0, 3),
 };
 
-const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL) {
+const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0) {
     for (const Inst &i : kInst)
-        if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL) return &i;
+        if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant) return &i;
     return nullptr;
 }
 
@@ -772,7 +803,8 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     if (Nc > 1 && LMASK == (1 << Nc) - 1) return no("several local controls are not instantiated");
     const int NL = pow2ceil(nfib);
     if (NL > 32) return no("more than 32 fibres per column");
-    const int GL = pow2ceil(NL * m) > 32 ? 32 : pow2ceil(NL * m);
+    int GL = pow2ceil(NL * m) > 32 ? 32 : pow2ceil(NL * m);
+    if (NL == 1 && (32 / m) * m > (32 / GL) * m) GL = m;     // one lane per column: pack m-lane groups without padding
     const int CPG = GL / NL, GPT = (m + CPG - 1) / CPG;
     const int NU = Nc * H.Nfreq * 2, UPL = (NU + GL - 1) / GL;
     if (UPL > 2) return no("too many (control, frequency) pairs for the group size");
@@ -826,7 +858,9 @@ int jq_traj_plan_kind(const TrajPlan *pl) { return pl ? pl->kind : 0; }
 
 cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta) {
-    const Inst *inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL);
+    const char *venv = getenv("JQ_TRAJ_VARIANT");
+    const Inst *inst = venv ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv)) : nullptr;
+    if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL);
     if (!inst) return cudaErrorNotSupported;
     TrajParams S{};
     S.P = P; S.A = A;
@@ -837,7 +871,9 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     int o = 0;
     auto take = [&](int cnt) { int at = o; o += (cnt + 1) & ~1; return at; };   // keep 16-byte alignment
     S.o_exch = take(pl->exch_per_unit * (pl->kind == 2 ? pl->ngroups : TRAJ_WARPS));
-    S.o_pcof = take(pl->TPC * A.Npar);
+    S.NparS = A.Npar | 1;
+    S.GPW = 32 / pl->GL;
+    S.o_pcof = take(pl->TPC * S.NparS);
     S.o_gsm = take(pl->ngroups * A.Npar);
     S.o_times = take(npts);
     S.o_tabb = take(3 * npts);
