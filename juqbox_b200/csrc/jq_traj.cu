@@ -132,6 +132,28 @@ struct SlotLane {
     __device__ __forceinline__ int row(int e) const { return own[e / C]; }
     __device__ __forceinline__ int col(int e) const { return c0 + e % C; }
 
+    // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
+    struct SC { double c[R][NC][WQ]; };
+    __device__ __forceinline__ void s_prescale(int level, SC &sc) const {
+        UNROLL for (int k = 0; k < R; ++k) UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int e = 0; e < WQ; ++e)
+            sc.c[k][qq][e] = q[level][qq] * ha[k][qq][e];
+    }
+    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
+        double *b = buf + parity * (nlr * C);
+        parity ^= 1;
+        UNROLL for (int k = 0; k < R; ++k) Xch<C>::st(b, own[k], nlr, &x[k * C]);
+        __syncwarp();
+        UNROLL for (int k = 0; k < R; ++k) {
+            UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq)
+                UNROLL for (int e = 0; e < WQ; ++e) {
+                    double xv[C];
+                    Xch<C>::ld(b, pos[k][qq][e], nlr, xv);
+                    UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = fma(sc.c[k][qq][e], xv[c], t[k * C + c]);
+                }
+        }
+    }
+
     template <bool WA, bool WD>
     __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
         double *b = buf + parity * (nlr * C);
@@ -188,6 +210,54 @@ struct FiberLane {
     __device__ __forceinline__ int row(int e) const { return row0 + e; }
     __device__ __forceinline__ int col(int) const { return colj; }
 
+    // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
+    struct SC { double lu[R > 1 ? R - 1 : 1], ll[R > 1 ? R - 1 : 1], r[NC][2]; };
+    __device__ __forceinline__ void s_prescale(int level, SC &sc) const {
+        UNROLL for (int k = 0; k < R - 1; ++k) {
+            double u = 0.0, l = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq)
+                if ((LMASK >> qq) & 1) { u = fma(q[level][qq], lau[qq][k], u); l = fma(q[level][qq], lal[qq][k], l); }
+            sc.lu[k] = u; sc.ll[k] = l;
+        }
+        UNROLL for (int qq = 0; qq < NC; ++qq)
+            if (!((LMASK >> qq) & 1)) { sc.r[qq][0] = q[level][qq] * rha[qq][0]; sc.r[qq][1] = q[level][qq] * rha[qq][1]; }
+    }
+    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
+        double *b = buf;
+        if (REMOTE && (XM == 0 || XM == 3)) {
+            b = buf + parity * (R * 32);
+            parity ^= 1;
+            Xch<R>::st(b, lane, 32, x);
+            __syncwarp();
+        }
+        UNROLL for (int k = 0; k < R; ++k) {       // local part first: independent of the exchange
+            double a = 0.0;
+            if (k + 1 < R) a = sc.lu[k] * x[k + 1];
+            if (k > 0) a = fma(sc.ll[k - 1], x[k - 1], a);
+            t[k] = a;
+        }
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            if (!((LMASK >> qq) & 1)) {
+                double x0[R], x1[R];
+                if (XM == 0) {
+                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
+                    Xch<R>::ld(b, rpos[qq][1], 32, x1);
+                } else if (XM == 2) {
+                    UNROLL for (int k = 0; k < R; ++k) { x0[k] = x[k]; x1[k] = x[R - 1 - k]; }
+                } else if (XM == 3) {
+                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
+                    UNROLL for (int k = 0; k < R; ++k) x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
+                } else {
+                    UNROLL for (int k = 0; k < R; ++k) {
+                        x0[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
+                        x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
+                    }
+                }
+                UNROLL for (int k = 0; k < R; ++k) t[k] = fma(sc.r[qq][1], x1[k], fma(sc.r[qq][0], x0[k], t[k]));
+            }
+        }
+    }
+
     template <bool WA, bool WD>
     __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
         double *b = buf;
@@ -232,22 +302,29 @@ struct FiberLane {
 };
 
 // ------------------------------------------------------------------------------------------------ steppers
-// X = sum_{j<=J} (h/2)^j S_level^j B   (src/linear_solvers.jl:94-106); B is consumed.
+// Sum over the GL lanes of a group, result on every lane.  Power-of-two groups use the xor butterfly; other sizes
+// (single-fibre columns with m = 3) gather the GL values in lane order.
+__device__ __forceinline__ double group_sum(double x, int GL, int base) {
+    if ((GL & (GL - 1)) == 0) {
+        for (int o = 1; o < GL; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        return x;
+    }
+    double s = 0.0;
+    for (int j = 0; j < GL; ++j) s += __shfl_sync(0xffffffffu, x, base + j);
+    return s;
+}
+
+// X = sum_{j<=J} (h/2)^j S^j B   (src/linear_solvers.jl:94-106); B is consumed.  `sc` = S(level) prescaled.
 template <class LaneT>
-__device__ __forceinline__ void neumann(LaneT &L, int J, double h, int level, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
-    constexpr int E = LaneT::E, NC = LaneT::NC;
-    double dummy[E][NC], D[E][NC];
+__device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
+    constexpr int E = LaneT::E;
     UNROLL for (int e = 0; e < E; ++e) X[e] = B[e];
     double coeff = 1.0;
     for (int it = 0; it < J; ++it) {
-        L.template pass<false, true>(B, dummy, D);
+        double T[E];
+        L.s_pass(sc, B, T);
         coeff *= 0.5 * h;
-        UNROLL for (int e = 0; e < E; ++e) {
-            double t = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq) t = fma(L.q[level][qq], D[e][qq], t);
-            B[e] = t;
-            X[e] = fma(coeff, t, X[e]);
-        }
+        UNROLL for (int e = 0; e < E; ++e) { B[e] = T[e]; X[e] = fma(coeff, T[e], X[e]); }
     }
 }
 
@@ -263,9 +340,14 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
         rhs[e] = r;            // K05 u
         s0u[e] = s;            // S0 u
     }
-    L.template pass<false, true>(v, A, D);
-    UNROLL for (int e = 0; e < E; ++e) UNROLL for (int qq = 0; qq < NC; ++qq) rhs[e] = fma(L.q[1][qq], D[e][qq], rhs[e]);   // + S05 v
-    neumann(L, J, h, 1, rhs, l1);
+    typename LaneT::SC sc;
+    L.s_prescale(1, sc);
+    {
+        double tv[E];
+        L.s_pass(sc, v, tv);
+        UNROLL for (int e = 0; e < E; ++e) rhs[e] += tv[e];                                    // + S05 v
+    }
+    neumann(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
     L.template pass<true, true>(v05, A, D);
     double k1v[E], s05v[E];
@@ -280,14 +362,14 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
         s05v[e] = s;                                   // S05 v05
         u[e] = fma(0.5 * h, s0u[e] - k0, u[e]);        // u + (h/2) kappa1,  kappa1 = S0 u - K0 v05
     }
-    L.template pass<false, true>(u, A, D);
-    UNROLL for (int e = 0; e < E; ++e) {
-        double s = -k1v[e];
-        UNROLL for (int qq = 0; qq < NC; ++qq) s = fma(L.q[2][qq], D[e][qq], s);
-        rhs[e] = s;                                    // S1 (u + (h/2) kappa1) - K1 v05
+    L.s_prescale(2, sc);
+    {
+        double tv[E];
+        L.s_pass(sc, u, tv);
+        UNROLL for (int e = 0; e < E; ++e) rhs[e] = tv[e] - k1v[e];                             // S1 (u + (h/2) kappa1) - K1 v05
     }
     double k2[E];
-    neumann(L, J, h, 2, rhs, k2);
+    neumann(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
     L.template pass<true, false>(u, A, D);
     UNROLL for (int e = 0; e < E; ++e) {
@@ -304,15 +386,13 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
 template <class LaneT>
 __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (&mu)[LaneT::E], double (&nu)[LaneT::E],
                                              const double (&vr0)[LaneT::E], const double (&vi05)[LaneT::E],
-                                             const double (&vr)[LaneT::E], double (&T)[LaneT::NC][5]) {
+                                             const double (&vr)[LaneT::E], double (&T)[LaneT::NC][5], int GL, int gbase_lane) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     double A[E][NC], D[E][NC], rhs[E], s05n[E];
-    L.template pass<false, true>(mu, A, D);
-    UNROLL for (int e = 0; e < E; ++e) {
-        double s = L.w[e] * vr0[e];                    // hr0
-        UNROLL for (int qq = 0; qq < NC; ++qq) s = fma(L.q[0][qq], D[e][qq], s);
-        rhs[e] = s;                                    // S0 mu + hr0
-    }
+    typename LaneT::SC sc;
+    L.s_prescale(0, sc);
+    L.s_pass(sc, mu, rhs);
+    UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(L.w[e], vr0[e], rhs[e]);                    // S0 mu + hr0
     L.template pass<true, true>(nu, A, D);
     UNROLL for (int e = 0; e < E; ++e) {
         double kk = L.d0[e] * nu[e], s = 0.0;
@@ -326,7 +406,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         s05n[e] = s;                                   // S05 nu
     }
     double k2[E];
-    neumann(L, J, h, 0, rhs, k2);
+    neumann(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) mu[e] = fma(0.5 * h, k2[e], mu[e]);   // X = mu
     L.template pass<true, true>(mu, A, D);
     double l2[E], k1x[E], s1x[E];
@@ -345,14 +425,16 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         k1x[e] = k1 + hi0;                             // K1 X + hi1
         s1x[e] = s;                                    // S1 X
     }
-    L.template pass<false, true>(l2, A, D);
-    UNROLL for (int e = 0; e < E; ++e) {
-        double s = 0.0;
-        UNROLL for (int qq = 0; qq < NC; ++qq) s = fma(L.q[1][qq], D[e][qq], s);
-        rhs[e] = s05n[e] + 0.5 * h * s + k1x[e];        // S05 nu + (h/2) S05 l2 + K1 X + hi1
+    // the three traces that only involve lr05 = X are complete: reduce them now, overlapped with the next products
+    UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) T[qq][a] = group_sum(T[qq][a], GL, gbase_lane);
+    L.s_prescale(1, sc);
+    {
+        double tv[E];
+        L.s_pass(sc, l2, tv);
+        UNROLL for (int e = 0; e < E; ++e) rhs[e] = s05n[e] + 0.5 * h * tv[e] + k1x[e];         // S05 nu + (h/2) S05 l2 + K1 X + hi1
     }
     double l1[E];
-    neumann(L, J, h, 1, rhs, l1);
+    neumann(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
     L.template pass<true, true>(nu, A, D);
     UNROLL for (int e = 0; e < E; ++e) {
@@ -364,18 +446,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         }
         mu[e] = fma(0.5 * h, s1x[e] - kk + L.w[e] * vr[e], mu[e]);   // kappa1 = S1 X - K05 nu + hr1
     }
-}
-
-// Sum over the GL lanes of a group, result on every lane.  Power-of-two groups use the xor butterfly; other sizes
-// (single-fibre columns with m = 3) gather the GL values in lane order.
-__device__ __forceinline__ double group_sum(double x, int GL, int base) {
-    if ((GL & (GL - 1)) == 0) {
-        for (int o = 1; o < GL; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        return x;
-    }
-    double s = 0.0;
-    for (int j = 0; j < GL; ++j) s += __shfl_sync(0xffffffffu, x, base + j);
-    return s;
+    UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 3; a < 5; ++a) T[qq][a] = group_sum(T[qq][a], GL, gbase_lane);
 }
 
 // Fill the control table for `nst` steps starting at time t (all threads of the CTA).
@@ -580,8 +651,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
             state_step(L, J, dt, vr, vi, vi05);
             double T[NC][5];
             UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = 0.0;
-            adjoint_step(L, J, dt, lr, li, vr0, vi05, vr, T);
-            UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = group_sum(T[qq][j], GL, gbase_lane);
+            adjoint_step(L, J, dt, lr, li, vr0, vi05, vr, T, GL, gbase_lane);      // returns the group-reduced traces
             UNROLL for (int j = 0; j < UPL; ++j) {
                 if (U[j].on) {
                     double Tq[5];
@@ -881,7 +951,8 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     S.o_tabpq = take(npts * pl->TPC * 2 * NC);
     S.o_red = take(pl->ngroups * 4);
     S.o_tabk = take((npts + 1) / 2);
-    const size_t bytes = (size_t)o * sizeof(double);
+    size_t bytes = (size_t)o * sizeof(double);
+    if (const char *pad = getenv("JQ_SMEM_PAD_KB")) bytes += (size_t)atoi(pad) * 1024;   // experiments: throttle CTAs/SM
     cudaError_t e = cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
