@@ -101,6 +101,18 @@ int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pco
                                  double *infid, double *leak, double *trace_infid, double *grad,
                                  double *infidgrad, double *leakgrad, void *cuda_stream);
 
+/* Multi-GPU (one process and one handle per GPU).  The path's only exchange step is the weighted sum over noise
+ * samples of eval_f_g_grad! (src/ipopt_interface.jl:48-59) when the samples are sharded across GPUs.
+ * jq_comm_unique_id fills a 128-byte NCCL unique id on one rank (distribute it with whatever the host has);
+ * jq_comm_init joins the communicator.  Afterwards every jq_traceobjgrad_batch[_device] call WITH weights ends with one
+ * grouped ncclAllReduce(sum, double) of the weighted outputs, so each rank passes its own shard of
+ * (h0_diag_shift, weights) and every rank receives the full risk-neutral objective and gradients.  Calls without
+ * weights (independent candidates / per-sample outputs) never communicate.  NCCL is loaded with dlopen("libnccl.so.2")
+ * at jq_comm_unique_id / jq_comm_init time; the library has no link-time NCCL dependency. */
+int jq_comm_unique_id(void *id128);
+int jq_comm_init(jq_handle *h, int32_t rank, int32_t nranks, const void *id128);
+int jq_comm_destroy(jq_handle *h);
+
 /* Kernel selection, for tests and profiling: 0 = automatic (3, else 2, else 1), 1 = generic (one CTA per trajectory,
  * any operators), 2 = register-resident kernel, slot layout (sparse rows with <= 2 entries per row and control),
  * 3 = register-resident kernel, fibre layout (Kronecker ladder structure).  2 and 3 fail with JQ_ERR_ARG if the

@@ -109,6 +109,26 @@ class Working_Arrays:
         vr, vi = np.asfortranarray(p.Utarget_r, dtype=np.float64), np.asfortranarray(p.Utarget_i, dtype=np.float64)
         _lib.check(self._lib.jq_update_target(self._handle, vr.ctypes.data_as(C.c_void_p), vi.ctypes.data_as(C.c_void_p)))
 
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes = None):
+        """Attach an NCCL communicator (jq_comm_init).  With torch.distributed initialised, the 128-byte unique id is
+        created on rank 0 and broadcast through it; otherwise pass `unique_id` explicitly."""
+        if unique_id is None:
+            import torch
+            import torch.distributed as dist
+            buf = C.create_string_buffer(128)
+            if rank == 0:
+                _lib.check(self._lib.jq_comm_unique_id(buf))
+            t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda(self.device)
+            dist.broadcast(t, src=0)
+            unique_id = bytes(t.cpu().tolist())
+        assert len(unique_id) == 128
+        _lib.check(self._lib.jq_comm_init(self._handle, int(rank), int(nranks), C.c_char_p(unique_id)))
+
+    def comm_destroy(self):
+        _lib.check(self._lib.jq_comm_destroy(self._handle))
+
     def set_kernel(self, kernel: int):
         """0 = automatic, 1 = generic kernel, 2 = warp-slot kernel."""
         _lib.check(self._lib.jq_set_kernel(self._handle, int(kernel)))

@@ -3,6 +3,8 @@
 #include "jq_common.h"
 #include "../../include/juqbox_b200.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -24,7 +26,25 @@ static int fail(int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(JQ_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// ---- NCCL through dlopen: only the five entry points the sample-sharded all-reduce needs ----
+typedef struct ncclComm *nccl_comm_t;
+typedef struct { char internal[128]; } nccl_uid_t;
+struct NcclApi {
+    int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static NcclApi g_nccl;
+static int load_nccl();
+
 struct jq_handle {
+    nccl_comm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
     int device = 0;
     DevProblem P{};
     int n = 0, m = 0, Nc = 0, Nfreq = 0;
@@ -110,6 +130,62 @@ static int append_rows(const jq_operator &op, int n, bool force_diag, std::vecto
     return 0;
 }
 
+static int load_nccl() {
+    if (g_nccl.ok) return 0;
+    void *lib = nullptr;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+        lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(JQ_ERR_ARG, "NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+#define SYM(field, name)                                                              \
+    *(void **)(&g_nccl.field) = dlsym(lib, name);                                     \
+    if (!g_nccl.field) return fail(JQ_ERR_ARG, "NCCL symbol %s missing", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.ok = true;
+    return 0;
+}
+#define NC(call)                                                                                           \
+    do {                                                                                                   \
+        int r_ = (call);                                                                                   \
+        if (r_ != 0) return fail(JQ_ERR_CUDA, "%s: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error"); \
+    } while (0)
+
+extern "C" int jq_comm_unique_id(void *id128) {
+    if (!id128) return fail(JQ_ERR_ARG, "jq_comm_unique_id: null argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    NC(g_nccl.GetUniqueId((nccl_uid_t *)id128));
+    return 0;
+}
+
+extern "C" int jq_comm_init(jq_handle *h, int32_t rank, int32_t nranks, const void *id128) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(JQ_ERR_ARG, "jq_comm_init: bad argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    CU(cudaSetDevice(h->device));
+    nccl_uid_t id;
+    memcpy(&id, id128, sizeof(id));
+    NC(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->comm_rank = rank; h->comm_size = nranks;
+    return 0;
+}
+
+extern "C" int jq_comm_destroy(jq_handle *h) {
+    if (!h) return fail(JQ_ERR_ARG, "jq_comm_destroy: null handle");
+    if (h->comm) { CU(cudaSetDevice(h->device)); cudaStreamSynchronize(h->stream); g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+    h->comm_size = 1; h->comm_rank = 0;
+    return 0;
+}
+
 extern "C" const char *jq_last_error(void) { return g_err; }
 extern "C" const char *jq_version(void) { return "juqbox_b200 0.1 (sm_100a)"; }
 
@@ -185,6 +261,7 @@ extern "C" int jq_destroy(jq_handle *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.ok) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
     for (void *p : h->owned) cudaFree(p);
     for (double *p : {h->d_scal, h->d_grad, h->d_igrad, h->d_in, h->d_out}) if (p) cudaFree(p);
     if (h->slot) jq_traj_plan_destroy(h->slot);
@@ -328,6 +405,21 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
                                           h->d_igrad, infid, leak, trace_infid, grad, infidgrad, leakgrad);
     CU(cudaGetLastError());
     h->last_launches = 2;
+    if (h->comm && weights && h->comm_size > 1) {
+        // the path's one exchange step: weighted sums over the sample shards of all ranks (sum, FP64), one grouped call
+        const size_t nb = (size_t)nbatch, ng = (size_t)nbatch * npar;
+        NC(g_nccl.GroupStart());
+        if (infid) NC(g_nccl.AllReduce(infid, infid, nb, 8 /*ncclDouble*/, 0 /*ncclSum*/, h->comm, st));
+        if (leak) NC(g_nccl.AllReduce(leak, leak, nb, 8, 0, h->comm, st));
+        if (trace_infid) NC(g_nccl.AllReduce(trace_infid, trace_infid, nb, 8, 0, h->comm, st));
+        if (A.evaladjoint) {
+            if (grad) NC(g_nccl.AllReduce(grad, grad, ng, 8, 0, h->comm, st));
+            if (infidgrad) NC(g_nccl.AllReduce(infidgrad, infidgrad, ng, 8, 0, h->comm, st));
+            if (leakgrad && h->P.objFuncType != 1) NC(g_nccl.AllReduce(leakgrad, leakgrad, ng, 8, 0, h->comm, st));
+        }
+        NC(g_nccl.GroupEnd());
+        h->last_launches = 3;
+    }
     return 0;
 }
 

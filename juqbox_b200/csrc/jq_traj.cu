@@ -177,7 +177,7 @@ struct SlotLane {
 
 template <int R_, int NC_, int LMASK_, int XM_ = 0>
 struct FiberLane {
-    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, C = 1, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles
+    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, C = 1, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (measured equal)
     static constexpr bool REMOTE = (LMASK_ != (1 << NC_) - 1);
     // local (inside the fibre) tridiagonal coefficients: x_{k+1} -> row k ("u"), x_k -> row k+1 ("l")
     double lsu[NC][R > 1 ? R - 1 : 1], lsl[NC][R > 1 ? R - 1 : 1], lau[NC][R > 1 ? R - 1 : 1], lal[NC][R > 1 ? R - 1 : 1];
@@ -224,7 +224,7 @@ struct FiberLane {
     }
     __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
         double *b = buf;
-        if (REMOTE && (XM == 0 || XM == 3)) {
+        if (REMOTE && XM == 0) {
             b = buf + parity * (R * 32);
             parity ^= 1;
             Xch<R>::st(b, lane, 32, x);
@@ -242,11 +242,6 @@ struct FiberLane {
                 if (XM == 0) {
                     Xch<R>::ld(b, rpos[qq][0], 32, x0);
                     Xch<R>::ld(b, rpos[qq][1], 32, x1);
-                } else if (XM == 2) {
-                    UNROLL for (int k = 0; k < R; ++k) { x0[k] = x[k]; x1[k] = x[R - 1 - k]; }
-                } else if (XM == 3) {
-                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
-                    UNROLL for (int k = 0; k < R; ++k) x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
                 } else {
                     UNROLL for (int k = 0; k < R; ++k) {
                         x0[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
@@ -261,7 +256,7 @@ struct FiberLane {
     template <bool WA, bool WD>
     __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
         double *b = buf;
-        if (REMOTE && (XM == 0 || XM == 3)) {
+        if (REMOTE && XM == 0) {
             b = buf + parity * (R * 32);
             parity ^= 1;
             Xch<R>::st(b, lane, 32, x);
@@ -281,11 +276,6 @@ struct FiberLane {
                 if (XM == 0) {
                     Xch<R>::ld(b, rpos[qq][0], 32, x0);
                     Xch<R>::ld(b, rpos[qq][1], 32, x1);
-                } else if (XM == 2) {          // EXPERIMENT ONLY (wrong results): exchange is free
-                    UNROLL for (int k = 0; k < R; ++k) { x0[k] = x[k]; x1[k] = x[R - 1 - k]; }
-                } else if (XM == 3) {          // hybrid: one neighbour through shared memory, the other by shuffle
-                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
-                    UNROLL for (int k = 0; k < R; ++k) x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
                 } else {
                     UNROLL for (int k = 0; k < R; ++k) {
                         x0[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
@@ -697,15 +687,14 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 #define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL>}
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL, MINB>}
-#define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, ((XM) == 1 ? 1 : (XM) == 2 ? 4 : (XM) == 3 ? 8 : 0) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, XM>, UPL, MINB>}
+#define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, XM>, UPL, MINB>}
 const Inst kInst[] = {
     SLOT(1, 2, 1, 2), SLOT(1, 3, 1, 2), SLOT(1, 4, 1, 2), SLOT(1, 4, 2, 2), SLOT(1, 2, 2, 2),
     SLOT(2, 2, 3, 2), SLOT(3, 1, 3, 2), SLOT(1, 1, 1, 2), SLOT(1, 1, 2, 2),
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
-    FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3), FIBERV(4, 2, 1, 1, 1, 3), FIBERV(4, 2, 1, 1, 2, 1), FIBERV(4, 2, 1, 1, 3, 1),
-    FIBERV(4, 3, 1, 1, 1, 1), FIBERV(4, 3, 1, 1, 0, 3), FIBERV(4, 3, 1, 1, 1, 3),
-    FIBERV(6, 1, 1, 2, 0, 3),
+    FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
+    FIBERV(4, 3, 1, 1, 1, 1),
 };
 
 const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0) {
