@@ -45,7 +45,7 @@ struct TrajParams {
     const int *plan_i;                       // layout-specific integer table
     const double *plan_d;                    // layout-specific coefficient table
     const double *plan_d0, *plan_w;          // per (padded) row: H0 diagonal, guard weight
-    int o_exch, o_pcof, o_gsm, o_times, o_tabb, o_tabph, o_tabpq, o_red, o_tabk;   // shared-memory offsets in doubles
+    int o_exch, o_pcof, o_gsm, o_times, o_tabb, o_tabph, o_tabpq, o_red, o_tabk, o_tred;   // shared-memory offsets in doubles
     int exch_per_unit;                       // doubles of exchange buffer per group (slot) / per warp (fibre)
     int NparS;                               // shared-memory row stride of the staged pcof vectors (odd: no bank conflicts)
     int GPW;                                 // groups per warp (32 / GL, rounded down: GL need not be a power of two)
@@ -53,7 +53,7 @@ struct TrajParams {
 
 struct TrajPlan {
     int kind;                                // 2 slot, 3 fibre
-    int R, C, NC, WQ, LMASK, UPL;
+    int R, C, NC, WQ, LMASK, UPL, AS;
     int NL, GL, GPT, TPC, ngroups, CPG, NLR, exch_per_unit;
     int *d_i = nullptr;
     double *d_d = nullptr, *d_d0 = nullptr, *d_w = nullptr;
@@ -132,6 +132,14 @@ struct SlotLane {
     __device__ __forceinline__ int row(int e) const { return own[e / C]; }
     __device__ __forceinline__ int col(int e) const { return c0 + e % C; }
 
+    __device__ __forceinline__ double *exchange(const double (&x)[E]) {
+        double *b = buf + parity * (nlr * C);
+        parity ^= 1;
+        UNROLL for (int k = 0; k < R; ++k) Xch<C>::st(b, own[k], nlr, &x[k * C]);
+        __syncwarp();
+        return b;
+    }
+
     // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
     struct SC { double c[R][NC][WQ]; };
     __device__ __forceinline__ void s_prescale(int level, SC &sc) const {
@@ -139,10 +147,7 @@ struct SlotLane {
             sc.c[k][qq][e] = q[level][qq] * ha[k][qq][e];
     }
     __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
-        double *b = buf + parity * (nlr * C);
-        parity ^= 1;
-        UNROLL for (int k = 0; k < R; ++k) Xch<C>::st(b, own[k], nlr, &x[k * C]);
-        __syncwarp();
+        const double *b = exchange(x);
         UNROLL for (int k = 0; k < R; ++k) {
             UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = 0.0;
             UNROLL for (int qq = 0; qq < NC; ++qq)
@@ -154,34 +159,39 @@ struct SlotLane {
         }
     }
 
-    template <bool WA, bool WD>
-    __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
-        double *b = buf + parity * (nlr * C);
-        parity ^= 1;
-        UNROLL for (int k = 0; k < R; ++k) Xch<C>::st(b, own[k], nlr, &x[k * C]);
-        __syncwarp();
-        UNROLL for (int k = 0; k < R; ++k)
+    // f(e, Ae, De) is called once per element with Ae[q] = (Hsym_q x)_e, De[q] = (Hanti_q x)_e: the per-control
+    // partial products only live for one row at a time.
+    template <bool WA, bool WD, class F>
+    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
+        const double *b = exchange(x);
+        UNROLL for (int k = 0; k < R; ++k) {
+            double Ar[C][NC], Dr[C][NC];
             UNROLL for (int qq = 0; qq < NC; ++qq) {
-                UNROLL for (int c = 0; c < C; ++c) { if (WA) A[k * C + c][qq] = 0.0; if (WD) D[k * C + c][qq] = 0.0; }
+                UNROLL for (int c = 0; c < C; ++c) { Ar[c][qq] = 0.0; Dr[c][qq] = 0.0; }
                 UNROLL for (int e = 0; e < WQ; ++e) {
                     double xv[C];
                     Xch<C>::ld(b, pos[k][qq][e], nlr, xv);
                     UNROLL for (int c = 0; c < C; ++c) {
-                        if (WA) A[k * C + c][qq] = fma(hs[k][qq][e], xv[c], A[k * C + c][qq]);
-                        if (WD) D[k * C + c][qq] = fma(ha[k][qq][e], xv[c], D[k * C + c][qq]);
+                        if (WA) Ar[c][qq] = fma(hs[k][qq][e], xv[c], Ar[c][qq]);
+                        if (WD) Dr[c][qq] = fma(ha[k][qq][e], xv[c], Dr[c][qq]);
                     }
                 }
             }
+            UNROLL for (int c = 0; c < C; ++c) f(k * C + c, Ar[c], Dr[c]);
+        }
     }
 };
 
-template <int R_, int NC_, int LMASK_, int XM_ = 0>
+// AS = 1: the control Hamiltonians have the ladder form Hanti = (upper part of Hsym) - (lower part of Hsym), i.e.
+// (a - a') next to (a + a'): only the Hsym coefficients are kept and D = upper - lower, A = upper + lower.
+template <int R_, int NC_, int LMASK_, int AS_ = 1, int XM_ = 0>
 struct FiberLane {
-    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, C = 1, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (measured equal)
+    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, AS = AS_, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (measured equal)
     static constexpr bool REMOTE = (LMASK_ != (1 << NC_) - 1);
+    static constexpr int RM1 = R_ > 1 ? R_ - 1 : 1;
     // local (inside the fibre) tridiagonal coefficients: x_{k+1} -> row k ("u"), x_k -> row k+1 ("l")
-    double lsu[NC][R > 1 ? R - 1 : 1], lsl[NC][R > 1 ? R - 1 : 1], lau[NC][R > 1 ? R - 1 : 1], lal[NC][R > 1 ? R - 1 : 1];
-    // remote: two neighbour fibres per control (lane position inside the warp) with fibre-uniform coefficients
+    double lsu[NC][RM1], lsl[NC][RM1], lau[NC][RM1], lal[NC][RM1];
+    // remote: lower (entry 0) and upper (entry 1) neighbour fibre per control, fibre-uniform coefficients
     int rpos[NC][2];
     double rhs[NC][2], rha[NC][2];
     double d0[E], w[E];
@@ -199,94 +209,106 @@ struct FiberLane {
         const double *pd = S.plan_d + rho * (NC * (4 * (R - 1) + 4));
         UNROLL for (int qq = 0; qq < NC; ++qq) {
             const double *c = pd + qq * (4 * (R - 1) + 4);
-            UNROLL for (int k = 0; k < R - 1; ++k) { lsu[qq][k] = c[4 * k]; lsl[qq][k] = c[4 * k + 1]; lau[qq][k] = c[4 * k + 2]; lal[qq][k] = c[4 * k + 3]; }
+            UNROLL for (int k = 0; k < R - 1; ++k) {
+                lsu[qq][k] = c[4 * k]; lsl[qq][k] = c[4 * k + 1];
+                if (!AS) { lau[qq][k] = c[4 * k + 2]; lal[qq][k] = c[4 * k + 3]; }
+            }
             UNROLL for (int e = 0; e < 2; ++e) {
                 rpos[qq][e] = g.lane + pi[qq * 2 + e];          // plan stores the fibre offset (0 = padding -> own lane)
                 rhs[qq][e] = c[4 * (R - 1) + 2 * e];
-                rha[qq][e] = c[4 * (R - 1) + 2 * e + 1];
+                if (!AS) rha[qq][e] = c[4 * (R - 1) + 2 * e + 1];
             }
         }
     }
     __device__ __forceinline__ int row(int e) const { return row0 + e; }
     __device__ __forceinline__ int col(int) const { return colj; }
 
+    // Publish the fibre and fetch the two neighbour fibres of every remote control.
+    __device__ __forceinline__ void exchange(const double (&x)[E], double (&xn)[NC][2][R]) {
+        if (!REMOTE) return;
+        const double *b = buf;
+        if (XM == 0) {
+            double *bw = buf + parity * (R * 32);
+            parity ^= 1;
+            Xch<R>::st(bw, lane, 32, x);
+            __syncwarp();
+            b = bw;
+        }
+        UNROLL for (int qq = 0; qq < NC; ++qq)
+            if (!((LMASK >> qq) & 1)) {
+                if (XM == 0) {
+                    Xch<R>::ld(b, rpos[qq][0], 32, xn[qq][0]);
+                    Xch<R>::ld(b, rpos[qq][1], 32, xn[qq][1]);
+                } else {
+                    UNROLL for (int k = 0; k < R; ++k) {
+                        xn[qq][0][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
+                        xn[qq][1][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
+                    }
+                }
+            }
+    }
+
     // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
-    struct SC { double lu[R > 1 ? R - 1 : 1], ll[R > 1 ? R - 1 : 1], r[NC][2]; };
+    struct SC { double lu[RM1], ll[RM1], r[NC][2]; };
     __device__ __forceinline__ void s_prescale(int level, SC &sc) const {
         UNROLL for (int k = 0; k < R - 1; ++k) {
             double u = 0.0, l = 0.0;
             UNROLL for (int qq = 0; qq < NC; ++qq)
-                if ((LMASK >> qq) & 1) { u = fma(q[level][qq], lau[qq][k], u); l = fma(q[level][qq], lal[qq][k], l); }
+                if ((LMASK >> qq) & 1) {
+                    u = fma(q[level][qq], AS ? lsu[qq][k] : lau[qq][k], u);
+                    l = AS ? fma(-q[level][qq], lsl[qq][k], l) : fma(q[level][qq], lal[qq][k], l);
+                }
             sc.lu[k] = u; sc.ll[k] = l;
         }
         UNROLL for (int qq = 0; qq < NC; ++qq)
-            if (!((LMASK >> qq) & 1)) { sc.r[qq][0] = q[level][qq] * rha[qq][0]; sc.r[qq][1] = q[level][qq] * rha[qq][1]; }
+            if (!((LMASK >> qq) & 1)) {
+                sc.r[qq][0] = AS ? -q[level][qq] * rhs[qq][0] : q[level][qq] * rha[qq][0];
+                sc.r[qq][1] = q[level][qq] * (AS ? rhs[qq][1] : rha[qq][1]);
+            }
     }
     __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
-        double *b = buf;
-        if (REMOTE && XM == 0) {
-            b = buf + parity * (R * 32);
-            parity ^= 1;
-            Xch<R>::st(b, lane, 32, x);
-            __syncwarp();
-        }
+        double xn[NC][2][R];
+        exchange(x, xn);
         UNROLL for (int k = 0; k < R; ++k) {       // local part first: independent of the exchange
             double a = 0.0;
             if (k + 1 < R) a = sc.lu[k] * x[k + 1];
             if (k > 0) a = fma(sc.ll[k - 1], x[k - 1], a);
             t[k] = a;
         }
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            if (!((LMASK >> qq) & 1)) {
-                double x0[R], x1[R];
-                if (XM == 0) {
-                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
-                    Xch<R>::ld(b, rpos[qq][1], 32, x1);
-                } else {
-                    UNROLL for (int k = 0; k < R; ++k) {
-                        x0[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
-                        x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
-                    }
-                }
-                UNROLL for (int k = 0; k < R; ++k) t[k] = fma(sc.r[qq][1], x1[k], fma(sc.r[qq][0], x0[k], t[k]));
-            }
-        }
+        UNROLL for (int qq = 0; qq < NC; ++qq)
+            if (!((LMASK >> qq) & 1))
+                UNROLL for (int k = 0; k < R; ++k) t[k] = fma(sc.r[qq][1], xn[qq][1][k], fma(sc.r[qq][0], xn[qq][0][k], t[k]));
     }
 
-    template <bool WA, bool WD>
-    __device__ __forceinline__ void pass(const double (&x)[E], double (&A)[E][NC], double (&D)[E][NC]) {
-        double *b = buf;
-        if (REMOTE && XM == 0) {
-            b = buf + parity * (R * 32);
-            parity ^= 1;
-            Xch<R>::st(b, lane, 32, x);
-            __syncwarp();
-        }
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            if ((LMASK >> qq) & 1) {
-                UNROLL for (int k = 0; k < R; ++k) {
-                    double a = 0.0, d = 0.0;
-                    if (k + 1 < R) { if (WA) a = lsu[qq][k] * x[k + 1]; if (WD) d = lau[qq][k] * x[k + 1]; }
-                    if (k > 0) { if (WA) a = fma(lsl[qq][k - 1], x[k - 1], a); if (WD) d = fma(lal[qq][k - 1], x[k - 1], d); }
-                    if (WA) A[k][qq] = a;
-                    if (WD) D[k][qq] = d;
-                }
-            } else {
-                double x0[R], x1[R];
-                if (XM == 0) {
-                    Xch<R>::ld(b, rpos[qq][0], 32, x0);
-                    Xch<R>::ld(b, rpos[qq][1], 32, x1);
+    template <bool WA, bool WD, class F>
+    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
+        double xn[NC][2][R];
+        exchange(x, xn);
+        UNROLL for (int k = 0; k < R; ++k) {
+            double Ae[NC], De[NC];
+            UNROLL for (int qq = 0; qq < NC; ++qq) {
+                double up = 0.0, lo = 0.0, a = 0.0, d = 0.0;
+                if ((LMASK >> qq) & 1) {
+                    if (AS) {
+                        if (k + 1 < R) up = lsu[qq][k] * x[k + 1];
+                        if (k > 0) lo = lsl[qq][k - 1] * x[k - 1];
+                    } else {
+                        if (k + 1 < R) { if (WA) a = lsu[qq][k] * x[k + 1]; if (WD) d = lau[qq][k] * x[k + 1]; }
+                        if (k > 0) { if (WA) a = fma(lsl[qq][k - 1], x[k - 1], a); if (WD) d = fma(lal[qq][k - 1], x[k - 1], d); }
+                    }
                 } else {
-                    UNROLL for (int k = 0; k < R; ++k) {
-                        x0[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
-                        x1[k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
+                    if (AS) {
+                        lo = rhs[qq][0] * xn[qq][0][k];
+                        up = rhs[qq][1] * xn[qq][1][k];
+                    } else {
+                        if (WA) a = fma(rhs[qq][1], xn[qq][1][k], rhs[qq][0] * xn[qq][0][k]);
+                        if (WD) d = fma(rha[qq][1], xn[qq][1][k], rha[qq][0] * xn[qq][0][k]);
                     }
                 }
-                UNROLL for (int k = 0; k < R; ++k) {
-                    if (WA) A[k][qq] = fma(rhs[qq][1], x1[k], rhs[qq][0] * x0[k]);
-                    if (WD) D[k][qq] = fma(rha[qq][1], x1[k], rha[qq][0] * x0[k]);
-                }
+                if (AS) { a = up + lo; d = up - lo; }
+                Ae[qq] = a; De[qq] = d;
             }
+            f(k, Ae, De);
         }
     }
 };
@@ -322,14 +344,13 @@ __device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, 
 template <class LaneT>
 __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E], double (&v05)[LaneT::E]) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
-    double A[E][NC], D[E][NC], rhs[E], l1[E], s0u[E];
-    L.template pass<true, true>(u, A, D);
-    UNROLL for (int e = 0; e < E; ++e) {
+    double rhs[E], l1[E], s0u[E];
+    L.template pass_each<true, true>(u, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
         double r = L.d0[e] * u[e], s = 0.0;
-        UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], A[e][qq], r); s = fma(L.q[0][qq], D[e][qq], s); }
+        UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], Ae[qq], r); s = fma(L.q[0][qq], De[qq], s); }
         rhs[e] = r;            // K05 u
         s0u[e] = s;            // S0 u
-    }
+    });
     typename LaneT::SC sc;
     L.s_prescale(1, sc);
     {
@@ -339,19 +360,18 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
     }
     neumann(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
-    L.template pass<true, true>(v05, A, D);
     double k1v[E], s05v[E];
-    UNROLL for (int e = 0; e < E; ++e) {
+    L.template pass_each<true, true>(v05, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
         double k0 = L.d0[e] * v05[e], k1 = k0, s = 0.0;
         UNROLL for (int qq = 0; qq < NC; ++qq) {
-            k0 = fma(L.p[0][qq], A[e][qq], k0);
-            k1 = fma(L.p[2][qq], A[e][qq], k1);
-            s = fma(L.q[1][qq], D[e][qq], s);
+            k0 = fma(L.p[0][qq], Ae[qq], k0);
+            k1 = fma(L.p[2][qq], Ae[qq], k1);
+            s = fma(L.q[1][qq], De[qq], s);
         }
         k1v[e] = k1;                                   // K1 v05
         s05v[e] = s;                                   // S05 v05
         u[e] = fma(0.5 * h, s0u[e] - k0, u[e]);        // u + (h/2) kappa1,  kappa1 = S0 u - K0 v05
-    }
+    });
     L.s_prescale(2, sc);
     {
         double tv[E];
@@ -361,82 +381,90 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
     double k2[E];
     neumann(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
-    L.template pass<true, false>(u, A, D);
-    UNROLL for (int e = 0; e < E; ++e) {
+    L.template pass_each<true, false>(u, [&](int e, const double (&Ae)[NC], const double (&)[NC]) {
         double l2 = fma(L.d0[e], u[e], s05v[e]);
-        UNROLL for (int qq = 0; qq < NC; ++qq) l2 = fma(L.p[1][qq], A[e][qq], l2);
+        UNROLL for (int qq = 0; qq < NC; ++qq) l2 = fma(L.p[1][qq], Ae[qq], l2);
         v[e] = fma(0.5 * h, l1[e] + l2, v[e]);
-    }
+    });
 }
 
 // src/StormerVerlet.jl:255-303 with the diagonal-W forcing of src/evalobjgrad.jl:862,882-888, fused with the five
 // traces per control of adjoint_grad_calc! (src/evalobjgrad.jl:2578-2618):
 //   T[q][0] = tr(vr0,Ha,lr05)  T[q][1] = tr(vi05,Hs,lr05)  T[q][2] = tr(vr,Ha,lr05)
 //   T[q][3] = tr(vr,Hs,li)+tr(vr0,Hs,li0)                   T[q][4] = tr(vi05,Ha,li)+tr(vi05,Ha,li0)
+// The group-reduced traces are left in shared memory at tred[q*5 + a] (written by lane 0 of the group).
 template <class LaneT>
 __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (&mu)[LaneT::E], double (&nu)[LaneT::E],
                                              const double (&vr0)[LaneT::E], const double (&vi05)[LaneT::E],
-                                             const double (&vr)[LaneT::E], double (&T)[LaneT::NC][5], int GL, int gbase_lane) {
+                                             const double (&vr)[LaneT::E], double *tred, int GL, int gbase_lane, bool writer) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
-    double A[E][NC], D[E][NC], rhs[E], s05n[E];
+    double rhs[E], s05n[E], Tb[NC][2];
     typename LaneT::SC sc;
     L.s_prescale(0, sc);
     L.s_pass(sc, mu, rhs);
-    UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(L.w[e], vr0[e], rhs[e]);                    // S0 mu + hr0
-    L.template pass<true, true>(nu, A, D);
-    UNROLL for (int e = 0; e < E; ++e) {
+    UNROLL for (int qq = 0; qq < NC; ++qq) { Tb[qq][0] = 0.0; Tb[qq][1] = 0.0; }
+    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
         double kk = L.d0[e] * nu[e], s = 0.0;
         UNROLL for (int qq = 0; qq < NC; ++qq) {
-            kk = fma(L.p[1][qq], A[e][qq], kk);
-            s = fma(L.q[1][qq], D[e][qq], s);
-            T[qq][3] = fma(vr0[e], A[e][qq], T[qq][3]);
-            T[qq][4] = fma(vi05[e], D[e][qq], T[qq][4]);
+            kk = fma(L.p[1][qq], Ae[qq], kk);
+            s = fma(L.q[1][qq], De[qq], s);
+            Tb[qq][0] = fma(vr0[e], Ae[qq], Tb[qq][0]);      // tr(vr0, Hs, li0)
+            Tb[qq][1] = fma(vi05[e], De[qq], Tb[qq][1]);     // tr(vi05, Ha, li0)
         }
-        rhs[e] -= kk;                                  // - K05 nu
-        s05n[e] = s;                                   // S05 nu
-    }
+        rhs[e] = fma(L.w[e], vr0[e], rhs[e]) - kk;           // S0 mu + hr0 - K05 nu
+        s05n[e] = s;                                         // S05 nu
+    });
     double k2[E];
     neumann(L, sc, J, h, rhs, k2);
-    UNROLL for (int e = 0; e < E; ++e) mu[e] = fma(0.5 * h, k2[e], mu[e]);   // X = mu
-    L.template pass<true, true>(mu, A, D);
-    double l2[E], k1x[E], s1x[E];
-    UNROLL for (int e = 0; e < E; ++e) {
-        double k0 = L.d0[e] * mu[e], k1 = k0, s = 0.0;
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            k0 = fma(L.p[0][qq], A[e][qq], k0);
-            k1 = fma(L.p[2][qq], A[e][qq], k1);
-            s = fma(L.q[2][qq], D[e][qq], s);
-            T[qq][0] = fma(vr0[e], D[e][qq], T[qq][0]);
-            T[qq][1] = fma(vi05[e], A[e][qq], T[qq][1]);
-            T[qq][2] = fma(vr[e], D[e][qq], T[qq][2]);
+    UNROLL for (int e = 0; e < E; ++e) mu[e] = fma(0.5 * h, k2[e], mu[e]);   // X = lr05
+    double l2[E], r0[E], mu2[E];
+    {
+        double Ta[NC][3];
+        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) Ta[qq][a] = 0.0;
+        L.template pass_each<true, true>(mu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
+            double k0 = L.d0[e] * mu[e], k1 = k0, s = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq) {
+                k0 = fma(L.p[0][qq], Ae[qq], k0);
+                k1 = fma(L.p[2][qq], Ae[qq], k1);
+                s = fma(L.q[2][qq], De[qq], s);
+                Ta[qq][0] = fma(vr0[e], De[qq], Ta[qq][0]);
+                Ta[qq][1] = fma(vi05[e], Ae[qq], Ta[qq][1]);
+                Ta[qq][2] = fma(vr[e], De[qq], Ta[qq][2]);
+            }
+            const double hi0 = L.w[e] * vi05[e];
+            l2[e] = k0 + s05n[e] + hi0;                              // K0 X + S05 nu + hi0
+            r0[e] = s05n[e] + k1 + hi0;                              // S05 nu + K1 X + hi1
+            mu2[e] = fma(0.5 * h, fma(L.w[e], vr[e], s), mu[e]);     // X + (h/2)(S1 X + hr1)
+        });
+        // the three traces that only involve lr05 = X are complete: reduce them now, overlapped with the next products
+        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) {
+            const double t = group_sum(Ta[qq][a], GL, gbase_lane);
+            if (writer) tred[qq * 5 + a] = t;
         }
-        const double hi0 = L.w[e] * vi05[e];
-        l2[e] = k0 + s05n[e] + hi0;                    // K0 X + S05 nu + hi0
-        k1x[e] = k1 + hi0;                             // K1 X + hi1
-        s1x[e] = s;                                    // S1 X
     }
-    // the three traces that only involve lr05 = X are complete: reduce them now, overlapped with the next products
-    UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) T[qq][a] = group_sum(T[qq][a], GL, gbase_lane);
     L.s_prescale(1, sc);
     {
         double tv[E];
         L.s_pass(sc, l2, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhs[e] = s05n[e] + 0.5 * h * tv[e] + k1x[e];         // S05 nu + (h/2) S05 l2 + K1 X + hi1
+        UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(0.5 * h, tv[e], r0[e]);   // S05 nu + (h/2) S05 l2 + K1 X + hi1
     }
     double l1[E];
     neumann(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
-    L.template pass<true, true>(nu, A, D);
-    UNROLL for (int e = 0; e < E; ++e) {
+    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
         double kk = L.d0[e] * nu[e];
         UNROLL for (int qq = 0; qq < NC; ++qq) {
-            kk = fma(L.p[1][qq], A[e][qq], kk);
-            T[qq][3] = fma(vr[e], A[e][qq], T[qq][3]);
-            T[qq][4] = fma(vi05[e], D[e][qq], T[qq][4]);
+            kk = fma(L.p[1][qq], Ae[qq], kk);
+            Tb[qq][0] = fma(vr[e], Ae[qq], Tb[qq][0]);       // + tr(vr, Hs, li)
+            Tb[qq][1] = fma(vi05[e], De[qq], Tb[qq][1]);     // + tr(vi05, Ha, li)
         }
-        mu[e] = fma(0.5 * h, s1x[e] - kk + L.w[e] * vr[e], mu[e]);   // kappa1 = S1 X - K05 nu + hr1
+        mu[e] = fma(-0.5 * h, kk, mu2[e]);                   // mu + (h/2) kappa1, kappa1 = S1 X - K05 nu + hr1
+    });
+    UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) {
+        const double t = group_sum(Tb[qq][a], GL, gbase_lane);
+        if (writer) tred[qq * 5 + 3 + a] = t;
     }
-    UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 3; a < 5; ++a) T[qq][a] = group_sum(T[qq][a], GL, gbase_lane);
+    __syncwarp();
 }
 
 // Fill the control table for `nst` steps starting at time t (all threads of the CTA).
@@ -626,6 +654,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         U[j].kw = D1; U[j].acc0 = 0.0; U[j].acc1 = 0.0; U[j].acc2 = 0.0;
     }
     double *gsm = sm + S.o_gsm + g.group * Npar;
+    double *tred = sm + S.o_tred + g.group * (NC * 5);
     const double *tabb = sm + S.o_tabb, *tabph = sm + S.o_tabph;
     const int *tabk = reinterpret_cast<const int *>(sm + S.o_tabk);
 
@@ -639,16 +668,11 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
             LOAD_LEVELS(ls);
             UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
             state_step(L, J, dt, vr, vi, vi05);
-            double T[NC][5];
-            UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int j = 0; j < 5; ++j) T[qq][j] = 0.0;
-            adjoint_step(L, J, dt, lr, li, vr0, vi05, vr, T, GL, gbase_lane);      // returns the group-reduced traces
+            adjoint_step(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
             UNROLL for (int j = 0; j < UPL; ++j) {
                 if (U[j].on) {
                     double Tq[5];
-                    UNROLL for (int a = 0; a < 5; ++a) {
-                        Tq[a] = T[0][a];
-                        UNROLL for (int qq = 1; qq < NC; ++qq) Tq[a] = (U[j].uq == qq) ? T[qq][a] : Tq[a];
-                    }
+                    UNROLL for (int a = 0; a < 5; ++a) Tq[a] = tred[U[j].uq * 5 + a];
                     // time points in decreasing order: t0 (row 2ls), t0 + dt/2 (2ls+1), t0 + dt (2ls+2)
                     UNROLL for (int tp = 0; tp < 3; ++tp) {
                         const int i = 2 * ls + tp;
@@ -665,6 +689,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
                     }
                 }
             }
+            __syncwarp();                        // the scatter roles have read tred before the next step overwrites it
             t = t + dt;
         }
     }
@@ -685,16 +710,17 @@ typedef void (*traj_kernel_t)(const TrajParams);
 // variant (experiments, env JQ_TRAJ_VARIANT): bit 0 = warp-shuffle exchange, bit 1 = 3 CTAs/SM register cap
 struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 #define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
-#define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL>}
-#define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK>, UPL, MINB>}
-#define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, XM>, UPL, MINB>}
+#define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
+#define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
+#define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
+#define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, MINB>}
 const Inst kInst[] = {
     SLOT(1, 2, 1, 2), SLOT(1, 3, 1, 2), SLOT(1, 4, 1, 2), SLOT(1, 4, 2, 2), SLOT(1, 2, 2, 2),
     SLOT(2, 2, 3, 2), SLOT(3, 1, 3, 2), SLOT(1, 1, 1, 2), SLOT(1, 1, 2, 2),
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
-    FIBERV(4, 3, 1, 1, 1, 1),
+    FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
 const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0) {
@@ -774,7 +800,7 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
     if (!inst) return no("no slot instantiation for this (rows per lane, columns per lane, controls)");
 
     TrajPlan *pl = new TrajPlan();
-    pl->kind = 2; pl->R = R; pl->C = C; pl->NC = Nc; pl->WQ = WQ; pl->LMASK = 0; pl->UPL = 1;
+    pl->kind = 2; pl->R = R; pl->C = C; pl->NC = Nc; pl->WQ = WQ; pl->LMASK = 0; pl->UPL = 1; pl->AS = 1;
     pl->NL = NL; pl->NLR = NL * R; pl->GL = NL; pl->GPT = m / C; pl->CPG = C;
     pl->ngroups = TRAJ_WARPS * (32 / NL);
     pl->TPC = pl->ngroups / pl->GPT;
@@ -842,7 +868,6 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
             for (int f = 0; f < nfib; ++f) {
                 Rem &x = rem[f][q];
                 x.off[0] = x.off[1] = 0; x.hs[0] = x.hs[1] = x.ha[0] = x.ha[1] = 0.0;
-                int cnt = 0;
                 for (int f2 = 0; f2 < nfib; ++f2) {
                     if (f2 == f) continue;
                     const double s0 = value_at(H, 1 + q, f * R, f2 * R), a0 = value_at(H, 1 + Nc + q, f * R, f2 * R);
@@ -852,10 +877,24 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
                         if (sk != s0 || ak != a0) return no("remote coupling is not uniform along the fibre");
                     }
                     if (!nz) continue;
-                    if (cnt == 2) return no("more than 2 neighbour fibres per control");
-                    x.off[cnt] = f2 - f; x.hs[cnt] = s0; x.ha[cnt] = a0; ++cnt;
+                    const int side = f2 < f ? 0 : 1;             // entry 0 = lower neighbour fibre, entry 1 = upper
+                    if (x.off[side] != 0) return no("more than one neighbour fibre on one side");
+                    x.off[side] = f2 - f; x.hs[side] = s0; x.ha[side] = a0;
                 }
             }
+        }
+    }
+    // AS: Hanti = upper(Hsym) - lower(Hsym) for every control (the a - a' / a + a' pair of ladder operators)
+    bool AS = true;
+    for (int q = 0; q < Nc && AS; ++q) {
+        if ((LMASK >> q) & 1) {
+            for (int r = 0; r + 1 < n && AS; ++r) {
+                if ((r + 1) % R == 0) continue;
+                AS = value_at(H, 1 + Nc + q, r, r + 1) == value_at(H, 1 + q, r, r + 1) &&
+                     value_at(H, 1 + Nc + q, r + 1, r) == -value_at(H, 1 + q, r + 1, r);
+            }
+        } else {
+            for (int f = 0; f < nfib && AS; ++f) AS = rem[f][q].ha[0] == -rem[f][q].hs[0] && rem[f][q].ha[1] == rem[f][q].hs[1];
         }
     }
     if (LMASK != 1 && LMASK != (1 << Nc) - 1) return no("only control 1 local (or all local) is instantiated");
@@ -867,11 +906,11 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     const int CPG = GL / NL, GPT = (m + CPG - 1) / CPG;
     const int NU = Nc * H.Nfreq * 2, UPL = (NU + GL - 1) / GL;
     if (UPL > 2) return no("too many (control, frequency) pairs for the group size");
-    const Inst *inst = find_inst(3, R, 1, Nc, 2, LMASK, UPL);
-    if (!inst) return no("no fibre instantiation for this (fibre length, controls, updaters per lane)");
+    const Inst *inst = find_inst(3, R, 1, Nc, 2, LMASK, UPL, AS ? 0 : 16);
+    if (!inst) return no("no fibre instantiation for this (fibre length, controls, updaters per lane, Hanti form)");
     // lane offsets of remote neighbours must stay inside the column block of NL lanes
     TrajPlan *pl = new TrajPlan();
-    pl->kind = 3; pl->R = R; pl->C = 1; pl->NC = Nc; pl->WQ = 2; pl->LMASK = LMASK; pl->UPL = UPL;
+    pl->kind = 3; pl->R = R; pl->C = 1; pl->NC = Nc; pl->WQ = 2; pl->LMASK = LMASK; pl->UPL = UPL; pl->AS = AS ? 1 : 0;
     pl->NL = NL; pl->NLR = NL * R; pl->GL = GL; pl->GPT = GPT; pl->CPG = CPG;
     pl->ngroups = TRAJ_WARPS * (32 / GL);
     pl->TPC = pl->ngroups / GPT;
@@ -918,8 +957,8 @@ int jq_traj_plan_kind(const TrajPlan *pl) { return pl ? pl->kind : 0; }
 cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta) {
     const char *venv = getenv("JQ_TRAJ_VARIANT");
-    const Inst *inst = venv ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv)) : nullptr;
-    if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL);
+    const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv)) : nullptr;
+    if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);
     if (!inst) return cudaErrorNotSupported;
     TrajParams S{};
     S.P = P; S.A = A;
@@ -940,6 +979,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     S.o_tabpq = take(npts * pl->TPC * 2 * NC);
     S.o_red = take(pl->ngroups * 4);
     S.o_tabk = take((npts + 1) / 2);
+    S.o_tred = take(pl->ngroups * NC * 5);
     size_t bytes = (size_t)o * sizeof(double);
     if (const char *pad = getenv("JQ_SMEM_PAD_KB")) bytes += (size_t)atoi(pad) * 1024;   // experiments: throttle CTAs/SM
     cudaError_t e = cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
