@@ -327,12 +327,14 @@ __device__ __forceinline__ double group_sum(double x, int GL, int base) {
 }
 
 // X = sum_{j<=J} (h/2)^j S^j B   (src/linear_solvers.jl:94-106); B is consumed.  `sc` = S(level) prescaled.
-template <class LaneT>
+template <int JT, class LaneT>
 __device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
     constexpr int E = LaneT::E;
     UNROLL for (int e = 0; e < E; ++e) X[e] = B[e];
     double coeff = 1.0;
-    for (int it = 0; it < J; ++it) {
+    const int JJ = JT > 0 ? JT : J;          // JT > 0: number of Neumann terms known at compile time (fully unrolled)
+#pragma unroll
+    for (int it = 0; it < JJ; ++it) {
         double T[E];
         L.s_pass(sc, B, T);
         coeff *= 0.5 * h;
@@ -341,7 +343,7 @@ __device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, 
 }
 
 // src/StormerVerlet.jl:461-504.  u, v updated in place; v05 returned.
-template <class LaneT>
+template <int JT, class LaneT>
 __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E], double (&v05)[LaneT::E]) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     double rhs[E], l1[E], s0u[E];
@@ -358,7 +360,7 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
         L.s_pass(sc, v, tv);
         UNROLL for (int e = 0; e < E; ++e) rhs[e] += tv[e];                                    // + S05 v
     }
-    neumann(L, sc, J, h, rhs, l1);
+    neumann<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
     double k1v[E], s05v[E];
     L.template pass_each<true, true>(v05, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
@@ -379,7 +381,7 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
         UNROLL for (int e = 0; e < E; ++e) rhs[e] = tv[e] - k1v[e];                             // S1 (u + (h/2) kappa1) - K1 v05
     }
     double k2[E];
-    neumann(L, sc, J, h, rhs, k2);
+    neumann<JT>(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
     L.template pass_each<true, false>(u, [&](int e, const double (&Ae)[NC], const double (&)[NC]) {
         double l2 = fma(L.d0[e], u[e], s05v[e]);
@@ -393,7 +395,7 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
 //   T[q][0] = tr(vr0,Ha,lr05)  T[q][1] = tr(vi05,Hs,lr05)  T[q][2] = tr(vr,Ha,lr05)
 //   T[q][3] = tr(vr,Hs,li)+tr(vr0,Hs,li0)                   T[q][4] = tr(vi05,Ha,li)+tr(vi05,Ha,li0)
 // The group-reduced traces are left in shared memory at tred[q*5 + a] (written by lane 0 of the group).
-template <class LaneT>
+template <int JT, class LaneT>
 __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (&mu)[LaneT::E], double (&nu)[LaneT::E],
                                              const double (&vr0)[LaneT::E], const double (&vi05)[LaneT::E],
                                              const double (&vr)[LaneT::E], double *tred, int GL, int gbase_lane, bool writer) {
@@ -415,7 +417,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         s05n[e] = s;                                         // S05 nu
     });
     double k2[E];
-    neumann(L, sc, J, h, rhs, k2);
+    neumann<JT>(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) mu[e] = fma(0.5 * h, k2[e], mu[e]);   // X = lr05
     double l2[E], r0[E], mu2[E];
     {
@@ -449,7 +451,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(0.5 * h, tv[e], r0[e]);   // S05 nu + (h/2) S05 l2 + K1 X + hi1
     }
     double l1[E];
-    neumann(L, sc, J, h, rhs, l1);
+    neumann<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
     L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
         double kk = L.d0[e] * nu[e];
@@ -535,7 +537,7 @@ struct Updater {
     double acc0, acc1, acc2;
 };
 
-template <class LaneT, int UPL, int MINB = 1>
+template <class LaneT, int UPL, int MINB = 1, int JT = 0>
 __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     extern __shared__ double sm[];
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         for (int ls = 0; ls < nst; ++ls) {
             LOAD_LEVELS(ls);
             UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e], pen);                              // penalf2aTrap
-            state_step(L, J, dt, vr, vi, vi05);
+            state_step<JT>(L, J, dt, vr, vi, vi05);
             UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e] + 2.0 * vi05[e] * vi05[e], pen);   // penalf2a
             t = t + dt;
         }
@@ -667,8 +669,8 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         for (int ls = 0; ls < nst; ++ls) {
             LOAD_LEVELS(ls);
             UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
-            state_step(L, J, dt, vr, vi, vi05);
-            adjoint_step(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
+            state_step<JT>(L, J, dt, vr, vi, vi05);
+            adjoint_step<JT>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
             UNROLL for (int j = 0; j < UPL; ++j) {
                 if (U[j].on) {
                     double Tq[5];
@@ -712,6 +714,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 #define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
+#define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, MINB>}
 const Inst kInst[] = {
@@ -720,6 +723,7 @@ const Inst kInst[] = {
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
+    FIBERJ(4, 2, 1, 1, 4), FIBERJ(6, 1, 1, 2, 3), FIBERJ(3, 2, 1, 1, 5),
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
@@ -958,6 +962,8 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
                            size_t *smem, int *traj_per_cta) {
     const char *venv = getenv("JQ_TRAJ_VARIANT");
     const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv)) : nullptr;
+    if (!inst && !venv && pl->AS)      // instantiations with the number of Neumann terms known at compile time
+        inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);
     if (!inst) return cudaErrorNotSupported;
     TrajParams S{};
