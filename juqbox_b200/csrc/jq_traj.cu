@@ -45,7 +45,7 @@ struct TrajParams {
     const int *plan_i;                       // layout-specific integer table
     const double *plan_d;                    // layout-specific coefficient table
     const double *plan_d0, *plan_w;          // per (padded) row: H0 diagonal, guard weight
-    int o_exch, o_pcof, o_gsm, o_times, o_tabb, o_tabph, o_tabpq, o_red, o_tabk, o_tred;   // shared-memory offsets in doubles
+    int o_exch, o_pcof, o_gsm, o_times, o_tabb, o_tabph, o_tabpq, o_red, o_tabk, o_tred, o_gsm2;   // shared-memory offsets in doubles
     int exch_per_unit;                       // doubles of exchange buffer per group (slot) / per warp (fibre)
     int NparS;                               // shared-memory row stride of the staged pcof vectors (odd: no bank conflicts)
     int GPW;                                 // groups per warp (32 / GL, rounded down: GL need not be a power of two)
@@ -395,7 +395,7 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
 //   T[q][0] = tr(vr0,Ha,lr05)  T[q][1] = tr(vi05,Hs,lr05)  T[q][2] = tr(vr,Ha,lr05)
 //   T[q][3] = tr(vr,Hs,li)+tr(vr0,Hs,li0)                   T[q][4] = tr(vi05,Ha,li)+tr(vi05,Ha,li0)
 // The group-reduced traces are left in shared memory at tred[q*5 + a] (written by lane 0 of the group).
-template <int JT, class LaneT>
+template <int JT, bool FORCING, class LaneT>
 __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (&mu)[LaneT::E], double (&nu)[LaneT::E],
                                              const double (&vr0)[LaneT::E], const double (&vi05)[LaneT::E],
                                              const double (&vr)[LaneT::E], double *tred, int GL, int gbase_lane, bool writer) {
@@ -413,7 +413,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
             Tb[qq][0] = fma(vr0[e], Ae[qq], Tb[qq][0]);      // tr(vr0, Hs, li0)
             Tb[qq][1] = fma(vi05[e], De[qq], Tb[qq][1]);     // tr(vi05, Ha, li0)
         }
-        rhs[e] = fma(L.w[e], vr0[e], rhs[e]) - kk;           // S0 mu + hr0 - K05 nu
+        rhs[e] = (FORCING ? fma(L.w[e], vr0[e], rhs[e]) : rhs[e]) - kk;   // S0 mu + hr0 - K05 nu
         s05n[e] = s;                                         // S05 nu
     });
     double k2[E];
@@ -433,10 +433,10 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
                 Ta[qq][1] = fma(vi05[e], Ae[qq], Ta[qq][1]);
                 Ta[qq][2] = fma(vr[e], De[qq], Ta[qq][2]);
             }
-            const double hi0 = L.w[e] * vi05[e];
+            const double hi0 = FORCING ? L.w[e] * vi05[e] : 0.0;
             l2[e] = k0 + s05n[e] + hi0;                              // K0 X + S05 nu + hi0
             r0[e] = s05n[e] + k1 + hi0;                              // S05 nu + K1 X + hi1
-            mu2[e] = fma(0.5 * h, fma(L.w[e], vr[e], s), mu[e]);     // X + (h/2)(S1 X + hr1)
+            mu2[e] = fma(0.5 * h, FORCING ? fma(L.w[e], vr[e], s) : s, mu[e]);     // X + (h/2)(S1 X + hr1)
         });
         // the three traces that only involve lr05 = X are complete: reduce them now, overlapped with the next products
         UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) {
@@ -537,7 +537,36 @@ struct Updater {
     double acc0, acc1, acc2;
 };
 
-template <class LaneT, int UPL, int MINB = 1, int JT = 0>
+// One step's contribution to the gradient windows of this lane's roles (src/evalobjgrad.jl:2578-2618, bsplines.jl:321-381).
+// Time points in decreasing order: t0 (table row 2ls), t0 + dt/2 (2ls+1), t0 + dt (2ls+2).
+template <int NC, int UPL>
+__device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, const double *tred, const double *tabb, const double *tabph,
+                                             const int *tabk, int ls, int Nfreq) {
+    UNROLL for (int j = 0; j < UPL; ++j) {
+        if (U[j].on) {
+            double Tq[5];
+            UNROLL for (int a = 0; a < 5; ++a) Tq[a] = tred[U[j].uq * 5 + a];
+            UNROLL for (int tp = 0; tp < 3; ++tp) {
+                const int i = 2 * ls + tp;
+                const double Pc = tp == 1 ? Tq[3] : -Tq[1];
+                const double Qc = tp == 0 ? -Tq[0] : (tp == 1 ? -Tq[4] : -Tq[2]);
+                const int ph = 2 * (i * NC * Nfreq + U[j].uq * Nfreq + U[j].uf);
+                const double cs = tabph[ph], sn = tabph[ph + 1];
+                const double X = U[j].ua == 0 ? Pc * cs + Qc * sn : Qc * cs - Pc * sn;
+                const int k = tabk[i];
+                while (U[j].kw > k) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; U[j].acc0 = U[j].acc1; U[j].acc1 = U[j].acc2; U[j].acc2 = 0.0; --U[j].kw; }
+                U[j].acc0 = fma(tabb[3 * i], X, U[j].acc0);
+                U[j].acc1 = fma(tabb[3 * i + 1], X, U[j].acc1);
+                U[j].acc2 = fma(tabb[3 * i + 2], X, U[j].acc2);
+            }
+        }
+    }
+    __syncwarp();                        // the roles have read tred before anything overwrites it
+}
+
+// OBJ = 1: objFuncType 2/3 — a second adjoint set without forcing gives the infidelity-only gradient
+// (src/evalobjgrad.jl:848-855, :905-918; step_no_forcing! src/StormerVerlet.jl:365-406).
+template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0>
 __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     extern __shared__ double sm[];
@@ -573,7 +602,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
         sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * Npar + k] : 0.0;
     }
-    for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += TRAJ_THREADS) sm[S.o_gsm + idx] = 0.0;
+    for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += TRAJ_THREADS) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
 
     double vr[E], vi[E], vi05[E];
     UNROLL for (int e = 0; e < E; ++e) {
@@ -643,9 +672,11 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         lr[e] = (rs * tr_ + is * ti_) / m;     // init_adjoint!, src/evalobjgrad.jl:2029-2042
         li[e] = (is * tr_ - rs * ti_) / m;
     }
+    double lrn[OBJ ? E : 1], lin[OBJ ? E : 1];
+    if constexpr (OBJ != 0) { UNROLL for (int e = 0; e < E; ++e) { lrn[e] = lr[e]; lin[e] = li[e]; } }
     // gradient scatter roles: role u = lg + j*GL < NU owns (control, frequency, alpha)
     const int NU = NC * Nfreq * 2;
-    Updater U[UPL];
+    Updater U[UPL], U2[OBJ ? UPL : 1];
     UNROLL for (int j = 0; j < UPL; ++j) {
         const int u = g.lg + j * GL;
         U[j].on = lane_on && u < NU;
@@ -654,9 +685,11 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         U[j].ua = u & 1;
         U[j].gbase = 2 * U[j].uq * Nfreq * D1 + U[j].uf * 2 * D1 + U[j].ua * D1 - 1;
         U[j].kw = D1; U[j].acc0 = 0.0; U[j].acc1 = 0.0; U[j].acc2 = 0.0;
+        if constexpr (OBJ != 0) U2[j] = U[j];
     }
     double *gsm = sm + S.o_gsm + g.group * Npar;
     double *tred = sm + S.o_tred + g.group * (NC * 5);
+    double *gsm2 = sm + S.o_gsm2 + g.group * Npar;
     const double *tabb = sm + S.o_tabb, *tabph = sm + S.o_tabph;
     const int *tabk = reinterpret_cast<const int *>(sm + S.o_tabk);
 
@@ -670,33 +703,19 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
             LOAD_LEVELS(ls);
             UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
             state_step<JT>(L, J, dt, vr, vi, vi05);
-            adjoint_step<JT>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
-            UNROLL for (int j = 0; j < UPL; ++j) {
-                if (U[j].on) {
-                    double Tq[5];
-                    UNROLL for (int a = 0; a < 5; ++a) Tq[a] = tred[U[j].uq * 5 + a];
-                    // time points in decreasing order: t0 (row 2ls), t0 + dt/2 (2ls+1), t0 + dt (2ls+2)
-                    UNROLL for (int tp = 0; tp < 3; ++tp) {
-                        const int i = 2 * ls + tp;
-                        const double Pc = tp == 1 ? Tq[3] : -Tq[1];
-                        const double Qc = tp == 0 ? -Tq[0] : (tp == 1 ? -Tq[4] : -Tq[2]);
-                        const int ph = 2 * (i * NC * Nfreq + U[j].uq * Nfreq + U[j].uf);
-                        const double cs = tabph[ph], sn = tabph[ph + 1];
-                        const double X = U[j].ua == 0 ? Pc * cs + Qc * sn : Qc * cs - Pc * sn;
-                        const int k = tabk[i];
-                        while (U[j].kw > k) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; U[j].acc0 = U[j].acc1; U[j].acc1 = U[j].acc2; U[j].acc2 = 0.0; --U[j].kw; }
-                        U[j].acc0 = fma(tabb[3 * i], X, U[j].acc0);
-                        U[j].acc1 = fma(tabb[3 * i + 1], X, U[j].acc1);
-                        U[j].acc2 = fma(tabb[3 * i + 2], X, U[j].acc2);
-                    }
-                }
+            adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
+            grad_scatter<NC, UPL>(U, gsm, tred, tabb, tabph, tabk, ls, Nfreq);
+            if constexpr (OBJ != 0) {
+                adjoint_step<JT, false>(L, J, dt, lrn, lin, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);
+                grad_scatter<NC, UPL>(U2, gsm2, tred, tabb, tabph, tabk, ls, Nfreq);
             }
-            __syncwarp();                        // the scatter roles have read tred before the next step overwrites it
             t = t + dt;
         }
     }
-    UNROLL for (int j = 0; j < UPL; ++j)
+    UNROLL for (int j = 0; j < UPL; ++j) {
         if (U[j].on) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; gsm[U[j].gbase + U[j].kw - 1] += U[j].acc1; gsm[U[j].gbase + U[j].kw - 2] += U[j].acc2; }
+        if constexpr (OBJ != 0) if (U2[j].on) { gsm2[U2[j].gbase + U2[j].kw] += U2[j].acc0; gsm2[U2[j].gbase + U2[j].kw - 1] += U2[j].acc1; gsm2[U2[j].gbase + U2[j].kw - 2] += U2[j].acc2; }
+    }
     __syncthreads();
     // total gradient of each resident trajectory = dt * sum of its groups' partial gradients, in group order
     for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += TRAJ_THREADS) {
@@ -705,6 +724,11 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         double gs = 0.0;
         for (int j = 0; j < S.GPT; ++j) gs += sm[S.o_gsm + (tr * S.GPT + j) * Npar + k];
         A.grad[(size_t)tg * Npar + k] = dt * gs;
+        if (OBJ) {
+            double g2 = 0.0;
+            for (int j = 0; j < S.GPT; ++j) g2 += sm[S.o_gsm2 + (tr * S.GPT + j) * Npar + k];
+            A.infidgrad[(size_t)tg * Npar + k] = dt * g2;
+        }
     }
 }
 
@@ -715,6 +739,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
 #define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
+#define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, MINB>}
 const Inst kInst[] = {
@@ -724,6 +749,7 @@ const Inst kInst[] = {
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
     FIBERJ(4, 2, 1, 1, 4), FIBERJ(6, 1, 1, 2, 3), FIBERJ(3, 2, 1, 1, 5),
+    FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
@@ -838,7 +864,6 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
 TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
-    if (P.objFuncType != 1) return no("objFuncType != 1 uses the generic kernel (second adjoint set)");
     std::vector<double> d0;
     if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
     // block size: first break of control 0's first off-diagonals
@@ -910,8 +935,9 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     const int CPG = GL / NL, GPT = (m + CPG - 1) / CPG;
     const int NU = Nc * H.Nfreq * 2, UPL = (NU + GL - 1) / GL;
     if (UPL > 2) return no("too many (control, frequency) pairs for the group size");
-    const Inst *inst = find_inst(3, R, 1, Nc, 2, LMASK, UPL, AS ? 0 : 16);
-    if (!inst) return no("no fibre instantiation for this (fibre length, controls, updaters per lane, Hanti form)");
+    const Inst *inst = find_inst(3, R, 1, Nc, 2, LMASK, UPL, P.objFuncType != 1 ? 64 : (AS ? 0 : 16));
+    if (P.objFuncType != 1 && !AS) inst = nullptr;
+    if (!inst) return no("no fibre instantiation for this (fibre length, controls, updaters per lane, Hanti form, objFuncType)");
     // lane offsets of remote neighbours must stay inside the column block of NL lanes
     TrajPlan *pl = new TrajPlan();
     pl->kind = 3; pl->R = R; pl->C = 1; pl->NC = Nc; pl->WQ = 2; pl->LMASK = LMASK; pl->UPL = UPL; pl->AS = AS ? 1 : 0;
@@ -961,8 +987,9 @@ int jq_traj_plan_kind(const TrajPlan *pl) { return pl ? pl->kind : 0; }
 cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta) {
     const char *venv = getenv("JQ_TRAJ_VARIANT");
+    if (P.objFuncType != 1) venv = "64";
     const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv)) : nullptr;
-    if (!inst && !venv && pl->AS)      // instantiations with the number of Neumann terms known at compile time
+    if (!inst && !venv && pl->AS && P.objFuncType == 1)      // instantiations with the number of Neumann terms known at compile time
         inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);
     if (!inst) return cudaErrorNotSupported;
@@ -986,6 +1013,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     S.o_red = take(pl->ngroups * 4);
     S.o_tabk = take((npts + 1) / 2);
     S.o_tred = take(pl->ngroups * NC * 5);
+    S.o_gsm2 = take(P.objFuncType != 1 ? pl->ngroups * A.Npar : 0);
     size_t bytes = (size_t)o * sizeof(double);
     if (const char *pad = getenv("JQ_SMEM_PAD_KB")) bytes += (size_t)atoi(pad) * 1024;   // experiments: throttle CTAs/SM
     cudaError_t e = cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -153,3 +153,30 @@ def test_full_size_properties_cnot2():
     assert np.array_equal(z["grad"], base["grad"])
     assert wa.evaluate(p0, evaladjoint=False)["objf"][0, 0] == base["objf"][0, 0]
     wa.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 3])
+@pytest.mark.parametrize("name", ["cnot2", "risk_neutral", "cnot1"])
+def test_objfunctype3_second_adjoint_vs_oracle(name, kernel):
+    """objFuncType = 3 (leak as inequality constraint): infidelity-only gradient from the adjoint set without forcing
+    and leakgrad = totalgrad - infidelgrad (src/evalobjgrad.jl:848-855, :905-918, :940-952)."""
+    from juqbox_b200 import configs
+    from oracle import oracle_traceobjgrad
+    cfg = configs.example(name)
+    p = cfg.params
+    p.objFuncType = 3
+    p.T, p.nsteps = p.T / 10.0, max(300, p.nsteps // 10)      # shorter horizon keeps the CPU oracle quick
+    pc = configs.synthetic_pcof(cfg, 3) * 30.0
+    shifts = configs.noise_shift(p.Ntot, cfg.nodes[:2]) if name == "risk_neutral" else None
+    o = oracle_traceobjgrad(p, pc, shifts, nthreads=6)
+    wa = _wa(cfg, kernel)
+    r = wa.evaluate(pc, shifts)
+    assert wa.last_kernel == kernel
+    wa.close()
+    for key in ("grad", "infidgrad", "leakgrad"):
+        for b in range(3):
+            for s in range(r[key].shape[1]):
+                # leakgrad is a difference of two nearly equal gradients: compare it on the scale of the total gradient
+                scale = np.linalg.norm(o["grad"][b, s])
+                assert np.linalg.norm(r[key][b, s] - o[key][b, s]) <= TOL * scale, (key, b, s)
+    assert np.allclose(r["leakgrad"], r["grad"] - r["infidgrad"], rtol=0, atol=1e-18)
