@@ -1,0 +1,78 @@
+// Latency/throughput micro-benchmarks used to reason about the trajectory kernel:
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/microbench tools/microbench.cu && /tmp/microbench
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__global__ void dfma_chain(double *out, long long *cyc, int iters, double a, double b) {
+    double x = threadIdx.x * 1e-3;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) x = fma(x, a, b);
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+template <int ILP>
+__global__ void dfma_ilp(double *out, long long *cyc, int iters, double a, double b) {
+    double x[ILP];
+    for (int k = 0; k < ILP; ++k) x[k] = threadIdx.x * 1e-3 + k;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) x[k] = fma(x[k], a, b);
+    }
+    long long t1 = clock64();
+    double s = 0;
+    for (int k = 0; k < ILP; ++k) s += x[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+__global__ void shfl_chain(double *out, long long *cyc, int iters) {
+    double x = threadIdx.x;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) x = __shfl_xor_sync(0xffffffffu, x, 1) + 1.0;
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+__global__ void smem_chain(double *out, long long *cyc, int iters) {
+    __shared__ double buf[64];
+    double x = threadIdx.x;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            buf[(u & 1) * 32 + threadIdx.x] = x;
+            __syncwarp();
+            x = buf[(u & 1) * 32 + (threadIdx.x ^ 1)] + 1.0;
+        }
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+
+int main() {
+    double *out; long long *cyc, h;
+    cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 8);
+    const int iters = 4096;
+    dfma_chain<<<1, 32>>>(out, cyc, iters, 0.999, 1e-9); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("dependent DFMA latency: %.2f cycles\n", (double)h / (iters * 16.0));
+    shfl_chain<<<1, 32>>>(out, cyc, iters); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("SHFL(64-bit)+DADD dependent round: %.2f cycles\n", (double)h / (iters * 16.0));
+    smem_chain<<<1, 32>>>(out, cyc, iters); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("STS.64 + syncwarp + LDS.64 + DADD dependent round: %.2f cycles\n", (double)h / (iters * 16.0));
+#define RUN(ILP, WARPS)                                                                                        \
+    dfma_ilp<ILP><<<1, 32 * WARPS>>>(out, cyc, iters, 0.999, 1e-9); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+    printf("1 SM, %d warps x ILP %d: %.2f cycles per warp-DFMA per SMSP-warp (%.1f%% of 2-cycle issue)\n", WARPS, ILP,         \
+           (double)h / (iters * 8.0 * ILP), 100.0 * 2.0 * ((WARPS + 3) / 4) / ((double)h / (iters * 8.0 * ILP)));
+    RUN(1, 4) RUN(2, 4) RUN(4, 4) RUN(8, 4) RUN(1, 8) RUN(2, 8) RUN(4, 8) RUN(1, 16) RUN(2, 16)
+    return 0;
+}
