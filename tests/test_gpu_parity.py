@@ -180,3 +180,23 @@ def test_objfunctype3_second_adjoint_vs_oracle(name, kernel):
                 scale = np.linalg.norm(o["grad"][b, s])
                 assert np.linalg.norm(r[key][b, s] - o[key][b, s]) <= TOL * scale, (key, b, s)
     assert np.allclose(r["leakgrad"], r["grad"] - r["infidgrad"], rtol=0, atol=1e-18)
+
+
+def test_optimizer_glue_reduces_objective():
+    """setup_ipopt_problem / run_optimizer mirror: a few L-BFGS-B iterations through the cached callbacks
+    (src/ipopt_interface.jl:77-148, 212-240) reduce the risk-neutral objective."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    cfg = configs.example("risk_neutral")
+    p = cfg.params
+    p.T, p.nsteps = 60.0, 1600
+    wa = jq.Working_Arrays(p, cfg.nCoeff)
+    pc0 = configs.synthetic_pcof(cfg, 1)[0]
+    minC, maxC = jq.assign_thresholds_freq([cfg.maxpar[0]] * p.Nfreq, p.Ncoupled, p.Nfreq, cfg.D1)
+    f0 = jq.eval_f_par(pc0, p, wa, cfg.nodes, cfg.weights)
+    prob = jq.setup_ipopt_problem(p, wa, cfg.nCoeff, minC, maxC, maxIter=8, lbfgsMax=5, nodes=cfg.nodes, weights=cfg.weights)
+    pc = jq.run_optimizer(prob, pc0)
+    f1 = jq.eval_f_par(pc, p, wa, cfg.nodes, cfg.weights)
+    wa.close()
+    assert np.all(pc >= minC - 1e-15) and np.all(pc <= maxC + 1e-15)
+    assert f1 < f0 - 1e-3 and len(p.objHist) >= 2 and p.objHist[-1] <= p.objHist[0]
