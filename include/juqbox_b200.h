@@ -101,6 +101,15 @@ int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pco
                                  double *infid, double *leak, double *trace_infid, double *grad,
                                  double *infidgrad, double *leakgrad, void *cuda_stream);
 
+/* Forward propagation with state history: eval_forward(U0 = Uinit, pcof, params; saveEndOnly=false, saveEvery)
+ * (src/evalobjgrad.jl:2727-2873) and the history that traceobjgrad(verbose=true, evaladjoint=false) returns
+ * (:676-680,:748-752,:1029-1031).  hist_r / hist_i receive Re / Im of the state (vr and -vi) at t = 0 and after every
+ * save_every-th step: [ntraj][nsteps/save_every + 1][n*m] doubles each, column-major n x m blocks (the Julia array
+ * Ntot x N x nsave of each trajectory).  nsteps must be divisible by save_every (reference :2797-2799).  infid / leak as in
+ * jq_traceobjgrad_batch (may be NULL).  Host pointers, blocking; runs on the generic kernel. */
+int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
+                    const double *h0_diag_shift, int32_t save_every, double *hist_r, double *hist_i, double *infid, double *leak);
+
 /* Multi-GPU (one process and one handle per GPU).  The path's only exchange step is the weighted sum over noise
  * samples of eval_f_g_grad! (src/ipopt_interface.jl:48-59) when the samples are sharded across GPUs.
  * jq_comm_unique_id fills a 128-byte NCCL unique id on one rank (distribute it with whatever the host has);

@@ -180,6 +180,27 @@ class Working_Arrays:
         out["objf"] = out["infid"] + out["leak"]
         return out
 
+    def forward_history(self, pcof, shifts=None, save_every: int = 1):
+        """Forward sweep with state history (jq_eval_forward).  Returns (hist, infid, leak): hist complex
+        [nbatch, nsamples, nsave, N, Ntot] — for one trajectory hist[b, s].transpose(2, 1, 0) is Julia's Ntot x N x nsave."""
+        p = self.params
+        pcof = _f64(np.atleast_2d(pcof))
+        nbatch, npar = pcof.shape
+        nsamples, sp = 1, None
+        if shifts is not None:
+            shifts = _f64(np.atleast_2d(shifts))
+            nsamples, sp = shifts.shape[0], shifts.ctypes.data_as(C.c_void_p)
+        if save_every < 1 or p.nsteps % save_every != 0:
+            raise ValueError(f"nsteps must be divisible by saveEvery. nsteps={p.nsteps}, saveEvery={save_every}")
+        nsave = p.nsteps // save_every + 1
+        hr = np.zeros((nbatch, nsamples, nsave, p.N, p.Ntot))
+        hi = np.zeros_like(hr)
+        infid, leak = np.zeros((nbatch, nsamples)), np.zeros((nbatch, nsamples))
+        _lib.check(self._lib.jq_eval_forward(self._handle, nbatch, pcof.ctypes.data_as(C.c_void_p), npar, nsamples, sp, int(save_every),
+                                             hr.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                                             infid.ctypes.data_as(C.c_void_p), leak.ctypes.data_as(C.c_void_p)))
+        return hr + 1j * hi, infid, leak
+
     def evaluate_device(self, pcof, shifts=None, weights=None, evaladjoint=True, out=None, stream=None):
         """Batched evaluation on torch CUDA tensors (no host copies, asynchronous on `stream` or torch's current
         stream).  pcof [nbatch, npar], shifts [nsamples, n], weights [nsamples]; returns dict of CUDA tensors."""
@@ -208,10 +229,14 @@ class Working_Arrays:
 
 def traceobjgrad(pcof0, params: objparams, wa: Working_Arrays, verbose: bool = False, evaladjoint: bool = True):
     """Drop-in for the reference method (src/evalobjgrad.jl:504): same return tuples (:1032-1035)."""
-    if verbose:
-        raise NotImplementedError("verbose=true (state history / forward-sensitivity check) stays on the reference's "
-                                  "CPU path (SURVEY.md rows 14 and 8f-4)")
     pcof0 = np.asarray(pcof0, dtype=np.float64)
+    if verbose:
+        if evaladjoint:
+            raise NotImplementedError("verbose=true with evaladjoint=true (forward-sensitivity check of one gradient "
+                                      "component) stays on the reference's CPU path (SURVEY.md row 14)")
+        # verbose && !evaladjoint: (objfv, unitary history Ntot x N x (nsteps+1), fidelity)  (src/evalobjgrad.jl:1029-1031)
+        hist, infid, leak = wa.forward_history(pcof0[None, :])
+        return infid[0, 0] + leak[0, 0], hist[0, 0].transpose(2, 1, 0), 1.0 - infid[0, 0]
     r = wa.evaluate(pcof0[None, :], evaladjoint=evaladjoint)
     objfv, primary, secondary = r["objf"][0, 0], r["infid"][0, 0], r["leak"][0, 0]
     if not evaladjoint:
@@ -222,6 +247,14 @@ def traceobjgrad(pcof0, params: objparams, wa: Working_Arrays, verbose: bool = F
     else:
         infidelgrad, leakgrad = totalgrad, np.zeros(0)
     return objfv, totalgrad, primary, secondary, r["trace_infid"][0, 0], infidelgrad, leakgrad
+
+
+def eval_forward(pcof0, params: objparams, wa: Working_Arrays, saveEndOnly: bool = True, saveEvery: int = 1):
+    """eval_forward(U0 = params.Uinit, pcof0, params; saveEndOnly, saveEvery) (src/evalobjgrad.jl:2727-2873):
+    the propagated state Ntot x N (saveEndOnly) or its history Ntot x N x (nsteps/saveEvery + 1), complex."""
+    hist, _, _ = wa.forward_history(np.asarray(pcof0, dtype=np.float64)[None, :], save_every=params.nsteps if saveEndOnly else saveEvery)
+    h = hist[0, 0].transpose(2, 1, 0)
+    return h[:, :, -1] if saveEndOnly else h
 
 
 def traceobjgrad_batch(pcofs, params: objparams, wa: Working_Arrays, nodes=None, weights=None, evaladjoint=True):

@@ -423,6 +423,46 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     return 0;
 }
 
+extern "C" int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples, const double *shift,
+                               int32_t save_every, double *hist_r, double *hist_i, double *infid, double *leak) {
+    int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift);
+    if (rc) return rc;
+    if (!hist_r || !hist_i) return fail(JQ_ERR_ARG, "jq_eval_forward: null history buffer");
+    if (save_every < 1 || h->P.nsteps % save_every != 0)     // src/evalobjgrad.jl:2797-2799
+        return fail(JQ_ERR_ARG, "nsteps must be divisible by saveEvery. nsteps=%lld, saveEvery=%d", (long long)h->P.nsteps, save_every);
+    if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024) return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory");
+    CU(cudaSetDevice(h->device));
+    const size_t ntraj = (size_t)nbatch * nsamples, len = (size_t)h->n * h->m;
+    const long long nsave = h->P.nsteps / save_every + 1;
+    const size_t n_pcof = (size_t)nbatch * npar, n_shift = shift ? (size_t)nsamples * h->n : 0, n_hist = ntraj * (size_t)nsave * len;
+    if ((rc = grow(&h->d_in, &h->cap_in, n_pcof + n_shift)) != 0) return rc;
+    if ((rc = grow(&h->d_out, &h->cap_out, 2 * n_hist)) != 0) return rc;
+    if ((rc = grow(&h->d_scal, &h->cap_traj, ntraj * 4)) != 0) return rc;
+    cudaStream_t st = h->stream;
+    double *d_pcof = h->d_in, *d_shift = shift ? h->d_in + n_pcof : nullptr;
+    CU(cudaMemcpyAsync(d_pcof, pcof, n_pcof * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (shift) CU(cudaMemcpyAsync(d_shift, shift, n_shift * sizeof(double), cudaMemcpyHostToDevice, st));
+    LaunchArgs A{};
+    A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = 0;
+    A.pcof = d_pcof; A.shift = d_shift; A.scal = h->d_scal; A.grad = nullptr; A.infidgrad = nullptr;
+    A.hist_r = h->d_out; A.hist_i = h->d_out + n_hist; A.save_every = save_every; A.nsave = nsave;
+    int ctas = 0, regs = 0;
+    size_t smem = 0;
+    CU(cudaEventRecord(h->ev0, st));
+    CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
+    CU(cudaEventRecord(h->ev1, st));
+    h->timed = true; h->last_kernel = 1; h->last_launches = 1; h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = 1;
+    CU(cudaMemcpyAsync(hist_r, A.hist_r, n_hist * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hist_i, A.hist_i, n_hist * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (infid || leak) {
+        std::vector<double> sc(ntraj * 4);
+        CU(cudaMemcpy(sc.data(), h->d_scal, sc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t t = 0; t < ntraj; ++t) { if (infid) infid[t] = sc[4 * t]; if (leak) leak[t] = sc[4 * t + 1]; }
+    }
+    return 0;
+}
+
 extern "C" int jq_traceobjgrad_batch(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
                                      const double *shift, const double *weights, int32_t evaladjoint, double *infid, double *leak,
                                      double *trace_infid, double *grad, double *infidgrad, double *leakgrad) {

@@ -24,6 +24,10 @@ struct LaunchArgs {
     double *scal;          // [ntraj][4]: infid, leak, trace_infid, spare
     double *grad;          // [ntraj][Npar] total gradient
     double *infidgrad;     // [ntraj][Npar] (objFuncType != 1) or nullptr
+    // forward-history output (generic kernel only): state after every save_every-th step, [ntraj][nsave][n*m]
+    double *hist_r, *hist_i;   // Re(psi) = vr, Im(psi) = -vi  (src/evalobjgrad.jl:679-680,750-751)
+    int save_every;
+    long long nsave;
 };
 
 // ---- generic kernel (jq_generic.cu): one CTA per trajectory, blocks in shared memory ----

@@ -1,7 +1,7 @@
 // Generic trajectory kernel: one CTA per trajectory, all n x m blocks in shared memory, operators as CSR rows
 // read through L1/L2.  Handles any operator sparsity (dense input is just CSR with full rows), any n*m that fits in
-// shared memory, and objFuncType 1/2/3.  It is the fallback for shapes the warp-slot kernel (jq_slot.cu) has no
-// instantiation for, and its independent cross-check in the tests.  The whole forward + backward time loop runs
+// shared memory, and objFuncType 1/2/3.  It is the fallback for shapes the register-resident kernels (jq_traj.cu) have
+// no instantiation for, their independent cross-check in the tests, and the kernel behind jq_eval_forward (state history).  The whole forward + backward time loop runs
 // inside the kernel; HBM is touched only for the launch inputs and the final outputs.
 //
 // Algorithm (reference lines): forward loop src/evalobjgrad.jl:698-753, infidelity :755-766, adjoint terminal
@@ -253,12 +253,19 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
 
         // ---------------- forward sweep ----------------
         double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
+        double *hr = A.hist_r ? A.hist_r + (size_t)traj * A.nsave * c.len : nullptr;
+        double *hi = A.hist_i ? A.hist_i + (size_t)traj * A.nsave * c.len : nullptr;
+        if (hr) FOR_E { hr[e] = c.vr[e]; hi[e] = -c.vi[e]; }
         for (long long step = 0; step < P.nsteps; ++step) {
             FOR_E pen += P.wdiag[i] * c.vr[e] * c.vr[e];                           // penalf2aTrap(vr)
             eval_controls(c, t, dt);
             state_step(c, dt);
             t = t + dt;
             FOR_E pen += P.wdiag[i] * (c.vr[e] * c.vr[e] + 2.0 * c.vi05[e] * c.vi05[e]);  // penalf2a(vr, vi05)
+            if (hr && (step + 1) % A.save_every == 0) {                                      // src/evalobjgrad.jl:2847-2849
+                const size_t o = (size_t)((step + 1) / A.save_every) * c.len;
+                FOR_E { hr[o + e] = c.vr[e]; hi[o + e] = -c.vi[e]; }
+            }
         }
         double re, im, pv[1] = {pen};
         block_sum(c, pv, 1);

@@ -62,22 +62,11 @@ def _csc(a):
     return np.array(colptr, dtype=np.int64), np.array(rowval, dtype=np.int64), np.array(nzval, dtype=np.float64)
 
 
-def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nthreads: int = 1):
-    """Run the oracle on a batch: pcof [nbatch, Npar] (or [Npar]), shifts [nsamples, n] or None.
-
-    Returns dict with objf, infid, leak, trace_infid  [nbatch, nsamples] and grad, infidgrad, leakgrad
-    [nbatch, nsamples, Npar] (infidgrad == grad and leakgrad == 0 for objFuncType 1, as in the reference).
-    """
-    lib = _lib()
-    pcof = np.ascontiguousarray(np.atleast_2d(np.asarray(pcof, dtype=np.float64)))
-    nbatch, Npar = pcof.shape
-    n, m, Nc = params.Ntot, params.N, params.Ncoupled
-    keep = []
-
+def _problem(params, keep):
     def ptr(a):
         keep.append(a)
         return a.ctypes.data_as(C.c_void_p)
-
+    n, m, Nc = params.Ntot, params.N, params.Ncoupled
     P = _Problem()
     P.n, P.m, P.Nc, P.Nfreq = n, m, Nc, params.Nfreq
     P.J, P.objFuncType, P.sparse = params.linear_solver.max_iter, params.objFuncType, int(bool(params.use_sparse))
@@ -94,6 +83,47 @@ def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nth
         P.H0 = ptr(_f(params.Hconst))
         P.Hsym = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hsym_ops]))
         P.Hanti = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hanti_ops]))
+    return P
+
+
+def oracle_forward_history(params, pcof, shift=None, save_every: int = 1):
+    """Forward sweep of ONE trajectory with state history.  Returns (hist [nsave, N, Ntot] complex as Julia's
+    Ntot x N x nsave read in C order, infid, leak)."""
+    lib = _lib()
+    keep = []
+    P = _problem(params, keep)
+    pcof = np.ascontiguousarray(pcof, dtype=np.float64)
+    nsave = params.nsteps // save_every + 1
+    hr = np.zeros((nsave, params.N, params.Ntot))
+    hi = np.zeros((nsave, params.N, params.Ntot))
+    out = np.zeros(2)
+    sh = None if shift is None else np.ascontiguousarray(shift, dtype=np.float64)
+    lib.jqo_forward_history.restype = C.c_int
+    rc = lib.jqo_forward_history(C.byref(P), C.c_int(len(pcof)), pcof.ctypes.data_as(C.c_void_p),
+                                 sh.ctypes.data_as(C.c_void_p) if sh is not None else None, C.c_int(save_every),
+                                 hr.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError("bad pcof length or nsteps not divisible by save_every")
+    return hr + 1j * hi, out[0], out[1]
+
+
+def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nthreads: int = 1):
+    """Run the oracle on a batch: pcof [nbatch, Npar] (or [Npar]), shifts [nsamples, n] or None.
+
+    Returns dict with objf, infid, leak, trace_infid  [nbatch, nsamples] and grad, infidgrad, leakgrad
+    [nbatch, nsamples, Npar] (infidgrad == grad and leakgrad == 0 for objFuncType 1, as in the reference).
+    """
+    lib = _lib()
+    pcof = np.ascontiguousarray(np.atleast_2d(np.asarray(pcof, dtype=np.float64)))
+    nbatch, Npar = pcof.shape
+    n, m, Nc = params.Ntot, params.N, params.Ncoupled
+    keep = []
+
+    def ptr(a):
+        keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+
+    P = _problem(params, keep)
     if shifts is not None:
         shifts = np.ascontiguousarray(np.atleast_2d(np.asarray(shifts, dtype=np.float64)))
         assert shifts.shape[1] == n

@@ -660,6 +660,39 @@ int jqo_traceobjgrad_batch(const jqo_problem *P, int Npar, int nbatch, const dou
     return 0;
 }
 
+/* Forward sweep with state history (eval_forward with saveEndOnly=false, src/evalobjgrad.jl:2727-2873, and the
+ * verbose=true history of traceobjgrad, :676-680,:748-752): hist_r/hist_i [nsteps/save_every + 1][n*m] = vr, -vi. */
+int jqo_forward_history(const jqo_problem *P, int Npar, const double *pcof, const double *shift, int save_every,
+                        double *hist_r, double *hist_i, double *out) {
+    if (P->Nc < 1 || Npar % (2 * P->Nc * P->Nfreq) != 0 || Npar < 3 * 2 * P->Nc) return -1;
+    if (save_every < 1 || P->nsteps % save_every != 0) return -2;
+    ws_t w;
+    ws_init(&w, P, Npar);
+    shift_h0(&w, shift, +1.0);
+    w.pcof = pcof;
+    int64_t len = (int64_t)w.n * w.m;
+    double dt = w.T / w.nsteps, t = 0.0, tinv = 1.0 / w.T, objfv = 0.0;
+    memcpy(w.vr, w.Uinit, sizeof(double) * len);
+    memset(w.vi, 0, sizeof(double) * len);
+    for (int64_t i = 0; i < len; i++) { hist_r[i] = w.vr[i]; hist_i[i] = -w.vi[i]; }
+    for (int64_t step = 1; step <= w.nsteps; step++) {
+        double forbidden0 = tinv * penalf2aTrap(&w, w.vr);
+        KS(&w, 0, t);
+        KS(&w, 1, t + 0.5 * dt);
+        KS(&w, 2, t + dt);
+        t = step_state(&w, t, w.vr, w.vi, w.vi05, dt);
+        objfv += dt * 0.5 * (forbidden0 + tinv * penalf2a(&w, w.vr, w.vi05));
+        if (step % save_every == 0) {
+            double *hr = hist_r + (step / save_every) * len, *hi = hist_i + (step / save_every) * len;
+            for (int64_t i = 0; i < len; i++) { hr[i] = w.vr[i]; hi[i] = -w.vi[i]; }
+        }
+    }
+    out[0] = 1.0 - tracefidabs2(&w, w.vr, w.vi);
+    out[1] = objfv;
+    ws_free(&w);
+    return 0;
+}
+
 int jqo_max_threads(void) {
     long nproc = sysconf(_SC_NPROCESSORS_ONLN);
     return nproc > 0 ? (int)nproc : 1;

@@ -200,3 +200,33 @@ def test_optimizer_glue_reduces_objective():
     wa.close()
     assert np.all(pc >= minC - 1e-15) and np.all(pc <= maxC + 1e-15)
     assert f1 < f0 - 1e-3 and len(p.objHist) >= 2 and p.objHist[-1] <= p.objHist[0]
+
+
+def test_forward_history_matches_oracle():
+    """jq_eval_forward / traceobjgrad(verbose=true, evaladjoint=false): state history Ntot x N x (nsteps/saveEvery + 1)
+    (src/evalobjgrad.jl:676-680, 748-752, 2797-2849)."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    from oracle import oracle_forward_history
+    cfg = configs.example("cnot2")
+    p = cfg.params
+    p.T, p.nsteps = 5.0, 600
+    pc = configs.synthetic_pcof(cfg, 2) * 50
+    wa = jq.Working_Arrays(p, cfg.nCoeff)
+    hist, infid, leak = wa.forward_history(pc, save_every=20)
+    assert hist.shape == (2, 1, 31, p.N, p.Ntot)
+    for b in range(2):
+        want, winf, wleak = oracle_forward_history(p, pc[b], save_every=20)
+        assert np.max(np.abs(hist[b, 0] - want)) < 1e-12
+        assert abs(infid[b, 0] - winf) < 1e-12 and abs(leak[b, 0] - wleak) <= 1e-10 * max(wleak, 1e-12)
+    # the columns stay orthonormal (unitarity of the propagation up to the scheme's error)
+    last = hist[0, 0, -1]                      # [N, Ntot]
+    assert np.allclose(last.conj() @ last.T, np.eye(p.N), atol=1e-6)
+    objfv, uhist, fid = jq.traceobjgrad(pc[0], p, wa, True, False)
+    assert uhist.shape == (p.Ntot, p.N, p.nsteps + 1) and np.array_equal(uhist[:, :, 0].real, p.Uinit)
+    assert abs(fid - (1 - infid[0, 0])) < 1e-14 and abs(objfv - (infid[0, 0] + leak[0, 0])) < 1e-14
+    uend = jq.eval_forward(pc[0], p, wa)
+    assert np.array_equal(uend, uhist[:, :, -1])
+    with pytest.raises(ValueError):
+        wa.forward_history(pc, save_every=7)
+    wa.close()
