@@ -236,6 +236,7 @@ def main():
     # ---- roofline of the dominant (trajectory) kernel
     flops_eval = alg_flops_per_eval(cfg.params, npar)
     peak = _lib.fp64_peak_tflops(local_rank)
+    peak3 = _lib.fp64_peak_tflops(local_rank, three_operand=True)
     achieved = flops_eval * B * nsamp / (kern_ms * 1e-3) / 1e12
     traffic = None                                  # DRAM bytes per launch from the committed ncu --set full capture
     try:
@@ -246,6 +247,7 @@ def main():
         pass
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": traffic, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_no_operand_reuse": peak3, "frac_of_peak_no_operand_reuse": achieved / peak3 if peak3 else None,
                 "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>"}[used_kernel],
                 "hbm_alg_bytes_per_launch": 8 * (B * npar + nsamp * cfg.params.Ntot + B * nsamp * (4 + npar))}
 

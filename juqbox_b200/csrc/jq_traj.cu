@@ -132,12 +132,23 @@ struct SlotLane {
     __device__ __forceinline__ int row(int e) const { return own[e / C]; }
     __device__ __forceinline__ int col(int e) const { return c0 + e % C; }
 
-    __device__ __forceinline__ double *exchange(const double (&x)[E]) {
-        double *b = buf + parity * (nlr * C);
+    __device__ __forceinline__ void sync_reset() { __syncwarp(); parity = 0; }
+    // Neighbour handle: for this layout the exchange buffer itself (neighbours are loaded entry by entry).
+    struct Nbr { const double *b; };
+    __device__ __forceinline__ void exchange(const double (&x)[E], Nbr &nb) {
+        double *b = buf + parity * (2 * nlr * C);
         parity ^= 1;
         UNROLL for (int k = 0; k < R; ++k) Xch<C>::st(b, own[k], nlr, &x[k * C]);
         __syncwarp();
-        return b;
+        nb.b = b;
+    }
+    // two blocks in one round (one __syncwarp)
+    __device__ __forceinline__ void exchange2(const double (&xa)[E], const double (&xb)[E], Nbr &na, Nbr &nb) {
+        double *b = buf + parity * (2 * nlr * C);
+        parity ^= 1;
+        UNROLL for (int k = 0; k < R; ++k) { Xch<C>::st(b, own[k], nlr, &xa[k * C]); Xch<C>::st(b + nlr * C, own[k], nlr, &xb[k * C]); }
+        __syncwarp();
+        na.b = b; nb.b = b + nlr * C;
     }
 
     // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
@@ -146,31 +157,34 @@ struct SlotLane {
         UNROLL for (int k = 0; k < R; ++k) UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int e = 0; e < WQ; ++e)
             sc.c[k][qq][e] = q[level][qq] * ha[k][qq][e];
     }
-    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
-        const double *b = exchange(x);
+    __device__ __forceinline__ void s_from(const SC &sc, const double (&)[E], const Nbr &nb, double (&t)[E]) const {
         UNROLL for (int k = 0; k < R; ++k) {
             UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = 0.0;
             UNROLL for (int qq = 0; qq < NC; ++qq)
                 UNROLL for (int e = 0; e < WQ; ++e) {
                     double xv[C];
-                    Xch<C>::ld(b, pos[k][qq][e], nlr, xv);
+                    Xch<C>::ld(nb.b, pos[k][qq][e], nlr, xv);
                     UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = fma(sc.c[k][qq][e], xv[c], t[k * C + c]);
                 }
         }
+    }
+    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
+        Nbr nb;
+        exchange(x, nb);
+        s_from(sc, x, nb, t);
     }
 
     // f(e, Ae, De) is called once per element with Ae[q] = (Hsym_q x)_e, De[q] = (Hanti_q x)_e: the per-control
     // partial products only live for one row at a time.
     template <bool WA, bool WD, class F>
-    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
-        const double *b = exchange(x);
+    __device__ __forceinline__ void each_from(const double (&)[E], const Nbr &nb, F f) const {
         UNROLL for (int k = 0; k < R; ++k) {
             double Ar[C][NC], Dr[C][NC];
             UNROLL for (int qq = 0; qq < NC; ++qq) {
                 UNROLL for (int c = 0; c < C; ++c) { Ar[c][qq] = 0.0; Dr[c][qq] = 0.0; }
                 UNROLL for (int e = 0; e < WQ; ++e) {
                     double xv[C];
-                    Xch<C>::ld(b, pos[k][qq][e], nlr, xv);
+                    Xch<C>::ld(nb.b, pos[k][qq][e], nlr, xv);
                     UNROLL for (int c = 0; c < C; ++c) {
                         if (WA) Ar[c][qq] = fma(hs[k][qq][e], xv[c], Ar[c][qq]);
                         if (WD) Dr[c][qq] = fma(ha[k][qq][e], xv[c], Dr[c][qq]);
@@ -179,6 +193,12 @@ struct SlotLane {
             }
             UNROLL for (int c = 0; c < C; ++c) f(k * C + c, Ar[c], Dr[c]);
         }
+    }
+    template <bool WA, bool WD, class F>
+    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
+        Nbr nb;
+        exchange(x, nb);
+        each_from<WA, WD>(x, nb, f);
     }
 };
 
@@ -223,29 +243,50 @@ struct FiberLane {
     __device__ __forceinline__ int row(int e) const { return row0 + e; }
     __device__ __forceinline__ int col(int) const { return colj; }
 
-    // Publish the fibre and fetch the two neighbour fibres of every remote control.
-    __device__ __forceinline__ void exchange(const double (&x)[E], double (&xn)[NC][2][R]) {
+    __device__ __forceinline__ void sync_reset() { if (REMOTE && XM == 0) { __syncwarp(); parity = 0; } }
+    // Neighbour handle: the two neighbour fibres of every remote control, in registers.
+    struct Nbr { double v[NC][2][R]; };
+    __device__ __forceinline__ void fetch(const double *b, const double (&x)[E], Nbr &nb) const {
+        UNROLL for (int qq = 0; qq < NC; ++qq)
+            if (!((LMASK >> qq) & 1)) {
+                if (XM == 0) {
+                    Xch<R>::ld(b, rpos[qq][0], 32, nb.v[qq][0]);
+                    Xch<R>::ld(b, rpos[qq][1], 32, nb.v[qq][1]);
+                } else {
+                    UNROLL for (int k = 0; k < R; ++k) {
+                        nb.v[qq][0][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
+                        nb.v[qq][1][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
+                    }
+                }
+            }
+    }
+    // Publish the fibre and fetch the neighbour fibres of every remote control.
+    __device__ __forceinline__ void exchange(const double (&x)[E], Nbr &nb) {
         if (!REMOTE) return;
         const double *b = buf;
         if (XM == 0) {
-            double *bw = buf + parity * (R * 32);
+            double *bw = buf + parity * (2 * R * 32);
             parity ^= 1;
             Xch<R>::st(bw, lane, 32, x);
             __syncwarp();
             b = bw;
         }
-        UNROLL for (int qq = 0; qq < NC; ++qq)
-            if (!((LMASK >> qq) & 1)) {
-                if (XM == 0) {
-                    Xch<R>::ld(b, rpos[qq][0], 32, xn[qq][0]);
-                    Xch<R>::ld(b, rpos[qq][1], 32, xn[qq][1]);
-                } else {
-                    UNROLL for (int k = 0; k < R; ++k) {
-                        xn[qq][0][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
-                        xn[qq][1][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
-                    }
-                }
-            }
+        fetch(b, x, nb);
+    }
+    // two blocks in one round (one __syncwarp, twice the independent work behind one exchange latency)
+    __device__ __forceinline__ void exchange2(const double (&xa)[E], const double (&xb)[E], Nbr &na, Nbr &nb) {
+        if (!REMOTE) return;
+        const double *b = buf;
+        if (XM == 0) {
+            double *bw = buf + parity * (2 * R * 32);
+            parity ^= 1;
+            Xch<R>::st(bw, lane, 32, xa);
+            Xch<R>::st(bw + R * 32, lane, 32, xb);
+            __syncwarp();
+            b = bw;
+        }
+        fetch(b, xa, na);
+        fetch(b + R * 32, xb, nb);
     }
 
     // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
@@ -266,9 +307,7 @@ struct FiberLane {
                 sc.r[qq][1] = q[level][qq] * (AS ? rhs[qq][1] : rha[qq][1]);
             }
     }
-    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
-        double xn[NC][2][R];
-        exchange(x, xn);
+    __device__ __forceinline__ void s_from(const SC &sc, const double (&x)[E], const Nbr &nb, double (&t)[E]) const {
         UNROLL for (int k = 0; k < R; ++k) {       // local part first: independent of the exchange
             double a = 0.0;
             if (k + 1 < R) a = sc.lu[k] * x[k + 1];
@@ -277,13 +316,16 @@ struct FiberLane {
         }
         UNROLL for (int qq = 0; qq < NC; ++qq)
             if (!((LMASK >> qq) & 1))
-                UNROLL for (int k = 0; k < R; ++k) t[k] = fma(sc.r[qq][1], xn[qq][1][k], fma(sc.r[qq][0], xn[qq][0][k], t[k]));
+                UNROLL for (int k = 0; k < R; ++k) t[k] = fma(sc.r[qq][1], nb.v[qq][1][k], fma(sc.r[qq][0], nb.v[qq][0][k], t[k]));
+    }
+    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
+        Nbr nb;
+        exchange(x, nb);
+        s_from(sc, x, nb, t);
     }
 
     template <bool WA, bool WD, class F>
-    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
-        double xn[NC][2][R];
-        exchange(x, xn);
+    __device__ __forceinline__ void each_from(const double (&x)[E], const Nbr &nb, F f) const {
         UNROLL for (int k = 0; k < R; ++k) {
             double Ae[NC], De[NC];
             UNROLL for (int qq = 0; qq < NC; ++qq) {
@@ -298,11 +340,11 @@ struct FiberLane {
                     }
                 } else {
                     if (AS) {
-                        lo = rhs[qq][0] * xn[qq][0][k];
-                        up = rhs[qq][1] * xn[qq][1][k];
+                        lo = rhs[qq][0] * nb.v[qq][0][k];
+                        up = rhs[qq][1] * nb.v[qq][1][k];
                     } else {
-                        if (WA) a = fma(rhs[qq][1], xn[qq][1][k], rhs[qq][0] * xn[qq][0][k]);
-                        if (WD) d = fma(rha[qq][1], xn[qq][1][k], rha[qq][0] * xn[qq][0][k]);
+                        if (WA) a = fma(rhs[qq][1], nb.v[qq][1][k], rhs[qq][0] * nb.v[qq][0][k]);
+                        if (WD) d = fma(rha[qq][1], nb.v[qq][1][k], rha[qq][0] * nb.v[qq][0][k]);
                     }
                 }
                 if (AS) { a = up + lo; d = up - lo; }
@@ -310,6 +352,12 @@ struct FiberLane {
             }
             f(k, Ae, De);
         }
+    }
+    template <bool WA, bool WD, class F>
+    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
+        Nbr nb;
+        exchange(x, nb);
+        each_from<WA, WD>(x, nb, f);
     }
 };
 
@@ -347,6 +395,7 @@ template <int JT, class LaneT>
 __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E], double (&v05)[LaneT::E]) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     double rhs[E], l1[E], s0u[E];
+    L.sync_reset();        // buffer parity restarts at 0: with compile-time J every exchange address is a constant offset
     L.template pass_each<true, true>(u, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
         double r = L.d0[e] * u[e], s = 0.0;
         UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], Ae[qq], r); s = fma(L.q[0][qq], De[qq], s); }
@@ -402,6 +451,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     constexpr int E = LaneT::E, NC = LaneT::NC;
     double rhs[E], s05n[E], Tb[NC][2];
     typename LaneT::SC sc;
+    L.sync_reset();
     L.s_prescale(0, sc);
     L.s_pass(sc, mu, rhs);
     UNROLL for (int qq = 0; qq < NC; ++qq) { Tb[qq][0] = 0.0; Tb[qq][1] = 0.0; }
@@ -465,6 +515,159 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) {
         const double t = group_sum(Tb[qq][a], GL, gbase_lane);
         if (writer) tred[qq * 5 + 3 + a] = t;
+    }
+    __syncwarp();
+}
+
+// Two Neumann solves advanced together: one exchange round serves both (src/linear_solvers.jl:94-106 twice).
+template <int JT, class LaneT>
+__device__ __forceinline__ void neumann2(LaneT &L, const typename LaneT::SC &sca, const typename LaneT::SC &scb, int J, double h,
+                                         double (&Ba)[LaneT::E], double (&Xa)[LaneT::E], double (&Bb)[LaneT::E], double (&Xb)[LaneT::E]) {
+    constexpr int E = LaneT::E;
+    UNROLL for (int e = 0; e < E; ++e) { Xa[e] = Ba[e]; Xb[e] = Bb[e]; }
+    double coeff = 1.0;
+    const int JJ = JT > 0 ? JT : J;
+#pragma unroll
+    for (int it = 0; it < JJ; ++it) {
+        typename LaneT::Nbr na, nb;
+        L.exchange2(Ba, Bb, na, nb);
+        double Ta[E], Tb[E];
+        L.s_from(sca, Ba, na, Ta);
+        L.s_from(scb, Bb, nb, Tb);
+        coeff *= 0.5 * h;
+        UNROLL for (int e = 0; e < E; ++e) { Ba[e] = Ta[e]; Xa[e] = fma(coeff, Ta[e], Xa[e]); Bb[e] = Tb[e]; Xb[e] = fma(coeff, Tb[e], Xb[e]); }
+    }
+}
+
+// One backward iteration with the state recomputation (src/StormerVerlet.jl:461-504, h < 0) and the adjoint step with
+// forcing (:255-303) advanced TOGETHER.  The state step and the adjoint step of the same iteration only meet through
+// the forcing and the gradient traces, so their products are paired round by round: 5 + 2J exchange rounds instead of
+// 2(5 + 2J), each with twice the independent work behind one exchange latency.  Two traces are taken in transposed
+// form, which is exact because Hanti is antisymmetric (checked by the planner):
+//   tr(vi05, Ha, li0) = -sum li0 .* (Ha vi05)      (Ha vi05 is a by-product of the state step's v05 product)
+//   tr(vr,   Ha, lr05) = -sum lr05 .* (Ha vr)      (Ha vr  is a by-product of the state step's last product)
+// Traces (src/evalobjgrad.jl:2578-2618) are left group-reduced in tred[q*5 + a], a as in adjoint_step.
+template <int JT, class LaneT>
+__device__ __forceinline__ void backward_step_fused(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E],
+                                                    double (&mu)[LaneT::E], double (&nu)[LaneT::E], double *tred, int GL,
+                                                    int gbase_lane, bool writer) {
+    constexpr int E = LaneT::E, NC = LaneT::NC;
+    double vr0[E], v05[E], rhsA[E], rhsB[E], s0u[E], s05n[E], l1[E], X[E];
+    double T4[NC], T5[NC];
+    UNROLL for (int qq = 0; qq < NC; ++qq) { T4[qq] = 0.0; T5[qq] = 0.0; }
+    UNROLL for (int e = 0; e < E; ++e) vr0[e] = u[e];
+    typename LaneT::SC scA, scB;
+    L.sync_reset();
+    // ---- round 1: K05 u, S0 u   |   S0 mu
+    L.s_prescale(0, scB);
+    {
+        typename LaneT::Nbr na, nb;
+        L.exchange2(u, mu, na, nb);
+        L.template each_from<true, true>(u, na, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
+            double r = L.d0[e] * u[e], s = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], Ae[qq], r); s = fma(L.q[0][qq], De[qq], s); }
+            rhsA[e] = r; s0u[e] = s;
+        });
+        L.s_from(scB, mu, nb, rhsB);
+    }
+    // ---- round 2: S05 v   |   K05 nu, S05 nu, tr(vr0, Hs, li0)
+    L.s_prescale(1, scA);
+    {
+        typename LaneT::Nbr na, nb;
+        L.exchange2(v, nu, na, nb);
+        double tv[E];
+        L.s_from(scA, v, na, tv);
+        UNROLL for (int e = 0; e < E; ++e) rhsA[e] += tv[e];
+        L.template each_from<true, true>(nu, nb, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
+            double kk = L.d0[e] * nu[e], s = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq) {
+                kk = fma(L.p[1][qq], Ae[qq], kk);
+                s = fma(L.q[1][qq], De[qq], s);
+                T4[qq] = fma(vr0[e], Ae[qq], T4[qq]);
+            }
+            rhsB[e] = fma(L.w[e], vr0[e], rhsB[e]) - kk;     // S0 mu + hr0 - K05 nu
+            s05n[e] = s;
+        });
+    }
+    // ---- first pair of solves: (I - h/2 S05) l1 = rhsA   |   (I - h/2 S0) k2 = rhsB
+    neumann2<JT>(L, scA, scB, J, h, rhsA, l1, rhsB, X);
+    UNROLL for (int e = 0; e < E; ++e) { v05[e] = fma(0.5 * h, l1[e], v[e]); X[e] = fma(0.5 * h, X[e], mu[e]); }   // X = lr05
+    // ---- round 3: K0 v05, K1 v05, S05 v05, -tr(li0, Ha, vi05)   |   K0 X, K1 X, S1 X, tr(vr0,Ha,X), tr(vi05,Hs,X)
+    double k1v[E], s05v[E], l2[E], r0[E], mu2[E];
+    {
+        typename LaneT::Nbr na, nb;
+        L.exchange2(v05, X, na, nb);
+        L.template each_from<true, true>(v05, na, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
+            double k0 = L.d0[e] * v05[e], k1 = k0, s = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq) {
+                k0 = fma(L.p[0][qq], Ae[qq], k0);
+                k1 = fma(L.p[2][qq], Ae[qq], k1);
+                s = fma(L.q[1][qq], De[qq], s);
+                T5[qq] = fma(-nu[e], De[qq], T5[qq]);        // tr(vi05, Ha, li0), transposed
+            }
+            k1v[e] = k1; s05v[e] = s;
+            u[e] = fma(0.5 * h, s0u[e] - k0, u[e]);          // u + (h/2) kappa1
+        });
+        double T1[NC], T2[NC];
+        UNROLL for (int qq = 0; qq < NC; ++qq) { T1[qq] = 0.0; T2[qq] = 0.0; }
+        L.template each_from<true, true>(X, nb, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
+            double k0 = L.d0[e] * X[e], k1 = k0, s = 0.0;
+            UNROLL for (int qq = 0; qq < NC; ++qq) {
+                k0 = fma(L.p[0][qq], Ae[qq], k0);
+                k1 = fma(L.p[2][qq], Ae[qq], k1);
+                s = fma(L.q[2][qq], De[qq], s);
+                T1[qq] = fma(vr0[e], De[qq], T1[qq]);
+                T2[qq] = fma(v05[e], Ae[qq], T2[qq]);
+            }
+            const double hi0 = L.w[e] * v05[e];
+            l2[e] = k0 + s05n[e] + hi0;                      // K0 X + S05 nu + hi0
+            r0[e] = s05n[e] + k1 + hi0;                      // S05 nu + K1 X + hi1
+            mu2[e] = fma(0.5 * h, s, X[e]);                  // X + (h/2) S1 X      (hr1 is added in round 5)
+        });
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            const double t1 = group_sum(T1[qq], GL, gbase_lane), t2 = group_sum(T2[qq], GL, gbase_lane);
+            if (writer) { tred[qq * 5 + 0] = t1; tred[qq * 5 + 1] = t2; }
+        }
+    }
+    // ---- round 4: S1 u'   |   S05 l2
+    L.s_prescale(2, scA);
+    L.s_prescale(1, scB);
+    {
+        typename LaneT::Nbr na, nb;
+        L.exchange2(u, l2, na, nb);
+        double ta[E], tb[E];
+        L.s_from(scA, u, na, ta);
+        L.s_from(scB, l2, nb, tb);
+        UNROLL for (int e = 0; e < E; ++e) { rhsA[e] = ta[e] - k1v[e]; rhsB[e] = fma(0.5 * h, tb[e], r0[e]); }
+    }
+    // ---- second pair of solves: (I - h/2 S1) kappa2 = rhsA   |   (I - h/2 S05) l1' = rhsB
+    double k2[E], l1b[E];
+    neumann2<JT>(L, scA, scB, J, h, rhsA, k2, rhsB, l1b);
+    UNROLL for (int e = 0; e < E; ++e) { u[e] = fma(0.5 * h, k2[e], u[e]); nu[e] = fma(0.5 * h, l2[e] + l1b[e], nu[e]); }
+    // ---- round 5: K05 u'', -tr(X, Ha, vr)   |   K05 nu', tr(vr,Hs,li), tr(vi05,Ha,li)
+    {
+        typename LaneT::Nbr na, nb;
+        L.exchange2(u, nu, na, nb);
+        double T3[NC];
+        UNROLL for (int qq = 0; qq < NC; ++qq) T3[qq] = 0.0;
+        L.template each_from<true, true>(u, na, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
+            double l2a = fma(L.d0[e], u[e], s05v[e]);
+            UNROLL for (int qq = 0; qq < NC; ++qq) { l2a = fma(L.p[1][qq], Ae[qq], l2a); T3[qq] = fma(-X[e], De[qq], T3[qq]); }
+            v[e] = fma(0.5 * h, l1[e] + l2a, v[e]);
+        });
+        L.template each_from<true, true>(nu, nb, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
+            double kk = L.d0[e] * nu[e];
+            UNROLL for (int qq = 0; qq < NC; ++qq) {
+                kk = fma(L.p[1][qq], Ae[qq], kk);
+                T4[qq] = fma(u[e], Ae[qq], T4[qq]);
+                T5[qq] = fma(v05[e], De[qq], T5[qq]);
+            }
+            mu[e] = fma(0.5 * h, fma(L.w[e], u[e], -kk), mu2[e]);      // + (h/2)(hr1 - K05 nu)
+        });
+        UNROLL for (int qq = 0; qq < NC; ++qq) {
+            const double t3 = group_sum(T3[qq], GL, gbase_lane), t4 = group_sum(T4[qq], GL, gbase_lane), t5 = group_sum(T5[qq], GL, gbase_lane);
+            if (writer) { tred[qq * 5 + 2] = t3; tred[qq * 5 + 3] = t4; tred[qq * 5 + 4] = t5; }
+        }
     }
     __syncwarp();
 }
@@ -566,7 +769,7 @@ __device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, con
 
 // OBJ = 1: objFuncType 2/3 — a second adjoint set without forcing gives the infidelity-only gradient
 // (src/evalobjgrad.jl:848-855, :905-918; step_no_forcing! src/StormerVerlet.jl:365-406).
-template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0>
+template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int FUSED = 0>
 __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     extern __shared__ double sm[];
@@ -701,9 +904,13 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         LOAD_LEVEL0();
         for (int ls = 0; ls < nst; ++ls) {
             LOAD_LEVELS(ls);
-            UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
-            state_step<JT>(L, J, dt, vr, vi, vi05);
-            adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
+            if constexpr (FUSED != 0) {
+                backward_step_fused<JT>(L, J, dt, vr, vi, lr, li, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
+            } else {
+                UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
+                state_step<JT>(L, J, dt, vr, vi, vi05);
+                adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
+            }
             grad_scatter<NC, UPL>(U, gsm, tred, tabb, tabph, tabk, ls, Nfreq);
             if constexpr (OBJ != 0) {
                 adjoint_step<JT, false>(L, J, dt, lrn, lin, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);
@@ -740,6 +947,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
 #define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
+#define FIBERF(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 256 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, 1>}   /* fused backward step */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, MINB>}
 const Inst kInst[] = {
@@ -750,6 +958,7 @@ const Inst kInst[] = {
     FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
     FIBERJ(4, 2, 1, 1, 4), FIBERJ(6, 1, 1, 2, 3), FIBERJ(3, 2, 1, 1, 5),
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
+    FIBERF(4, 2, 1, 1, 4), FIBERF(4, 2, 1, 1, 0), FIBERF(4, 3, 1, 1, 0),      // experiment: paired state/adjoint rounds, measured +-1%
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
@@ -834,7 +1043,7 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
     pl->NL = NL; pl->NLR = NL * R; pl->GL = NL; pl->GPT = m / C; pl->CPG = C;
     pl->ngroups = TRAJ_WARPS * (32 / NL);
     pl->TPC = pl->ngroups / pl->GPT;
-    pl->exch_per_unit = 2 * pl->NLR * C;
+    pl->exch_per_unit = 4 * pl->NLR * C;      // 2 parities x 2 blocks per round
     if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
     const int NLR = pl->NLR;
     std::vector<int> pos((size_t)NLR * Nc * WQ);
@@ -944,7 +1153,7 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     pl->NL = NL; pl->NLR = NL * R; pl->GL = GL; pl->GPT = GPT; pl->CPG = CPG;
     pl->ngroups = TRAJ_WARPS * (32 / GL);
     pl->TPC = pl->ngroups / GPT;
-    pl->exch_per_unit = 2 * R * 32;
+    pl->exch_per_unit = 4 * R * 32;           // 2 parities x 2 fibres per round
     if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
     const int per = Nc * (4 * (R - 1) + 4);
     std::vector<int> pi((size_t)NL * Nc * 2, 0);

@@ -31,6 +31,28 @@ __global__ void dfma_ilp(double *out, long long *cyc, int iters, double a, doubl
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
+// DFMA with three distinct, changing register operands (no operand reuse): register-file bandwidth test
+template <int ILP>
+__global__ void dfma_3op(double *out, long long *cyc, int iters) {
+    double x[ILP], y[ILP], z[ILP];
+    for (int k = 0; k < ILP; ++k) { x[k] = threadIdx.x * 1e-3 + k; y[k] = 0.999 + 1e-6 * k; z[k] = 1.0 - 1e-7 * k; }
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < ILP; ++k) {
+                x[k] = fma(y[k], z[(k + 1) % ILP], x[k]);
+                y[k] = fma(z[k], x[(k + 3) % ILP], y[k]);
+                z[k] = fma(x[k], y[(k + 5) % ILP], z[k]);
+            }
+    }
+    long long t1 = clock64();
+    double s = 0;
+    for (int k = 0; k < ILP; ++k) s += x[k] + y[k] + z[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
 __global__ void shfl_chain(double *out, long long *cyc, int iters) {
     double x = threadIdx.x;
     long long t0 = clock64();
@@ -74,5 +96,10 @@ int main() {
     printf("1 SM, %d warps x ILP %d: %.2f cycles per warp-DFMA per SMSP-warp (%.1f%% of 2-cycle issue)\n", WARPS, ILP,         \
            (double)h / (iters * 8.0 * ILP), 100.0 * 2.0 * ((WARPS + 3) / 4) / ((double)h / (iters * 8.0 * ILP)));
     RUN(1, 4) RUN(2, 4) RUN(4, 4) RUN(8, 4) RUN(1, 8) RUN(2, 8) RUN(4, 8) RUN(1, 16) RUN(2, 16)
+#define RUN3(ILP, WARPS)                                                                                       \
+    dfma_3op<ILP><<<1, 32 * WARPS>>>(out, cyc, 1024); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);             \
+    printf("3-operand DFMA, %d warps x ILP %d: %.2f cycles per warp-DFMA per scheduler\n", WARPS, ILP,               \
+           (double)h / (1024 * 4.0 * 3 * ILP) / ((WARPS + 3) / 4));
+    RUN3(8, 4) RUN3(8, 8) RUN3(4, 8) RUN3(8, 16)
     return 0;
 }
