@@ -230,3 +230,42 @@ def test_forward_history_matches_oracle():
     with pytest.raises(ValueError):
         wa.forward_history(pc, save_every=7)
     wa.close()
+
+
+def test_c_abi_error_paths_and_update_target():
+    """Error behaviour of the boundary (src/evalobjgrad.jl:604-606, src/bsplines.jl:178-181, :2797-2799) and
+    change_target! (src/evalobjgrad.jl:1492-1505) followed by jq_update_target."""
+    import ctypes as C
+    import juqbox_b200 as jq
+    from juqbox_b200 import _lib, configs
+    from oracle import oracle_traceobjgrad
+    cfg, _ = golden_config("swap02")
+    p = cfg.params
+    wa = jq.Working_Arrays(p, len(cfg.pcof0))
+    lib = _lib.load()
+    pc = np.ascontiguousarray(cfg.pcof0)
+    null = C.c_void_p()
+    # nsamples > 1 without shifts, zero batch, bad kernel id, pcof length not a multiple of 2*Nc*Nfreq
+    assert lib.jq_traceobjgrad_batch(wa._handle, 1, pc.ctypes.data_as(C.c_void_p), len(pc), 3, null, null, 1, null, null, null, null, null, null) == -1
+    assert "nsamples" in _lib.last_error()
+    assert lib.jq_traceobjgrad_batch(wa._handle, 0, pc.ctypes.data_as(C.c_void_p), len(pc), 1, null, null, 1, null, null, null, null, null, null) == -1
+    assert lib.jq_set_kernel(wa._handle, 9) == -1
+    assert lib.jq_traceobjgrad_batch(wa._handle, 1, pc.ctypes.data_as(C.c_void_p), 38, 1, null, null, 1, null, null, null, null, null, null) == -2
+    with pytest.raises(ValueError):
+        wa.evaluate(np.zeros(14))               # 14 % (2*Nc) == 0 but not a multiple of 2*Nc*Nfreq
+    with pytest.raises(ValueError):
+        jq.Working_Arrays(p, 10)
+    # a handle survives errors; all-NULL outputs are allowed
+    assert lib.jq_traceobjgrad_batch(wa._handle, 1, pc.ctypes.data_as(C.c_void_p), len(pc), 1, null, null, 1, null, null, null, null, null, null) == 0
+    before = wa.evaluate(pc)
+    # change the target: swap two columns of the target unitary
+    newU = (p.Utarget_r + 1j * p.Utarget_i)[:, [1, 0, 2]]
+    jq.change_target(p, newU)
+    wa.update_target()
+    after = wa.evaluate(pc)
+    want = oracle_traceobjgrad(p, pc)
+    assert abs(after["infid"][0, 0] - want["infid"][0, 0]) < 1e-12 and abs(after["infid"][0, 0] - before["infid"][0, 0]) > 1e-3
+    assert _rel(after["grad"][0, 0], want["grad"][0, 0]) < TOL
+    assert after["leak"][0, 0] == before["leak"][0, 0]          # the guard-level integral does not depend on the target
+    wa.close()
+    wa.close()                                   # idempotent
