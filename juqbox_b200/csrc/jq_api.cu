@@ -380,18 +380,29 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = evaladjoint ? 1 : 0;
     A.pcof = pcof; A.shift = shift; A.scal = h->d_scal; A.grad = h->d_grad; A.infidgrad = h->P.objFuncType != 1 ? h->d_igrad : nullptr;
 
+    // candidates in order of preference; a register-resident kernel whose shared-memory layout does not fit
+    // (cudaErrorInvalidConfiguration, e.g. very long pcof vectors) hands over to the next one in automatic mode
+    TrajPlan *cands[2] = {nullptr, nullptr};
+    int ncand = 0;
+    if (h->kernel_pref == 3 || (h->kernel_pref == 0 && h->fiber)) cands[ncand++] = h->fiber;
+    if (h->kernel_pref == 2 || (h->kernel_pref == 0 && h->slot)) cands[ncand++] = h->slot;
     TrajPlan *plan = nullptr;
-    if (h->kernel_pref == 3 || (h->kernel_pref == 0 && h->fiber)) plan = h->fiber;
-    else if (h->kernel_pref == 2 || (h->kernel_pref == 0 && h->slot)) plan = h->slot;
-    const bool use_slot = plan != nullptr;
     int ctas = 0, regs = 0, tpc = 1;
     size_t smem = 0;
     CU(cudaEventRecord(h->ev0, st));
-    if (use_slot) {
-        CU(jq_traj_launch(plan, h->P, A, st, &ctas, &regs, &smem, &tpc));
-    } else {
+    for (int i = 0; i < ncand && !plan; ++i) {
+        cudaError_t e = jq_traj_launch(cands[i], h->P, A, st, &ctas, &regs, &smem, &tpc);
+        if (e == cudaSuccess) { plan = cands[i]; break; }
+        if (e != cudaErrorInvalidConfiguration || h->kernel_pref != 0)
+            return fail(JQ_ERR_CUDA, "trajectory kernel launch failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    const bool use_slot = plan != nullptr;
+    if (!use_slot) {
+        if (h->kernel_pref > 1) return fail(JQ_ERR_ARG, "requested kernel is not available for this problem");
         if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024)
             return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory (n*m = %d)", h->n * h->m);
+        tpc = 1;
         CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
     }
     CU(cudaEventRecord(h->ev1, st));

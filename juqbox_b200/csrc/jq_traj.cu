@@ -1225,6 +1225,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     S.o_gsm2 = take(P.objFuncType != 1 ? pl->ngroups * A.Npar : 0);
     size_t bytes = (size_t)o * sizeof(double);
     if (const char *pad = getenv("JQ_SMEM_PAD_KB")) bytes += (size_t)atoi(pad) * 1024;   // experiments: throttle CTAs/SM
+    if (bytes > 227 * 1024) return cudaErrorInvalidConfiguration;   // e.g. very long pcof vectors: the caller falls back
     cudaError_t e = cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;

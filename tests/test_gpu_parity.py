@@ -269,3 +269,25 @@ def test_c_abi_error_paths_and_update_target():
     assert after["leak"][0, 0] == before["leak"][0, 0]          # the guard-level integral does not depend on the target
     wa.close()
     wa.close()                                   # idempotent
+
+
+def test_long_pcof_falls_back_when_shared_memory_does_not_fit():
+    """Very long coefficient vectors (D1 = 200 knots) overflow the per-CTA gradient windows of the register-resident
+    kernels; automatic mode must hand over to a kernel that fits and still match the oracle."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    from oracle import oracle_traceobjgrad
+    cfg = configs.example("risk_neutral")
+    p = cfg.params
+    p.T, p.nsteps = 40.0, 1200
+    D1 = 200
+    npar = 2 * p.Ncoupled * p.Nfreq * D1
+    pc = (np.random.default_rng(3).random((2, npar)) - 0.5) * 0.02
+    wa = jq.Working_Arrays(p, npar)
+    r = wa.evaluate(pc)
+    used = wa.last_kernel
+    o = oracle_traceobjgrad(p, pc)
+    wa.close()
+    assert used in (1, 2)
+    for b in range(2):
+        assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL and abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12
