@@ -690,7 +690,7 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
     }
     __syncthreads();
     const double width = 3.0 * dtknot;
-    for (int idx = threadIdx.x; idx < npts * (NC * Nfreq + 1); idx += TRAJ_THREADS) {
+    for (int idx = threadIdx.x; idx < npts * (NC * Nfreq + 1); idx += blockDim.x) {
         const int i = idx / (NC * Nfreq + 1), j = idx % (NC * Nfreq + 1);
         const double tt = times[i];
         if (j == NC * Nfreq) {             // src/bsplines.jl:224-253
@@ -713,7 +713,7 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
     }
     __syncthreads();
     const double *pcof = sm + S.o_pcof;
-    for (int idx = threadIdx.x; idx < npts * S.TPC * NC; idx += TRAJ_THREADS) {
+    for (int idx = threadIdx.x; idx < npts * S.TPC * NC; idx += blockDim.x) {
         const int i = idx / (S.TPC * NC), rem = idx % (S.TPC * NC), tr = rem / NC, qq = rem % NC;
         const int k = tabk[i];
         const double b0 = tabb[3 * i], b1 = tabb[3 * i + 1], b2 = tabb[3 * i + 2];
@@ -801,11 +801,11 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         L.w[e] = ok[e] ? S.plan_w[r] * tinv : 0.0;
     }
     // stage this CTA's pcof vectors and zero the per-group gradient accumulators
-    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += TRAJ_THREADS) {
+    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += blockDim.x) {
         const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
         sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * Npar + k] : 0.0;
     }
-    for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += TRAJ_THREADS) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
+    for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += blockDim.x) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
 
     double vr[E], vi[E], vi05[E];
     UNROLL for (int e = 0; e < E; ++e) {
@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
     }
     __syncthreads();
     // total gradient of each resident trajectory = dt * sum of its groups' partial gradients, in group order
-    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += TRAJ_THREADS) {
+    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += blockDim.x) {
         const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
         if (tg >= A.ntraj) continue;
         double gs = 0.0;
@@ -1204,38 +1204,50 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     if (!inst) return cudaErrorNotSupported;
     TrajParams S{};
     S.P = P; S.A = A;
-    S.NL = pl->NL; S.NLR = pl->NLR; S.GL = pl->GL; S.GPT = pl->GPT; S.TPC = pl->TPC; S.ngroups = pl->ngroups; S.CPG = pl->CPG;
+    S.NL = pl->NL; S.NLR = pl->NLR; S.GL = pl->GL; S.GPT = pl->GPT; S.CPG = pl->CPG;
     S.plan_i = pl->d_i; S.plan_d = pl->d_d; S.plan_d0 = pl->d_d0; S.plan_w = pl->d_w;
     S.exch_per_unit = pl->exch_per_unit;
-    const int npts = 2 * TRAJ_CH + 1, NC = pl->NC;
-    int o = 0;
-    auto take = [&](int cnt) { int at = o; o += (cnt + 1) & ~1; return at; };   // keep 16-byte alignment
-    S.o_exch = take(pl->exch_per_unit * (pl->kind == 2 ? pl->ngroups : TRAJ_WARPS));
     S.NparS = A.Npar | 1;
     S.GPW = 32 / pl->GL;
-    S.o_pcof = take(pl->TPC * S.NparS);
-    S.o_gsm = take(pl->ngroups * A.Npar);
-    S.o_times = take(npts);
-    S.o_tabb = take(3 * npts);
-    S.o_tabph = take(2 * npts * NC * P.Nfreq);
-    S.o_tabpq = take(npts * pl->TPC * 2 * NC);
-    S.o_red = take(pl->ngroups * 4);
-    S.o_tabk = take((npts + 1) / 2);
-    S.o_tred = take(pl->ngroups * NC * 5);
-    S.o_gsm2 = take(P.objFuncType != 1 ? pl->ngroups * A.Npar : 0);
-    size_t bytes = (size_t)o * sizeof(double);
+    const int npts = 2 * TRAJ_CH + 1, NC = pl->NC;
+    // warps per CTA: 4 normally; fewer when the per-CTA gradient windows / pcof staging of very long coefficient
+    // vectors would not fit in shared memory (the kernel only uses blockDim.x and the counts below)
+    int nw = TRAJ_WARPS, TPC = 0, ngroups = 0;
+    size_t bytes = 0;
+    for (; nw >= 1; nw >>= 1) {
+        ngroups = nw * S.GPW;
+        TPC = ngroups / pl->GPT;
+        if (TPC < 1) return cudaErrorInvalidConfiguration;
+        int o = 0;
+        auto take = [&](int cnt) { int at = o; o += (cnt + 1) & ~1; return at; };   // keep 16-byte alignment
+        S.o_exch = take(pl->exch_per_unit * (pl->kind == 2 ? ngroups : nw));
+        S.o_pcof = take(TPC * S.NparS);
+        S.o_gsm = take(ngroups * A.Npar);
+        S.o_times = take(npts);
+        S.o_tabb = take(3 * npts);
+        S.o_tabph = take(2 * npts * NC * P.Nfreq);
+        S.o_tabpq = take(npts * TPC * 2 * NC);
+        S.o_red = take(ngroups * 4);
+        S.o_tabk = take((npts + 1) / 2);
+        S.o_tred = take(ngroups * NC * 5);
+        S.o_gsm2 = take(P.objFuncType != 1 ? ngroups * A.Npar : 0);
+        bytes = (size_t)o * sizeof(double);
+        if (bytes <= 227 * 1024) break;
+    }
+    if (nw < 1) return cudaErrorInvalidConfiguration;       // does not fit even with one warp per CTA: caller falls back
+    S.TPC = TPC; S.ngroups = ngroups;
     if (const char *pad = getenv("JQ_SMEM_PAD_KB")) bytes += (size_t)atoi(pad) * 1024;   // experiments: throttle CTAs/SM
-    if (bytes > 227 * 1024) return cudaErrorInvalidConfiguration;   // e.g. very long pcof vectors: the caller falls back
+    if (bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, inst->fn);
     if (e != cudaSuccess) return e;
-    const int grid = (A.ntraj + pl->TPC - 1) / pl->TPC;
-    inst->fn<<<grid, TRAJ_THREADS, bytes, st>>>(S);
+    const int grid = (A.ntraj + TPC - 1) / TPC;
+    inst->fn<<<grid, nw * 32, bytes, st>>>(S);
     if (nctas) *nctas = grid;
     if (regs) *regs = fa.numRegs;
     if (smem) *smem = bytes;
-    if (traj_per_cta) *traj_per_cta = pl->TPC;
+    if (traj_per_cta) *traj_per_cta = TPC;
     return cudaGetLastError();
 }
