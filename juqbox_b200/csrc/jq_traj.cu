@@ -6,20 +6,23 @@
 //  SlotLane<R,C,NC,WQ>  (kernel id 2) generic sparse rows.  A group = NL lanes; lane l owns rows l, l+NL, .. (R rows)
 //      and C columns.  Every row keeps per control <= WQ entries (neighbour position, Hsym value, Hanti value); one
 //      product pass stores the lane's elements to the group's exchange buffer and loads every neighbour.
-//  FiberLane<R,NC,LMASK> (kernel id 3) Kronecker ladder structure.  A lane owns a whole fibre of R consecutive rows
+//  FiberLane<R,NC,LMASK,AS,XM> (kernel id 3) Kronecker ladder structure.  A lane owns a whole fibre of R consecutive rows
 //      (the levels of the fastest subsystem) of ONE column.  Controls in LMASK couple only rows inside a fibre
 //      (tridiagonal, coefficients in registers, no memory traffic at all); the other controls couple whole fibres
 //      with a fibre-uniform coefficient, so a pass exchanges one R-vector per neighbour fibre instead of one load
 //      per nonzero.  Single-subsystem problems (n = R) never touch shared memory inside the time loops.
 //
-// Common structure.  4 warps per CTA; a group of GL lanes (power of two <= 32) covers (part of) one trajectory,
-// GPT groups per trajectory, TPC trajectories per CTA.  Columns never couple inside the time loops, so products
-// only need __syncwarp; groups meet through shared memory + __syncthreads once per CH-step chunk (control table),
-// at the infidelity between the sweeps and at the final gradient sum.
+// Common structure.  Up to 4 warps per CTA (fewer only when very long pcof vectors would overflow shared memory); a
+// group of GL lanes (a power of two, or m lanes for single-fibre columns) covers (part of) one trajectory, GPT groups
+// per trajectory, TPC trajectories per CTA.  Columns never couple inside the time loops, so products only need
+// __syncwarp; groups meet through shared memory + __syncthreads once per CH-step chunk (control table), at the
+// infidelity between the sweeps and at the final gradient sum.
 //   pass(x):  A_q = Hsym_q x and/or D_q = Hanti_q x ;  K(t)x = h0.*x + sum_q p_q(t) A_q ;  S(t)x = sum_q q_q(t) D_q
 // The A_q, D_q of the adjoint passes are exactly what the gradient traces need (tr(A'HC) = sum A.*(HC)), so the
 // gradient costs no extra products.  Control table: every CH steps all threads fill knot index, the three B-spline
 // values and cos/sin of every carrier at the 2CH+1 time points, then p_q, q_q for every resident trajectory.
+// Template switches: UPL gradient-scatter roles per lane, MINB register cap, JT compile-time number of Neumann terms,
+// OBJ second adjoint set (objFuncType 2/3), FUSED state and adjoint step advanced in paired rounds (experiment).
 //
 // Reference lines: forward loop src/evalobjgrad.jl:698-753, infidelity :755-766, adjoint init :810-844/:2026-2042,
 // backward loop :859-921, steppers src/StormerVerlet.jl:255-303,:461-504, Neumann src/linear_solvers.jl:94-106,
@@ -940,7 +943,8 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
 }
 
 typedef void (*traj_kernel_t)(const TrajParams);
-// variant (experiments, env JQ_TRAJ_VARIANT): bit 0 = warp-shuffle exchange, bit 1 = 3 CTAs/SM register cap
+// variant: 0 default, 16 general Hanti, 32+J compile-time J, 64 objFuncType 2/3; experiments selectable with the env
+// variable JQ_TRAJ_VARIANT: 1 warp-shuffle exchange, 2 three CTAs/SM register cap, 256(+J) paired state/adjoint rounds
 struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 #define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
