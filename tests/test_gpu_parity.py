@@ -66,13 +66,15 @@ def test_traceobjgrad_dropin_tuple(kernel):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("name", ["rabi", "cnot1", "cnot2", "risk_neutral"])
+@pytest.mark.parametrize("name", ["rabi", "cnot1", "cnot2", "risk_neutral", "cnot3"])
 def test_example_configs_batch_vs_oracle(name, kernel):
     """BASELINE configs on seeded synthetic pcof batches (no reference golden exists for these: oracle is the pin)."""
     from juqbox_b200 import configs
     from oracle import oracle_traceobjgrad
     cfg = configs.example(name)
-    nb = 5
+    if name == "cnot3" and kernel == 1:
+        pytest.skip("generic kernel on the 31325-step cnot3 example: covered by the cnot3 golden")
+    nb = 5 if name != "cnot3" else 2
     pc = configs.synthetic_pcof(cfg, nb)
     pc[-1] = np.random.default_rng(7).uniform(-1, 1, cfg.nCoeff) * cfg.maxpar[0]     # full-amplitude stress vector
     shifts = configs.noise_shift(cfg.params.Ntot, cfg.nodes) if name == "risk_neutral" else None
