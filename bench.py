@@ -114,7 +114,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     args = ap.parse_args()
-    assert args.warmup >= 3 or args.impl == "reference", "timing rules: W >= 3"
+    if args.impl != "reference" and args.warmup < 3:
+        args.warmup = 3          # timing rules: at least 3 warm-up steps; the JSON line reports the value actually used
+    args.steps = max(1, args.steps)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
