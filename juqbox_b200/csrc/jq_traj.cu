@@ -947,6 +947,7 @@ typedef void (*traj_kernel_t)(const TrajParams);
 // variable JQ_TRAJ_VARIANT: 1 warp-shuffle exchange, 2 three CTAs/SM register cap, 256(+J) paired state/adjoint rounds
 struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 #define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
+#define SLOTO(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 64, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
 #define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
@@ -957,6 +958,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
 const Inst kInst[] = {
     SLOT(1, 2, 1, 2), SLOT(1, 3, 1, 2), SLOT(1, 4, 1, 2), SLOT(1, 4, 2, 2), SLOT(1, 2, 2, 2),
     SLOT(2, 2, 3, 2), SLOT(3, 1, 3, 2), SLOT(1, 1, 1, 2), SLOT(1, 1, 2, 2),
+    SLOTO(1, 4, 2, 2), SLOTO(1, 3, 1, 2), SLOTO(1, 4, 1, 2), SLOTO(1, 2, 1, 2),
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
@@ -1010,7 +1012,6 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
-    if (P.objFuncType != 1) return no("objFuncType != 1 uses the generic kernel (second adjoint set)");
     if (n > 128) return no("n > 128");
     std::vector<double> d0;
     if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
@@ -1038,9 +1039,10 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
     const int R = (n + NL - 1) / NL;
     int C = 1;
     for (int c = 1; c <= 4; ++c) if (m % c == 0 && R * c <= 4) C = c;
-    const Inst *inst = find_inst(2, R, C, Nc, WQ, 0, 1);
-    if (!inst && C > 1) { for (int c = C - 1; c >= 1 && !inst; --c) if (m % c == 0) { inst = find_inst(2, R, c, Nc, WQ, 0, 1); if (inst) C = c; } }
-    if (!inst) return no("no slot instantiation for this (rows per lane, columns per lane, controls)");
+    const int var = P.objFuncType != 1 ? 64 : 0;
+    const Inst *inst = find_inst(2, R, C, Nc, WQ, 0, 1, var);
+    if (!inst && C > 1) { for (int c = C - 1; c >= 1 && !inst; --c) if (m % c == 0) { inst = find_inst(2, R, c, Nc, WQ, 0, 1, var); if (inst) C = c; } }
+    if (!inst) return no("no slot instantiation for this (rows per lane, columns per lane, controls, objFuncType)");
 
     TrajPlan *pl = new TrajPlan();
     pl->kind = 2; pl->R = R; pl->C = C; pl->NC = Nc; pl->WQ = WQ; pl->LMASK = 0; pl->UPL = 1; pl->AS = 1;

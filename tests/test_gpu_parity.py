@@ -157,7 +157,7 @@ def test_full_size_properties_cnot2():
     wa.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 3])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 @pytest.mark.parametrize("name", ["cnot2", "risk_neutral", "cnot1"])
 def test_objfunctype3_second_adjoint_vs_oracle(name, kernel):
     """objFuncType = 3 (leak as inequality constraint): infidelity-only gradient from the adjoint set without forcing
