@@ -377,6 +377,27 @@ __device__ __forceinline__ double group_sum(double x, int GL, int base) {
     return s;
 }
 
+// The same for N values at once, ROUNDS OUTER / VALUES INNER: the N shuffles of a round are independent and pipeline,
+// so the dependent chain is log2(GL) shuffle latencies in total instead of N * log2(GL) (measured: the value-by-value
+// form was 22% of all stall samples of the kernel).
+template <int N>
+__device__ __forceinline__ void group_sum_n(double (&v)[N], int GL, int base) {
+    if ((GL & (GL - 1)) == 0) {
+        for (int o = 1; o < GL; o <<= 1) {
+            double r[N];
+            UNROLL for (int i = 0; i < N; ++i) r[i] = __shfl_xor_sync(0xffffffffu, v[i], o);
+            UNROLL for (int i = 0; i < N; ++i) v[i] += r[i];
+        }
+        return;
+    }
+    double s[N];
+    UNROLL for (int i = 0; i < N; ++i) s[i] = 0.0;
+    for (int j = 0; j < GL; ++j) {
+        UNROLL for (int i = 0; i < N; ++i) s[i] += __shfl_sync(0xffffffffu, v[i], base + j);
+    }
+    UNROLL for (int i = 0; i < N; ++i) v[i] = s[i];
+}
+
 // X = sum_{j<=J} (h/2)^j S^j B   (src/linear_solvers.jl:94-106); B is consumed.  `sc` = S(level) prescaled.
 template <int JT, class LaneT>
 __device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
@@ -492,10 +513,10 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
             mu2[e] = fma(0.5 * h, FORCING ? fma(L.w[e], vr[e], s) : s, mu[e]);     // X + (h/2)(S1 X + hr1)
         });
         // the three traces that only involve lr05 = X are complete: reduce them now, overlapped with the next products
-        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) {
-            const double t = group_sum(Ta[qq][a], GL, gbase_lane);
-            if (writer) tred[qq * 5 + a] = t;
-        }
+        double tv3[NC * 3];
+        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tv3[qq * 3 + a] = Ta[qq][a];
+        group_sum_n(tv3, GL, gbase_lane);
+        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tred[qq * 5 + a] = tv3[qq * 3 + a]; }
     }
     L.s_prescale(1, sc);
     {
@@ -515,9 +536,11 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         }
         mu[e] = fma(-0.5 * h, kk, mu2[e]);                   // mu + (h/2) kappa1, kappa1 = S1 X - K05 nu + hr1
     });
-    UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) {
-        const double t = group_sum(Tb[qq][a], GL, gbase_lane);
-        if (writer) tred[qq * 5 + 3 + a] = t;
+    {
+        double tv2[NC * 2];
+        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tv2[qq * 2 + a] = Tb[qq][a];
+        group_sum_n(tv2, GL, gbase_lane);
+        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tred[qq * 5 + 3 + a] = tv2[qq * 2 + a]; }
     }
     __syncwarp();
 }
@@ -627,10 +650,10 @@ __device__ __forceinline__ void backward_step_fused(LaneT &L, int J, double h, d
             r0[e] = s05n[e] + k1 + hi0;                      // S05 nu + K1 X + hi1
             mu2[e] = fma(0.5 * h, s, X[e]);                  // X + (h/2) S1 X      (hr1 is added in round 5)
         });
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            const double t1 = group_sum(T1[qq], GL, gbase_lane), t2 = group_sum(T2[qq], GL, gbase_lane);
-            if (writer) { tred[qq * 5 + 0] = t1; tred[qq * 5 + 1] = t2; }
-        }
+        double tv[NC * 2];
+        UNROLL for (int qq = 0; qq < NC; ++qq) { tv[2 * qq] = T1[qq]; tv[2 * qq + 1] = T2[qq]; }
+        group_sum_n(tv, GL, gbase_lane);
+        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) { tred[qq * 5 + 0] = tv[2 * qq]; tred[qq * 5 + 1] = tv[2 * qq + 1]; } }
     }
     // ---- round 4: S1 u'   |   S05 l2
     L.s_prescale(2, scA);
@@ -667,10 +690,10 @@ __device__ __forceinline__ void backward_step_fused(LaneT &L, int J, double h, d
             }
             mu[e] = fma(0.5 * h, fma(L.w[e], u[e], -kk), mu2[e]);      // + (h/2)(hr1 - K05 nu)
         });
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            const double t3 = group_sum(T3[qq], GL, gbase_lane), t4 = group_sum(T4[qq], GL, gbase_lane), t5 = group_sum(T5[qq], GL, gbase_lane);
-            if (writer) { tred[qq * 5 + 2] = t3; tred[qq * 5 + 3] = t4; tred[qq * 5 + 4] = t5; }
-        }
+        double tv[NC * 3];
+        UNROLL for (int qq = 0; qq < NC; ++qq) { tv[3 * qq] = T3[qq]; tv[3 * qq + 1] = T4[qq]; tv[3 * qq + 2] = T5[qq]; }
+        group_sum_n(tv, GL, gbase_lane);
+        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) { tred[qq * 5 + 2] = tv[3 * qq]; tred[qq * 5 + 3] = tv[3 * qq + 1]; tred[qq * 5 + 4] = tv[3 * qq + 2]; } }
     }
     __syncwarp();
 }
@@ -852,7 +875,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
             re += vr[e] * tr_ - vi[e] * ti_;
             im += vr[e] * ti_ + vi[e] * tr_;
         }
-        re = group_sum(re, GL, gbase_lane); im = group_sum(im, GL, gbase_lane); pen = group_sum(pen, GL, gbase_lane);
+        double rip[3] = {re, im, pen};
+        group_sum_n(rip, GL, gbase_lane);
+        re = rip[0]; im = rip[1]; pen = rip[2];
         __syncthreads();
         if (lane_on && g.lg == 0) { red[g.group * 4] = re; red[g.group * 4 + 1] = im; red[g.group * 4 + 2] = pen; }
         __syncthreads();
