@@ -383,7 +383,8 @@ __device__ __forceinline__ double group_sum(double x, int GL, int base) {
 template <int N>
 __device__ __forceinline__ void group_sum_n(double (&v)[N], int GL, int base) {
     if ((GL & (GL - 1)) == 0) {
-        for (int o = 1; o < GL; o <<= 1) {
+#pragma unroll
+        for (int o = 1; o < GL; o <<= 1) {       // unrolled when GL is a compile-time constant (GLT instantiations)
             double r[N];
             UNROLL for (int i = 0; i < N; ++i) r[i] = __shfl_xor_sync(0xffffffffu, v[i], o);
             UNROLL for (int i = 0; i < N; ++i) v[i] += r[i];
@@ -795,7 +796,7 @@ __device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, con
 
 // OBJ = 1: objFuncType 2/3 — a second adjoint set without forcing gives the infidelity-only gradient
 // (src/evalobjgrad.jl:848-855, :905-918; step_no_forcing! src/StormerVerlet.jl:365-406).
-template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int FUSED = 0>
+template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int FUSED = 0, int GLT = 0>
 __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     extern __shared__ double sm[];
@@ -803,7 +804,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
     const LaunchArgs &A = S.A;
     Geo g;
     g.lane = threadIdx.x & 31; g.warp = threadIdx.x >> 5;
-    const int GL = S.GL;
+    const int GL = GLT > 0 ? GLT : S.GL;       // GLT: group size known at compile time (reductions unroll and overlap)
     g.lg = g.lane % GL;
     const int gw = g.lane / GL;                              // group inside the warp; lanes past GPW*GL are idle
     const bool lane_on = gw < S.GPW;
@@ -970,12 +971,13 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
 typedef void (*traj_kernel_t)(const TrajParams);
 // variant: 0 default, 16 general Hanti, 32+J compile-time J, 64 objFuncType 2/3; experiments selectable with the env
 // variable JQ_TRAJ_VARIANT: 1 warp-shuffle exchange, 2 three CTAs/SM register cap, 256(+J) paired state/adjoint rounds
-struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; };
+struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; };
 #define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
 #define SLOTO(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 64, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
 #define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
+#define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, 0, GLT>, GLT}   /* compile-time J and group size */
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBERF(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 256 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, 1>}   /* fused backward step */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
@@ -987,15 +989,16 @@ const Inst kInst[] = {
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
-    FIBERJ(4, 2, 1, 1, 4), FIBERJ(6, 1, 1, 2, 3), FIBERJ(3, 2, 1, 1, 5),
+    FIBERJG(4, 2, 1, 1, 4, 16), FIBERJG(6, 1, 1, 2, 3, 4), FIBERJ(3, 2, 1, 1, 5),
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
     FIBERF(4, 2, 1, 1, 4), FIBERF(4, 2, 1, 1, 0), FIBERF(4, 3, 1, 1, 0),      // experiment: paired state/adjoint rounds, measured +-1%
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
-const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0) {
+const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0) {
     for (const Inst &i : kInst)
-        if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant) return &i;
+        if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant &&
+            (i.glt == 0 || i.glt == GL)) return &i;
     return nullptr;
 }
 
@@ -1230,7 +1233,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     if (P.objFuncType != 1) venv = "64";
     const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv)) : nullptr;
     if (!inst && !venv && pl->AS && P.objFuncType == 1)      // instantiations with the number of Neumann terms known at compile time
-        inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J);
+        inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J, pl->GL);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);
     if (!inst) return cudaErrorNotSupported;
     TrajParams S{};
