@@ -51,10 +51,10 @@ typedef struct jq_problem {
     int32_t m;             /* N, number of propagated columns           (:508)               */
     int32_t ncoupled;      /* length(Hsym_ops) == length(Hanti_ops)     (:170,:243)          */
     int32_t nfreq;         /* size(Cfreq, 2)                            (:169)               */
-    int32_t neumann_terms; /* linear_solver.max_iter (Neumann solver)   (linear_solvers.jl:46) */
+    int32_t neumann_terms; /* linear_solver.max_iter: Neumann terms, or the Jacobi sweep limit (linear_solvers.jl:41,46) */
     int32_t obj_func_type; /* objFuncType: 1 = infidelity+leak, 2/3 = also return infidelity-only gradient (:848-855) */
     int32_t pfid_type;     /* pFidType; only 2 is built (hard-wired by the reference constructor, :164) */
-    int32_t reserved;
+    int32_t linear_solver; /* linear_solver.solver_id: 0 or 1 = NEUMANN_SOLVER, 2 = JACOBI_SOLVER (linear_solvers.jl:4-5) */
     int64_t nsteps;
     double T;
     const double *uinit;     /* n*m, params.Uinit */
@@ -65,6 +65,7 @@ typedef struct jq_problem {
     jq_operator h0;          /* params.Hconst */
     const jq_operator *hsym; /* ncoupled */
     const jq_operator *hanti;/* ncoupled */
+    double solver_tol;       /* linear_solver.tol (Jacobi only; already multiplied by sqrt(nrhs), linear_solvers.jl:40) */
 } jq_problem;
 
 /* Replaces Working_Arrays(params, nCoeff) (src/evalobjgrad.jl:405): copies the problem to the GPU `device`,

@@ -25,13 +25,14 @@ end
 
 struct JqProblem             # == jq_problem
     n::Int32; m::Int32; ncoupled::Int32; nfreq::Int32
-    neumann_terms::Int32; obj_func_type::Int32; pfid_type::Int32; reserved::Int32
+    neumann_terms::Int32; obj_func_type::Int32; pfid_type::Int32; linear_solver::Int32
     nsteps::Int64
     T::Float64
     uinit::Ptr{Float64}; vtarget_r::Ptr{Float64}; vtarget_i::Ptr{Float64}; wdiag::Ptr{Float64}; cfreq::Ptr{Float64}
     h0::JqOperator
     hsym::Ptr{JqOperator}
     hanti::Ptr{JqOperator}
+    solver_tol::Float64
 end
 
 jq_error() = unsafe_string(ccall((:jq_last_error, libjq), Cstring, ()))
@@ -56,7 +57,7 @@ end
 
 function Working_Arrays_B200(params::objparams, nCoeff::Int64; device::Int = 0)
     @assert params.Nunc == 0 "uncoupled controls stay on the CPU path"
-    @assert params.linear_solver.solver_id == NEUMANN_SOLVER "only the Neumann solver is built for B200"
+    @assert params.linear_solver.solver_id in (NEUMANN_SOLVER, JACOBI_SOLVER) "Neumann and Jacobi solvers are built for B200"
     @assert params.Integrator_id == Stormer_Verlet
     @assert isa(params.wmat_real, Diagonal) "custom forbidden-state weights stay on the CPU path"
     keep = Any[]
@@ -67,8 +68,9 @@ function Working_Arrays_B200(params::objparams, nCoeff::Int64; device::Int = 0)
     ha = [jq_operator(h, keep) for h in params.Hanti_ops]
     append!(keep, (Cf, wd, hs, ha, params.Uinit, params.Utarget_r, params.Utarget_i))
     pb = JqProblem(Ntot, params.N, params.Ncoupled, params.Nfreq, params.linear_solver.max_iter, params.objFuncType,
-                   params.pFidType, 0, params.nsteps, params.T, pointer(params.Uinit), pointer(params.Utarget_r),
-                   pointer(params.Utarget_i), pointer(wd), pointer(Cf), jq_operator(params.Hconst, keep), pointer(hs), pointer(ha))
+                   params.pFidType, params.linear_solver.solver_id, params.nsteps, params.T, pointer(params.Uinit), pointer(params.Utarget_r),
+                   pointer(params.Utarget_i), pointer(wd), pointer(Cf), jq_operator(params.Hconst, keep), pointer(hs), pointer(ha),
+                   params.linear_solver.tol)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep pb jq_check(ccall((:jq_create, libjq), Cint, (Ref{JqProblem}, Cint, Ref{Ptr{Cvoid}}), pb, device, h))
     wa = Working_Arrays_B200(h[], nCoeff, Any[])

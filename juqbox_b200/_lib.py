@@ -19,10 +19,10 @@ class jq_operator(C.Structure):
 class jq_problem(C.Structure):
     _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("ncoupled", C.c_int32), ("nfreq", C.c_int32),
                 ("neumann_terms", C.c_int32), ("obj_func_type", C.c_int32), ("pfid_type", C.c_int32),
-                ("reserved", C.c_int32), ("nsteps", C.c_int64), ("T", C.c_double),
+                ("linear_solver", C.c_int32), ("nsteps", C.c_int64), ("T", C.c_double),
                 ("uinit", C.c_void_p), ("vtarget_r", C.c_void_p), ("vtarget_i", C.c_void_p), ("wdiag", C.c_void_p),
                 ("cfreq", C.c_void_p), ("h0", jq_operator), ("hsym", C.POINTER(jq_operator)),
-                ("hanti", C.POINTER(jq_operator))]
+                ("hanti", C.POINTER(jq_operator)), ("solver_tol", C.c_double)]
 
 
 JQ_DENSE, JQ_CSC = 0, 1

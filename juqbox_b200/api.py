@@ -76,6 +76,7 @@ class Working_Arrays:
         pb = _lib.jq_problem()
         pb.n, pb.m, pb.ncoupled, pb.nfreq = p.Ntot, p.N, p.Ncoupled, p.Nfreq
         pb.neumann_terms = p.linear_solver.max_iter
+        pb.linear_solver, pb.solver_tol = p.linear_solver.solver_id, p.linear_solver.tol
         pb.obj_func_type, pb.pfid_type = p.objFuncType, p.pFidType
         pb.nsteps, pb.T = p.nsteps, p.T
         pb.uinit = self._ptr(np.asfortranarray(p.Uinit, dtype=np.float64))

@@ -18,7 +18,7 @@ from typing import List, Optional
 
 import numpy as np
 
-from .params import (objparams, lsolver_object, calculate_timestep, estimate_Neumann, initial_cond,
+from .params import (objparams, lsolver_object, JACOBI_SOLVER, calculate_timestep, estimate_Neumann, initial_cond,
                      orig_wmatsetup, setup_rotmatrices)
 
 EPS = np.finfo(float).eps
@@ -137,8 +137,9 @@ def _case_swap02(pcof0) -> Config:
     return Config("swap02", p, pc, len(pc) // (2 * Nfreq), [maxpar])
 
 
-def _case_cnot2(pcof0, objFuncType=1, name="cnot2") -> Config:
-    # test/cases/cnot2-setup.jl, cnot2-leakieq-setup.jl
+def _case_cnot2(pcof0, objFuncType=1, name="cnot2", jacobi=False) -> Config:
+    # test/cases/cnot2-setup.jl, cnot2-leakieq-setup.jl, cnot2-jacobi-setup.jl (:186 Jacobi solver object; the later
+    # estimate_Neumann! call, :259, overwrites its max_iter exactly as it does for the Neumann solver)
     Ne, Ng = [2, 2], [1, 2]
     Nt = [3, 4]
     Ntot, N = 12, 4
@@ -157,7 +158,8 @@ def _case_cnot2(pcof0, objFuncType=1, name="cnot2") -> Config:
     vt = _rot_target(ut, Ne, Ng, [fa, fb], T)
     p = objparams(Ne, Ng, T, nsteps, Uinit=initial_cond(Ne, Ng), Utarget=vt, Cfreq=om, Rfreq=[fa, fb],
                   Hconst=H0, Hsym_ops=[amat + amat.T, bmat + bmat.T], Hanti_ops=[amat - amat.T, bmat - bmat.T],
-                  use_sparse=False, objFuncType=objFuncType, leak_ubound=1e-3)
+                  use_sparse=False, objFuncType=objFuncType, leak_ubound=1e-3,
+                  linear_solver=lsolver_object(solver=JACOBI_SOLVER, max_iter=100, tol=1e-15, nrhs=4) if jacobi else None)
     p.wmat_real = orig_wmatsetup(Ne, Ng)
     pc = np.asarray(pcof0, dtype=float)
     estimate_Neumann(EPS, p, maxpar)
@@ -243,6 +245,8 @@ def test_case(name: str, pcof0=None) -> Config:
         return _case_cnot2(pcof0)
     if name == "cnot2-leakieq":
         return _case_cnot2(pcof0, objFuncType=3, name="cnot2-leakieq")
+    if name == "cnot2-jacobi":
+        return _case_cnot2(pcof0, name="cnot2-jacobi", jacobi=True)
     if name == "cnot3":
         return _case_cnot3(pcof0)
     if name == "flux":

@@ -196,6 +196,8 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
     if (pb->ncoupled < 1) return fail(JQ_ERR_ARG, "jq_create: ncoupled must be >= 1 (uncoupled-only controls are not on this path)");
     if (pb->nfreq < 1 || pb->nsteps < 1 || !(pb->T > 0.0) || pb->neumann_terms < 0)
         return fail(JQ_ERR_ARG, "jq_create: need nfreq >= 1, nsteps >= 1, T > 0, neumann_terms >= 0");
+    if (pb->linear_solver < 0 || pb->linear_solver > 2)
+        return fail(JQ_ERR_ARG, "jq_create: linear_solver must be NEUMANN_SOLVER (1) or JACOBI_SOLVER (2), got %d", pb->linear_solver);
     if (pb->pfid_type != 2) return fail(JQ_ERR_ARG, "jq_create: only pFidType == 2 is built (got %d)", pb->pfid_type);
     if (pb->obj_func_type < 1 || pb->obj_func_type > 3) return fail(JQ_ERR_ARG, "jq_create: objFuncType must be 1, 2 or 3");
     if (!pb->uinit || !pb->vtarget_r || !pb->vtarget_i || !pb->wdiag || !pb->cfreq || !pb->hsym || !pb->hanti)
@@ -220,6 +222,7 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
 
     DevProblem &P = h->P;
     P.n = n; P.m = m; P.Nc = Nc; P.Nfreq = pb->nfreq; P.J = pb->neumann_terms; P.objFuncType = pb->obj_func_type;
+    P.solver = pb->linear_solver == 2 ? 2 : 1; P.tol = pb->solver_tol;
     P.nsteps = pb->nsteps; P.T = pb->T;
     double *tmp = nullptr;
     int *itmp = nullptr;

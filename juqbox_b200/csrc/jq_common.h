@@ -7,6 +7,8 @@
 // o in {0: Hconst (diagonal included even if zero), 1..Nc: Hsym_q, Nc+1..2Nc: Hanti_q}.
 struct DevProblem {
     int n, m, Nc, Nfreq, J, objFuncType;
+    int solver;            // 1 Neumann (J terms), 2 Jacobi (at most J sweeps, stop at ||dX||_F < tol)
+    double tol;
     long long nsteps;
     double T;
     const double *uinit, *vtr, *vti, *wdiag, *cfreq;  // n*m, n*m, n*m, n, Nc*Nfreq

@@ -98,12 +98,34 @@ __device__ void neumann(const Ctx &c, int level, double h, double *B, double *T,
     }
 }
 
+// Jacobi sweeps (src/linear_solvers.jl:110-152): X = B; T = B + (h/2) S X; err = ||T - X||_F; X = T; stop when
+// err < tol or after J sweeps.  B is preserved, the result is left in X.  The reference multiplies S by -h/2 in place
+// and computes B - (scaled S) X; the sign and factor are folded here (differences are rounding-level only).
+__device__ void block_sum(const Ctx &c, double *v, int cnt);
+__device__ void jacobi(const Ctx &c, int level, double h, const double *B, double *T, double *X) {
+    FOR_E X[e] = B[e];
+    __syncthreads();
+    for (int it = 0; it < c.J; ++it) {
+        double err[1] = {0.0};
+        FOR_E { double tv = B[e] + 0.5 * h * applyS(c, level, X, i, j); double d = tv - X[e]; err[0] += d * d; T[e] = tv; }
+        block_sum(c, err, 1);                 // also orders the T writes before the copy below
+        FOR_E X[e] = T[e];
+        __syncthreads();
+        if (sqrt(err[0]) < c.P->tol) break;   // uniform across the CTA: block_sum broadcasts
+    }
+}
+
+__device__ __forceinline__ void solve(const Ctx &c, int level, double h, double *B, double *T, double *X) {
+    if (c.P->solver == 2) jacobi(c, level, h, B, T, X);
+    else neumann(c, level, h, B, T, X);
+}
+
 // src/StormerVerlet.jl:461-504
 __device__ void state_step(const Ctx &c, double h) {
     double *u = c.vr, *v = c.vi, *v05 = c.vi05;
     FOR_E c.rhs[e] = applyK(c, 1, u, i, j) + applyS(c, 1, v, i, j);
     __syncthreads();
-    neumann(c, 1, h, c.rhs, c.scr, c.l1);
+    solve(c, 1, h, c.rhs, c.scr, c.l1);
     FOR_E v05[e] = v[e] + 0.5 * h * c.l1[e];
     __syncthreads();
     FOR_E c.k1[e] = applyS(c, 0, u, i, j) - applyK(c, 0, v05, i, j);
@@ -111,7 +133,7 @@ __device__ void state_step(const Ctx &c, double h) {
     FOR_E c.rhs[e] = applyS(c, 2, u, i, j) + 0.5 * h * applyS(c, 2, c.k1, i, j) - applyK(c, 2, v05, i, j);
     __syncthreads();
     FOR_E u[e] += 0.5 * h * c.k1[e];
-    neumann(c, 2, h, c.rhs, c.scr, c.k2);
+    solve(c, 2, h, c.rhs, c.scr, c.k2);
     FOR_E u[e] += 0.5 * h * c.k2[e];
     __syncthreads();
     FOR_E { c.l2[e] = applyK(c, 1, u, i, j) + applyS(c, 1, v05, i, j); v[e] += 0.5 * h * (c.l1[e] + c.l2[e]); }
@@ -126,7 +148,7 @@ __device__ void adjoint_step(const Ctx &c, double *mu, double *nu, double *X, do
         c.rhs[e] = applyS(c, 0, mu, i, j) - applyK(c, 1, nu, i, j) + f;
     }
     __syncthreads();
-    neumann(c, 0, h, c.rhs, c.scr, c.k2);
+    solve(c, 0, h, c.rhs, c.scr, c.k2);
     FOR_E { mu[e] += 0.5 * h * c.k2[e]; X[e] = mu[e]; }
     __syncthreads();
     FOR_E {
@@ -139,7 +161,7 @@ __device__ void adjoint_step(const Ctx &c, double *mu, double *nu, double *X, do
         c.rhs[e] = applyS(c, 1, nu, i, j) + 0.5 * h * applyS(c, 1, c.l2, i, j) + applyK(c, 2, X, i, j) + f;
     }
     __syncthreads();
-    neumann(c, 1, h, c.rhs, c.scr, c.l1);
+    solve(c, 1, h, c.rhs, c.scr, c.l1);
     FOR_E nu[e] += 0.5 * h * (c.l2[e] + c.l1[e]);
     __syncthreads();
     FOR_E {

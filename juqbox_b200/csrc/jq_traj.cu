@@ -1040,6 +1040,7 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.solver != 1) return no("Jacobi solver (data-dependent sweep count) runs on the generic kernel");
     if (n > 128) return no("n > 128");
     std::vector<double> d0;
     if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
@@ -1107,6 +1108,7 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
 TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.solver != 1) return no("Jacobi solver (data-dependent sweep count) runs on the generic kernel");
     std::vector<double> d0;
     if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
     // block size: first break of control 0's first off-diagonals

@@ -5,7 +5,7 @@ hot path); nothing here is on the per-evaluation path. Names, argument meaning a
 behaviour follow the reference so that a Juqbox setup script translates line by line:
 
   objparams            /root/reference/src/evalobjgrad.jl:152-343
-  lsolver_object       /root/reference/src/linear_solvers.jl:28-65   (Neumann only)
+  lsolver_object       /root/reference/src/linear_solvers.jl:28-65   (Neumann + Jacobi)
   wmatsetup            /root/reference/src/evalobjgrad.jl:1544-1669
   orig_wmatsetup       /root/reference/src/evalobjgrad.jl:1683-1808
   setup_rotmatrices    /root/reference/src/evalobjgrad.jl:1822-1886
@@ -24,27 +24,35 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 NEUMANN_SOLVER = 1
+JACOBI_SOLVER = 2
 Stormer_Verlet = 1
 
 
 class lsolver_object:
     """Linear-solver selection (reference: src/linear_solvers.jl:28-65).
 
-    Only the truncated Neumann series is on the hot path (every named config uses it);
-    asking for another solver raises, exactly like the reference's `error("Please specify a
-    supported linear solver")` does for unknown ids.
+    NEUMANN_SOLVER (truncated series, every named config) and JACOBI_SOLVER (fixed-point sweeps until
+    ||X_k+1 - X_k||_F < tol*sqrt(nrhs), test case cnot2-jacobi) are built.  GAUSSIAN_ELIM_SOLVER is not: the
+    reference's own closure for it writes into the scratch argument (:50 vs :75), and JACOBI_SOLVER_M belongs to
+    the implicit-midpoint integrator.  Other ids raise like the reference's `error("Please specify a supported
+    linear solver")`.
     """
 
     def __init__(self, tol: float = 1e-10, max_iter: int = 3, nrhs: int = 1, solver: int = NEUMANN_SOLVER):
-        if solver != NEUMANN_SOLVER:
-            raise ValueError("Please specify a supported linear solver (only NEUMANN_SOLVER is built for B200)")
+        if solver == JACOBI_SOLVER:
+            tol = tol * np.sqrt(nrhs)            # linear_solvers.jl:40
+            self.solver_name = "Jacobi"
+        elif solver == NEUMANN_SOLVER:
+            self.solver_name = "Neumann"
+        else:
+            raise ValueError("Please specify a supported linear solver (NEUMANN_SOLVER or JACOBI_SOLVER)")
         self.tol = float(tol)
         self.max_iter = int(max_iter)
         self.solver_id = solver
-        self.solver_name = "Neumann"
 
     def print_info(self):
-        print("*** Using linear solver: ", self.solver_name, " with max_iter = ", self.max_iter)
+        extra = f", tol = {self.tol}" if self.solver_id == JACOBI_SOLVER else ""
+        print("*** Using linear solver: ", self.solver_name, " with max_iter = ", self.max_iter, extra)
 
 
 def _diag_weights(Ne, Ng, orig: bool) -> np.ndarray:

@@ -21,7 +21,8 @@ class _Problem(C.Structure):
                 ("objFuncType", C.c_int), ("sparse", C.c_int), ("nsteps", C.c_int64), ("T", C.c_double),
                 ("Uinit", C.c_void_p), ("Vtr", C.c_void_p), ("Vti", C.c_void_p), ("wdiag", C.c_void_p),
                 ("Cfreq", C.c_void_p), ("H0", C.c_void_p), ("Hsym", C.c_void_p), ("Hanti", C.c_void_p),
-                ("colptr", C.c_void_p), ("rowval", C.c_void_p), ("nzval", C.c_void_p)]
+                ("colptr", C.c_void_p), ("rowval", C.c_void_p), ("nzval", C.c_void_p),
+                ("solver", C.c_int), ("tol", C.c_double)]
 
 
 def build(force: bool = False) -> str:
@@ -71,6 +72,7 @@ def _problem(params, keep):
     P.n, P.m, P.Nc, P.Nfreq = n, m, Nc, params.Nfreq
     P.J, P.objFuncType, P.sparse = params.linear_solver.max_iter, params.objFuncType, int(bool(params.use_sparse))
     P.nsteps, P.T = params.nsteps, params.T
+    P.solver, P.tol = params.linear_solver.solver_id, params.linear_solver.tol
     P.Uinit, P.Vtr, P.Vti = ptr(_f(params.Uinit)), ptr(_f(params.Utarget_r)), ptr(_f(params.Utarget_i))
     P.wdiag = ptr(np.ascontiguousarray(params.wmat_real, dtype=np.float64))
     P.Cfreq = ptr(_f(params.Cfreq[:Nc, :]))

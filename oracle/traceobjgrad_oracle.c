@@ -17,6 +17,7 @@
  *   step! (adjoint, forcing) ....... StormerVerlet.jl:255-303, :306-356
  *   step_no_forcing! ............... StormerVerlet.jl:365-406, :409-451
  *   neumann! ....................... linear_solvers.jl:81-106
+ *   jacobi! ........................ linear_solvers.jl:110-152
  *   KS! / accumulate_matrix! ....... evalobjgrad.jl:2354-2441
  *   bcarrier2 / gradbcarrier2! ..... bsplines.jl:211-304, :321-415
  *   adjoint_grad_calc! ............. evalobjgrad.jl:2567-2619
@@ -51,6 +52,10 @@ typedef struct {
 typedef struct {
     /* problem */
     int n, m, Nc, Nfreq, D1, J, objFuncType, sparse;
+    int solver;       /* 1 = Neumann (J terms), 2 = Jacobi (J = max_iter, tol) — linear_solvers.jl:4-5 */
+    double tol;
+    double *jac_scaled; /* Jacobi: the S.*=coeff copy */
+    csc_t jac_scaled_s;
     int64_t nsteps;
     double T;
     const double *Uinit, *Vtr, *Vti, *wdiag, *Cfreq;
@@ -192,6 +197,41 @@ static void neumann(const ws_t *w, double h, op_t S, double *B, double *Tm, doub
     }
 }
 
+/* linear_solvers.jl:110-152 (jacobi!, dense and sparse twins): X = B; repeat T = B - (-h/2 S) X; err = ||T - X||_F;
+ * X = T; until err < tol or max_iter sweeps.  The reference scales S in place by -h/2 and restores it on exit; the
+ * scaled copy lives in scratch here so that S itself keeps its bits (S*coeff/coeff need not round-trip). B survives. */
+static void jacobi(ws_t *w, double h, op_t S, const double *B, double *Tm, double *X) {
+    int64_t len = (int64_t)w->n * w->m;
+    double coeff = -0.5 * h;
+    op_t Sc;
+    if (w->sparse) {
+        csc_t *d = &w->jac_scaled_s;
+        if (!d->nzval || d->nnz < S.s->nnz) { free(d->nzval); d->nzval = (double *)malloc(sizeof(double) * (S.s->nnz + 1)); }
+        d->n = S.s->n; d->nnz = S.s->nnz; d->colptr = S.s->colptr; d->rowval = S.s->rowval;
+        for (int64_t k = 0; k < S.s->nnz; k++) d->nzval[k] = S.s->nzval[k] * coeff;
+        Sc.s = d; Sc.d = NULL;
+    } else {
+        int64_t nn = (int64_t)w->n * w->n;
+        if (!w->jac_scaled) w->jac_scaled = (double *)malloc(sizeof(double) * nn);
+        for (int64_t k = 0; k < nn; k++) w->jac_scaled[k] = S.d[k] * coeff;
+        Sc.d = w->jac_scaled; Sc.s = NULL;
+    }
+    memcpy(X, B, sizeof(double) * len);
+    for (int j = 1; j <= w->J; j++) {
+        mul(w, Tm, Sc, X, 1.0, 0.0);
+        double err = 0.0;
+        for (int64_t k = 0; k < len; k++) { Tm[k] = B[k] - Tm[k]; double d = Tm[k] - X[k]; err += d * d; }
+        memcpy(X, Tm, sizeof(double) * len);
+        if (sqrt(err) < w->tol) return;
+    }
+}
+
+/* linear_solver.solve(h, S, rhs, T, X) of the steppers (StormerVerlet.jl:266,285,470,487) */
+static void solve(ws_t *w, double h, op_t S, double *B, double *Tm, double *X) {
+    if (w->solver == 2) jacobi(w, h, S, B, Tm, X);
+    else neumann(w, h, S, B, Tm, X);
+}
+
 /* ------------------------------------------------------------------ KS! */
 static void KS(ws_t *w, int level, double t) {
     int n = w->n, Nc = w->Nc;
@@ -240,7 +280,7 @@ static double step_state(ws_t *w, double t, double *u, double *v, double *v05, d
     double *k1 = w->k1, *k2 = w->k2, *l1 = w->l1, *l2 = w->l2, *rhs = w->rhs;
     mul(w, rhs, K05, u, 1.0, 0.0);
     mul(w, rhs, S05, v, 1.0, 1.0);
-    neumann(w, h, S05, rhs, v05, l1);
+    solve(w, h, S05, rhs, v05, l1);
     memcpy(v05, v, sizeof(double) * len);
     axpy(len, 0.5 * h, l1, v05);
     mul(w, k1, S0, u, 1.0, 0.0);
@@ -249,7 +289,7 @@ static double step_state(ws_t *w, double t, double *u, double *v, double *v05, d
     mul(w, rhs, S1, k1, 0.5 * h, 1.0);
     mul(w, rhs, K1, v05, -1.0, 1.0);
     axpy(len, 0.5 * h, k1, u);
-    neumann(w, h, S1, rhs, k1, k2);
+    solve(w, h, S1, rhs, k1, k2);
     axpy(len, 0.5 * h, k2, u);
     mul(w, l2, K05, u, 1.0, 0.0);
     mul(w, l2, S05, v05, 1.0, 1.0);
@@ -266,7 +306,7 @@ static void step_adjoint(ws_t *w, double *mu, double *nu, double *X, double h, c
     mul(w, rhs, S0, mu, 1.0, 0.0);
     mul(w, rhs, K05, nu, -1.0, 1.0);
     if (uf0) axpy(len, 1.0, uf0, rhs);
-    neumann(w, h, S0, rhs, k1, k2);
+    solve(w, h, S0, rhs, k1, k2);
     axpy(len, 0.5 * h, k2, mu);
     memcpy(X, mu, sizeof(double) * len);
     mul(w, l2, K0, X, 1.0, 0.0);
@@ -276,7 +316,7 @@ static void step_adjoint(ws_t *w, double *mu, double *nu, double *X, double h, c
     mul(w, rhs, S05, l2, 0.5 * h, 1.0);
     mul(w, rhs, K1, X, 1.0, 1.0);
     if (vf1) axpy(len, 1.0, vf1, rhs);
-    neumann(w, h, S05, rhs, k2, l1);
+    solve(w, h, S05, rhs, k2, l1);
     for (int64_t i = 0; i < len; i++) nu[i] = nu[i] + (0.5 * h) * (l2[i] + l1[i]);
     mul(w, k1, S1, X, 1.0, 0.0);
     mul(w, k1, K05, nu, -1.0, 1.0);
@@ -430,6 +470,8 @@ typedef struct {
     const double *H0, *Hsym, *Hanti;
     const int64_t *colptr, *rowval;
     const double *nzval;
+    int solver;   /* 0/1 Neumann, 2 Jacobi */
+    double tol;   /* Jacobi tolerance (already scaled by sqrt(nrhs), linear_solvers.jl:40) */
 } jqo_problem;
 
 static void ws_init(ws_t *w, const jqo_problem *P, int Npar) {
@@ -437,6 +479,7 @@ static void ws_init(ws_t *w, const jqo_problem *P, int Npar) {
     int n = P->n, m = P->m, Nc = P->Nc;
     w->n = n; w->m = m; w->Nc = Nc; w->Nfreq = P->Nfreq; w->J = P->J; w->objFuncType = P->objFuncType;
     w->sparse = P->sparse; w->nsteps = P->nsteps; w->T = P->T;
+    w->solver = P->solver == 2 ? 2 : 1; w->tol = P->tol;
     w->Uinit = P->Uinit; w->Vtr = P->Vtr; w->Vti = P->Vti; w->wdiag = P->wdiag; w->Cfreq = P->Cfreq;
     w->Npar = Npar;
     w->D1 = Npar / (2 * Nc * P->Nfreq);
@@ -492,6 +535,7 @@ static void ws_init(ws_t *w, const jqo_problem *P, int Npar) {
 
 static void ws_free(ws_t *w) {
     int Nc = w->Nc;
+    free(w->jac_scaled); free(w->jac_scaled_s.nzval);
     if (!w->sparse) {
         free(w->H0d); free(w->K0d); free(w->S0d); free(w->K05d); free(w->S05d); free(w->K1d); free(w->S1d);
     } else {

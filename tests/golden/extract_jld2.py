@@ -93,7 +93,7 @@ def read_dat(path):
     return [float(x) for x in open(path).read().split()]
 
 
-CASES = ["rabi", "swap02", "flux", "cnot2", "cnot3", "cnot2-leakieq"]
+CASES = ["rabi", "swap02", "flux", "cnot2", "cnot3", "cnot2-leakieq", "cnot2-jacobi"]
 
 
 def main():

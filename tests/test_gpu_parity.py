@@ -28,7 +28,7 @@ def _wa(cfg, kernel):
 
 
 KERNELS = [1, 2, 3]
-GOLDEN_CASES = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq", "cnot3"]
+GOLDEN_CASES = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq", "cnot2-jacobi", "cnot3"]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -293,3 +293,26 @@ def test_long_pcof_falls_back_when_shared_memory_does_not_fit():
     assert used == 3          # the fibre kernel shrinks its CTAs (fewer warps) instead of falling back
     for b in range(2):
         assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL and abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12
+
+
+def test_jacobi_solver_tolerance_exit_vs_oracle():
+    """JACOBI_SOLVER (src/linear_solvers.jl:110-152) with a loose tolerance, so the sweep count is decided by the
+    residual test, not by max_iter; the auto choice must fall back to the generic kernel (data-dependent sweeps)."""
+    import juqbox_b200 as jq
+    from juqbox_b200.params import lsolver_object, JACOBI_SOLVER
+    from oracle import oracle_traceobjgrad
+    cfg, _ = golden_config("swap02")
+    cfg.params.linear_solver = lsolver_object(solver=JACOBI_SOLVER, max_iter=50, tol=1e-9, nrhs=cfg.params.N)
+    wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
+    res = wa.evaluate(cfg.pcof0)
+    assert wa.last_kernel == 1
+    o = oracle_traceobjgrad(cfg.params, cfg.pcof0)
+    assert abs(res["infid"][0, 0] - o["infid"][0, 0]) < 1e-10 and abs(res["leak"][0, 0] - o["leak"][0, 0]) < 1e-10
+    assert _rel(res["grad"][0, 0], o["grad"][0, 0]) < 1e-8
+    cfg.params.linear_solver = lsolver_object(solver=JACOBI_SOLVER, max_iter=50, tol=1e-3, nrhs=cfg.params.N)
+    wa2 = jq.Working_Arrays(cfg.params, cfg.nCoeff)          # a different tolerance must change the answer
+    res2 = wa2.evaluate(cfg.pcof0)
+    o2 = oracle_traceobjgrad(cfg.params, cfg.pcof0)
+    assert abs(res2["infid"][0, 0] - o2["infid"][0, 0]) < 1e-10
+    assert abs(res2["infid"][0, 0] - res["infid"][0, 0]) > 1e-11
+    wa.close(); wa2.close()

@@ -6,7 +6,7 @@ import pytest
 from helpers import golden_config, ref_pass, with_tikhonov
 from oracle import oracle_traceobjgrad
 
-FAST = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq"]
+FAST = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq", "cnot2-jacobi"]
 
 
 @pytest.mark.parametrize("case", FAST + ["cnot3"])
