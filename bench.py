@@ -30,13 +30,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def alg_flops_per_eval(p, npar):
-    """algorithmic flops of one obj+grad evaluation (structural nonzeros, FMA = 2)."""
+def alg_flops_per_eval(p, npar, dense=False):
+    """algorithmic flops of one obj+grad evaluation (structural nonzeros, FMA = 2).
+    dense=True: the same scheme with every operator product counted as a full n x n contraction (what a
+    tensor-core formulation would have to execute)."""
     n, m, J, Nc, Nf = p.Ntot, p.N, p.linear_solver.max_iter, p.Ncoupled, p.Nfreq
     h0 = np.asarray(p.Hconst)
     nnzK = n + int(np.count_nonzero(h0 - np.diag(np.diag(h0)))) + sum(int(np.count_nonzero(h)) for h in p.Hsym_ops)
     nnzS = sum(int(np.count_nonzero(h)) for h in p.Hanti_ops)
     nnzq = [int(np.count_nonzero(h)) for h in p.Hsym_ops]
+    if dense:
+        nnzK, nnzS, nnzq = n * n, n * n, [n * n] * Nc
     f_state = 2 * m * (4 * nnzK + (4 + 2 * J) * nnzS) + (9 + 4 * J) * n * m
     f_adj = 2 * m * (4 * nnzK + (4 + 2 * J) * nnzS) + (16 + 4 * J) * n * m
     f_pen = 6 * n * m
@@ -240,6 +244,8 @@ def main():
     peak = _lib.fp64_peak_tflops(local_rank)
     peak3 = _lib.fp64_peak_tflops(local_rank, three_operand=True)
     achieved = flops_eval * B * nsamp / (kern_ms * 1e-3) / 1e12
+    peak_dmma = _lib.fp64_peak_tflops(local_rank, tensor=True)
+    dense_ratio = alg_flops_per_eval(cfg.params, npar, dense=True) / flops_eval
     traffic = None                                  # DRAM bytes per launch from the committed ncu --set full capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json"))).get(args.workload)
@@ -250,6 +256,11 @@ def main():
     roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": traffic, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "peak_no_operand_reuse": peak3, "frac_of_peak_no_operand_reuse": achieved / peak3 if peak3 else None,
+                "tensor_pipe": {"util": 0.0, "fp64_mma_peak": peak_dmma, "dense_to_nnz_flop_ratio": dense_ratio,
+                                "nnz_equivalent_ceiling": peak_dmma / dense_ratio if dense_ratio else None,
+                                "note": "FP64 MMA (mma.sync m16n8k16) peak measured in this run; a dense contraction executes "
+                                        "dense_to_nnz_flop_ratio x the structural flops, so its ceiling in this line's units is "
+                                        "nnz_equivalent_ceiling TFLOP/s; the path stays on the DFMA pipe when that is below `achieved`"},
                 "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>"}[used_kernel],
                 "hbm_alg_bytes_per_launch": 8 * (B * npar + nsamp * cfg.params.Ntot + B * nsamp * (4 + npar))}
 

@@ -140,6 +140,9 @@ int jq_fp64_peak(int device, double *tflops);
  * sustains one warp-DFMA per 3 cycles per scheduler instead of 2, i.e. 2/3 of the figure above — the realistic ceiling for
  * FMAs that are not coefficient-broadcast shaped.  Reported next to the roofline, not used as its denominator. */
 int jq_fp64_peak_3op(int device, double *tflops);
+/* FP64 tensor-core (DMMA, mma.sync m16n8k16) peak of `device` in TFLOP/s; reported next to the roofline, the path
+ * itself does not use the tensor pipe. */
+int jq_fp64_peak_dmma(int device, double *tflops);
 
 const char *jq_last_error(void);
 const char *jq_version(void);

@@ -29,7 +29,7 @@ JQ_DENSE, JQ_CSC = 0, 1
 JQ_ERR_PCOF_LENGTH = -2
 
 EXPORTS = ["jq_create", "jq_destroy", "jq_update_target", "jq_traceobjgrad_batch", "jq_traceobjgrad_batch_device", "jq_eval_forward",
-           "jq_set_kernel", "jq_query", "jq_fp64_peak", "jq_fp64_peak_3op", "jq_comm_unique_id", "jq_comm_init", "jq_comm_destroy",
+           "jq_set_kernel", "jq_query", "jq_fp64_peak", "jq_fp64_peak_3op", "jq_fp64_peak_dmma", "jq_comm_unique_id", "jq_comm_init", "jq_comm_destroy",
            "jq_last_error", "jq_version"]
 
 _lib = None
@@ -70,6 +70,7 @@ def load(build_if_missing: bool = True):
     lib.jq_query.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.jq_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.jq_fp64_peak_3op.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.jq_fp64_peak_dmma.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.jq_comm_unique_id.argtypes = [vp]
     lib.jq_comm_init.argtypes = [vp, i32, i32, vp]
     lib.jq_comm_destroy.argtypes = [vp]
@@ -94,8 +95,8 @@ def check(rc: int):
     raise JuqboxCudaError(f"juqbox_b200 error {rc}: {msg}")
 
 
-def fp64_peak_tflops(device: int = 0, three_operand: bool = False) -> float:
+def fp64_peak_tflops(device: int = 0, three_operand: bool = False, tensor: bool = False) -> float:
     v = C.c_double()
-    fn = load().jq_fp64_peak_3op if three_operand else load().jq_fp64_peak
+    fn = load().jq_fp64_peak_dmma if tensor else load().jq_fp64_peak_3op if three_operand else load().jq_fp64_peak
     check(fn(device, C.byref(v)))
     return v.value

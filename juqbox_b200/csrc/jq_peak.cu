@@ -35,6 +35,29 @@ __global__ void __launch_bounds__(256) jq_dfma_3op_kernel(double *out, int iters
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// FP64 tensor-core (DMMA) issue rate: mma.sync m16n8k16 f64, four independent accumulator tiles per warp.  The
+// trajectory kernels do not use this pipe (the control operators have <= 2 nonzeros per row, so a dense contraction
+// would spend 4.4x (cnot2) to 15x (cnot3) more flops than the structural-nonzero form); the number is reported so
+// that the decision can be checked: DMMA peak / dense-to-nnz flop ratio < achieved DFMA rate.
+__global__ void __launch_bounds__(256) jq_dmma_peak_kernel(double *out, int iters) {
+    double a[8], b[4], c[4][4];
+    for (int k = 0; k < 8; ++k) a[k] = 1e-3 * (threadIdx.x % 7) + 1e-4 * k;
+    for (int k = 0; k < 4; ++k) b[k] = 1e-3 * (threadIdx.x % 5) - 1e-4 * k;
+    for (int t = 0; t < 4; ++t) for (int k = 0; k < 4; ++k) c[t][k] = t + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+                         "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                         : "+d"(c[t][0]), "+d"(c[t][1]), "+d"(c[t][2]), "+d"(c[t][3])
+                         : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+                           "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+    }
+    double s = 0;
+    for (int t = 0; t < 4; ++t) for (int k = 0; k < 4; ++k) s += c[t][k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 static int time_kernel(int device, int which, double *tflops) {
     if (!tflops) return JQ_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return JQ_ERR_CUDA;
@@ -50,12 +73,14 @@ static int time_kernel(int device, int which, double *tflops) {
     for (int rep = 0; rep < 6; ++rep) {
         cudaEventRecord(e0);
         if (which == 0) jq_dfma_peak_kernel<<<blocks, threads>>>(buf, iters, 0.999999, 1e-9);
-        else jq_dfma_3op_kernel<<<blocks, threads>>>(buf, iters);
+        else if (which == 1) jq_dfma_3op_kernel<<<blocks, threads>>>(buf, iters);
+        else jq_dmma_peak_kernel<<<blocks, threads>>>(buf, iters);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(buf); return JQ_ERR_CUDA; }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double fmas = (which == 0 ? 64.0 : 24.0) * iters * (double)blocks * threads;
+        // per thread and iteration: 64 / 24 DFMA, or 4 warp-wide m16n8k16 MMAs = 4*16*8*16/32 multiply-adds per lane
+        const double fmas = (which == 0 ? 64.0 : which == 1 ? 24.0 : 256.0) * iters * (double)blocks * threads;
         if (rep > 0 && ms > 0.f) best = best > 2.0 * fmas / (ms * 1e9) ? best : 2.0 * fmas / (ms * 1e9);
     }
     cudaEventDestroy(e0);
@@ -64,6 +89,8 @@ static int time_kernel(int device, int which, double *tflops) {
     *tflops = best;
     return 0;
 }
+
+extern "C" int jq_fp64_peak_dmma(int device, double *tflops) { return time_kernel(device, 2, tflops); }
 
 extern "C" int jq_fp64_peak_3op(int device, double *tflops) { return time_kernel(device, 1, tflops); }
 
