@@ -390,6 +390,49 @@ def _ex_risk_neutral(nquad: int = 9) -> Config:
     return Config("risk_neutral", p, None, 12, [maxpar], nodes, weights)
 
 
+def qudit_system(Ne, Ng, T: float = 20.0, Nfreq: int = 2, D1: int = 6, maxamp: float = 0.03, exchange: float = 0.0,
+                 use_sparse: Optional[bool] = None, seed: int = 11) -> Config:
+    """Coupled anharmonic qudits in the rotating frame, built the way every examples/*-setup.jl builds its model
+    (e.g. examples/cnot2-setup.jl:76-135): H0 = -sum_k x_k/2 (N_k^2 - N_k) - sum_{k<l} x_kl N_k N_l (diagonal),
+    one control pair (a_k + a_k', a_k - a_k') per subsystem, carrier frequencies 0 and -x-shift, a random unitary
+    permutation of the essential levels as the target.  `exchange` adds J (a_k' a_l + a_k a_l') to H0 (off-diagonal
+    drift, Jaynes-Cummings-type coupling), which only the generic kernel handles.  Used to exercise kernel selection
+    on shapes beyond the five named configurations; the oracle is the pin.
+    """
+    Ne, Ng = list(Ne), list(Ng)
+    Nt = [a + b for a, b in zip(Ne, Ng)]
+    nsub = len(Nt)
+    rng = np.random.default_rng(seed)
+    amats, nums = kron_ops(Nt)
+    xk = [2 * np.pi * (0.2 + 0.02 * k) for k in range(nsub)]
+    n = int(np.prod(Nt))
+    H0 = np.zeros((n, n))
+    for k in range(nsub):
+        H0 -= xk[k] / 2 * (nums[k] @ nums[k] - nums[k])
+        for l in range(k + 1, nsub):
+            H0 -= 2 * np.pi * 0.05 * (nums[k] @ nums[l])
+            if exchange:
+                H0 += exchange * (amats[k].T @ amats[l] + amats[k] @ amats[l].T)
+    Hsym = [a + a.T for a in amats]
+    Hanti = [a - a.T for a in amats]
+    maxpar = [maxamp] * nsub
+    nsteps = calculate_timestep(T, H0, Hsym, Hanti, maxpar, 40)
+    om = np.zeros((nsub, Nfreq))
+    for f in range(1, Nfreq):
+        om[:, f] = [-xk[k] * f for k in range(nsub)]
+    U0 = initial_cond(Ne, Ng)
+    N = U0.shape[1]
+    gate = np.eye(N)[:, rng.permutation(N)].astype(complex)
+    if use_sparse is None:
+        use_sparse = nsub > 1
+    p = objparams(Ne, Ng, T, nsteps, Uinit=U0, Utarget=U0 @ gate, Cfreq=om, Rfreq=[4.0 + k for k in range(nsub)],
+                  Hconst=H0, Hsym_ops=Hsym, Hanti_ops=Hanti, use_sparse=use_sparse)
+    estimate_Neumann(1e-12, p, maxpar)
+    cfg = Config("qudits" + "x".join(str(t) for t in Nt), p, None, D1, maxpar)
+    cfg.pcof0 = rng.uniform(-1, 1, cfg.nCoeff) * maxamp * 0.5
+    return cfg
+
+
 def example(name: str) -> Config:
     """One of the five BASELINE.json configurations."""
     return {"rabi": _ex_rabi, "cnot1": _ex_cnot1, "cnot2": _ex_cnot2, "cnot3": _ex_cnot3,

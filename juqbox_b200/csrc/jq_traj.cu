@@ -68,7 +68,16 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------ exchange access
 // V doubles per position, laid out in planes of `stride` positions so that consecutive lanes hit consecutive banks.
-template <int V> struct Xch;
+template <int V> struct Xch {          // general V: V/2 planes of double2 followed by one plane of double when V is odd
+    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) {
+        UNROLL for (int p = 0; p < V / 2; ++p) reinterpret_cast<double2 *>(b)[p * s + pos] = make_double2(x[2 * p], x[2 * p + 1]);
+        if (V & 1) b[2 * (V / 2) * s + pos] = x[V - 1];
+    }
+    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) {
+        UNROLL for (int p = 0; p < V / 2; ++p) { double2 v = reinterpret_cast<const double2 *>(b)[p * s + pos]; x[2 * p] = v.x; x[2 * p + 1] = v.y; }
+        if (V & 1) x[V - 1] = b[2 * (V / 2) * s + pos];
+    }
+};
 template <> struct Xch<1> {
     static __device__ __forceinline__ void st(double *b, int pos, int, const double *x) { b[pos] = x[0]; }
     static __device__ __forceinline__ void ld(const double *b, int pos, int, double *x) { x[0] = b[pos]; }
@@ -988,6 +997,7 @@ const Inst kInst[] = {
     SLOTO(1, 4, 2, 2), SLOTO(1, 3, 1, 2), SLOTO(1, 4, 1, 2), SLOTO(1, 2, 1, 2),
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
+    FIBER(5, 2, 1, 1), FIBER(5, 3, 1, 1), FIBER(6, 2, 1, 1), FIBER(5, 1, 1, 2), FIBERO(5, 2, 1, 1),      // 5- and 6-level fastest subsystem
     FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
     FIBERJG(4, 2, 1, 1, 4, 16), FIBERJG(6, 1, 1, 2, 3, 4), FIBERJ(3, 2, 1, 1, 5),
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
@@ -1119,7 +1129,7 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
         if (!any) { R = r + 1; break; }
     }
     if (n % R != 0) return no("rows do not split into equal fibres");
-    if (R < 2 || R > 6 || R == 5) return no("fibre length not instantiated");
+    if (R < 2 || R > 6) return no("fibre length not instantiated");
     const int nfib = n / R;
     int LMASK = 0;
     struct Rem { int off[2]; double hs[2], ha[2]; };

@@ -316,3 +316,25 @@ def test_jacobi_solver_tolerance_exit_vs_oracle():
     assert abs(res2["infid"][0, 0] - o2["infid"][0, 0]) < 1e-10
     assert abs(res2["infid"][0, 0] - res["infid"][0, 0]) > 1e-11
     wa.close(); wa2.close()
+
+
+@pytest.mark.parametrize("Ne,Ng,kw,kernel", [
+    ([2], [1], {}, 3), ([3], [2], {}, 3), ([5], [3], {}, 2), ([2, 2], [0, 0], {}, 3), ([3, 3], [2, 2], {}, 3),
+    ([3, 2], [2, 1], {}, 3), ([2, 2, 2], [1, 1, 1], {}, 3), ([2, 2], [2, 2], {"exchange": 0.02}, 1), ([2, 2], [2, 2], {"Nfreq": 3}, 3),
+])
+def test_other_shapes_auto_kernel_vs_oracle(Ne, Ng, kw, kernel):
+    """Shapes beyond the named configs (tools/kernel_coverage.py): the auto-selected kernel is the expected one and
+    matches the oracle; an off-diagonal drift Hamiltonian must fall back to the generic kernel, not be mis-planned."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    from oracle import oracle_traceobjgrad
+    cfg = configs.qudit_system(Ne, Ng, **kw)
+    wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
+    pc = np.random.default_rng(5).uniform(-1, 1, (3, cfg.nCoeff)) * cfg.maxpar[0] * 0.5
+    r = wa.evaluate(pc)
+    assert wa.last_kernel == kernel
+    o = oracle_traceobjgrad(cfg.params, pc)
+    for b in range(3):
+        assert abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12 and abs(r["leak"][b, 0] - o["leak"][b, 0]) < 1e-12
+        assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL
+    wa.close()
