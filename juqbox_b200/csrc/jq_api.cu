@@ -316,7 +316,7 @@ extern "C" int jq_query(jq_handle *h, int32_t what, double *value) {
 }
 
 // Per-candidate outputs: copies (weights == nullptr) or weighted sums over the samples of each candidate
-// (src/ipopt_interface.jl:48-59), always in sample order -> deterministic.
+// (src/ipopt_interface.jl:48-59) in sample order (few samples; jq_weighted_sum_kernel takes over from 64 samples).
 __global__ void jq_finalize_kernel(int nbatch, int nsamples, int Npar, int objFuncType, int evaladjoint, const double *w,
                                    const double *scal, const double *gt, const double *igt, double *infid, double *leak,
                                    double *tinfid, double *grad, double *infidgrad, double *leakgrad) {
@@ -349,6 +349,46 @@ __global__ void jq_finalize_kernel(int nbatch, int nsamples, int Npar, int objFu
             } else if (infidgrad) {
                 infidgrad[(size_t)o * Npar + k] = g;                      // infidelgrad = totalgrad, :951
             }
+        }
+    }
+}
+
+// Weighted sums over many samples of one candidate (risk-neutral quadrature / noise sweeps with thousands of nodes):
+// block (tile of 32 output columns, candidate); thread (column c, sample lane l) sums samples l, l+32, ... in order,
+// the 32 lane partials are then added in lane order -> deterministic for a given nsamples.  Columns 0..Npar-1 are the
+// gradient entries, Npar..Npar+2 the three scalars.
+#define WS_LANES 32
+__global__ void __launch_bounds__(32 * WS_LANES) jq_weighted_sum_kernel(int nsamples, int Npar, int objFuncType, int evaladjoint,
+                                   const double *w, const double *scal, const double *gt, const double *igt, double *infid, double *leak,
+                                   double *tinfid, double *grad, double *infidgrad, double *leakgrad) {
+    __shared__ double part[2][WS_LANES][33];
+    const int c = threadIdx.x & 31, l = threadIdx.x >> 5, k = blockIdx.x * 32 + c, o = blockIdx.y;
+    const size_t t0 = (size_t)o * nsamples;
+    double g = 0.0, ig = 0.0;
+    if (k < Npar) {
+        if (evaladjoint)
+            for (int s = l; s < nsamples; s += WS_LANES) {
+                g += w[s] * gt[(t0 + s) * Npar + k];
+                if (objFuncType != 1) ig += w[s] * igt[(t0 + s) * Npar + k];
+            }
+    } else if (k < Npar + 3) {
+        for (int s = l; s < nsamples; s += WS_LANES) g += w[s] * scal[(t0 + s) * 4 + (k - Npar)];
+    }
+    part[0][l][c] = g; part[1][l][c] = ig;
+    __syncthreads();
+    if (l != 0 || k >= Npar + 3) return;
+    g = 0.0; ig = 0.0;
+    for (int j = 0; j < WS_LANES; ++j) { g += part[0][j][c]; ig += part[1][j][c]; }
+    if (k >= Npar) {
+        double *dst = k == Npar ? infid : k == Npar + 1 ? leak : tinfid;
+        if (dst) dst[o] = g;
+    } else if (evaladjoint) {
+        if (grad) grad[(size_t)o * Npar + k] = g;
+        if (objFuncType != 1) {
+            if (infidgrad) infidgrad[(size_t)o * Npar + k] = ig;
+            if (leakgrad) leakgrad[(size_t)o * Npar + k] = g - ig;
+        } else if (infidgrad) {
+            infidgrad[(size_t)o * Npar + k] = g;
         }
     }
 }
@@ -415,8 +455,12 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     const int nout = weights ? nbatch : (int)ntraj;
     const long long total = (long long)nout * (npar + 1);
     const int fb = 256, fg = (int)std::min<long long>((total + fb - 1) / fb, 148 * 8);
-    jq_finalize_kernel<<<fg, fb, 0, st>>>(nbatch, nsamples, npar, h->P.objFuncType, A.evaladjoint, weights, h->d_scal, h->d_grad,
-                                          h->d_igrad, infid, leak, trace_infid, grad, infidgrad, leakgrad);
+    if (weights && nsamples >= 64)
+        jq_weighted_sum_kernel<<<dim3((npar + 3 + 31) / 32, nbatch), 32 * WS_LANES, 0, st>>>(nsamples, npar, h->P.objFuncType, A.evaladjoint,
+                                          weights, h->d_scal, h->d_grad, h->d_igrad, infid, leak, trace_infid, grad, infidgrad, leakgrad);
+    else
+        jq_finalize_kernel<<<fg, fb, 0, st>>>(nbatch, nsamples, npar, h->P.objFuncType, A.evaladjoint, weights, h->d_scal, h->d_grad,
+                                              h->d_igrad, infid, leak, trace_infid, grad, infidgrad, leakgrad);
     CU(cudaGetLastError());
     h->last_launches = 2;
     if (h->comm && weights && h->comm_size > 1) {

@@ -338,3 +338,31 @@ def test_other_shapes_auto_kernel_vs_oracle(Ne, Ng, kw, kernel):
         assert abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12 and abs(r["leak"][b, 0] - o["leak"][b, 0]) < 1e-12
         assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL
     wa.close()
+
+
+@pytest.mark.parametrize("objFuncType", [1, 3])
+def test_weighted_sum_over_many_samples(objFuncType):
+    """eval_f_g_grad!'s accumulation (src/ipopt_interface.jl:48-59) with hundreds of quadrature nodes goes through
+    the parallel weighted-sum kernel; it must equal the weighted sum of the per-sample outputs of the same library."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    cfg = configs.example("risk_neutral")
+    cfg.params.T, cfg.params.nsteps, cfg.params.objFuncType = 30.0, 800, objFuncType
+    ns = 333
+    eps = np.linspace(-0.06, 0.06, ns)
+    w = np.random.default_rng(2).uniform(0.1, 1.0, ns)
+    w /= w.sum()
+    shifts = configs.noise_shift(cfg.params.Ntot, eps)
+    pc = configs.synthetic_pcof(cfg, 2) * 20
+    wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
+    per = wa.evaluate(pc, shifts)
+    tot = wa.evaluate(pc, shifts, w)
+    for key in ("infid", "leak", "trace_infid"):
+        ref = (per[key] * w[None, :]).sum(axis=1)
+        assert np.allclose(tot[key].ravel(), ref, rtol=1e-13, atol=1e-15), key
+    for key in ("grad", "infidgrad") + (("leakgrad",) if objFuncType != 1 else ()):
+        ref = (per[key] * w[None, :, None]).sum(axis=1)
+        assert np.allclose(tot[key].reshape(ref.shape), ref, rtol=1e-12, atol=1e-15), key
+    tot2 = wa.evaluate(pc, shifts, w)
+    assert np.array_equal(tot["grad"], tot2["grad"])          # deterministic
+    wa.close()
