@@ -989,6 +989,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int
 #define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, 0, GLT>, GLT}   /* compile-time J and group size */
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBERF(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 256 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, 1>}   /* fused backward step */
+#define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, MINB>}
 const Inst kInst[] = {
@@ -998,8 +999,9 @@ const Inst kInst[] = {
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBER(5, 2, 1, 1), FIBER(5, 3, 1, 1), FIBER(6, 2, 1, 1), FIBER(5, 1, 1, 2), FIBERO(5, 2, 1, 1),      // 5- and 6-level fastest subsystem
-    FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3),
-    FIBERJG(4, 2, 1, 1, 4, 16), FIBERJG(6, 1, 1, 2, 3, 4), FIBERJ(3, 2, 1, 1, 5),
+    FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3), FIBERV(4, 3, 1, 1, 1, 1), FIBERV(3, 2, 1, 1, 1, 1), FIBERV(3, 3, 1, 1, 1, 1),
+    FIBERX(4, 2, 1, 1, 4, 16, 1, 32 + 4),          // cnot2 example shape: warp-shuffle exchange measured 3.5% faster than shared memory (variant 512)
+    FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4), FIBERJ(3, 2, 1, 1, 5),
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
     FIBERF(4, 2, 1, 1, 4), FIBERF(4, 2, 1, 1, 0), FIBERF(4, 3, 1, 1, 0),      // experiment: paired state/adjoint rounds, measured +-1%
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
@@ -1243,7 +1245,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
                            size_t *smem, int *traj_per_cta) {
     const char *venv = getenv("JQ_TRAJ_VARIANT");
     if (P.objFuncType != 1) venv = "64";
-    const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv)) : nullptr;
+    const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv), pl->GL) : nullptr;
     if (!inst && !venv && pl->AS && P.objFuncType == 1)      // instantiations with the number of Neumann terms known at compile time
         inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J, pl->GL);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);
