@@ -81,6 +81,50 @@ __global__ void smem_chain(double *out, long long *cyc, int iters) {
     if (threadIdx.x == 0) *cyc = t1 - t0;
 }
 
+// Do FP64 MMA (mma.sync m8n8k4) and DFMA share an execution pipe?  MODE 0: DFMA only, 1: DMMA only, 2: both interleaved.
+// NF independent DFMA chains and ND independent DMMA accumulators per thread per inner iteration.
+template <int MODE, int NF, int ND>
+__global__ void dmma_dfma_mix(double *out, long long *cyc, int iters, double a, double b) {
+    double x[NF], c[ND][2];
+    for (int k = 0; k < NF; ++k) x[k] = threadIdx.x * 1e-3 + k;
+    for (int k = 0; k < ND; ++k) { c[k][0] = k; c[k][1] = -k; }
+    double fa = 1e-3 * (threadIdx.x % 7), fb = 1e-3 * (threadIdx.x % 5);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (MODE != 1) {
+#pragma unroll
+                for (int k = 0; k < NF; ++k) x[k] = fma(x[k], a, b);
+            }
+            if (MODE != 0) {
+#pragma unroll
+                for (int k = 0; k < ND; ++k)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(fa), "d"(fb));
+            }
+        }
+    }
+    long long t1 = clock64();
+    double s = 0;
+    for (int k = 0; k < NF; ++k) s += x[k];
+    for (int k = 0; k < ND; ++k) s += c[k][0] + c[k][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+__global__ void dmma_chain(double *out, long long *cyc, int iters) {
+    double c0 = 0, c1 = 1, fa = 1e-3 * (threadIdx.x % 7), fb = 1e-3 * (threadIdx.x % 5);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(fa), "d"(fb));
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = c0 + c1;
+    if (threadIdx.x == 0) *cyc = t1 - t0;
+}
+
 int main() {
     double *out; long long *cyc, h;
     cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 8);
@@ -101,5 +145,12 @@ int main() {
     printf("3-operand DFMA, %d warps x ILP %d: %.2f cycles per warp-DFMA per scheduler\n", WARPS, ILP,               \
            (double)h / (1024 * 4.0 * 3 * ILP) / ((WARPS + 3) / 4));
     RUN3(8, 4) RUN3(8, 8) RUN3(4, 8) RUN3(8, 16)
+    dmma_chain<<<1, 32>>>(out, cyc, iters); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("dependent DMMA m8n8k4 latency: %.2f cycles\n", (double)h / (iters * 16.0));
+#define MIX(MODE, NF, ND, WARPS)                                                                                 \
+    dmma_dfma_mix<MODE, NF, ND><<<1, 32 * WARPS>>>(out, cyc, 1024, 0.999, 1e-9); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); \
+    printf("1 SM, %d warps, per inner iteration %d DFMA + %d DMMA (mode %d): %.1f cycles\n", WARPS, MODE == 1 ? 0 : NF, MODE == 0 ? 0 : ND, MODE, \
+           (double)h / (1024 * 4.0));
+    MIX(0, 8, 2, 8) MIX(1, 8, 2, 8) MIX(2, 8, 2, 8) MIX(0, 8, 4, 8) MIX(1, 8, 4, 8) MIX(2, 8, 4, 8) MIX(1, 8, 1, 8) MIX(2, 8, 1, 8)
     return 0;
 }
