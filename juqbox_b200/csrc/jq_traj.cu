@@ -22,7 +22,7 @@
 // gradient costs no extra products.  Control table: every CH steps all threads fill knot index, the three B-spline
 // values and cos/sin of every carrier at the 2CH+1 time points, then p_q, q_q for every resident trajectory.
 // Template switches: UPL gradient-scatter roles per lane, MINB register cap, JT compile-time number of Neumann terms,
-// OBJ second adjoint set (objFuncType 2/3), FUSED state and adjoint step advanced in paired rounds (experiment).
+// OBJ second adjoint set (objFuncType 2/3), GLT compile-time group size.
 //
 // Reference lines: forward loop src/evalobjgrad.jl:698-753, infidelity :755-766, adjoint init :810-844/:2026-2042,
 // backward loop :859-921, steppers src/StormerVerlet.jl:255-303,:461-504, Neumann src/linear_solvers.jl:94-106,
@@ -154,14 +154,6 @@ struct SlotLane {
         __syncwarp();
         nb.b = b;
     }
-    // two blocks in one round (one __syncwarp)
-    __device__ __forceinline__ void exchange2(const double (&xa)[E], const double (&xb)[E], Nbr &na, Nbr &nb) {
-        double *b = buf + parity * (2 * nlr * C);
-        parity ^= 1;
-        UNROLL for (int k = 0; k < R; ++k) { Xch<C>::st(b, own[k], nlr, &xa[k * C]); Xch<C>::st(b + nlr * C, own[k], nlr, &xb[k * C]); }
-        __syncwarp();
-        na.b = b; nb.b = b + nlr * C;
-    }
 
     // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
     struct SC { double c[R][NC][WQ]; };
@@ -284,21 +276,6 @@ struct FiberLane {
             b = bw;
         }
         fetch(b, x, nb);
-    }
-    // two blocks in one round (one __syncwarp, twice the independent work behind one exchange latency)
-    __device__ __forceinline__ void exchange2(const double (&xa)[E], const double (&xb)[E], Nbr &na, Nbr &nb) {
-        if (!REMOTE) return;
-        const double *b = buf;
-        if (XM == 0) {
-            double *bw = buf + parity * (2 * R * 32);
-            parity ^= 1;
-            Xch<R>::st(bw, lane, 32, xa);
-            Xch<R>::st(bw + R * 32, lane, 32, xb);
-            __syncwarp();
-            b = bw;
-        }
-        fetch(b, xa, na);
-        fetch(b + R * 32, xb, nb);
     }
 
     // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
@@ -555,159 +532,6 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     __syncwarp();
 }
 
-// Two Neumann solves advanced together: one exchange round serves both (src/linear_solvers.jl:94-106 twice).
-template <int JT, class LaneT>
-__device__ __forceinline__ void neumann2(LaneT &L, const typename LaneT::SC &sca, const typename LaneT::SC &scb, int J, double h,
-                                         double (&Ba)[LaneT::E], double (&Xa)[LaneT::E], double (&Bb)[LaneT::E], double (&Xb)[LaneT::E]) {
-    constexpr int E = LaneT::E;
-    UNROLL for (int e = 0; e < E; ++e) { Xa[e] = Ba[e]; Xb[e] = Bb[e]; }
-    double coeff = 1.0;
-    const int JJ = JT > 0 ? JT : J;
-#pragma unroll
-    for (int it = 0; it < JJ; ++it) {
-        typename LaneT::Nbr na, nb;
-        L.exchange2(Ba, Bb, na, nb);
-        double Ta[E], Tb[E];
-        L.s_from(sca, Ba, na, Ta);
-        L.s_from(scb, Bb, nb, Tb);
-        coeff *= 0.5 * h;
-        UNROLL for (int e = 0; e < E; ++e) { Ba[e] = Ta[e]; Xa[e] = fma(coeff, Ta[e], Xa[e]); Bb[e] = Tb[e]; Xb[e] = fma(coeff, Tb[e], Xb[e]); }
-    }
-}
-
-// One backward iteration with the state recomputation (src/StormerVerlet.jl:461-504, h < 0) and the adjoint step with
-// forcing (:255-303) advanced TOGETHER.  The state step and the adjoint step of the same iteration only meet through
-// the forcing and the gradient traces, so their products are paired round by round: 5 + 2J exchange rounds instead of
-// 2(5 + 2J), each with twice the independent work behind one exchange latency.  Two traces are taken in transposed
-// form, which is exact because Hanti is antisymmetric (checked by the planner):
-//   tr(vi05, Ha, li0) = -sum li0 .* (Ha vi05)      (Ha vi05 is a by-product of the state step's v05 product)
-//   tr(vr,   Ha, lr05) = -sum lr05 .* (Ha vr)      (Ha vr  is a by-product of the state step's last product)
-// Traces (src/evalobjgrad.jl:2578-2618) are left group-reduced in tred[q*5 + a], a as in adjoint_step.
-template <int JT, class LaneT>
-__device__ __forceinline__ void backward_step_fused(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E],
-                                                    double (&mu)[LaneT::E], double (&nu)[LaneT::E], double *tred, int GL,
-                                                    int gbase_lane, bool writer) {
-    constexpr int E = LaneT::E, NC = LaneT::NC;
-    double vr0[E], v05[E], rhsA[E], rhsB[E], s0u[E], s05n[E], l1[E], X[E];
-    double T4[NC], T5[NC];
-    UNROLL for (int qq = 0; qq < NC; ++qq) { T4[qq] = 0.0; T5[qq] = 0.0; }
-    UNROLL for (int e = 0; e < E; ++e) vr0[e] = u[e];
-    typename LaneT::SC scA, scB;
-    L.sync_reset();
-    // ---- round 1: K05 u, S0 u   |   S0 mu
-    L.s_prescale(0, scB);
-    {
-        typename LaneT::Nbr na, nb;
-        L.exchange2(u, mu, na, nb);
-        L.template each_from<true, true>(u, na, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-            double r = L.d0[e] * u[e], s = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], Ae[qq], r); s = fma(L.q[0][qq], De[qq], s); }
-            rhsA[e] = r; s0u[e] = s;
-        });
-        L.s_from(scB, mu, nb, rhsB);
-    }
-    // ---- round 2: S05 v   |   K05 nu, S05 nu, tr(vr0, Hs, li0)
-    L.s_prescale(1, scA);
-    {
-        typename LaneT::Nbr na, nb;
-        L.exchange2(v, nu, na, nb);
-        double tv[E];
-        L.s_from(scA, v, na, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhsA[e] += tv[e];
-        L.template each_from<true, true>(nu, nb, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-            double kk = L.d0[e] * nu[e], s = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq) {
-                kk = fma(L.p[1][qq], Ae[qq], kk);
-                s = fma(L.q[1][qq], De[qq], s);
-                T4[qq] = fma(vr0[e], Ae[qq], T4[qq]);
-            }
-            rhsB[e] = fma(L.w[e], vr0[e], rhsB[e]) - kk;     // S0 mu + hr0 - K05 nu
-            s05n[e] = s;
-        });
-    }
-    // ---- first pair of solves: (I - h/2 S05) l1 = rhsA   |   (I - h/2 S0) k2 = rhsB
-    neumann2<JT>(L, scA, scB, J, h, rhsA, l1, rhsB, X);
-    UNROLL for (int e = 0; e < E; ++e) { v05[e] = fma(0.5 * h, l1[e], v[e]); X[e] = fma(0.5 * h, X[e], mu[e]); }   // X = lr05
-    // ---- round 3: K0 v05, K1 v05, S05 v05, -tr(li0, Ha, vi05)   |   K0 X, K1 X, S1 X, tr(vr0,Ha,X), tr(vi05,Hs,X)
-    double k1v[E], s05v[E], l2[E], r0[E], mu2[E];
-    {
-        typename LaneT::Nbr na, nb;
-        L.exchange2(v05, X, na, nb);
-        L.template each_from<true, true>(v05, na, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-            double k0 = L.d0[e] * v05[e], k1 = k0, s = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq) {
-                k0 = fma(L.p[0][qq], Ae[qq], k0);
-                k1 = fma(L.p[2][qq], Ae[qq], k1);
-                s = fma(L.q[1][qq], De[qq], s);
-                T5[qq] = fma(-nu[e], De[qq], T5[qq]);        // tr(vi05, Ha, li0), transposed
-            }
-            k1v[e] = k1; s05v[e] = s;
-            u[e] = fma(0.5 * h, s0u[e] - k0, u[e]);          // u + (h/2) kappa1
-        });
-        double T1[NC], T2[NC];
-        UNROLL for (int qq = 0; qq < NC; ++qq) { T1[qq] = 0.0; T2[qq] = 0.0; }
-        L.template each_from<true, true>(X, nb, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-            double k0 = L.d0[e] * X[e], k1 = k0, s = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq) {
-                k0 = fma(L.p[0][qq], Ae[qq], k0);
-                k1 = fma(L.p[2][qq], Ae[qq], k1);
-                s = fma(L.q[2][qq], De[qq], s);
-                T1[qq] = fma(vr0[e], De[qq], T1[qq]);
-                T2[qq] = fma(v05[e], Ae[qq], T2[qq]);
-            }
-            const double hi0 = L.w[e] * v05[e];
-            l2[e] = k0 + s05n[e] + hi0;                      // K0 X + S05 nu + hi0
-            r0[e] = s05n[e] + k1 + hi0;                      // S05 nu + K1 X + hi1
-            mu2[e] = fma(0.5 * h, s, X[e]);                  // X + (h/2) S1 X      (hr1 is added in round 5)
-        });
-        double tv[NC * 2];
-        UNROLL for (int qq = 0; qq < NC; ++qq) { tv[2 * qq] = T1[qq]; tv[2 * qq + 1] = T2[qq]; }
-        group_sum_n(tv, GL, gbase_lane);
-        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) { tred[qq * 5 + 0] = tv[2 * qq]; tred[qq * 5 + 1] = tv[2 * qq + 1]; } }
-    }
-    // ---- round 4: S1 u'   |   S05 l2
-    L.s_prescale(2, scA);
-    L.s_prescale(1, scB);
-    {
-        typename LaneT::Nbr na, nb;
-        L.exchange2(u, l2, na, nb);
-        double ta[E], tb[E];
-        L.s_from(scA, u, na, ta);
-        L.s_from(scB, l2, nb, tb);
-        UNROLL for (int e = 0; e < E; ++e) { rhsA[e] = ta[e] - k1v[e]; rhsB[e] = fma(0.5 * h, tb[e], r0[e]); }
-    }
-    // ---- second pair of solves: (I - h/2 S1) kappa2 = rhsA   |   (I - h/2 S05) l1' = rhsB
-    double k2[E], l1b[E];
-    neumann2<JT>(L, scA, scB, J, h, rhsA, k2, rhsB, l1b);
-    UNROLL for (int e = 0; e < E; ++e) { u[e] = fma(0.5 * h, k2[e], u[e]); nu[e] = fma(0.5 * h, l2[e] + l1b[e], nu[e]); }
-    // ---- round 5: K05 u'', -tr(X, Ha, vr)   |   K05 nu', tr(vr,Hs,li), tr(vi05,Ha,li)
-    {
-        typename LaneT::Nbr na, nb;
-        L.exchange2(u, nu, na, nb);
-        double T3[NC];
-        UNROLL for (int qq = 0; qq < NC; ++qq) T3[qq] = 0.0;
-        L.template each_from<true, true>(u, na, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-            double l2a = fma(L.d0[e], u[e], s05v[e]);
-            UNROLL for (int qq = 0; qq < NC; ++qq) { l2a = fma(L.p[1][qq], Ae[qq], l2a); T3[qq] = fma(-X[e], De[qq], T3[qq]); }
-            v[e] = fma(0.5 * h, l1[e] + l2a, v[e]);
-        });
-        L.template each_from<true, true>(nu, nb, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-            double kk = L.d0[e] * nu[e];
-            UNROLL for (int qq = 0; qq < NC; ++qq) {
-                kk = fma(L.p[1][qq], Ae[qq], kk);
-                T4[qq] = fma(u[e], Ae[qq], T4[qq]);
-                T5[qq] = fma(v05[e], De[qq], T5[qq]);
-            }
-            mu[e] = fma(0.5 * h, fma(L.w[e], u[e], -kk), mu2[e]);      // + (h/2)(hr1 - K05 nu)
-        });
-        double tv[NC * 3];
-        UNROLL for (int qq = 0; qq < NC; ++qq) { tv[3 * qq] = T3[qq]; tv[3 * qq + 1] = T4[qq]; tv[3 * qq + 2] = T5[qq]; }
-        group_sum_n(tv, GL, gbase_lane);
-        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) { tred[qq * 5 + 2] = tv[3 * qq]; tred[qq * 5 + 3] = tv[3 * qq + 1]; tred[qq * 5 + 4] = tv[3 * qq + 2]; } }
-    }
-    __syncwarp();
-}
-
 // Fill the control table for `nst` steps starting at time t (all threads of the CTA).
 template <int NC>
 __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt, int nst, double dtknot) {
@@ -805,7 +629,7 @@ __device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, con
 
 // OBJ = 1: objFuncType 2/3 — a second adjoint set without forcing gives the infidelity-only gradient
 // (src/evalobjgrad.jl:848-855, :905-918; step_no_forcing! src/StormerVerlet.jl:365-406).
-template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int FUSED = 0, int GLT = 0>
+template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0>
 __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     extern __shared__ double sm[];
@@ -942,13 +766,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         LOAD_LEVEL0();
         for (int ls = 0; ls < nst; ++ls) {
             LOAD_LEVELS(ls);
-            if constexpr (FUSED != 0) {
-                backward_step_fused<JT>(L, J, dt, vr, vi, lr, li, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
-            } else {
-                UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
-                state_step<JT>(L, J, dt, vr, vi, vi05);
-                adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
-            }
+            UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
+            state_step<JT>(L, J, dt, vr, vi, vi05);
+            adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
             grad_scatter<NC, UPL>(U, gsm, tred, tabb, tabph, tabk, ls, Nfreq);
             if constexpr (OBJ != 0) {
                 adjoint_step<JT, false>(L, J, dt, lrn, lin, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);
@@ -978,20 +798,19 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
 }
 
 typedef void (*traj_kernel_t)(const TrajParams);
-// variant: 0 default, 16 general Hanti, 32+J compile-time J, 64 objFuncType 2/3; experiments selectable with the env
-// variable JQ_TRAJ_VARIANT: 1 warp-shuffle exchange, 2 three CTAs/SM register cap, 256(+J) paired state/adjoint rounds
+// variant: 0 default, 16 general Hanti, 32+J compile-time J, 64 objFuncType 2/3; selectable for comparisons with the env
+// variable JQ_TRAJ_VARIANT: 1 warp-shuffle exchange (runtime J), 512 shared-memory twin of the cnot2 instantiation
 struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; };
 #define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
 #define SLOTO(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 64, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
 #define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
-#define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, 0, GLT>, GLT}   /* compile-time J and group size */
+#define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size */
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
-#define FIBERF(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 256 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, 1>}   /* fused backward step */
-#define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
+#define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
-#define FIBERV(R, NC, LMASK, UPL, XM, MINB) {3, R, 1, NC, 2, LMASK, UPL, (XM) | ((MINB) == 3 ? 2 : 0), jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, MINB>}
+#define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
 const Inst kInst[] = {
     SLOT(1, 2, 1, 2), SLOT(1, 3, 1, 2), SLOT(1, 4, 1, 2), SLOT(1, 4, 2, 2), SLOT(1, 2, 2, 2),
     SLOT(2, 2, 3, 2), SLOT(3, 1, 3, 2), SLOT(1, 1, 1, 2), SLOT(1, 1, 2, 2),
@@ -999,11 +818,10 @@ const Inst kInst[] = {
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBER(5, 2, 1, 1), FIBER(5, 3, 1, 1), FIBER(6, 2, 1, 1), FIBER(5, 1, 1, 2), FIBERO(5, 2, 1, 1),      // 5- and 6-level fastest subsystem
-    FIBERV(4, 2, 1, 1, 1, 1), FIBERV(4, 2, 1, 1, 0, 3), FIBERV(4, 3, 1, 1, 1, 1), FIBERV(3, 2, 1, 1, 1, 1), FIBERV(3, 3, 1, 1, 1, 1),
+    FIBERV(4, 2, 1, 1, 1), FIBERV(4, 3, 1, 1, 1), FIBERV(3, 2, 1, 1, 1), FIBERV(3, 3, 1, 1, 1),
     FIBERX(4, 2, 1, 1, 4, 16, 1, 32 + 4),          // cnot2 example shape: warp-shuffle exchange measured 3.5% faster than shared memory (variant 512)
     FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4), FIBERJ(3, 2, 1, 1, 5),
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
-    FIBERF(4, 2, 1, 1, 4), FIBERF(4, 2, 1, 1, 0), FIBERF(4, 3, 1, 1, 0),      // experiment: paired state/adjoint rounds, measured +-1%
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
