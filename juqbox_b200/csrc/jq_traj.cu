@@ -379,7 +379,8 @@ __device__ __forceinline__ void group_sum_n(double (&v)[N], int GL, int base) {
     }
     double s[N];
     UNROLL for (int i = 0; i < N; ++i) s[i] = 0.0;
-    for (int j = 0; j < GL; ++j) {
+#pragma unroll
+    for (int j = 0; j < GL; ++j) {           // unrolled for GLT instantiations
         UNROLL for (int i = 0; i < N; ++i) s[i] += __shfl_sync(0xffffffffu, v[i], base + j);
     }
     UNROLL for (int i = 0; i < N; ++i) v[i] = s[i];
@@ -808,6 +809,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int
 #define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
 #define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size */
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
+#define FIBERJGM(R, NC, LMASK, UPL, JT, GLT, MINB, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB, JT, 0, GLT>, GLT}
 #define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
@@ -820,7 +822,8 @@ const Inst kInst[] = {
     FIBER(5, 2, 1, 1), FIBER(5, 3, 1, 1), FIBER(6, 2, 1, 1), FIBER(5, 1, 1, 2), FIBERO(5, 2, 1, 1),      // 5- and 6-level fastest subsystem
     FIBERV(4, 2, 1, 1, 1), FIBERV(4, 3, 1, 1, 1), FIBERV(3, 2, 1, 1, 1), FIBERV(3, 3, 1, 1, 1),
     FIBERX(4, 2, 1, 1, 4, 16, 1, 32 + 4),          // cnot2 example shape: warp-shuffle exchange measured 3.5% faster than shared memory (variant 512)
-    FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4), FIBERJ(3, 2, 1, 1, 5),
+    FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4),
+    FIBERJGM(4, 1, 1, 2, 5, 3, 3, 32 + 5), FIBERJGM(4, 1, 1, 2, 5, 3, 2, 1024 + 5),      // risk-neutral SWAP 0-2 shape (n = 4, m = 3, J = 5)
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };

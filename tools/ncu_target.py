@@ -8,5 +8,6 @@ nb = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 cfg = configs.example(name)
 pc = configs.synthetic_pcof(cfg, nb)
 wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
-r = wa.evaluate(pc)
+shifts = configs.noise_shift(cfg.params.Ntot, cfg.nodes) if name == "risk_neutral" else None
+r = wa.evaluate(pc, shifts)
 print(name, nb, "kernel", wa.last_kernel, "ms", wa.last_kernel_ms)
