@@ -111,6 +111,11 @@ int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pco
 int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
                     const double *h0_diag_shift, int32_t save_every, double *hist_r, double *hist_i, double *infid, double *leak);
 
+/* evalctrl(params, pcof, td, func) (src/plotstatectrl.jl:246-276): the control functions p_q(t), q_q(t) (rad/ns) of EVERY
+ * coupled control q on the time grid `times`, evaluated by the device function the time loop uses (bcarrier2,
+ * src/bsplines.jl:211-304).  p, q: [ncoupled][ntimes] doubles, host pointers, blocking. */
+int jq_eval_controls(jq_handle *h, const double *pcof, int32_t npar, int32_t ntimes, const double *times, double *p, double *q);
+
 /* Multi-GPU (one process and one handle per GPU).  The path's only exchange step is the weighted sum over noise
  * samples of eval_f_g_grad! (src/ipopt_interface.jl:48-59) when the samples are sharded across GPUs.
  * jq_comm_unique_id fills a 128-byte NCCL unique id on one rank (distribute it with whatever the host has);

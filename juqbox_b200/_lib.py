@@ -28,7 +28,7 @@ class jq_problem(C.Structure):
 JQ_DENSE, JQ_CSC = 0, 1
 JQ_ERR_PCOF_LENGTH = -2
 
-EXPORTS = ["jq_create", "jq_destroy", "jq_update_target", "jq_traceobjgrad_batch", "jq_traceobjgrad_batch_device", "jq_eval_forward",
+EXPORTS = ["jq_create", "jq_destroy", "jq_update_target", "jq_traceobjgrad_batch", "jq_traceobjgrad_batch_device", "jq_eval_forward", "jq_eval_controls",
            "jq_set_kernel", "jq_query", "jq_fp64_peak", "jq_fp64_peak_3op", "jq_fp64_peak_dmma", "jq_comm_unique_id", "jq_comm_init", "jq_comm_destroy",
            "jq_last_error", "jq_version"]
 
@@ -66,6 +66,7 @@ def load(build_if_missing: bool = True):
     lib.jq_traceobjgrad_batch.argtypes = [vp, i32, dp, i32, i32, dp, dp, i32, dp, dp, dp, dp, dp, dp]
     lib.jq_traceobjgrad_batch_device.argtypes = [vp, i32, dp, i32, i32, dp, dp, i32, dp, dp, dp, dp, dp, dp, vp]
     lib.jq_eval_forward.argtypes = [vp, i32, dp, i32, i32, dp, i32, dp, dp, dp, dp]
+    lib.jq_eval_controls.argtypes = [vp, dp, i32, i32, dp, dp, dp]
     lib.jq_set_kernel.argtypes = [vp, i32]
     lib.jq_query.argtypes = [vp, i32, C.POINTER(C.c_double)]
     lib.jq_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -74,7 +75,7 @@ def load(build_if_missing: bool = True):
     lib.jq_comm_unique_id.argtypes = [vp]
     lib.jq_comm_init.argtypes = [vp, i32, i32, vp]
     lib.jq_comm_destroy.argtypes = [vp]
-    for name in EXPORTS[:13]:
+    for name in EXPORTS[:-2]:
         getattr(lib, name).restype = C.c_int
     lib.jq_last_error.restype = C.c_char_p
     lib.jq_version.restype = C.c_char_p

@@ -202,6 +202,15 @@ class Working_Arrays:
                                              infid.ctypes.data_as(C.c_void_p), leak.ctypes.data_as(C.c_void_p)))
         return hr + 1j * hi, infid, leak
 
+    def controls(self, pcof, times):
+        """p_q(t), q_q(t) of every coupled control at `times` (jq_eval_controls).  Returns p, q of shape [Ncoupled, ntimes]."""
+        pcof, times = _f64(np.ravel(pcof)), _f64(np.ravel(times))
+        p = np.zeros((self.params.Ncoupled, len(times)))
+        q = np.zeros_like(p)
+        _lib.check(self._lib.jq_eval_controls(self._handle, pcof.ctypes.data_as(C.c_void_p), len(pcof), len(times),
+                                              times.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p)))
+        return p, q
+
     def evaluate_device(self, pcof, shifts=None, weights=None, evaladjoint=True, out=None, stream=None):
         """Batched evaluation on torch CUDA tensors (no host copies, asynchronous on `stream` or torch's current
         stream).  pcof [nbatch, npar], shifts [nsamples, n], weights [nsamples]; returns dict of CUDA tensors."""
@@ -256,6 +265,24 @@ def eval_forward(pcof0, params: objparams, wa: Working_Arrays, saveEndOnly: bool
     hist, _, _ = wa.forward_history(np.asarray(pcof0, dtype=np.float64)[None, :], save_every=params.nsteps if saveEndOnly else saveEvery)
     h = hist[0, 0].transpose(2, 1, 0)
     return h[:, :, -1] if saveEndOnly else h
+
+
+def evalctrl(params: objparams, pcof0, td, jFunc: int, wa: Optional[Working_Arrays] = None):
+    """pj, qj = evalctrl(params, pcof0, td, func) (src/plotstatectrl.jl:246-276): control function number `jFunc`
+    (1-based, as in the reference) on the time grid `td`, in rad/ns.  Evaluated on the GPU; `wa` avoids building a
+    temporary handle."""
+    if not 1 <= jFunc <= params.Ncoupled:
+        raise ValueError(f"jFunc must be in 1..{params.Ncoupled} (uncoupled controls are not built)")
+    pcof0 = np.asarray(pcof0, dtype=np.float64)
+    own = wa is None
+    if own:
+        wa = Working_Arrays(params, len(pcof0))
+    try:
+        p, q = wa.controls(pcof0, td)
+    finally:
+        if own:
+            wa.close()
+    return p[jFunc - 1].copy(), q[jFunc - 1].copy()
 
 
 def traceobjgrad_batch(pcofs, params: objparams, wa: Working_Arrays, nodes=None, weights=None, evaladjoint=True):

@@ -521,6 +521,25 @@ extern "C" int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof,
     return 0;
 }
 
+extern "C" int jq_eval_controls(jq_handle *h, const double *pcof, int32_t npar, int32_t ntimes, const double *times, double *p, double *q) {
+    int rc = check_batch_args(h, 1, pcof, npar, 1, nullptr);
+    if (rc) return rc;
+    if (ntimes < 0 || (ntimes > 0 && (!times || !p || !q))) return fail(JQ_ERR_ARG, "jq_eval_controls: null time or output array");
+    if (ntimes == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const size_t nout = (size_t)h->Nc * ntimes;
+    if ((rc = grow(&h->d_in, &h->cap_in, (size_t)npar + ntimes)) != 0) return rc;
+    if ((rc = grow(&h->d_out, &h->cap_out, 2 * nout)) != 0) return rc;
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(h->d_in, pcof, (size_t)npar * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->d_in + npar, times, (size_t)ntimes * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(jq_controls_launch(h->P, npar / (2 * h->Nc * h->Nfreq), h->d_in, ntimes, h->d_in + npar, h->d_out, h->d_out + nout, st));
+    CU(cudaMemcpyAsync(p, h->d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(q, h->d_out + nout, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int jq_traceobjgrad_batch(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
                                      const double *shift, const double *weights, int32_t evaladjoint, double *infid, double *leak,
                                      double *trace_infid, double *grad, double *infidgrad, double *leakgrad) {

@@ -35,6 +35,8 @@ struct LaunchArgs {
 // ---- generic kernel (jq_generic.cu): one CTA per trajectory, blocks in shared memory ----
 size_t jq_generic_smem_bytes(const DevProblem &P, int Npar);
 cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem);
+cudaError_t jq_controls_launch(const DevProblem &P, int D1, const double *pcof, int ntimes, const double *times, double *p, double *q,
+                               cudaStream_t st);
 
 // Host copy of the operators in row-wise form, used by the planners.
 struct HostOps {

@@ -341,6 +341,28 @@ size_t jq_generic_smem_bytes(const DevProblem &P, int Npar) {
     return sizeof(double) * (nblk * len + Npar * (P.objFuncType == 1 ? 2 : 3) + 6 * P.Nc + P.n + (GEN_THREADS / 32) * 8);
 }
 
+// evalctrl (src/plotstatectrl.jl:246-276): the control functions of every coupled control on an arbitrary time grid,
+// with the same device function the time loop uses.  p, q: [Nc][ntimes].
+__global__ void jq_controls_kernel(DevProblem P, int D1, const double *pcof, int ntimes, const double *times, double *p, double *q) {
+    Ctx c{};
+    c.P = &P; c.Nc = P.Nc; c.Nfreq = P.Nfreq; c.D1 = D1; c.pcof = const_cast<double *>(pcof); c.dtknot = P.T / (D1 - 2);
+    const long long total = (long long)P.Nc * ntimes;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int q_ = (int)(idx / ntimes);
+        const double t = times[idx % ntimes];
+        p[idx] = bcarrier2(c, t, 2 * q_);
+        q[idx] = bcarrier2(c, t, 2 * q_ + 1);
+    }
+}
+
+cudaError_t jq_controls_launch(const DevProblem &P, int D1, const double *pcof, int ntimes, const double *times, double *p, double *q,
+                               cudaStream_t st) {
+    const long long total = (long long)P.Nc * ntimes;
+    const int grid = (int)((total + 127) / 128 < 148 * 8 ? (total + 127) / 128 : 148 * 8);
+    jq_controls_kernel<<<grid > 0 ? grid : 1, 128, 0, st>>>(P, D1, pcof, ntimes, times, p, q);
+    return cudaGetLastError();
+}
+
 cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem) {
     const size_t bytes = jq_generic_smem_bytes(P, A.Npar);
     cudaError_t e = cudaFuncSetAttribute(jq_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

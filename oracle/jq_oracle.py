@@ -109,6 +109,23 @@ def oracle_forward_history(params, pcof, shift=None, save_every: int = 1):
     return hr + 1j * hi, out[0], out[1]
 
 
+def oracle_eval_controls(params, pcof, times):
+    """p_q(t), q_q(t) of every coupled control at `times` (reference evalctrl, plotstatectrl.jl:246).  Returns p, q [Nc, ntimes]."""
+    lib = _lib()
+    keep = []
+    P = _problem(params, keep)
+    pcof = np.ascontiguousarray(pcof, dtype=np.float64)
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    p = np.zeros((params.Ncoupled, len(times)))
+    q = np.zeros_like(p)
+    lib.jqo_eval_controls.restype = C.c_int
+    rc = lib.jqo_eval_controls(C.byref(P), C.c_int(len(pcof)), pcof.ctypes.data_as(C.c_void_p), C.c_int(len(times)),
+                               times.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError("bad pcof length")
+    return p, q
+
+
 def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nthreads: int = 1):
     """Run the oracle on a batch: pcof [nbatch, Npar] (or [Npar]), shifts [nsamples, n] or None.
 

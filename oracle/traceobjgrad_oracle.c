@@ -737,6 +737,23 @@ int jqo_forward_history(const jqo_problem *P, int Npar, const double *pcof, cons
     return 0;
 }
 
+/* evalctrl (plotstatectrl.jl:246-276): p_q(t), q_q(t) for every coupled control at the given times.
+ * p, q: [Nc][ntimes].  Only the fields of the problem that the control functions read are used. */
+int jqo_eval_controls(const jqo_problem *P, int Npar, const double *pcof, int ntimes, const double *times, double *p, double *q) {
+    if (Npar % (2 * P->Nc * P->Nfreq) != 0 || Npar / (2 * P->Nc * P->Nfreq) < 3) return -2;
+    ws_t w;
+    memset(&w, 0, sizeof(w));
+    w.Nc = P->Nc; w.Nfreq = P->Nfreq; w.Cfreq = P->Cfreq; w.T = P->T; w.Npar = Npar; w.pcof = pcof;
+    w.D1 = Npar / (2 * P->Nc * P->Nfreq);
+    w.dtknot = P->T / (w.D1 - 2);
+    for (int c = 0; c < P->Nc; c++)
+        for (int i = 0; i < ntimes; i++) {
+            p[(int64_t)c * ntimes + i] = bcarrier2(times[i], &w, 2 * c);
+            q[(int64_t)c * ntimes + i] = bcarrier2(times[i], &w, 2 * c + 1);
+        }
+    return 0;
+}
+
 int jqo_max_threads(void) {
     long nproc = sysconf(_SC_NPROCESSORS_ONLN);
     return nproc > 0 ? (int)nproc : 1;

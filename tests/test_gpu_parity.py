@@ -366,3 +366,27 @@ def test_weighted_sum_over_many_samples(objFuncType):
     tot2 = wa.evaluate(pc, shifts, w)
     assert np.array_equal(tot["grad"], tot2["grad"])          # deterministic
     wa.close()
+
+
+@pytest.mark.parametrize("name", ["rabi", "cnot2", "cnot3", "risk_neutral"])
+def test_evalctrl_matches_oracle(name):
+    """evalctrl (src/plotstatectrl.jl:246): device bcarrier2 on an arbitrary time grid vs the oracle's."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    from oracle import oracle_eval_controls
+    cfg = configs.example(name)
+    p = cfg.params
+    pc = np.random.default_rng(4).uniform(-1, 1, cfg.nCoeff) * cfg.maxpar[0]
+    t = np.concatenate([[0.0, p.T], np.random.default_rng(5).uniform(0, p.T, 1000), np.linspace(0, p.T, cfg.D1 - 1)])
+    wa = jq.Working_Arrays(p, cfg.nCoeff)
+    pv, qv = wa.controls(pc, t)
+    po, qo = oracle_eval_controls(p, pc, t)
+    scale = np.abs(po).max()
+    assert np.abs(pv - po).max() <= 1e-13 * scale and np.abs(qv - qo).max() <= 1e-13 * scale
+    pj, qj = jq.evalctrl(p, pc, t, p.Ncoupled, wa)           # 1-based control index, as in the reference
+    assert np.array_equal(pj, pv[-1]) and np.array_equal(qj, qv[-1])
+    with pytest.raises(ValueError):
+        jq.evalctrl(p, pc, t, 0, wa)
+    with pytest.raises(ValueError):                          # wrong coefficient count, like bcparams (src/bsplines.jl:178-181)
+        wa.controls(pc[:-1], t)
+    wa.close()

@@ -62,3 +62,24 @@ def test_oracle_threads_and_samples_are_independent():
     # zero shift == no shift
     ns = oracle_traceobjgrad(cfg.params, pc[0])
     assert np.allclose(ns["grad"][0, 0], a["grad"][0, 1], rtol=0, atol=1e-15)
+
+
+def test_oracle_controls_partition_of_unity():
+    """bcarrier2 (src/bsplines.jl:211-304): with every B-spline coefficient of a carrier equal, the quadratic splines
+    sum to one inside the interval, so p(t) = sum_f [a_f cos(w_f t) - b_f sin(w_f t)], q(t) = sum_f [a_f sin + b_f cos]."""
+    from oracle import oracle_eval_controls
+    cfg, _ = golden_config("cnot2")
+    p = cfg.params
+    Nc, Nf, D1 = p.Ncoupled, p.Nfreq, cfg.D1
+    rng = np.random.default_rng(0)
+    a, b = rng.standard_normal((Nc, Nf)), rng.standard_normal((Nc, Nf))
+    pcof = np.zeros((Nc, Nf, 2, D1))
+    pcof[:, :, 0, :] = a[:, :, None]
+    pcof[:, :, 1, :] = b[:, :, None]
+    t = np.linspace(0.0, p.T, 41)
+    pv, qv = oracle_eval_controls(p, pcof.ravel(), t)
+    for c in range(Nc):
+        w = p.Cfreq[c, :]
+        pe = sum(a[c, f] * np.cos(w[f] * t) - b[c, f] * np.sin(w[f] * t) for f in range(Nf))
+        qe = sum(a[c, f] * np.sin(w[f] * t) + b[c, f] * np.cos(w[f] * t) for f in range(Nf))
+        assert np.allclose(pv[c], pe, atol=1e-13) and np.allclose(qv[c], qe, atol=1e-13)
