@@ -134,3 +134,24 @@ function eval_f_g_grad!(pcof::Vector{Float64}, params::objparams, wa::Working_Ar
     params.lastTraceInfidelity = params.last_infidelity
     params.lastLeakIntegral = params.last_leak
 end
+
+# evalctrl (src/plotstatectrl.jl:246-276) on the GPU handle: control `jFunc` (1-based) on the grid `td`, rad/ns.
+function evalctrl(params::objparams, pcof0::Array{Float64,1}, td::Array{Float64,1}, jFunc::Int64, wa::Working_Arrays_B200)
+    nt = length(td)
+    p = zeros(nt, params.Ncoupled); q = zeros(nt, params.Ncoupled)       # column c = control c  ==  ABI [ncoupled][ntimes]
+    jq_check(ccall((:jq_eval_controls, libjq), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   wa.handle, pcof0, length(pcof0), nt, td, p, q))
+    return p[:, jFunc], q[:, jFunc]
+end
+
+# eval_forward(U0, pcof, params; saveEndOnly=false, saveEvery) (src/evalobjgrad.jl:2727-2873) with U0 = params.Uinit:
+# returns the Ntot x N x nsave complex state history.
+function eval_forward(pcof0::Array{Float64,1}, params::objparams, wa::Working_Arrays_B200; saveEvery::Int64 = 1)
+    Ntot = params.N + params.Nguard
+    nsave = div(params.nsteps, saveEvery) + 1
+    hr = zeros(Ntot, params.N, nsave); hi = zeros(Ntot, params.N, nsave)
+    jq_check(ccall((:jq_eval_forward, libjq), Cint,
+                   (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   wa.handle, 1, pcof0, length(pcof0), 1, C_NULL, saveEvery, hr, hi, C_NULL, C_NULL))
+    return hr .+ im .* hi
+end
