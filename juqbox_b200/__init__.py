@@ -5,4 +5,4 @@ from .params import (objparams, lsolver_object, wmatsetup, orig_wmatsetup, setup
 from . import configs
 from .api import (Working_Arrays, traceobjgrad, traceobjgrad_batch, eval_forward, evalctrl, eval_f_g_grad, eval_f_par, eval_grad_f_par,
                   eval_g_par, eval_jac_g_par)
-from .optimize import setup_ipopt_problem, run_optimizer
+from .optimize import setup_ipopt_problem, run_optimizer, run_optimizer_multistart

@@ -104,3 +104,99 @@ def run_optimizer(prob: IpoptProblemMirror, pcof0, baseName: str = ""):
     if baseName:
         np.savetxt(baseName + ".dat", prob.x, fmt="%.13e")      # the reference's .dat format (one %.13e per line)
     return prob.x
+
+
+def run_optimizer_multistart(prob: IpoptProblemMirror, pcof0s, maxIter: Optional[int] = None, lbfgsMax: Optional[int] = None,
+                             gtol: float = 1e-7, max_backtracks: int = 12):
+    """Many independent optimisations advanced in lock step (north star: "batched candidate pcof vectors for multi-start
+    or line search").  Start vectors pcof0s [B, nCoeff]; every objective/gradient request of all B members is ONE
+    jq_traceobjgrad_batch call, so B starts cost about as much wall time as one while the GPU has idle SMs.
+
+    Each member runs the same deterministic algorithm: projected L-BFGS (two-loop recursion over the last `lbfgsMax`
+    pairs, box-scaled variables as in run_optimizer) with Armijo backtracking; the objective is infidelity + leak +
+    Tikhonov (eval_f_par's objective, src/ipopt_interface.jl:77-100), with the risk-neutral nodes/weights of `prob`.
+    Returns (pcofs [B, nCoeff], objective [B], history [iters + 1, B]).  A member's iterates do not depend on which other
+    members share the batch.
+    """
+    from .api import tikhonov_grad, tikhonov_pen
+    from .configs import noise_shift
+    p, wa = prob.params, prob.wa
+    if p.objFuncType != 1:
+        raise ValueError("run_optimizer_multistart handles objFuncType == 1 (no inequality constraint)")
+    X = np.clip(np.atleast_2d(np.asarray(pcof0s, float)).copy(), prob.minCoeff, prob.maxCoeff)
+    B, n = X.shape
+    maxIter = prob.maxIter if maxIter is None else maxIter
+    mem = prob.lbfgsMax if lbfgsMax is None else lbfgsMax
+    scale = np.maximum(np.abs(prob.minCoeff), np.abs(prob.maxCoeff))
+    scale[scale == 0] = 1.0
+    lo, hi = prob.minCoeff / scale, prob.maxCoeff / scale
+    plain = len(prob.nodes) == 1 and prob.nodes[0] == 0.0 and prob.weights[0] == 1.0
+    shifts = None if plain else noise_shift(p.Ntot, prob.nodes)
+    w = None if plain else prob.weights
+
+    def fg(Y, need_grad=True):
+        Xc = Y * scale
+        r = wa.evaluate(Xc, shifts, w, evaladjoint=need_grad)
+        f = (r["infid"] + r["leak"]).reshape(B) + np.array([tikhonov_pen(x, p) for x in Xc])
+        if not need_grad:
+            return f, None
+        g = r["grad"].reshape(B, n) + np.array([tikhonov_grad(x, p) for x in Xc])
+        return f, g * scale
+
+    Y = X / scale
+    f, g = fg(Y)
+    hist = [f.copy()]
+    S, Yd = [], []                                   # per-iteration [B, n] curvature pairs
+    valid = []                                       # [B] masks: pair usable for that member
+    active = np.ones(B, bool)
+    for _ in range(maxIter):
+        # projected gradient: components pushing out of the box at an active bound are dropped
+        pg = g.copy()
+        pg[(Y <= lo) & (g > 0)] = 0.0
+        pg[(Y >= hi) & (g < 0)] = 0.0
+        active &= np.abs(pg).max(axis=1) > gtol
+        if not active.any():
+            break
+        # two-loop recursion, all members at once
+        q = pg.copy()
+        alphas = []
+        for s, yv, ok in zip(reversed(S), reversed(Yd), reversed(valid)):
+            rho = np.where(ok, 1.0 / np.where(ok, (s * yv).sum(1), 1.0), 0.0)
+            a = rho * (s * q).sum(1)
+            q -= a[:, None] * yv
+            alphas.append((a, rho))
+        if S:
+            s, yv, ok = S[-1], Yd[-1], valid[-1]
+            gamma = np.where(ok, (s * yv).sum(1) / np.where(ok, (yv * yv).sum(1), 1.0), 1.0)
+            q *= gamma[:, None]
+        for (a, rho), s, yv in zip(reversed(alphas), S, Yd):
+            b = rho * (yv * q).sum(1)
+            q += (a - b)[:, None] * s
+        d = -q
+        bad = (d * pg).sum(1) >= 0                    # not a descent direction: steepest descent
+        d[bad] = -pg[bad]
+        if not S:
+            d /= np.maximum(1.0, np.abs(d).max(axis=1))[:, None] * 4.0       # first step: a quarter of the box at most
+        slope = (d * pg).sum(1)
+        step = np.where(active, 1.0, 0.0)
+        Ynew, fnew = Y.copy(), f.copy()
+        todo = active.copy()
+        for _bt in range(max_backtracks):
+            Yt = np.where(todo[:, None], np.clip(Y + step[:, None] * d, lo, hi), Ynew)
+            ft, _ = fg(Yt, need_grad=False)
+            acc = todo & (ft <= f + 1e-4 * step * slope)
+            Ynew[acc], fnew[acc] = Yt[acc], ft[acc]
+            todo &= ~acc
+            if not todo.any():
+                break
+            step[todo] *= 0.5
+        active &= ~todo                               # members whose line search failed stop here
+        fchk, gnew = fg(Ynew)
+        s, yv = Ynew - Y, gnew - g
+        ok = (s * yv).sum(1) > 1e-12 * np.sqrt((s * s).sum(1) * (yv * yv).sum(1))
+        S.append(s); Yd.append(yv); valid.append(ok)
+        if len(S) > mem:
+            S.pop(0); Yd.pop(0); valid.pop(0)
+        Y, f, g = Ynew, fchk, gnew
+        hist.append(f.copy())
+    return Y * scale, f, np.array(hist)

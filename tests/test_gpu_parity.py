@@ -390,3 +390,30 @@ def test_evalctrl_matches_oracle(name):
     with pytest.raises(ValueError):                          # wrong coefficient count, like bcparams (src/bsplines.jl:178-181)
         wa.controls(pc[:-1], t)
     wa.close()
+
+
+@pytest.mark.parametrize("risk_neutral", [False, True])
+def test_multistart_lockstep_optimizer(risk_neutral):
+    """run_optimizer_multistart: B optimisations in lock step, one batched GPU call per objective/gradient request.
+    Every member's objective decreases monotonically, stays in the box, and its iterates do not depend on the batch."""
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    cfg = configs.example("risk_neutral")
+    p = cfg.params
+    p.T, p.nsteps = 60.0, 1600
+    wa = jq.Working_Arrays(p, cfg.nCoeff)
+    minC, maxC = jq.assign_thresholds_freq([cfg.maxpar[0]] * p.Nfreq, p.Ncoupled, p.Nfreq, cfg.D1)
+    nodes, weights = (cfg.nodes, cfg.weights) if risk_neutral else ((0.0,), (1.0,))
+    prob = jq.setup_ipopt_problem(p, wa, cfg.nCoeff, minC, maxC, maxIter=10, lbfgsMax=5, nodes=nodes, weights=weights)
+    starts = configs.synthetic_pcof(cfg, 12) * 3.0
+    pcs, f, hist = jq.run_optimizer_multistart(prob, starts)
+    assert hist.shape[1] == 12 and hist.shape[0] >= 3
+    assert np.all(np.diff(hist, axis=0) <= 1e-15)                         # Armijo: never increases
+    assert np.all(hist[-1] < hist[0] - 1e-3)                              # every start makes progress
+    assert np.all(pcs >= minC - 1e-15) and np.all(pcs <= maxC + 1e-15)
+    # the final objective is what the reference-shaped callback reports for that vector
+    f3 = jq.eval_f_par(pcs[3], p, wa, nodes, weights)
+    assert abs(f3 - f[3]) <= 1e-12
+    pcs1, f1, hist1 = jq.run_optimizer_multistart(prob, starts[3:4])
+    assert np.allclose(pcs1[0], pcs[3], rtol=0, atol=1e-12) and abs(f1[0] - f[3]) <= 1e-12
+    wa.close()
