@@ -354,7 +354,7 @@ __global__ void jq_finalize_kernel(int nbatch, int nsamples, int Npar, int objFu
 }
 
 // Weighted sums over many samples of one candidate (risk-neutral quadrature / noise sweeps with thousands of nodes):
-// block (tile of 32 output columns, candidate); thread (column c, sample lane l) sums samples l, l+32, ... in order,
+// block (candidate, tile of 32 output columns); thread (column c, sample lane l) sums samples l, l+32, ... in order,
 // the 32 lane partials are then added in lane order -> deterministic for a given nsamples.  Columns 0..Npar-1 are the
 // gradient entries, Npar..Npar+2 the three scalars.
 #define WS_LANES 32
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(32 * WS_LANES) jq_weighted_sum_kernel(int nsam
                                    const double *w, const double *scal, const double *gt, const double *igt, double *infid, double *leak,
                                    double *tinfid, double *grad, double *infidgrad, double *leakgrad) {
     __shared__ double part[2][WS_LANES][33];
-    const int c = threadIdx.x & 31, l = threadIdx.x >> 5, k = blockIdx.x * 32 + c, o = blockIdx.y;
+    const int c = threadIdx.x & 31, l = threadIdx.x >> 5, k = blockIdx.y * 32 + c, o = blockIdx.x;   // candidates on grid.x (no 65535 limit)
     const size_t t0 = (size_t)o * nsamples;
     double g = 0.0, ig = 0.0;
     if (k < Npar) {
@@ -402,6 +402,7 @@ static int check_batch_args(jq_handle *h, int nbatch, const double *pcof, int np
     if (npar % (nsig * h->Nfreq) != 0 || npar / (nsig * h->Nfreq) < 3)   // src/bsplines.jl:177-181 (and k >= 3 needs D1 >= 3)
         return fail(JQ_ERR_PCOF_LENGTH, "Inconsistent number of coefficients and size of parameter vector (nCoeff = %d, Nfreq = %d, Ncoupled = %d)", npar, h->Nfreq, h->Nc);
     if (nsamples < 1) return fail(JQ_ERR_ARG, "nsamples must be >= 1");
+    if ((long long)nbatch * nsamples > 0x7fffffffLL) return fail(JQ_ERR_ARG, "nbatch * nsamples exceeds 2^31 - 1 trajectories per call");
     if (!shift && nsamples != 1) return fail(JQ_ERR_ARG, "nsamples > 1 needs h0_diag_shift");
     return 0;
 }
@@ -456,7 +457,7 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     const long long total = (long long)nout * (npar + 1);
     const int fb = 256, fg = (int)std::min<long long>((total + fb - 1) / fb, 148 * 8);
     if (weights && nsamples >= 64)
-        jq_weighted_sum_kernel<<<dim3((npar + 3 + 31) / 32, nbatch), 32 * WS_LANES, 0, st>>>(nsamples, npar, h->P.objFuncType, A.evaladjoint,
+        jq_weighted_sum_kernel<<<dim3(nbatch, (npar + 3 + 31) / 32), 32 * WS_LANES, 0, st>>>(nsamples, npar, h->P.objFuncType, A.evaladjoint,
                                           weights, h->d_scal, h->d_grad, h->d_igrad, infid, leak, trace_infid, grad, infidgrad, leakgrad);
     else
         jq_finalize_kernel<<<fg, fb, 0, st>>>(nbatch, nsamples, npar, h->P.objFuncType, A.evaladjoint, weights, h->d_scal, h->d_grad,
