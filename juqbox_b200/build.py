@@ -50,6 +50,8 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
         hdrs = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
         if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in [src] + hdrs):
             cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj]
+            if os.environ.get("JQ_FAST_BUILD"):      # development only: 3x faster, slightly different register allocation
+                cmd.insert(1, "--split-compile=0")
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd))

@@ -820,10 +820,10 @@ const Inst kInst[] = {
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBER(5, 2, 1, 1), FIBER(5, 3, 1, 1), FIBER(6, 2, 1, 1), FIBER(5, 1, 1, 2), FIBERO(5, 2, 1, 1),      // 5- and 6-level fastest subsystem
-    FIBERV(4, 2, 1, 1, 1), FIBERV(4, 3, 1, 1, 1), FIBERV(3, 2, 1, 1, 1), FIBERV(3, 3, 1, 1, 1),
+    FIBERV(4, 2, 1, 1, 1), FIBERV(4, 3, 1, 1, 1),      // shuffle twins of the cnot2 / cnot3 runtime-J kernels (JQ_TRAJ_VARIANT=1)
     FIBERX(4, 2, 1, 1, 4, 16, 1, 32 + 4),          // cnot2 example shape: warp-shuffle exchange measured 3.5% faster than shared memory (variant 512)
     FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4),
-    FIBERJGM(4, 1, 1, 2, 5, 3, 3, 32 + 5), FIBERJGM(4, 1, 1, 2, 5, 3, 2, 1024 + 5),      // risk-neutral SWAP 0-2 shape (n = 4, m = 3, J = 5)
+    FIBERJGM(4, 1, 1, 2, 5, 3, 3, 32 + 5),      // risk-neutral SWAP 0-2 shape (n = 4, m = 3, J = 5)
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
