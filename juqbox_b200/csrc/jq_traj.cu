@@ -210,7 +210,7 @@ struct SlotLane {
 // (a - a') next to (a + a'): only the Hsym coefficients are kept and D = upper - lower, A = upper + lower.
 template <int R_, int NC_, int LMASK_, int AS_ = 1, int XM_ = 0>
 struct FiberLane {
-    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, AS = AS_, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (measured equal)
+    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, AS = AS_, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (16 instead of 24 data-pipe wavefronts per round for R = 4, NC = 2, but 16 instead of 7 instructions)
     static constexpr bool REMOTE = (LMASK_ != (1 << NC_) - 1);
     static constexpr int RM1 = R_ > 1 ? R_ - 1 : 1;
     // local (inside the fibre) tridiagonal coefficients: x_{k+1} -> row k ("u"), x_k -> row k+1 ("l")
@@ -1105,7 +1105,6 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     }
     if (nw < 1) return cudaErrorInvalidConfiguration;       // does not fit even with one warp per CTA: caller falls back
     S.TPC = TPC; S.ngroups = ngroups;
-    if (const char *pad = getenv("JQ_SMEM_PAD_KB")) bytes += (size_t)atoi(pad) * 1024;   // experiments: throttle CTAs/SM
     if (bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
