@@ -107,7 +107,7 @@ int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pco
  * (:676-680,:748-752,:1029-1031).  hist_r / hist_i receive Re / Im of the state (vr and -vi) at t = 0 and after every
  * save_every-th step: [ntraj][nsteps/save_every + 1][n*m] doubles each, column-major n x m blocks (the Julia array
  * Ntot x N x nsave of each trajectory).  nsteps must be divisible by save_every (reference :2797-2799).  infid / leak as in
- * jq_traceobjgrad_batch (may be NULL).  Host pointers, blocking; runs on the generic kernel. */
+ * jq_traceobjgrad_batch (may be NULL).  Host pointers, blocking; same kernel selection as jq_traceobjgrad_batch. */
 int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
                     const double *h0_diag_shift, int32_t save_every, double *hist_r, double *hist_i, double *infid, double *leak);
 

@@ -489,7 +489,6 @@ extern "C" int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof,
     if (!hist_r || !hist_i) return fail(JQ_ERR_ARG, "jq_eval_forward: null history buffer");
     if (save_every < 1 || h->P.nsteps % save_every != 0)     // src/evalobjgrad.jl:2797-2799
         return fail(JQ_ERR_ARG, "nsteps must be divisible by saveEvery. nsteps=%lld, saveEvery=%d", (long long)h->P.nsteps, save_every);
-    if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024) return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory");
     CU(cudaSetDevice(h->device));
     const size_t ntraj = (size_t)nbatch * nsamples, len = (size_t)h->n * h->m;
     const long long nsave = h->P.nsteps / save_every + 1;
@@ -507,10 +506,29 @@ extern "C" int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof,
     A.hist_r = h->d_out; A.hist_i = h->d_out + n_hist; A.save_every = save_every; A.nsave = nsave;
     int ctas = 0, regs = 0;
     size_t smem = 0;
+    // same kernel choice as jq_traceobjgrad_batch: fibre, slot, then generic
+    TrajPlan *cands[2] = {nullptr, nullptr};
+    int ncand = 0, tpc = 1;
+    if (h->kernel_pref == 3 || (h->kernel_pref == 0 && h->fiber)) cands[ncand++] = h->fiber;
+    if (h->kernel_pref == 2 || (h->kernel_pref == 0 && h->slot)) cands[ncand++] = h->slot;
+    TrajPlan *plan = nullptr;
     CU(cudaEventRecord(h->ev0, st));
-    CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
+    for (int i = 0; i < ncand && !plan; ++i) {
+        cudaError_t e = jq_traj_launch(cands[i], h->P, A, st, &ctas, &regs, &smem, &tpc);
+        if (e == cudaSuccess) { plan = cands[i]; break; }
+        if (e != cudaErrorInvalidConfiguration || h->kernel_pref != 0)
+            return fail(JQ_ERR_CUDA, "trajectory kernel launch failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    if (!plan) {
+        if (h->kernel_pref > 1) return fail(JQ_ERR_ARG, "requested kernel is not available for this problem");
+        if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024) return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory");
+        tpc = 1;
+        CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
+    }
     CU(cudaEventRecord(h->ev1, st));
-    h->timed = true; h->last_kernel = 1; h->last_launches = 1; h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = 1;
+    h->timed = true; h->last_kernel = plan ? jq_traj_plan_kind(plan) : 1; h->last_launches = 1; h->last_ctas = ctas; h->last_regs = regs;
+    h->last_smem = smem; h->last_tpc = tpc;
     CU(cudaMemcpyAsync(hist_r, A.hist_r, n_hist * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hist_i, A.hist_i, n_hist * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -29,6 +29,7 @@
 // controls src/bsplines.jl:211-304,:321-381, gradient src/evalobjgrad.jl:2567-2619.  The only algebraic regrouping
 // is S1*u + (h/2) S1*k1 = S1*(u + (h/2) k1)  (src/StormerVerlet.jl:483-484).
 #include "jq_common.h"
+#include <type_traits>
 
 #include <cstdio>
 #include <cstdlib>
@@ -688,18 +689,37 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
 
     // ------------------------------------------------------------ forward sweep (src/evalobjgrad.jl:698-753)
     double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
-    for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
-        const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
-        fill_table<NC>(S, sm, t, dt, nst, dtknot);
-        LOAD_LEVEL0();
-        for (int ls = 0; ls < nst; ++ls) {
-            LOAD_LEVELS(ls);
-            UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e], pen);                              // penalf2aTrap
-            state_step<JT>(L, J, dt, vr, vi, vi05);
-            UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e] + 2.0 * vi05[e] * vi05[e], pen);   // penalf2a
-            t = t + dt;
+    // forward history (jq_eval_forward; src/evalobjgrad.jl:2847-2849): Re = vr, Im = -vi after every save_every-th step
+    const bool hist = A.hist_r != nullptr;
+    size_t hpos = hist ? (size_t)(live_t ? traj : 0) * A.nsave * ((size_t)n * m) : 0;      // start of the next saved block
+    int hcount = hist ? A.save_every : 0;                                                // steps until the next save
+    auto save_state = [&]() {
+        UNROLL for (int e = 0; e < E; ++e)
+            if (ok[e]) {
+                const size_t ix = hpos + L.row(e) + (size_t)n * L.col(e);
+                A.hist_r[ix] = vr[e]; A.hist_i[ix] = -vi[e];
+            }
+        hpos += (size_t)n * m;
+    };
+    if (hist) save_state();
+    // two copies of the loop (generic lambda, both inlined): the evaluation path carries no per-step history test
+    auto forward_sweep = [&](auto with_hist) {
+        for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
+            const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+            fill_table<NC>(S, sm, t, dt, nst, dtknot);
+            LOAD_LEVEL0();
+            for (int ls = 0; ls < nst; ++ls) {
+                LOAD_LEVELS(ls);
+                UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e], pen);                              // penalf2aTrap
+                state_step<JT>(L, J, dt, vr, vi, vi05);
+                UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e] + 2.0 * vi05[e] * vi05[e], pen);   // penalf2a
+                t = t + dt;
+                if constexpr (decltype(with_hist)::value) { if (--hcount == 0) { hcount = A.save_every; save_state(); } }
+            }
         }
-    }
+    };
+    if (hist) forward_sweep(std::true_type{});
+    else forward_sweep(std::false_type{});
     // infidelity (pFidType 2) and leak: group partials -> shared -> per-trajectory sums in group order
     double *red = sm + S.o_red;
     {

@@ -204,9 +204,10 @@ def test_optimizer_glue_reduces_objective():
     assert f1 < f0 - 1e-3 and len(p.objHist) >= 2 and p.objHist[-1] <= p.objHist[0]
 
 
-def test_forward_history_matches_oracle():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_forward_history_matches_oracle(kernel):
     """jq_eval_forward / traceobjgrad(verbose=true, evaladjoint=false): state history Ntot x N x (nsteps/saveEvery + 1)
-    (src/evalobjgrad.jl:676-680, 748-752, 2797-2849)."""
+    (src/evalobjgrad.jl:676-680, 748-752, 2797-2849), from every kernel."""
     import juqbox_b200 as jq
     from juqbox_b200 import configs
     from oracle import oracle_forward_history
@@ -214,8 +215,9 @@ def test_forward_history_matches_oracle():
     p = cfg.params
     p.T, p.nsteps = 5.0, 600
     pc = configs.synthetic_pcof(cfg, 2) * 50
-    wa = jq.Working_Arrays(p, cfg.nCoeff)
+    wa = _wa(cfg, kernel)
     hist, infid, leak = wa.forward_history(pc, save_every=20)
+    assert wa.last_kernel == kernel
     assert hist.shape == (2, 1, 31, p.N, p.Ntot)
     for b in range(2):
         want, winf, wleak = oracle_forward_history(p, pc[b], save_every=20)
