@@ -226,18 +226,21 @@ def main():
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     pin_in = torch.from_numpy(pc_h).pin_memory()
     pc_pin = pin_in.numpy()
+    pins = {k: torch.zeros((B, nsamp) + ((npar,) if k == "grad" else ()), dtype=torch.float64).pin_memory()
+            for k in ("infid", "leak", "trace_infid", "grad")}          # pinned result buffers, reused like Working_Arrays
+    r = {k: v.numpy() for k, v in pins.items()}
     for _ in range(1):
-        wa.evaluate(pc_pin, shifts_h)
+        r = wa.evaluate(pc_pin, shifts_h, out=r)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = wa.evaluate(pc_pin, shifts_h)
+        r = wa.evaluate(pc_pin, shifts_h, out=r)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_val = evals_per_step * args.steps / e2e_s
     h2d = pc_pin.nbytes + (shifts_h.nbytes if shifts_h is not None else 0)
-    d2h = sum(r[k].nbytes for k in ("infid", "leak", "trace_infid", "grad", "infidgrad"))
+    d2h = sum(r[k].nbytes for k in ("infid", "leak", "trace_infid", "grad"))       # objFuncType 1: infidgrad aliases grad
 
     # ---- roofline of the dominant (trajectory) kernel
     flops_eval = alg_flops_per_eval(cfg.params, npar)

@@ -148,8 +148,13 @@ class Working_Arrays:
         return self.query(1)
 
     # -- evaluation ---------------------------------------------------------------------------
-    def evaluate(self, pcof, shifts=None, weights=None, evaladjoint=True):
-        """Batched evaluation with host arrays (copies inside): see jq_traceobjgrad_batch."""
+    def evaluate(self, pcof, shifts=None, weights=None, evaladjoint=True, out=None):
+        """Batched evaluation with host arrays (copies inside): see jq_traceobjgrad_batch.
+
+        `out`: a dict returned by an earlier call with the same shapes (or built by the caller, e.g. on pinned
+        memory) whose arrays are reused instead of allocating fresh ones — the Working_Arrays idea applied to outputs.
+        With objFuncType == 1 `infidgrad` is the same array as `grad` (the reference's infidelgrad aliases totalgrad,
+        src/evalobjgrad.jl:951) and `leakgrad` is a read-only zero view: only one gradient crosses the bus."""
         p = self.params
         pcof = _f64(np.atleast_2d(pcof))
         nbatch, npar = pcof.shape
@@ -167,13 +172,26 @@ class Working_Arrays:
                 raise ValueError("weights must have one entry per sample")
             wp = weights.ctypes.data_as(C.c_void_p)
         shape = (nbatch,) if weights is not None else (nbatch, nsamples)
-        out = {k: np.zeros(shape) for k in ("infid", "leak", "trace_infid")}
+        two_sets = p.objFuncType != 1
+
+        def buf(key, shp):
+            a = out.get(key) if out is not None else None
+            if a is None or a.shape != shp or a.dtype != np.float64 or not a.flags.c_contiguous or not a.flags.writeable:
+                a = np.zeros(shp)
+            return a
+        res = {k: buf(k, shape) for k in ("infid", "leak", "trace_infid")}
         gptr = [None, None, None]
         if evaladjoint:
-            out["grad"] = np.zeros(shape + (npar,))
-            out["infidgrad"] = np.zeros(shape + (npar,))
-            out["leakgrad"] = np.zeros(shape + (npar,))
-            gptr = [out[k].ctypes.data_as(C.c_void_p) for k in ("grad", "infidgrad", "leakgrad")]
+            res["grad"] = buf("grad", shape + (npar,))
+            gptr[0] = res["grad"].ctypes.data_as(C.c_void_p)
+            if two_sets:
+                res["infidgrad"] = buf("infidgrad", shape + (npar,))
+                res["leakgrad"] = buf("leakgrad", shape + (npar,))
+                gptr[1:] = [res[k].ctypes.data_as(C.c_void_p) for k in ("infidgrad", "leakgrad")]
+            else:
+                res["infidgrad"] = res["grad"]
+                res["leakgrad"] = np.broadcast_to(0.0, shape + (npar,))
+        out = res
         _lib.check(self._lib.jq_traceobjgrad_batch(
             self._handle, nbatch, pcof.ctypes.data_as(C.c_void_p), npar, nsamples, sp, wp, int(bool(evaladjoint)),
             out["infid"].ctypes.data_as(C.c_void_p), out["leak"].ctypes.data_as(C.c_void_p),
