@@ -90,12 +90,16 @@ function traceobjgrad_batch(pcof::Array{Float64,2}, params::objparams, wa::Worki
     nsamples = shifts === nothing ? 1 : size(shifts, 2)
     nout = weights === nothing ? nbatch * nsamples : nbatch
     infid = zeros(nout); leak = zeros(nout); tinf = zeros(nout)
-    grad = zeros(Npar, nout); igrad = zeros(Npar, nout); lgrad = zeros(Npar, nout)
+    two = params.objFuncType != 1                        # objFuncType 1: infidelgrad aliases totalgrad (src/evalobjgrad.jl:951),
+    grad = zeros(Npar, nout)                             # so only one gradient is fetched from the device
+    igrad = two ? zeros(Npar, nout) : grad
+    lgrad = two ? zeros(Npar, nout) : zeros(Npar, 0)
     jq_check(ccall((:jq_traceobjgrad_batch, libjq), Cint,
                    (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Int32,
                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                    wa.handle, nbatch, pcof, Npar, nsamples, shifts === nothing ? C_NULL : shifts,
-                   weights === nothing ? C_NULL : weights, evaladjoint, infid, leak, tinf, grad, igrad, lgrad))
+                   weights === nothing ? C_NULL : weights, evaladjoint, infid, leak, tinf, grad,
+                   two ? pointer(igrad) : Ptr{Float64}(C_NULL), two ? pointer(lgrad) : Ptr{Float64}(C_NULL)))
     return infid, leak, tinf, grad, igrad, lgrad
 end
 
