@@ -115,6 +115,15 @@ def main():
         json.dump({"name": name, "hdf5_dims": dims, "data": data,
                    "source": "test/reference_solutions/err-mat-ref.jld2"}, f)
     print("err-mat", name, dims, data[:2])
+    # optimised pulses shipped with the reference's examples (examples/drives/*.jld2, key "pcof"): the EXAMPLE
+    # configurations (examples/cnot2-setup.jl at T = 50, examples/rabi-setup.jl) must turn them into a high-fidelity gate
+    drives = {}
+    for f, cfgname in (("cnot2-pcof-opt-t50", "cnot2"), ("rabi-pcof-opt-t100", "rabi")):
+        g = read_jld2(f"/root/reference/examples/drives/{f}.jld2")
+        drives[cfgname] = {"source": f"examples/drives/{f}.jld2", "pcof": g["pcof"][1]}
+        print("drive", f, len(g["pcof"][1]))
+    with open(os.path.join(here, "drives.json"), "w") as f:
+        json.dump(drives, f, indent=0)
 
 
 if __name__ == "__main__":

@@ -453,3 +453,23 @@ def test_random_dense_operators_fall_back_to_generic_and_match_oracle(use_sparse
         assert abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12 and abs(r["leak"][b, 0] - o["leak"][b, 0]) < 1e-12
         assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL
     wa.close()
+
+
+@pytest.mark.parametrize("name", ["cnot2", "rabi"])
+def test_reference_optimised_pulse_on_gpu(name):
+    """The reference's own optimised pulse (examples/drives) on the example config: GPU = oracle, and the gate is good."""
+    import json
+    import os
+    import juqbox_b200 as jq
+    from helpers import GOLDEN_DIR
+    from juqbox_b200 import configs
+    from oracle import oracle_traceobjgrad
+    pc = np.array(json.load(open(os.path.join(GOLDEN_DIR, "drives.json")))[name]["pcof"])
+    cfg = configs.example(name)
+    wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
+    r = wa.evaluate(pc)
+    o = oracle_traceobjgrad(cfg.params, pc)
+    assert abs(r["infid"][0, 0] - o["infid"][0, 0]) < 1e-12 and abs(r["leak"][0, 0] - o["leak"][0, 0]) < 1e-12
+    assert _rel(r["grad"][0, 0], o["grad"][0, 0]) < TOL
+    assert abs(r["infid"][0, 0]) < 1e-3
+    wa.close()
