@@ -313,11 +313,11 @@ def _ex_cnot1() -> Config:
     return Config("cnot1", p, None, 10, [float(maxamp.max())])
 
 
-def _ex_cnot2() -> Config:
-    # examples/cnot2-setup.jl (rotating frame branch, sparse)
+def _ex_cnot2(T: float = 50.0) -> Config:
+    # examples/cnot2-setup.jl (rotating frame branch, sparse); T is the script's gate duration (50 ns as shipped; the
+    # reference also ships pulses optimised for 100 and 200 ns, examples/drives/cnot2-pcof-opt-t{50,100,200}.jld2)
     Ne, Ng = [2, 2], [2, 2]
     Nt = [4, 4]
-    T = 50.0
     fa, fb = 4.10595, 4.81526
     x1, x2, x12 = 2 * 0.1099, 2 * 0.1126, 0.1
     (amat, bmat), (N1, N2) = kron_ops(Nt)
@@ -433,10 +433,11 @@ def qudit_system(Ne, Ng, T: float = 20.0, Nfreq: int = 2, D1: int = 6, maxamp: f
     return cfg
 
 
-def example(name: str) -> Config:
-    """One of the five BASELINE.json configurations."""
+def example(name: str, **kw) -> Config:
+    """One of the five BASELINE.json configurations (keyword arguments: the knobs the example script itself exposes,
+    e.g. example("cnot2", T=100.0))."""
     return {"rabi": _ex_rabi, "cnot1": _ex_cnot1, "cnot2": _ex_cnot2, "cnot3": _ex_cnot3,
-            "risk_neutral": _ex_risk_neutral}[name]()
+            "risk_neutral": _ex_risk_neutral}[name](**kw)
 
 
 def synthetic_pcof(cfg: Config, nbatch: int, seed_offset: int = 0) -> np.ndarray:

@@ -118,7 +118,8 @@ def main():
     # optimised pulses shipped with the reference's examples (examples/drives/*.jld2, key "pcof"): the EXAMPLE
     # configurations (examples/cnot2-setup.jl at T = 50, examples/rabi-setup.jl) must turn them into a high-fidelity gate
     drives = {}
-    for f, cfgname in (("cnot2-pcof-opt-t50", "cnot2"), ("rabi-pcof-opt-t100", "rabi")):
+    for f, cfgname in (("cnot2-pcof-opt-t50", "cnot2"), ("cnot2-pcof-opt-t100", "cnot2-T100"), ("cnot2-pcof-opt-t200", "cnot2-T200"),
+                       ("rabi-pcof-opt-t100", "rabi")):
         g = read_jld2(f"/root/reference/examples/drives/{f}.jld2")
         drives[cfgname] = {"source": f"examples/drives/{f}.jld2", "pcof": g["pcof"][1]}
         print("drive", f, len(g["pcof"][1]))

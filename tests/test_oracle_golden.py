@@ -85,7 +85,7 @@ def test_oracle_controls_partition_of_unity():
         assert np.allclose(pv[c], pe, atol=1e-13) and np.allclose(qv[c], qe, atol=1e-13)
 
 
-@pytest.mark.parametrize("name,max_infid", [("cnot2", 1e-3), ("rabi", 1e-5)])
+@pytest.mark.parametrize("name,max_infid", [("cnot2", 1e-3), ("cnot2-T100", 3e-3), ("cnot2-T200", 1e-4), ("rabi", 1e-5)])
 def test_reference_optimised_pulses_give_high_fidelity_on_example_configs(name, max_infid):
     """examples/drives/*-pcof-opt*.jld2 were optimised BY THE REFERENCE on its example models; evaluating them on our
     restatement of those models (juqbox_b200.configs.example) must give a high-fidelity gate with almost no leakage.
@@ -96,7 +96,7 @@ def test_reference_optimised_pulses_give_high_fidelity_on_example_configs(name, 
     from helpers import GOLDEN_DIR
     from juqbox_b200 import configs
     pc = np.array(json.load(open(os.path.join(GOLDEN_DIR, "drives.json")))[name]["pcof"])
-    cfg = configs.example(name)
+    cfg = configs.example(*name.split("-T")[:1], **({"T": float(name.split("-T")[1])} if "-T" in name else {}))
     assert len(pc) == cfg.nCoeff
     o = oracle_traceobjgrad(cfg.params, pc, evaladjoint=False)
     print(name, "infidelity", o["infid"][0, 0], "leak", o["leak"][0, 0])
