@@ -342,19 +342,27 @@ def _ex_cnot2(T: float = 50.0) -> Config:
     return Config("cnot2", p, None, 10, maxpar)
 
 
-def _ex_cnot3() -> Config:
-    # examples/cnot3-setup.jl (sparse, Nfreq = 2, 3 guard levels on the resonator, default J = 3)
+def _ex_cnot3(Nfreq: int = 2) -> Config:
+    # examples/cnot3-setup.jl (sparse, Nfreq = 2 as shipped, 3 guard levels on the resonator, default J = 3); Nfreq = 3 is the
+    # script's alternative branch (:153-158), the one examples/drives/cnot3-pcof-opt.jld2 was optimised with
     Ne, Ng, Nt, (xa, xb, xs, xab, xas, xbs), (amat, bmat, cmat), H0 = _cnot3_system(3)
     T = 550.0
     maxpar = [0.05, 0.1, 0.1]
     Hsym = [amat + amat.T, bmat + bmat.T, cmat + cmat.T]
     Hanti = [amat - amat.T, bmat - bmat.T, cmat - cmat.T]
     nsteps = calculate_timestep(T, H0, Hsym, Hanti, maxpar, 40)
-    Nfreq = 2
     om = np.zeros((3, Nfreq))
-    om[0, 1] = -2.0 * np.pi * xa
-    om[1, 1] = -2.0 * np.pi * xb
-    om[2, 1] = -2.0 * np.pi * math.sqrt(xas * xbs)
+    if Nfreq == 2:
+        om[0, 1] = -2.0 * np.pi * xa
+        om[1, 1] = -2.0 * np.pi * xb
+        om[2, 1] = -2.0 * np.pi * math.sqrt(xas * xbs)
+    elif Nfreq == 3:
+        om[0:2, 1] = -2.0 * np.pi * xa
+        om[0:2, 2] = -2.0 * np.pi * xb
+        om[2, 1] = -2.0 * np.pi * xas
+        om[2, 2] = -2.0 * np.pi * xbs
+    else:
+        raise ValueError("cnot3 example: Nfreq must be 2 or 3")
     gate = np.zeros((4, 4), dtype=complex)
     gate[0, 0] = gate[1, 1] = gate[2, 3] = gate[3, 2] = 1.0
     U0 = initial_cond(Ne, Ng)

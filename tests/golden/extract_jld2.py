@@ -119,7 +119,7 @@ def main():
     # configurations (examples/cnot2-setup.jl at T = 50, examples/rabi-setup.jl) must turn them into a high-fidelity gate
     drives = {}
     for f, cfgname in (("cnot2-pcof-opt-t50", "cnot2"), ("cnot2-pcof-opt-t100", "cnot2-T100"), ("cnot2-pcof-opt-t200", "cnot2-T200"),
-                       ("rabi-pcof-opt-t100", "rabi")):
+                       ("rabi-pcof-opt-t100", "rabi"), ("cnot3-pcof-opt", "cnot3-Nfreq3")):
         g = read_jld2(f"/root/reference/examples/drives/{f}.jld2")
         drives[cfgname] = {"source": f"examples/drives/{f}.jld2", "pcof": g["pcof"][1]}
         print("drive", f, len(g["pcof"][1]))
