@@ -125,6 +125,7 @@ struct SlotLane {
     double p[3][NC], q[3][NC];
     double *buf;
     int nlr, parity, c0;
+    int sGL, sbase; double stol;             // Jacobi instantiations: group geometry and tolerance for the residual norm
 
     __device__ __forceinline__ void setup(const TrajParams &S, double *sm, const Geo &g) {
         nlr = S.NLR; parity = 0; c0 = g.gi * C;
@@ -223,6 +224,7 @@ struct FiberLane {
     double p[3][NC], q[3][NC];
     double *buf;
     int parity, lane, row0, colj;
+    int sGL, sbase; double stol;             // Jacobi instantiations: group geometry and tolerance for the residual norm
 
     __device__ __forceinline__ void setup(const TrajParams &S, double *sm, const Geo &g) {
         parity = 0; lane = g.lane;
@@ -403,6 +405,33 @@ __device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, 
     }
 }
 
+// JACOBI_SOLVER (src/linear_solvers.jl:110-152): X = B; T = B + (h/2) S X; err = ||T - X||_F over the whole n x m block;
+// X = T; stop when err < tol or after J sweeps.  The block of a trajectory is one group here (the planner only admits
+// GPT == 1), so the norm is one group reduction; groups of a warp that have converged keep exchanging (the passes need
+// the whole warp) but stop updating, and the warp leaves the loop when all its groups are done.  B is preserved.
+template <class LaneT>
+__device__ __forceinline__ void jacobi(LaneT &L, const typename LaneT::SC &sc, int maxit, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
+    constexpr int E = LaneT::E;
+    UNROLL for (int e = 0; e < E; ++e) X[e] = B[e];
+    bool active = true;
+    for (int it = 0; it < maxit; ++it) {
+        double T[E], err = 0.0;
+        L.s_pass(sc, X, T);
+        UNROLL for (int e = 0; e < E; ++e) { T[e] = fma(0.5 * h, T[e], B[e]); const double d = T[e] - X[e]; err = fma(d, d, err); }
+        err = group_sum(err, L.sGL, L.sbase);
+        if (active) { UNROLL for (int e = 0; e < E; ++e) X[e] = T[e]; }
+        active = active && !(sqrt(err) < L.stol);
+        if (!__any_sync(0xffffffffu, active)) break;
+    }
+}
+
+// linear_solver.solve of the steppers: JT >= 0 truncated Neumann series (JT > 0: compile-time J), JT < 0 Jacobi sweeps.
+template <int JT, class LaneT>
+__device__ __forceinline__ void solve(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
+    if constexpr (JT < 0) jacobi(L, sc, J, h, B, X);
+    else neumann<JT>(L, sc, J, h, B, X);
+}
+
 // src/StormerVerlet.jl:461-504.  u, v updated in place; v05 returned.
 template <int JT, class LaneT>
 __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E], double (&v05)[LaneT::E]) {
@@ -422,7 +451,7 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
         L.s_pass(sc, v, tv);
         UNROLL for (int e = 0; e < E; ++e) rhs[e] += tv[e];                                    // + S05 v
     }
-    neumann<JT>(L, sc, J, h, rhs, l1);
+    solve<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
     double k1v[E], s05v[E];
     L.template pass_each<true, true>(v05, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
@@ -443,7 +472,7 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
         UNROLL for (int e = 0; e < E; ++e) rhs[e] = tv[e] - k1v[e];                             // S1 (u + (h/2) kappa1) - K1 v05
     }
     double k2[E];
-    neumann<JT>(L, sc, J, h, rhs, k2);
+    solve<JT>(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
     L.template pass_each<true, false>(u, [&](int e, const double (&Ae)[NC], const double (&)[NC]) {
         double l2 = fma(L.d0[e], u[e], s05v[e]);
@@ -480,7 +509,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         s05n[e] = s;                                         // S05 nu
     });
     double k2[E];
-    neumann<JT>(L, sc, J, h, rhs, k2);
+    solve<JT>(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) mu[e] = fma(0.5 * h, k2[e], mu[e]);   // X = lr05
     double l2[E], r0[E], mu2[E];
     {
@@ -514,7 +543,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(0.5 * h, tv[e], r0[e]);   // S05 nu + (h/2) S05 l2 + K1 X + hi1
     }
     double l1[E];
-    neumann<JT>(L, sc, J, h, rhs, l1);
+    solve<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
     L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
         double kk = L.d0[e] * nu[e];
@@ -655,6 +684,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
 
     LaneT L;
     L.setup(S, sm, g);
+    L.sGL = GL; L.sbase = gbase_lane; L.stol = P.tol;
     bool ok[E];
     UNROLL for (int e = 0; e < E; ++e) {
         const int r = L.row(e);
@@ -831,6 +861,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBERJGM(R, NC, LMASK, UPL, JT, GLT, MINB, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB, JT, 0, GLT>, GLT}
 #define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
+#define FIBERJAC(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 128, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, -1>}   /* Jacobi solver */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
 const Inst kInst[] = {
@@ -845,6 +876,7 @@ const Inst kInst[] = {
     FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4),
     FIBERJGM(4, 1, 1, 2, 5, 3, 3, 32 + 5),      // risk-neutral SWAP 0-2 shape (n = 4, m = 3, J = 5)
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
+    FIBERJAC(3, 2, 1, 1), FIBERJAC(4, 2, 1, 1), FIBERJAC(4, 1, 1, 2), FIBERJAC(6, 1, 1, 2),
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
@@ -961,7 +993,6 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
 TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
-    if (P.solver != 1) return no("Jacobi solver (data-dependent sweep count) runs on the generic kernel");
     std::vector<double> d0;
     if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
     // block size: first break of control 0's first off-diagonals
@@ -1035,6 +1066,10 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     if (UPL > 2) return no("too many (control, frequency) pairs for the group size");
     const Inst *inst = find_inst(3, R, 1, Nc, 2, LMASK, UPL, P.objFuncType != 1 ? 64 : (AS ? 0 : 16));
     if (P.objFuncType != 1 && !AS) inst = nullptr;
+    if (P.solver != 1) {       // Jacobi: residual norm over the whole block = one group reduction -> one group per trajectory only
+        inst = (AS && P.objFuncType == 1 && GPT == 1) ? find_inst(3, R, 1, Nc, 2, LMASK, UPL, 128) : nullptr;
+        if (!inst) return no("Jacobi solver: no fibre instantiation for this shape (or the trajectory spans several groups)");
+    }
     if (!inst) return no("no fibre instantiation for this (fibre length, controls, updaters per lane, Hanti form, objFuncType)");
     // lane offsets of remote neighbours must stay inside the column block of NL lanes
     TrajPlan *pl = new TrajPlan();
@@ -1086,7 +1121,9 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
                            size_t *smem, int *traj_per_cta) {
     const char *venv = getenv("JQ_TRAJ_VARIANT");
     if (P.objFuncType != 1) venv = "64";
+    if (P.solver != 1) venv = "128";
     const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv), pl->GL) : nullptr;
+    if (P.solver != 1 && !inst) return cudaErrorNotSupported;        // never substitute the Neumann series for Jacobi
     if (!inst && !venv && pl->AS && P.objFuncType == 1)      // instantiations with the number of Neumann terms known at compile time
         inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J, pl->GL);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);
