@@ -57,7 +57,7 @@ struct TrajParams {
 
 struct TrajPlan {
     int kind;                                // 2 slot, 3 fibre
-    int R, C, NC, WQ, LMASK, UPL, AS;
+    int R, C, NC, WQ, LMASK, UPL, AS, HX = 0;
     int NL, GL, GPT, TPC, ngroups, CPG, NLR, exch_per_unit;
     int *d_i = nullptr;
     double *d_d = nullptr, *d_d0 = nullptr, *d_w = nullptr;
@@ -118,7 +118,7 @@ struct Geo {
 
 template <int R_, int C_, int NC_, int WQ_>
 struct SlotLane {
-    static constexpr int R = R_, C = C_, NC = NC_, WQ = WQ_, E = R_ * C_;
+    static constexpr int R = R_, C = C_, NC = NC_, WQ = WQ_, E = R_ * C_, HX = 0;
     int pos[R][NC][WQ], own[R];
     double hs[R][NC][WQ], ha[R][NC][WQ];
     double d0[E], w[E];
@@ -185,7 +185,8 @@ struct SlotLane {
     template <bool WA, bool WD, class F>
     __device__ __forceinline__ void each_from(const double (&)[E], const Nbr &nb, F f) const {
         UNROLL for (int k = 0; k < R; ++k) {
-            double Ar[C][NC], Dr[C][NC];
+            double Ar[C][NC + 1], Dr[C][NC];          // Ar[.][NC]: off-diagonal drift product (fibre layout only)
+            UNROLL for (int c = 0; c < C; ++c) Ar[c][NC] = 0.0;
             UNROLL for (int qq = 0; qq < NC; ++qq) {
                 UNROLL for (int c = 0; c < C; ++c) { Ar[c][qq] = 0.0; Dr[c][qq] = 0.0; }
                 UNROLL for (int e = 0; e < WQ; ++e) {
@@ -210,9 +211,12 @@ struct SlotLane {
 
 // AS = 1: the control Hamiltonians have the ladder form Hanti = (upper part of Hsym) - (lower part of Hsym), i.e.
 // (a - a') next to (a + a'): only the Hsym coefficients are kept and D = upper - lower, A = upper + lower.
-template <int R_, int NC_, int LMASK_, int AS_ = 1, int XM_ = 0>
+// HX != 0: the drift Hamiltonian has exchange-type couplings a_0' a_q + a_0 a_q' between the fastest subsystem and the remote
+// subsystems (bit q of HX): row k of this fibre takes element k+1 of the lower and element k-1 of the upper neighbour fibre of
+// control q -- fibres every K-product fetches anyway.
+template <int R_, int NC_, int LMASK_, int AS_ = 1, int XM_ = 0, int HX_ = 0>
 struct FiberLane {
-    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, AS = AS_, XM = XM_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (16 instead of 24 data-pipe wavefronts per round for R = 4, NC = 2, but 16 instead of 7 instructions)
+    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, AS = AS_, XM = XM_, HX = HX_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (16 instead of 24 data-pipe wavefronts per round for R = 4, NC = 2, but 16 instead of 7 instructions)
     static constexpr bool REMOTE = (LMASK_ != (1 << NC_) - 1);
     static constexpr int RM1 = R_ > 1 ? R_ - 1 : 1;
     // local (inside the fibre) tridiagonal coefficients: x_{k+1} -> row k ("u"), x_k -> row k+1 ("l")
@@ -220,6 +224,7 @@ struct FiberLane {
     // remote: lower (entry 0) and upper (entry 1) neighbour fibre per control, fibre-uniform coefficients
     int rpos[NC][2];
     double rhs[NC][2], rha[NC][2];
+    double xlo[HX_ ? NC : 1][RM1], xhi[HX_ ? NC : 1][RM1];   // drift exchange coefficients (HX only)
     double d0[E], w[E];
     double p[3][NC], q[3][NC];
     double *buf;
@@ -233,9 +238,13 @@ struct FiberLane {
         colj = g.gi * S.CPG + cj;
         buf = sm + S.o_exch + g.warp * S.exch_per_unit;
         const int *pi = S.plan_i + rho * (NC * 2);
-        const double *pd = S.plan_d + rho * (NC * (4 * (R - 1) + 4));
+        constexpr int PERQ = 4 * (R - 1) + 4 + (HX ? 2 * (R - 1) : 0);
+        const double *pd = S.plan_d + rho * (NC * PERQ);
         UNROLL for (int qq = 0; qq < NC; ++qq) {
-            const double *c = pd + qq * (4 * (R - 1) + 4);
+            const double *c = pd + qq * PERQ;
+            if constexpr (HX != 0) {
+                UNROLL for (int k = 0; k < R - 1; ++k) { xlo[qq][k] = c[4 * (R - 1) + 4 + 2 * k]; xhi[qq][k] = c[4 * (R - 1) + 4 + 2 * k + 1]; }
+            }
             UNROLL for (int k = 0; k < R - 1; ++k) {
                 lsu[qq][k] = c[4 * k]; lsl[qq][k] = c[4 * k + 1];
                 if (!AS) { lau[qq][k] = c[4 * k + 2]; lal[qq][k] = c[4 * k + 3]; }
@@ -319,7 +328,15 @@ struct FiberLane {
     template <bool WA, bool WD, class F>
     __device__ __forceinline__ void each_from(const double (&x)[E], const Nbr &nb, F f) const {
         UNROLL for (int k = 0; k < R; ++k) {
-            double Ae[NC], De[NC];
+            double Ae[NC + 1], De[NC];                 // Ae[NC]: off-diagonal drift product of row k
+            Ae[NC] = 0.0;
+            if constexpr (HX != 0 && WA) {
+                UNROLL for (int qq = 0; qq < NC; ++qq)
+                    if ((HX >> qq) & 1) {
+                        if (k + 1 < R) Ae[NC] = fma(xlo[qq][k], nb.v[qq][0][k + 1], Ae[NC]);
+                        if (k > 0) Ae[NC] = fma(xhi[qq][k - 1], nb.v[qq][1][k - 1], Ae[NC]);
+                    }
+            }
             UNROLL for (int qq = 0; qq < NC; ++qq) {
                 double up = 0.0, lo = 0.0, a = 0.0, d = 0.0;
                 if ((LMASK >> qq) & 1) {
@@ -389,6 +406,13 @@ __device__ __forceinline__ void group_sum_n(double (&v)[N], int GL, int base) {
     UNROLL for (int i = 0; i < N; ++i) v[i] = s[i];
 }
 
+// (H0 x)_e for the lane's element e: diagonal entry times x_e, plus the off-diagonal drift product x0 in HX layouts.
+template <class LaneT>
+__device__ __forceinline__ double kdiag(const LaneT &L, int e, double xe, double x0) {
+    if constexpr (LaneT::HX != 0) return fma(L.d0[e], xe, x0);
+    else return L.d0[e] * xe;
+}
+
 // X = sum_{j<=J} (h/2)^j S^j B   (src/linear_solvers.jl:94-106); B is consumed.  `sc` = S(level) prescaled.
 template <int JT, class LaneT>
 __device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
@@ -438,8 +462,8 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
     constexpr int E = LaneT::E, NC = LaneT::NC;
     double rhs[E], l1[E], s0u[E];
     L.sync_reset();        // buffer parity restarts at 0: with compile-time J every exchange address is a constant offset
-    L.template pass_each<true, true>(u, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-        double r = L.d0[e] * u[e], s = 0.0;
+    L.template pass_each<true, true>(u, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
+        double r = kdiag(L, e, u[e], Ae[NC]), s = 0.0;
         UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], Ae[qq], r); s = fma(L.q[0][qq], De[qq], s); }
         rhs[e] = r;            // K05 u
         s0u[e] = s;            // S0 u
@@ -454,8 +478,8 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
     solve<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
     double k1v[E], s05v[E];
-    L.template pass_each<true, true>(v05, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-        double k0 = L.d0[e] * v05[e], k1 = k0, s = 0.0;
+    L.template pass_each<true, true>(v05, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
+        double k0 = kdiag(L, e, v05[e], Ae[NC]), k1 = k0, s = 0.0;
         UNROLL for (int qq = 0; qq < NC; ++qq) {
             k0 = fma(L.p[0][qq], Ae[qq], k0);
             k1 = fma(L.p[2][qq], Ae[qq], k1);
@@ -474,8 +498,8 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
     double k2[E];
     solve<JT>(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
-    L.template pass_each<true, false>(u, [&](int e, const double (&Ae)[NC], const double (&)[NC]) {
-        double l2 = fma(L.d0[e], u[e], s05v[e]);
+    L.template pass_each<true, false>(u, [&](int e, const double (&Ae)[NC + 1], const double (&)[NC]) {
+        double l2 = kdiag(L, e, u[e], Ae[NC]) + s05v[e];
         UNROLL for (int qq = 0; qq < NC; ++qq) l2 = fma(L.p[1][qq], Ae[qq], l2);
         v[e] = fma(0.5 * h, l1[e] + l2, v[e]);
     });
@@ -497,8 +521,8 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     L.s_prescale(0, sc);
     L.s_pass(sc, mu, rhs);
     UNROLL for (int qq = 0; qq < NC; ++qq) { Tb[qq][0] = 0.0; Tb[qq][1] = 0.0; }
-    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-        double kk = L.d0[e] * nu[e], s = 0.0;
+    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
+        double kk = kdiag(L, e, nu[e], Ae[NC]), s = 0.0;
         UNROLL for (int qq = 0; qq < NC; ++qq) {
             kk = fma(L.p[1][qq], Ae[qq], kk);
             s = fma(L.q[1][qq], De[qq], s);
@@ -515,8 +539,8 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     {
         double Ta[NC][3];
         UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) Ta[qq][a] = 0.0;
-        L.template pass_each<true, true>(mu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-            double k0 = L.d0[e] * mu[e], k1 = k0, s = 0.0;
+        L.template pass_each<true, true>(mu, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
+            double k0 = kdiag(L, e, mu[e], Ae[NC]), k1 = k0, s = 0.0;
             UNROLL for (int qq = 0; qq < NC; ++qq) {
                 k0 = fma(L.p[0][qq], Ae[qq], k0);
                 k1 = fma(L.p[2][qq], Ae[qq], k1);
@@ -545,8 +569,8 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     double l1[E];
     solve<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
-    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC], const double (&De)[NC]) {
-        double kk = L.d0[e] * nu[e];
+    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
+        double kk = kdiag(L, e, nu[e], Ae[NC]);
         UNROLL for (int qq = 0; qq < NC; ++qq) {
             kk = fma(L.p[1][qq], Ae[qq], kk);
             Tb[qq][0] = fma(vr[e], Ae[qq], Tb[qq][0]);       // + tr(vr, Hs, li)
@@ -861,6 +885,7 @@ struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBERJGM(R, NC, LMASK, UPL, JT, GLT, MINB, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB, JT, 0, GLT>, GLT}
 #define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
+#define FIBERHX(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 8, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, 0, ((1 << NC) - 1) & ~LMASK>, UPL>}   /* exchange-coupled drift */
 #define FIBERJAC(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 128, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, -1>}   /* Jacobi solver */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
@@ -876,6 +901,7 @@ const Inst kInst[] = {
     FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4),
     FIBERJGM(4, 1, 1, 2, 5, 3, 3, 32 + 5),      // risk-neutral SWAP 0-2 shape (n = 4, m = 3, J = 5)
     FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
+    FIBERHX(4, 2, 1, 1), FIBERHX(3, 2, 1, 1), FIBERHX(2, 2, 1, 1), FIBERHX(5, 2, 1, 1), FIBERHX(4, 3, 1, 1), FIBERHX(3, 3, 1, 1), FIBERHX(2, 3, 1, 1),
     FIBERJAC(3, 2, 1, 1), FIBERJAC(4, 2, 1, 1), FIBERJAC(4, 1, 1, 2), FIBERJAC(6, 1, 1, 2),
     FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
@@ -906,15 +932,17 @@ bool upload_plan(TrajPlan *pl, const std::vector<int> &pi, const std::vector<dou
     return true;
 }
 
-// H0 must be diagonal for both register layouts; returns false otherwise.
-bool h0_diagonal(const HostOps &H, std::vector<double> &d0) {
+// Diagonal of H0; returns false when H0 has off-diagonal entries (listed in `off` as (row, col, value) if given).
+struct OffDiag { int r, c; double v; };
+bool h0_diagonal(const HostOps &H, std::vector<double> &d0, std::vector<OffDiag> *off = nullptr) {
     d0.assign(H.n, 0.0);
+    bool diag = true;
     for (int r = 0; r < H.n; ++r)
         for (int p = H.rowptr[r]; p < H.rowptr[r + 1]; ++p) {
             if (H.col[p] == r) d0[r] = H.val[p];
-            else if (H.val[p] != 0.0) return false;
+            else if (H.val[p] != 0.0) { diag = false; if (off) off->push_back({r, H.col[p], H.val[p]}); else return false; }
         }
-    return true;
+    return diag;
 }
 
 int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -994,7 +1022,8 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
     std::vector<double> d0;
-    if (!h0_diagonal(H, d0)) return no("Hconst has off-diagonal entries");
+    std::vector<OffDiag> h0off;
+    const bool h0diag = h0_diagonal(H, d0, &h0off);
     // block size: first break of control 0's first off-diagonals
     int R = n;
     for (int r = 0; r + 1 < n; ++r) {
@@ -1055,6 +1084,25 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
             for (int f = 0; f < nfib && AS; ++f) AS = rem[f][q].ha[0] == -rem[f][q].hs[0] && rem[f][q].ha[1] == rem[f][q].hs[1];
         }
     }
+    // off-diagonal drift: only exchange couplings between the fibre subsystem and a remote one, i.e. entries
+    // (fibre f, level k) <- (lower neighbour fibre of control q, level k+1) or (upper neighbour fibre, level k-1)
+    int HX = 0;
+    std::vector<double> xco;                       // [fibre][control][R-1][lo, hi]
+    if (!h0diag) {
+        if (P.objFuncType != 1 || P.solver != 1) return no("off-diagonal Hconst: only objFuncType 1 with the Neumann solver is instantiated");
+        xco.assign((size_t)nfib * Nc * (R - 1) * 2, 0.0);
+        for (const OffDiag &e : h0off) {
+            const int f = e.r / R, k = e.r % R, f2 = e.c / R, k2 = e.c % R;
+            int hit = -1, side = f2 < f ? 0 : 1;
+            for (int q = 0; q < Nc && hit < 0; ++q)
+                if (!((LMASK >> q) & 1) && f2 != f && rem[f][q].off[side] == f2 - f) hit = q;
+            if (hit < 0 || k2 != (side == 0 ? k + 1 : k - 1))
+                return no("Hconst has off-diagonal entries that are not exchange couplings with the fibre subsystem");
+            xco[(((size_t)f * Nc + hit) * (R - 1) + (side == 0 ? k : k - 1)) * 2 + side] += e.v;
+            HX |= 1 << hit;
+        }
+        HX = ((1 << Nc) - 1) & ~LMASK;             // one instantiation per shape: every remote control carries (possibly zero) coefficients
+    }
     if (LMASK != 1 && LMASK != (1 << Nc) - 1) return no("only control 1 local (or all local) is instantiated");
     if (Nc > 1 && LMASK == (1 << Nc) - 1) return no("several local controls are not instantiated");
     const int NL = pow2ceil(nfib);
@@ -1070,23 +1118,30 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
         inst = (AS && P.objFuncType == 1 && GPT == 1) ? find_inst(3, R, 1, Nc, 2, LMASK, UPL, 128) : nullptr;
         if (!inst) return no("Jacobi solver: no fibre instantiation for this shape (or the trajectory spans several groups)");
     }
+    if (HX) {
+        inst = AS ? find_inst(3, R, 1, Nc, 2, LMASK, UPL, 8) : nullptr;
+        if (!inst) return no("off-diagonal (exchange) Hconst: no fibre instantiation for this shape");
+    }
     if (!inst) return no("no fibre instantiation for this (fibre length, controls, updaters per lane, Hanti form, objFuncType)");
     // lane offsets of remote neighbours must stay inside the column block of NL lanes
     TrajPlan *pl = new TrajPlan();
-    pl->kind = 3; pl->R = R; pl->C = 1; pl->NC = Nc; pl->WQ = 2; pl->LMASK = LMASK; pl->UPL = UPL; pl->AS = AS ? 1 : 0;
+    pl->kind = 3; pl->R = R; pl->C = 1; pl->NC = Nc; pl->WQ = 2; pl->LMASK = LMASK; pl->UPL = UPL; pl->AS = AS ? 1 : 0; pl->HX = HX;
     pl->NL = NL; pl->NLR = NL * R; pl->GL = GL; pl->GPT = GPT; pl->CPG = CPG;
     pl->ngroups = TRAJ_WARPS * (32 / GL);
     pl->TPC = pl->ngroups / GPT;
     pl->exch_per_unit = 4 * R * 32;           // 2 parities x 2 fibres per round
     if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
-    const int per = Nc * (4 * (R - 1) + 4);
+    const int perq = 4 * (R - 1) + 4 + (HX ? 2 * (R - 1) : 0), per = Nc * perq;
     std::vector<int> pi((size_t)NL * Nc * 2, 0);
     std::vector<double> pd((size_t)NL * per, 0.0), d0p((size_t)NL * R, 0.0), wp((size_t)NL * R, 0.0);
     for (int f = 0; f < NL; ++f) {
         if (f >= nfib) continue;                       // padding fibres: zero coefficients, own lane
         for (int k = 0; k < R; ++k) { d0p[f * R + k] = d0[f * R + k]; wp[f * R + k] = wdiag[f * R + k]; }
         for (int q = 0; q < Nc; ++q) {
-            double *c = pd.data() + (size_t)f * per + q * (4 * (R - 1) + 4);
+            double *c = pd.data() + (size_t)f * per + q * perq;
+            if (HX)
+                for (int k = 0; k < R - 1; ++k)
+                    for (int sd = 0; sd < 2; ++sd) c[4 * (R - 1) + 4 + 2 * k + sd] = xco[(((size_t)f * Nc + q) * (R - 1) + k) * 2 + sd];
             if ((LMASK >> q) & 1) {
                 for (int k = 0; k < R - 1; ++k) {
                     const int r = f * R + k;
@@ -1122,8 +1177,9 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     const char *venv = getenv("JQ_TRAJ_VARIANT");
     if (P.objFuncType != 1) venv = "64";
     if (P.solver != 1) venv = "128";
+    if (pl->HX) venv = "8";
     const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv), pl->GL) : nullptr;
-    if (P.solver != 1 && !inst) return cudaErrorNotSupported;        // never substitute the Neumann series for Jacobi
+    if ((P.solver != 1 || pl->HX) && !inst) return cudaErrorNotSupported;   // never substitute the Neumann series for Jacobi, or drop the drift couplings
     if (!inst && !venv && pl->AS && P.objFuncType == 1)      // instantiations with the number of Neumann terms known at compile time
         inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J, pl->GL);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);

@@ -21,7 +21,8 @@ SHAPES = [
     ([2, 2], [0, 0], {}), ([2, 2], [1, 1], {}), ([2, 2], [1, 2], {}), ([2, 2], [2, 2], {}), ([3, 3], [1, 1], {}),
     ([3, 3], [2, 2], {}), ([2, 3], [2, 1], {}), ([2, 2, 2], [0, 0, 0], {}), ([2, 2, 2], [1, 1, 1], {}),
     ([3, 2], [2, 1], {}), ([3, 3], [3, 1], {}), ([3], [2], {"use_sparse": True}), ([3, 2, 2], [2, 1, 1], {}),
-    ([2, 2, 1], [2, 2, 3], {}), ([2, 2], [2, 2], {"exchange": 0.02}), ([2, 2], [2, 2], {"Nfreq": 3}), ([4], [2], {"Nfreq": 1}),
+    ([2, 2, 1], [2, 2, 3], {}), ([2, 2], [2, 2], {"exchange": 0.02}), ([3, 3], [1, 1], {"exchange": 0.02}), ([2, 2, 2], [1, 1, 1], {"exchange": 0.02}),
+    ([2, 2], [2, 2], {"Nfreq": 3}), ([4], [2], {"Nfreq": 1}),
 ]
 
 
