@@ -35,7 +35,8 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    deps = (sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+            glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -43,20 +44,25 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=()) ->
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    objs = []
+    objs, cmds = [], []
     nvcc = _nvcc()
+    hdrs = (glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+            glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     for src in sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        hdrs = glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
         if force or not os.path.exists(obj) or any(os.path.getmtime(d) > os.path.getmtime(obj) for d in [src] + hdrs):
             cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj]
-            if os.environ.get("JQ_FAST_BUILD"):      # development only: 3x faster, slightly different register allocation
+            if os.environ.get("JQ_FAST_BUILD"):      # development only: faster, slightly different register allocation
                 cmd.insert(1, "--split-compile=0")
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd))
-            subprocess.check_call(cmd)
+            cmds.append(cmd)
         objs.append(obj)
+    # the translation units are independent (the trajectory-kernel instantiations are split over three of them): compile in parallel
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=max(1, min(len(cmds), os.cpu_count() or 1))) as pool:
+        list(pool.map(subprocess.check_call, cmds))
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     subprocess.check_call(cmd)
     return LIB

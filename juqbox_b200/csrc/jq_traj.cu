@@ -1,915 +1,24 @@
-// Register-resident trajectory kernels: the state of a trajectory lives in REGISTERS for the whole forward and
-// backward time loops; shared memory is only the exchange medium of the sparse operator products.
-//
-// One kernel template, two lane layouts ("how the n x m block is cut into per-lane register elements"):
-//
-//  SlotLane<R,C,NC,WQ>  (kernel id 2) generic sparse rows.  A group = NL lanes; lane l owns rows l, l+NL, .. (R rows)
-//      and C columns.  Every row keeps per control <= WQ entries (neighbour position, Hsym value, Hanti value); one
-//      product pass stores the lane's elements to the group's exchange buffer and loads every neighbour.
-//  FiberLane<R,NC,LMASK,AS,XM> (kernel id 3) Kronecker ladder structure.  A lane owns a whole fibre of R consecutive rows
-//      (the levels of the fastest subsystem) of ONE column.  Controls in LMASK couple only rows inside a fibre
-//      (tridiagonal, coefficients in registers, no memory traffic at all); the other controls couple whole fibres
-//      with a fibre-uniform coefficient, so a pass exchanges one R-vector per neighbour fibre instead of one load
-//      per nonzero.  Single-subsystem problems (n = R) never touch shared memory inside the time loops.
-//
-// Common structure.  Up to 4 warps per CTA (fewer only when very long pcof vectors would overflow shared memory); a
-// group of GL lanes (a power of two, or m lanes for single-fibre columns) covers (part of) one trajectory, GPT groups
-// per trajectory, TPC trajectories per CTA.  Columns never couple inside the time loops, so products only need
-// __syncwarp; groups meet through shared memory + __syncthreads once per CH-step chunk (control table), at the
-// infidelity between the sweeps and at the final gradient sum.
-//   pass(x):  A_q = Hsym_q x and/or D_q = Hanti_q x ;  K(t)x = h0.*x + sum_q p_q(t) A_q ;  S(t)x = sum_q q_q(t) D_q
-// The A_q, D_q of the adjoint passes are exactly what the gradient traces need (tr(A'HC) = sum A.*(HC)), so the
-// gradient costs no extra products.  Control table: every CH steps all threads fill knot index, the three B-spline
-// values and cos/sin of every carrier at the 2CH+1 time points, then p_q, q_q for every resident trajectory.
-// Template switches: UPL gradient-scatter roles per lane, MINB register cap, JT compile-time number of Neumann terms,
-// OBJ second adjoint set (objFuncType 2/3), GLT compile-time group size.
-//
-// Reference lines: forward loop src/evalobjgrad.jl:698-753, infidelity :755-766, adjoint init :810-844/:2026-2042,
-// backward loop :859-921, steppers src/StormerVerlet.jl:255-303,:461-504, Neumann src/linear_solvers.jl:94-106,
-// controls src/bsplines.jl:211-304,:321-381, gradient src/evalobjgrad.jl:2567-2619.  The only algebraic regrouping
-// is S1*u + (h/2) S1*k1 = S1*(u + (h/2) k1)  (src/StormerVerlet.jl:483-484).
-#include "jq_common.h"
-#include <type_traits>
-
-#include <cstdio>
-#include <cstdlib>
-#include <vector>
-
-#define TRAJ_WARPS 4
-#define TRAJ_THREADS (TRAJ_WARPS * 32)
-#define TRAJ_CH 16   // steps per control-table chunk
-
-struct TrajParams {
-    DevProblem P;
-    LaunchArgs A;
-    int NL;                                  // lanes per column block (slot: lanes per slot; fibre: fibres per column)
-    int GL, GPT, TPC, ngroups;               // lanes per group, groups per trajectory, trajectories / groups per CTA
-    int CPG;                                 // fibre layout: columns per group
-    int NLR;                                 // slot layout: NL * R (rows incl. padding)
-    const int *plan_i;                       // layout-specific integer table
-    const double *plan_d;                    // layout-specific coefficient table
-    const double *plan_d0, *plan_w;          // per (padded) row: H0 diagonal, guard weight
-    int o_exch, o_pcof, o_gsm, o_times, o_tabb, o_tabph, o_tabpq, o_red, o_tabk, o_tred, o_gsm2;   // shared-memory offsets in doubles
-    int exch_per_unit;                       // doubles of exchange buffer per group (slot) / per warp (fibre)
-    int NparS;                               // shared-memory row stride of the staged pcof vectors (odd: no bank conflicts)
-    int GPW;                                 // groups per warp (32 / GL, rounded down: GL need not be a power of two)
-};
-
-struct TrajPlan {
-    int kind;                                // 2 slot, 3 fibre
-    int R, C, NC, WQ, LMASK, UPL, AS, HX = 0;
-    int NL, GL, GPT, TPC, ngroups, CPG, NLR, exch_per_unit;
-    int *d_i = nullptr;
-    double *d_d = nullptr, *d_d0 = nullptr, *d_w = nullptr;
-};
+// Planners, launch and instantiation lookup of the register-resident trajectory kernels; the kernels themselves are in
+// jq_traj_kernels.cuh (shared with jq_traj_inst_b.cu / jq_traj_inst_c.cu, which hold the other parts of the table).
+#include "jq_traj_kernels.cuh"
 
 namespace {
 
-#define UNROLL _Pragma("unroll")
-
-// ------------------------------------------------------------------------------------------------ exchange access
-// V doubles per position, laid out in planes of `stride` positions so that consecutive lanes hit consecutive banks.
-template <int V> struct Xch {          // general V: V/2 planes of double2 followed by one plane of double when V is odd
-    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) {
-        UNROLL for (int p = 0; p < V / 2; ++p) reinterpret_cast<double2 *>(b)[p * s + pos] = make_double2(x[2 * p], x[2 * p + 1]);
-        if (V & 1) b[2 * (V / 2) * s + pos] = x[V - 1];
-    }
-    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) {
-        UNROLL for (int p = 0; p < V / 2; ++p) { double2 v = reinterpret_cast<const double2 *>(b)[p * s + pos]; x[2 * p] = v.x; x[2 * p + 1] = v.y; }
-        if (V & 1) x[V - 1] = b[2 * (V / 2) * s + pos];
-    }
-};
-template <> struct Xch<1> {
-    static __device__ __forceinline__ void st(double *b, int pos, int, const double *x) { b[pos] = x[0]; }
-    static __device__ __forceinline__ void ld(const double *b, int pos, int, double *x) { x[0] = b[pos]; }
-};
-template <> struct Xch<2> {
-    static __device__ __forceinline__ void st(double *b, int pos, int, const double *x) { reinterpret_cast<double2 *>(b)[pos] = make_double2(x[0], x[1]); }
-    static __device__ __forceinline__ void ld(const double *b, int pos, int, double *x) { double2 v = reinterpret_cast<const double2 *>(b)[pos]; x[0] = v.x; x[1] = v.y; }
-};
-template <> struct Xch<3> {
-    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) { b[pos] = x[0]; b[s + pos] = x[1]; b[2 * s + pos] = x[2]; }
-    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) { x[0] = b[pos]; x[1] = b[s + pos]; x[2] = b[2 * s + pos]; }
-};
-template <> struct Xch<4> {
-    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) {
-        reinterpret_cast<double2 *>(b)[pos] = make_double2(x[0], x[1]);
-        reinterpret_cast<double2 *>(b)[s + pos] = make_double2(x[2], x[3]);
-    }
-    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) {
-        double2 v = reinterpret_cast<const double2 *>(b)[pos], w = reinterpret_cast<const double2 *>(b)[s + pos];
-        x[0] = v.x; x[1] = v.y; x[2] = w.x; x[3] = w.y;
-    }
-};
-template <> struct Xch<6> {
-    static __device__ __forceinline__ void st(double *b, int pos, int s, const double *x) {
-        UNROLL for (int p = 0; p < 3; ++p) reinterpret_cast<double2 *>(b)[p * s + pos] = make_double2(x[2 * p], x[2 * p + 1]);
-    }
-    static __device__ __forceinline__ void ld(const double *b, int pos, int s, double *x) {
-        UNROLL for (int p = 0; p < 3; ++p) { double2 v = reinterpret_cast<const double2 *>(b)[p * s + pos]; x[2 * p] = v.x; x[2 * p + 1] = v.y; }
-    }
-};
-
-// ------------------------------------------------------------------------------------------------ lane layouts
-// Geometry of this thread inside the CTA, common to both layouts.
-struct Geo {
-    int lane, warp, lg, group, tloc, gi;     // lane in warp, warp, lane in group, group in CTA, trajectory in CTA, group in trajectory
-};
-
-template <int R_, int C_, int NC_, int WQ_>
-struct SlotLane {
-    static constexpr int R = R_, C = C_, NC = NC_, WQ = WQ_, E = R_ * C_, HX = 0;
-    int pos[R][NC][WQ], own[R];
-    double hs[R][NC][WQ], ha[R][NC][WQ];
-    double d0[E], w[E];
-    double p[3][NC], q[3][NC];
-    double *buf;
-    int nlr, parity, c0;
-    int sGL, sbase; double stol;             // Jacobi instantiations: group geometry and tolerance for the residual norm
-
-    __device__ __forceinline__ void setup(const TrajParams &S, double *sm, const Geo &g) {
-        nlr = S.NLR; parity = 0; c0 = g.gi * C;
-        buf = sm + S.o_exch + g.group * S.exch_per_unit;
-        UNROLL for (int k = 0; k < R; ++k) {
-            const int r = k * S.NL + g.lg;
-            own[k] = r;
-            UNROLL for (int qq = 0; qq < NC; ++qq)
-                UNROLL for (int e = 0; e < WQ; ++e) {
-                    const int ix = (r * NC + qq) * WQ + e;
-                    pos[k][qq][e] = S.plan_i[ix];
-                    hs[k][qq][e] = S.plan_d[2 * ix];
-                    ha[k][qq][e] = S.plan_d[2 * ix + 1];
-                }
-        }
-    }
-    // (padded) row and column of element e
-    __device__ __forceinline__ int row(int e) const { return own[e / C]; }
-    __device__ __forceinline__ int col(int e) const { return c0 + e % C; }
-
-    __device__ __forceinline__ void sync_reset() { __syncwarp(); parity = 0; }
-    // Neighbour handle: for this layout the exchange buffer itself (neighbours are loaded entry by entry).
-    struct Nbr { const double *b; };
-    __device__ __forceinline__ void exchange(const double (&x)[E], Nbr &nb) {
-        double *b = buf + parity * (2 * nlr * C);
-        parity ^= 1;
-        UNROLL for (int k = 0; k < R; ++k) Xch<C>::st(b, own[k], nlr, &x[k * C]);
-        __syncwarp();
-        nb.b = b;
-    }
-
-    // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
-    struct SC { double c[R][NC][WQ]; };
-    __device__ __forceinline__ void s_prescale(int level, SC &sc) const {
-        UNROLL for (int k = 0; k < R; ++k) UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int e = 0; e < WQ; ++e)
-            sc.c[k][qq][e] = q[level][qq] * ha[k][qq][e];
-    }
-    __device__ __forceinline__ void s_from(const SC &sc, const double (&)[E], const Nbr &nb, double (&t)[E]) const {
-        UNROLL for (int k = 0; k < R; ++k) {
-            UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq)
-                UNROLL for (int e = 0; e < WQ; ++e) {
-                    double xv[C];
-                    Xch<C>::ld(nb.b, pos[k][qq][e], nlr, xv);
-                    UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = fma(sc.c[k][qq][e], xv[c], t[k * C + c]);
-                }
-        }
-    }
-    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
-        Nbr nb;
-        exchange(x, nb);
-        s_from(sc, x, nb, t);
-    }
-
-    // f(e, Ae, De) is called once per element with Ae[q] = (Hsym_q x)_e, De[q] = (Hanti_q x)_e: the per-control
-    // partial products only live for one row at a time.
-    template <bool WA, bool WD, class F>
-    __device__ __forceinline__ void each_from(const double (&)[E], const Nbr &nb, F f) const {
-        UNROLL for (int k = 0; k < R; ++k) {
-            double Ar[C][NC + 1], Dr[C][NC];          // Ar[.][NC]: off-diagonal drift product (fibre layout only)
-            UNROLL for (int c = 0; c < C; ++c) Ar[c][NC] = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq) {
-                UNROLL for (int c = 0; c < C; ++c) { Ar[c][qq] = 0.0; Dr[c][qq] = 0.0; }
-                UNROLL for (int e = 0; e < WQ; ++e) {
-                    double xv[C];
-                    Xch<C>::ld(nb.b, pos[k][qq][e], nlr, xv);
-                    UNROLL for (int c = 0; c < C; ++c) {
-                        if (WA) Ar[c][qq] = fma(hs[k][qq][e], xv[c], Ar[c][qq]);
-                        if (WD) Dr[c][qq] = fma(ha[k][qq][e], xv[c], Dr[c][qq]);
-                    }
-                }
-            }
-            UNROLL for (int c = 0; c < C; ++c) f(k * C + c, Ar[c], Dr[c]);
-        }
-    }
-    template <bool WA, bool WD, class F>
-    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
-        Nbr nb;
-        exchange(x, nb);
-        each_from<WA, WD>(x, nb, f);
-    }
-};
-
-// AS = 1: the control Hamiltonians have the ladder form Hanti = (upper part of Hsym) - (lower part of Hsym), i.e.
-// (a - a') next to (a + a'): only the Hsym coefficients are kept and D = upper - lower, A = upper + lower.
-// HX != 0: the drift Hamiltonian has exchange-type couplings a_0' a_q + a_0 a_q' between the fastest subsystem and the remote
-// subsystems (bit q of HX): row k of this fibre takes element k+1 of the lower and element k-1 of the upper neighbour fibre of
-// control q -- fibres every K-product fetches anyway.
-template <int R_, int NC_, int LMASK_, int AS_ = 1, int XM_ = 0, int HX_ = 0>
-struct FiberLane {
-    static constexpr int R = R_, NC = NC_, LMASK = LMASK_, E = R_, AS = AS_, XM = XM_, HX = HX_;   // XM: 0 = shared-memory exchange, 1 = warp shuffles (16 instead of 24 data-pipe wavefronts per round for R = 4, NC = 2, but 16 instead of 7 instructions)
-    static constexpr bool REMOTE = (LMASK_ != (1 << NC_) - 1);
-    static constexpr int RM1 = R_ > 1 ? R_ - 1 : 1;
-    // local (inside the fibre) tridiagonal coefficients: x_{k+1} -> row k ("u"), x_k -> row k+1 ("l")
-    double lsu[NC][RM1], lsl[NC][RM1], lau[NC][RM1], lal[NC][RM1];
-    // remote: lower (entry 0) and upper (entry 1) neighbour fibre per control, fibre-uniform coefficients
-    int rpos[NC][2];
-    double rhs[NC][2], rha[NC][2];
-    double xlo[HX_ ? NC : 1][RM1], xhi[HX_ ? NC : 1][RM1];   // drift exchange coefficients (HX only)
-    double d0[E], w[E];
-    double p[3][NC], q[3][NC];
-    double *buf;
-    int parity, lane, row0, colj;
-    int sGL, sbase; double stol;             // Jacobi instantiations: group geometry and tolerance for the residual norm
-
-    __device__ __forceinline__ void setup(const TrajParams &S, double *sm, const Geo &g) {
-        parity = 0; lane = g.lane;
-        const int rho = g.lg % S.NL, cj = g.lg / S.NL;
-        row0 = rho * R;
-        colj = g.gi * S.CPG + cj;
-        buf = sm + S.o_exch + g.warp * S.exch_per_unit;
-        const int *pi = S.plan_i + rho * (NC * 2);
-        constexpr int PERQ = 4 * (R - 1) + 4 + (HX ? 2 * (R - 1) : 0);
-        const double *pd = S.plan_d + rho * (NC * PERQ);
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            const double *c = pd + qq * PERQ;
-            if constexpr (HX != 0) {
-                UNROLL for (int k = 0; k < R - 1; ++k) { xlo[qq][k] = c[4 * (R - 1) + 4 + 2 * k]; xhi[qq][k] = c[4 * (R - 1) + 4 + 2 * k + 1]; }
-            }
-            UNROLL for (int k = 0; k < R - 1; ++k) {
-                lsu[qq][k] = c[4 * k]; lsl[qq][k] = c[4 * k + 1];
-                if (!AS) { lau[qq][k] = c[4 * k + 2]; lal[qq][k] = c[4 * k + 3]; }
-            }
-            UNROLL for (int e = 0; e < 2; ++e) {
-                rpos[qq][e] = g.lane + pi[qq * 2 + e];          // plan stores the fibre offset (0 = padding -> own lane)
-                rhs[qq][e] = c[4 * (R - 1) + 2 * e];
-                if (!AS) rha[qq][e] = c[4 * (R - 1) + 2 * e + 1];
-            }
-        }
-    }
-    __device__ __forceinline__ int row(int e) const { return row0 + e; }
-    __device__ __forceinline__ int col(int) const { return colj; }
-
-    __device__ __forceinline__ void sync_reset() { if (REMOTE && XM == 0) { __syncwarp(); parity = 0; } }
-    // Neighbour handle: the two neighbour fibres of every remote control, in registers.
-    struct Nbr { double v[NC][2][R]; };
-    __device__ __forceinline__ void fetch(const double *b, const double (&x)[E], Nbr &nb) const {
-        UNROLL for (int qq = 0; qq < NC; ++qq)
-            if (!((LMASK >> qq) & 1)) {
-                if (XM == 0) {
-                    Xch<R>::ld(b, rpos[qq][0], 32, nb.v[qq][0]);
-                    Xch<R>::ld(b, rpos[qq][1], 32, nb.v[qq][1]);
-                } else {
-                    UNROLL for (int k = 0; k < R; ++k) {
-                        nb.v[qq][0][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][0]);
-                        nb.v[qq][1][k] = __shfl_sync(0xffffffffu, x[k], rpos[qq][1]);
-                    }
-                }
-            }
-    }
-    // Publish the fibre and fetch the neighbour fibres of every remote control.
-    __device__ __forceinline__ void exchange(const double (&x)[E], Nbr &nb) {
-        if (!REMOTE) return;
-        const double *b = buf;
-        if (XM == 0) {
-            double *bw = buf + parity * (2 * R * 32);
-            parity ^= 1;
-            Xch<R>::st(bw, lane, 32, x);
-            __syncwarp();
-            b = bw;
-        }
-        fetch(b, x, nb);
-    }
-
-    // S(level) with the control values folded into the coefficients: one solve uses it for J+1 products
-    struct SC { double lu[RM1], ll[RM1], r[NC][2]; };
-    __device__ __forceinline__ void s_prescale(int level, SC &sc) const {
-        UNROLL for (int k = 0; k < R - 1; ++k) {
-            double u = 0.0, l = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq)
-                if ((LMASK >> qq) & 1) {
-                    u = fma(q[level][qq], AS ? lsu[qq][k] : lau[qq][k], u);
-                    l = AS ? fma(-q[level][qq], lsl[qq][k], l) : fma(q[level][qq], lal[qq][k], l);
-                }
-            sc.lu[k] = u; sc.ll[k] = l;
-        }
-        UNROLL for (int qq = 0; qq < NC; ++qq)
-            if (!((LMASK >> qq) & 1)) {
-                sc.r[qq][0] = AS ? -q[level][qq] * rhs[qq][0] : q[level][qq] * rha[qq][0];
-                sc.r[qq][1] = q[level][qq] * (AS ? rhs[qq][1] : rha[qq][1]);
-            }
-    }
-    __device__ __forceinline__ void s_from(const SC &sc, const double (&x)[E], const Nbr &nb, double (&t)[E]) const {
-        UNROLL for (int k = 0; k < R; ++k) {       // local part first: independent of the exchange
-            double a = 0.0;
-            if (k + 1 < R) a = sc.lu[k] * x[k + 1];
-            if (k > 0) a = fma(sc.ll[k - 1], x[k - 1], a);
-            t[k] = a;
-        }
-        UNROLL for (int qq = 0; qq < NC; ++qq)
-            if (!((LMASK >> qq) & 1))
-                UNROLL for (int k = 0; k < R; ++k) t[k] = fma(sc.r[qq][1], nb.v[qq][1][k], fma(sc.r[qq][0], nb.v[qq][0][k], t[k]));
-    }
-    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
-        Nbr nb;
-        exchange(x, nb);
-        s_from(sc, x, nb, t);
-    }
-
-    template <bool WA, bool WD, class F>
-    __device__ __forceinline__ void each_from(const double (&x)[E], const Nbr &nb, F f) const {
-        UNROLL for (int k = 0; k < R; ++k) {
-            double Ae[NC + 1], De[NC];                 // Ae[NC]: off-diagonal drift product of row k
-            Ae[NC] = 0.0;
-            if constexpr (HX != 0 && WA) {
-                UNROLL for (int qq = 0; qq < NC; ++qq)
-                    if ((HX >> qq) & 1) {
-                        if (k + 1 < R) Ae[NC] = fma(xlo[qq][k], nb.v[qq][0][k + 1], Ae[NC]);
-                        if (k > 0) Ae[NC] = fma(xhi[qq][k - 1], nb.v[qq][1][k - 1], Ae[NC]);
-                    }
-            }
-            UNROLL for (int qq = 0; qq < NC; ++qq) {
-                double up = 0.0, lo = 0.0, a = 0.0, d = 0.0;
-                if ((LMASK >> qq) & 1) {
-                    if (AS) {
-                        if (k + 1 < R) up = lsu[qq][k] * x[k + 1];
-                        if (k > 0) lo = lsl[qq][k - 1] * x[k - 1];
-                    } else {
-                        if (k + 1 < R) { if (WA) a = lsu[qq][k] * x[k + 1]; if (WD) d = lau[qq][k] * x[k + 1]; }
-                        if (k > 0) { if (WA) a = fma(lsl[qq][k - 1], x[k - 1], a); if (WD) d = fma(lal[qq][k - 1], x[k - 1], d); }
-                    }
-                } else {
-                    if (AS) {
-                        lo = rhs[qq][0] * nb.v[qq][0][k];
-                        up = rhs[qq][1] * nb.v[qq][1][k];
-                    } else {
-                        if (WA) a = fma(rhs[qq][1], nb.v[qq][1][k], rhs[qq][0] * nb.v[qq][0][k]);
-                        if (WD) d = fma(rha[qq][1], nb.v[qq][1][k], rha[qq][0] * nb.v[qq][0][k]);
-                    }
-                }
-                if (AS) { a = up + lo; d = up - lo; }
-                Ae[qq] = a; De[qq] = d;
-            }
-            f(k, Ae, De);
-        }
-    }
-    template <bool WA, bool WD, class F>
-    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
-        Nbr nb;
-        exchange(x, nb);
-        each_from<WA, WD>(x, nb, f);
-    }
-};
-
-// ------------------------------------------------------------------------------------------------ steppers
-// Sum over the GL lanes of a group, result on every lane.  Power-of-two groups use the xor butterfly; other sizes
-// (single-fibre columns with m = 3) gather the GL values in lane order.
-__device__ __forceinline__ double group_sum(double x, int GL, int base) {
-    if ((GL & (GL - 1)) == 0) {
-        for (int o = 1; o < GL; o <<= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        return x;
-    }
-    double s = 0.0;
-    for (int j = 0; j < GL; ++j) s += __shfl_sync(0xffffffffu, x, base + j);
-    return s;
-}
-
-// The same for N values at once, ROUNDS OUTER / VALUES INNER: the N shuffles of a round are independent and pipeline,
-// so the dependent chain is log2(GL) shuffle latencies in total instead of N * log2(GL) (measured: the value-by-value
-// form was 22% of all stall samples of the kernel).
-template <int N>
-__device__ __forceinline__ void group_sum_n(double (&v)[N], int GL, int base) {
-    if ((GL & (GL - 1)) == 0) {
-#pragma unroll
-        for (int o = 1; o < GL; o <<= 1) {       // unrolled when GL is a compile-time constant (GLT instantiations)
-            double r[N];
-            UNROLL for (int i = 0; i < N; ++i) r[i] = __shfl_xor_sync(0xffffffffu, v[i], o);
-            UNROLL for (int i = 0; i < N; ++i) v[i] += r[i];
-        }
-        return;
-    }
-    double s[N];
-    UNROLL for (int i = 0; i < N; ++i) s[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < GL; ++j) {           // unrolled for GLT instantiations
-        UNROLL for (int i = 0; i < N; ++i) s[i] += __shfl_sync(0xffffffffu, v[i], base + j);
-    }
-    UNROLL for (int i = 0; i < N; ++i) v[i] = s[i];
-}
-
-// (H0 x)_e for the lane's element e: diagonal entry times x_e, plus the off-diagonal drift product x0 in HX layouts.
-template <class LaneT>
-__device__ __forceinline__ double kdiag(const LaneT &L, int e, double xe, double x0) {
-    if constexpr (LaneT::HX != 0) return fma(L.d0[e], xe, x0);
-    else return L.d0[e] * xe;
-}
-
-// X = sum_{j<=J} (h/2)^j S^j B   (src/linear_solvers.jl:94-106); B is consumed.  `sc` = S(level) prescaled.
-template <int JT, class LaneT>
-__device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
-    constexpr int E = LaneT::E;
-    UNROLL for (int e = 0; e < E; ++e) X[e] = B[e];
-    double coeff = 1.0;
-    const int JJ = JT > 0 ? JT : J;          // JT > 0: number of Neumann terms known at compile time (fully unrolled)
-#pragma unroll
-    for (int it = 0; it < JJ; ++it) {
-        double T[E];
-        L.s_pass(sc, B, T);
-        coeff *= 0.5 * h;
-        UNROLL for (int e = 0; e < E; ++e) { B[e] = T[e]; X[e] = fma(coeff, T[e], X[e]); }
-    }
-}
-
-// JACOBI_SOLVER (src/linear_solvers.jl:110-152): X = B; T = B + (h/2) S X; err = ||T - X||_F over the whole n x m block;
-// X = T; stop when err < tol or after J sweeps.  The block of a trajectory is one group here (the planner only admits
-// GPT == 1), so the norm is one group reduction; groups of a warp that have converged keep exchanging (the passes need
-// the whole warp) but stop updating, and the warp leaves the loop when all its groups are done.  B is preserved.
-template <class LaneT>
-__device__ __forceinline__ void jacobi(LaneT &L, const typename LaneT::SC &sc, int maxit, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
-    constexpr int E = LaneT::E;
-    UNROLL for (int e = 0; e < E; ++e) X[e] = B[e];
-    bool active = true;
-    for (int it = 0; it < maxit; ++it) {
-        double T[E], err = 0.0;
-        L.s_pass(sc, X, T);
-        UNROLL for (int e = 0; e < E; ++e) { T[e] = fma(0.5 * h, T[e], B[e]); const double d = T[e] - X[e]; err = fma(d, d, err); }
-        err = group_sum(err, L.sGL, L.sbase);
-        if (active) { UNROLL for (int e = 0; e < E; ++e) X[e] = T[e]; }
-        active = active && !(sqrt(err) < L.stol);
-        if (!__any_sync(0xffffffffu, active)) break;
-    }
-}
-
-// linear_solver.solve of the steppers: JT >= 0 truncated Neumann series (JT > 0: compile-time J), JT < 0 Jacobi sweeps.
-template <int JT, class LaneT>
-__device__ __forceinline__ void solve(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
-    if constexpr (JT < 0) jacobi(L, sc, J, h, B, X);
-    else neumann<JT>(L, sc, J, h, B, X);
-}
-
-// src/StormerVerlet.jl:461-504.  u, v updated in place; v05 returned.
-template <int JT, class LaneT>
-__device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u)[LaneT::E], double (&v)[LaneT::E], double (&v05)[LaneT::E]) {
-    constexpr int E = LaneT::E, NC = LaneT::NC;
-    double rhs[E], l1[E], s0u[E];
-    L.sync_reset();        // buffer parity restarts at 0: with compile-time J every exchange address is a constant offset
-    L.template pass_each<true, true>(u, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
-        double r = kdiag(L, e, u[e], Ae[NC]), s = 0.0;
-        UNROLL for (int qq = 0; qq < NC; ++qq) { r = fma(L.p[1][qq], Ae[qq], r); s = fma(L.q[0][qq], De[qq], s); }
-        rhs[e] = r;            // K05 u
-        s0u[e] = s;            // S0 u
-    });
-    typename LaneT::SC sc;
-    L.s_prescale(1, sc);
-    {
-        double tv[E];
-        L.s_pass(sc, v, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhs[e] += tv[e];                                    // + S05 v
-    }
-    solve<JT>(L, sc, J, h, rhs, l1);
-    UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
-    double k1v[E], s05v[E];
-    L.template pass_each<true, true>(v05, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
-        double k0 = kdiag(L, e, v05[e], Ae[NC]), k1 = k0, s = 0.0;
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            k0 = fma(L.p[0][qq], Ae[qq], k0);
-            k1 = fma(L.p[2][qq], Ae[qq], k1);
-            s = fma(L.q[1][qq], De[qq], s);
-        }
-        k1v[e] = k1;                                   // K1 v05
-        s05v[e] = s;                                   // S05 v05
-        u[e] = fma(0.5 * h, s0u[e] - k0, u[e]);        // u + (h/2) kappa1,  kappa1 = S0 u - K0 v05
-    });
-    L.s_prescale(2, sc);
-    {
-        double tv[E];
-        L.s_pass(sc, u, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhs[e] = tv[e] - k1v[e];                             // S1 (u + (h/2) kappa1) - K1 v05
-    }
-    double k2[E];
-    solve<JT>(L, sc, J, h, rhs, k2);
-    UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
-    L.template pass_each<true, false>(u, [&](int e, const double (&Ae)[NC + 1], const double (&)[NC]) {
-        double l2 = kdiag(L, e, u[e], Ae[NC]) + s05v[e];
-        UNROLL for (int qq = 0; qq < NC; ++qq) l2 = fma(L.p[1][qq], Ae[qq], l2);
-        v[e] = fma(0.5 * h, l1[e] + l2, v[e]);
-    });
-}
-
-// src/StormerVerlet.jl:255-303 with the diagonal-W forcing of src/evalobjgrad.jl:862,882-888, fused with the five
-// traces per control of adjoint_grad_calc! (src/evalobjgrad.jl:2578-2618):
-//   T[q][0] = tr(vr0,Ha,lr05)  T[q][1] = tr(vi05,Hs,lr05)  T[q][2] = tr(vr,Ha,lr05)
-//   T[q][3] = tr(vr,Hs,li)+tr(vr0,Hs,li0)                   T[q][4] = tr(vi05,Ha,li)+tr(vi05,Ha,li0)
-// The group-reduced traces are left in shared memory at tred[q*5 + a] (written by lane 0 of the group).
-template <int JT, bool FORCING, class LaneT>
-__device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (&mu)[LaneT::E], double (&nu)[LaneT::E],
-                                             const double (&vr0)[LaneT::E], const double (&vi05)[LaneT::E],
-                                             const double (&vr)[LaneT::E], double *tred, int GL, int gbase_lane, bool writer) {
-    constexpr int E = LaneT::E, NC = LaneT::NC;
-    double rhs[E], s05n[E], Tb[NC][2];
-    typename LaneT::SC sc;
-    L.sync_reset();
-    L.s_prescale(0, sc);
-    L.s_pass(sc, mu, rhs);
-    UNROLL for (int qq = 0; qq < NC; ++qq) { Tb[qq][0] = 0.0; Tb[qq][1] = 0.0; }
-    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
-        double kk = kdiag(L, e, nu[e], Ae[NC]), s = 0.0;
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            kk = fma(L.p[1][qq], Ae[qq], kk);
-            s = fma(L.q[1][qq], De[qq], s);
-            Tb[qq][0] = fma(vr0[e], Ae[qq], Tb[qq][0]);      // tr(vr0, Hs, li0)
-            Tb[qq][1] = fma(vi05[e], De[qq], Tb[qq][1]);     // tr(vi05, Ha, li0)
-        }
-        rhs[e] = (FORCING ? fma(L.w[e], vr0[e], rhs[e]) : rhs[e]) - kk;   // S0 mu + hr0 - K05 nu
-        s05n[e] = s;                                         // S05 nu
-    });
-    double k2[E];
-    solve<JT>(L, sc, J, h, rhs, k2);
-    UNROLL for (int e = 0; e < E; ++e) mu[e] = fma(0.5 * h, k2[e], mu[e]);   // X = lr05
-    double l2[E], r0[E], mu2[E];
-    {
-        double Ta[NC][3];
-        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) Ta[qq][a] = 0.0;
-        L.template pass_each<true, true>(mu, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
-            double k0 = kdiag(L, e, mu[e], Ae[NC]), k1 = k0, s = 0.0;
-            UNROLL for (int qq = 0; qq < NC; ++qq) {
-                k0 = fma(L.p[0][qq], Ae[qq], k0);
-                k1 = fma(L.p[2][qq], Ae[qq], k1);
-                s = fma(L.q[2][qq], De[qq], s);
-                Ta[qq][0] = fma(vr0[e], De[qq], Ta[qq][0]);
-                Ta[qq][1] = fma(vi05[e], Ae[qq], Ta[qq][1]);
-                Ta[qq][2] = fma(vr[e], De[qq], Ta[qq][2]);
-            }
-            const double hi0 = FORCING ? L.w[e] * vi05[e] : 0.0;
-            l2[e] = k0 + s05n[e] + hi0;                              // K0 X + S05 nu + hi0
-            r0[e] = s05n[e] + k1 + hi0;                              // S05 nu + K1 X + hi1
-            mu2[e] = fma(0.5 * h, FORCING ? fma(L.w[e], vr[e], s) : s, mu[e]);     // X + (h/2)(S1 X + hr1)
-        });
-        // the three traces that only involve lr05 = X are complete: reduce them now, overlapped with the next products
-        double tv3[NC * 3];
-        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tv3[qq * 3 + a] = Ta[qq][a];
-        group_sum_n(tv3, GL, gbase_lane);
-        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tred[qq * 5 + a] = tv3[qq * 3 + a]; }
-    }
-    L.s_prescale(1, sc);
-    {
-        double tv[E];
-        L.s_pass(sc, l2, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(0.5 * h, tv[e], r0[e]);   // S05 nu + (h/2) S05 l2 + K1 X + hi1
-    }
-    double l1[E];
-    solve<JT>(L, sc, J, h, rhs, l1);
-    UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
-    L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
-        double kk = kdiag(L, e, nu[e], Ae[NC]);
-        UNROLL for (int qq = 0; qq < NC; ++qq) {
-            kk = fma(L.p[1][qq], Ae[qq], kk);
-            Tb[qq][0] = fma(vr[e], Ae[qq], Tb[qq][0]);       // + tr(vr, Hs, li)
-            Tb[qq][1] = fma(vi05[e], De[qq], Tb[qq][1]);     // + tr(vi05, Ha, li)
-        }
-        mu[e] = fma(-0.5 * h, kk, mu2[e]);                   // mu + (h/2) kappa1, kappa1 = S1 X - K05 nu + hr1
-    });
-    {
-        double tv2[NC * 2];
-        UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tv2[qq * 2 + a] = Tb[qq][a];
-        group_sum_n(tv2, GL, gbase_lane);
-        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tred[qq * 5 + 3 + a] = tv2[qq * 2 + a]; }
-    }
-    __syncwarp();
-}
-
-// Fill the control table for `nst` steps starting at time t (all threads of the CTA).
-template <int NC>
-__device__ void fill_table(const TrajParams &S, double *sm, double t, double dt, int nst, double dtknot) {
-    double *times = sm + S.o_times, *tabb = sm + S.o_tabb, *tabph = sm + S.o_tabph, *tabpq = sm + S.o_tabpq;
-    int *tabk = reinterpret_cast<int *>(sm + S.o_tabk);
-    const int npts = 2 * nst + 1, Nfreq = S.P.Nfreq, D1 = S.A.D1;
-    __syncthreads();                       // the previous chunk's table is no longer in use
-    if (threadIdx.x == 0) {
-        double tt = t;
-        times[0] = tt;
-        for (int i = 0; i < nst; ++i) {    // same recurrence as the reference: t + 0.5 dt, then t = t + dt
-            times[2 * i + 1] = tt + 0.5 * dt;
-            tt = tt + dt;
-            times[2 * i + 2] = tt;
-        }
-    }
-    __syncthreads();
-    const double width = 3.0 * dtknot;
-    for (int idx = threadIdx.x; idx < npts * (NC * Nfreq + 1); idx += blockDim.x) {
-        const int i = idx / (NC * Nfreq + 1), j = idx % (NC * Nfreq + 1);
-        const double tt = times[i];
-        if (j == NC * Nfreq) {             // src/bsplines.jl:224-253
-            long long k = (long long)ceil(tt / dtknot + 2.0);
-            k = k < 3 ? 3 : (k > D1 ? D1 : k);
-            tabk[i] = (int)k;
-            double tau = (tt - dtknot * ((double)k - 1.5)) / width;
-            tabb[3 * i + 0] = 9.0 / 8 + 4.5 * tau + 4.5 * tau * tau;
-            tau = (tt - dtknot * ((double)(k - 1) - 1.5)) / width;
-            tabb[3 * i + 1] = 0.75 - 9.0 * tau * tau;
-            tau = (tt - dtknot * ((double)(k - 2) - 1.5)) / width;
-            tabb[3 * i + 2] = 9.0 / 8 - 4.5 * tau + 4.5 * tau * tau;
-        } else {
-            const int qq = j / Nfreq, fr = j % Nfreq;
-            double sn, cs;
-            sincos(S.P.cfreq[qq + NC * fr] * tt, &sn, &cs);
-            tabph[2 * (i * NC * Nfreq + j)] = cs;
-            tabph[2 * (i * NC * Nfreq + j) + 1] = sn;
-        }
-    }
-    __syncthreads();
-    const double *pcof = sm + S.o_pcof;
-    for (int idx = threadIdx.x; idx < npts * S.TPC * NC; idx += blockDim.x) {
-        const int i = idx / (S.TPC * NC), rem = idx % (S.TPC * NC), tr = rem / NC, qq = rem % NC;
-        const int k = tabk[i];
-        const double b0 = tabb[3 * i], b1 = tabb[3 * i + 1], b2 = tabb[3 * i + 2];
-        const double *pc = pcof + tr * S.NparS;
-        double pv = 0.0, qv = 0.0;
-        for (int fr = 0; fr < Nfreq; ++fr) {   // src/bsplines.jl:229-261
-            const int off1 = 2 * qq * Nfreq * D1 + fr * 2 * D1 - 1, off2 = off1 + D1;
-            const double fbs1 = pc[off1 + k] * b0 + pc[off1 + k - 1] * b1 + pc[off1 + k - 2] * b2;
-            const double fbs2 = pc[off2 + k] * b0 + pc[off2 + k - 1] * b1 + pc[off2 + k - 2] * b2;
-            const double cs = tabph[2 * (i * NC * Nfreq + qq * Nfreq + fr)], sn = tabph[2 * (i * NC * Nfreq + qq * Nfreq + fr) + 1];
-            pv += fbs1 * cs - fbs2 * sn;
-            qv += fbs1 * sn + fbs2 * cs;
-        }
-        tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq] = pv;
-        tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq + 1] = qv;
-    }
-    __syncthreads();
-}
-
-// Gradient scatter role: (control, frequency, alpha) with a 3-knot register window.
-struct Updater {
-    bool on;
-    int uq, uf, ua, gbase, kw;
-    double acc0, acc1, acc2;
-};
-
-// One step's contribution to the gradient windows of this lane's roles (src/evalobjgrad.jl:2578-2618, bsplines.jl:321-381).
-// Time points in decreasing order: t0 (table row 2ls), t0 + dt/2 (2ls+1), t0 + dt (2ls+2).
-template <int NC, int UPL>
-__device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, const double *tred, const double *tabb, const double *tabph,
-                                             const int *tabk, int ls, int Nfreq) {
-    UNROLL for (int j = 0; j < UPL; ++j) {
-        if (U[j].on) {
-            double Tq[5];
-            UNROLL for (int a = 0; a < 5; ++a) Tq[a] = tred[U[j].uq * 5 + a];
-            UNROLL for (int tp = 0; tp < 3; ++tp) {
-                const int i = 2 * ls + tp;
-                const double Pc = tp == 1 ? Tq[3] : -Tq[1];
-                const double Qc = tp == 0 ? -Tq[0] : (tp == 1 ? -Tq[4] : -Tq[2]);
-                const int ph = 2 * (i * NC * Nfreq + U[j].uq * Nfreq + U[j].uf);
-                const double cs = tabph[ph], sn = tabph[ph + 1];
-                const double X = U[j].ua == 0 ? Pc * cs + Qc * sn : Qc * cs - Pc * sn;
-                const int k = tabk[i];
-                while (U[j].kw > k) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; U[j].acc0 = U[j].acc1; U[j].acc1 = U[j].acc2; U[j].acc2 = 0.0; --U[j].kw; }
-                U[j].acc0 = fma(tabb[3 * i], X, U[j].acc0);
-                U[j].acc1 = fma(tabb[3 * i + 1], X, U[j].acc1);
-                U[j].acc2 = fma(tabb[3 * i + 2], X, U[j].acc2);
-            }
-        }
-    }
-    __syncwarp();                        // the roles have read tred before anything overwrites it
-}
-
-// OBJ = 1: objFuncType 2/3 — a second adjoint set without forcing gives the infidelity-only gradient
-// (src/evalobjgrad.jl:848-855, :905-918; step_no_forcing! src/StormerVerlet.jl:365-406).
-template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0>
-__global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
-    constexpr int E = LaneT::E, NC = LaneT::NC;
-    extern __shared__ double sm[];
-    const DevProblem &P = S.P;
-    const LaunchArgs &A = S.A;
-    Geo g;
-    g.lane = threadIdx.x & 31; g.warp = threadIdx.x >> 5;
-    const int GL = GLT > 0 ? GLT : S.GL;       // GLT: group size known at compile time (reductions unroll and overlap)
-    g.lg = g.lane % GL;
-    const int gw = g.lane / GL;                              // group inside the warp; lanes past GPW*GL are idle
-    const bool lane_on = gw < S.GPW;
-    g.group = g.warp * S.GPW + (lane_on ? gw : 0);
-    g.tloc = g.group / S.GPT; g.gi = g.group % S.GPT;
-    const int gbase_lane = (lane_on ? gw : 0) * GL;          // first lane of this group
-    const int traj = blockIdx.x * S.TPC + g.tloc;
-    const bool live_t = lane_on && g.tloc < S.TPC && traj < A.ntraj;    // dead groups compute on zeros and write nothing
-    const int s = live_t ? traj % A.nsamples : 0;
-    const int n = P.n, m = P.m, Npar = A.Npar, D1 = A.D1, Nfreq = P.Nfreq, J = P.J;
-    const double tinv = 1.0 / P.T, dtknot = P.T / (D1 - 2);
-    const int tl = g.tloc < S.TPC ? g.tloc : 0;              // table row used by this group
-
-    LaneT L;
-    L.setup(S, sm, g);
-    L.sGL = GL; L.sbase = gbase_lane; L.stol = P.tol;
-    bool ok[E];
-    UNROLL for (int e = 0; e < E; ++e) {
-        const int r = L.row(e);
-        ok[e] = live_t && r < n && L.col(e) < m;
-        L.d0[e] = ok[e] ? S.plan_d0[r] + (A.shift ? A.shift[(size_t)s * n + r] : 0.0) : 0.0;
-        L.w[e] = ok[e] ? S.plan_w[r] * tinv : 0.0;
-    }
-    // stage this CTA's pcof vectors and zero the per-group gradient accumulators
-    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += blockDim.x) {
-        const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
-        sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * Npar + k] : 0.0;
-    }
-    for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += blockDim.x) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
-
-    double vr[E], vi[E], vi05[E];
-    UNROLL for (int e = 0; e < E; ++e) {
-        vr[e] = ok[e] ? P.uinit[L.row(e) + (size_t)n * L.col(e)] : 0.0;
-        vi[e] = 0.0;
-        vi05[e] = 0.0;
-    }
-    const double *tabpq = sm + S.o_tabpq;
-
-#define LOAD_LEVELS(ls)                                                                                              \
-    UNROLL for (int qq = 0; qq < NC; ++qq) {                                                                         \
-        L.p[0][qq] = L.p[2][qq]; L.q[0][qq] = L.q[2][qq];                                                            \
-        const double *r1 = tabpq + ((2 * (ls) + 1) * S.TPC + tl) * 2 * NC, *r2 = tabpq + ((2 * (ls) + 2) * S.TPC + tl) * 2 * NC; \
-        L.p[1][qq] = r1[2 * qq]; L.q[1][qq] = r1[2 * qq + 1];                                                        \
-        L.p[2][qq] = r2[2 * qq]; L.q[2][qq] = r2[2 * qq + 1];                                                        \
-    }
-#define LOAD_LEVEL0()                                                                                                \
-    UNROLL for (int qq = 0; qq < NC; ++qq) { L.p[2][qq] = tabpq[tl * 2 * NC + 2 * qq]; L.q[2][qq] = tabpq[tl * 2 * NC + 2 * qq + 1]; }
-
-    // ------------------------------------------------------------ forward sweep (src/evalobjgrad.jl:698-753)
-    double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
-    // forward history (jq_eval_forward; src/evalobjgrad.jl:2847-2849): Re = vr, Im = -vi after every save_every-th step
-    const bool hist = A.hist_r != nullptr;
-    size_t hpos = hist ? (size_t)(live_t ? traj : 0) * A.nsave * ((size_t)n * m) : 0;      // start of the next saved block
-    int hcount = hist ? A.save_every : 0;                                                // steps until the next save
-    auto save_state = [&]() {
-        UNROLL for (int e = 0; e < E; ++e)
-            if (ok[e]) {
-                const size_t ix = hpos + L.row(e) + (size_t)n * L.col(e);
-                A.hist_r[ix] = vr[e]; A.hist_i[ix] = -vi[e];
-            }
-        hpos += (size_t)n * m;
-    };
-    if (hist) save_state();
-    // two copies of the loop (generic lambda, both inlined): the evaluation path carries no per-step history test
-    auto forward_sweep = [&](auto with_hist) {
-        for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
-            const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
-            fill_table<NC>(S, sm, t, dt, nst, dtknot);
-            LOAD_LEVEL0();
-            for (int ls = 0; ls < nst; ++ls) {
-                LOAD_LEVELS(ls);
-                UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e], pen);                              // penalf2aTrap
-                state_step<JT>(L, J, dt, vr, vi, vi05);
-                UNROLL for (int e = 0; e < E; ++e) pen = fma(L.w[e], vr[e] * vr[e] + 2.0 * vi05[e] * vi05[e], pen);   // penalf2a
-                t = t + dt;
-                if constexpr (decltype(with_hist)::value) { if (--hcount == 0) { hcount = A.save_every; save_state(); } }
-            }
-        }
-    };
-    if (hist) forward_sweep(std::true_type{});
-    else forward_sweep(std::false_type{});
-    // infidelity (pFidType 2) and leak: group partials -> shared -> per-trajectory sums in group order
-    double *red = sm + S.o_red;
-    {
-        double re = 0.0, im = 0.0;
-        UNROLL for (int e = 0; e < E; ++e) {
-            const size_t ix = L.row(e) + (size_t)n * L.col(e);
-            const double tr_ = ok[e] ? P.vtr[ix] : 0.0, ti_ = ok[e] ? P.vti[ix] : 0.0;
-            re += vr[e] * tr_ - vi[e] * ti_;
-            im += vr[e] * ti_ + vi[e] * tr_;
-        }
-        double rip[3] = {re, im, pen};
-        group_sum_n(rip, GL, gbase_lane);
-        re = rip[0]; im = rip[1]; pen = rip[2];
-        __syncthreads();
-        if (lane_on && g.lg == 0) { red[g.group * 4] = re; red[g.group * 4 + 1] = im; red[g.group * 4 + 2] = pen; }
-        __syncthreads();
-    }
-    double rs = 0.0, is = 0.0, pens = 0.0;
-    for (int j = 0; j < S.GPT; ++j) {
-        const int gg = tl * S.GPT + j;
-        rs += red[gg * 4]; is += red[gg * 4 + 1]; pens += red[gg * 4 + 2];
-    }
-    rs /= m; is /= m;
-    const double infid = 1.0 - (rs * rs + is * is);
-    if (live_t && g.gi == 0 && g.lg == 0) {
-        double *o = A.scal + (size_t)traj * 4;
-        o[0] = infid; o[1] = 0.5 * dt * pens; o[2] = infid; o[3] = 0.0;   // w already carries 1/T
-    }
-    if (!A.evaladjoint) return;
-
-    // ------------------------------------------------------------ backward sweep (src/evalobjgrad.jl:810-921)
-    double lr[E], li[E], vr0[E];
-    UNROLL for (int e = 0; e < E; ++e) {
-        const size_t ix = L.row(e) + (size_t)n * L.col(e);
-        const double tr_ = ok[e] ? P.vtr[ix] : 0.0, ti_ = ok[e] ? P.vti[ix] : 0.0;
-        lr[e] = (rs * tr_ + is * ti_) / m;     // init_adjoint!, src/evalobjgrad.jl:2029-2042
-        li[e] = (is * tr_ - rs * ti_) / m;
-    }
-    double lrn[OBJ ? E : 1], lin[OBJ ? E : 1];
-    if constexpr (OBJ != 0) { UNROLL for (int e = 0; e < E; ++e) { lrn[e] = lr[e]; lin[e] = li[e]; } }
-    // gradient scatter roles: role u = lg + j*GL < NU owns (control, frequency, alpha)
-    const int NU = NC * Nfreq * 2;
-    Updater U[UPL], U2[OBJ ? UPL : 1];
-    UNROLL for (int j = 0; j < UPL; ++j) {
-        const int u = g.lg + j * GL;
-        U[j].on = lane_on && u < NU;
-        U[j].uq = U[j].on ? u / (2 * Nfreq) : 0;
-        U[j].uf = U[j].on ? (u >> 1) % Nfreq : 0;
-        U[j].ua = u & 1;
-        U[j].gbase = 2 * U[j].uq * Nfreq * D1 + U[j].uf * 2 * D1 + U[j].ua * D1 - 1;
-        U[j].kw = D1; U[j].acc0 = 0.0; U[j].acc1 = 0.0; U[j].acc2 = 0.0;
-        if constexpr (OBJ != 0) U2[j] = U[j];
-    }
-    double *gsm = sm + S.o_gsm + g.group * Npar;
-    double *tred = sm + S.o_tred + g.group * (NC * 5);
-    double *gsm2 = sm + S.o_gsm2 + g.group * Npar;
-    const double *tabb = sm + S.o_tabb, *tabph = sm + S.o_tabph;
-    const int *tabk = reinterpret_cast<const int *>(sm + S.o_tabk);
-
-    t = P.T;
-    dt = -dt;
-    for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
-        const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
-        fill_table<NC>(S, sm, t, dt, nst, dtknot);
-        LOAD_LEVEL0();
-        for (int ls = 0; ls < nst; ++ls) {
-            LOAD_LEVELS(ls);
-            UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
-            state_step<JT>(L, J, dt, vr, vi, vi05);
-            adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
-            grad_scatter<NC, UPL>(U, gsm, tred, tabb, tabph, tabk, ls, Nfreq);
-            if constexpr (OBJ != 0) {
-                adjoint_step<JT, false>(L, J, dt, lrn, lin, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);
-                grad_scatter<NC, UPL>(U2, gsm2, tred, tabb, tabph, tabk, ls, Nfreq);
-            }
-            t = t + dt;
-        }
-    }
-    UNROLL for (int j = 0; j < UPL; ++j) {
-        if (U[j].on) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; gsm[U[j].gbase + U[j].kw - 1] += U[j].acc1; gsm[U[j].gbase + U[j].kw - 2] += U[j].acc2; }
-        if constexpr (OBJ != 0) if (U2[j].on) { gsm2[U2[j].gbase + U2[j].kw] += U2[j].acc0; gsm2[U2[j].gbase + U2[j].kw - 1] += U2[j].acc1; gsm2[U2[j].gbase + U2[j].kw - 2] += U2[j].acc2; }
-    }
-    __syncthreads();
-    // total gradient of each resident trajectory = dt * sum of its groups' partial gradients, in group order
-    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += blockDim.x) {
-        const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
-        if (tg >= A.ntraj) continue;
-        double gs = 0.0;
-        for (int j = 0; j < S.GPT; ++j) gs += sm[S.o_gsm + (tr * S.GPT + j) * Npar + k];
-        A.grad[(size_t)tg * Npar + k] = dt * gs;
-        if (OBJ) {
-            double g2 = 0.0;
-            for (int j = 0; j < S.GPT; ++j) g2 += sm[S.o_gsm2 + (tr * S.GPT + j) * Npar + k];
-            A.infidgrad[(size_t)tg * Npar + k] = dt * g2;
-        }
-    }
-}
-
-typedef void (*traj_kernel_t)(const TrajParams);
-// variant: 0 default, 16 general Hanti, 32+J compile-time J, 64 objFuncType 2/3; selectable for comparisons with the env
-// variable JQ_TRAJ_VARIANT: 1 warp-shuffle exchange (runtime J), 512 shared-memory twin of the cnot2 instantiation
-struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; };
-#define SLOT(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 0, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1>}
-#define SLOTO(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 64, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1, 1, 0, 1>}   /* objFuncType 2/3 */
-#define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
-#define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
-#define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
-#define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size */
-#define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
-#define FIBERJGM(R, NC, LMASK, UPL, JT, GLT, MINB, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB, JT, 0, GLT>, GLT}
-#define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
-#define FIBERHX(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 8, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, 0, ((1 << NC) - 1) & ~LMASK>, UPL>}   /* exchange-coupled drift */
-#define FIBERJAC(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 128, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, -1>}   /* Jacobi solver */
-#define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
-#define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
 const Inst kInst[] = {
-    SLOT(1, 2, 1, 2), SLOT(1, 3, 1, 2), SLOT(1, 4, 1, 2), SLOT(1, 4, 2, 2), SLOT(1, 2, 2, 2),
-    SLOT(2, 2, 3, 2), SLOT(3, 1, 3, 2), SLOT(1, 1, 1, 2), SLOT(1, 1, 2, 2),
-    SLOTO(1, 4, 2, 2), SLOTO(1, 3, 1, 2), SLOTO(1, 4, 1, 2), SLOTO(1, 2, 1, 2),
     FIBERM(2, 1, 1, 1, 4), FIBERM(4, 1, 1, 1, 3), FIBERM(4, 1, 1, 2, 3), FIBER(6, 1, 1, 2), FIBERM(3, 1, 1, 1, 3), FIBERM(3, 1, 1, 2, 3),
     FIBER(4, 2, 1, 1), FIBER(3, 2, 1, 1), FIBER(2, 2, 1, 1), FIBER(4, 3, 1, 1), FIBER(3, 3, 1, 1), FIBER(2, 3, 1, 1),
     FIBER(5, 2, 1, 1), FIBER(5, 3, 1, 1), FIBER(6, 2, 1, 1), FIBER(5, 1, 1, 2), FIBERO(5, 2, 1, 1),      // 5- and 6-level fastest subsystem
-    FIBERV(4, 2, 1, 1, 1), FIBERV(4, 3, 1, 1, 1),      // shuffle twins of the cnot2 / cnot3 runtime-J kernels (JQ_TRAJ_VARIANT=1)
-    FIBERX(4, 2, 1, 1, 4, 16, 1, 32 + 4),          // cnot2 example shape: warp-shuffle exchange measured 3.5% faster than shared memory (variant 512)
-    FIBERX(4, 2, 1, 1, 4, 16, 0, 512), FIBERJG(6, 1, 1, 2, 3, 4),
-    FIBERJGM(4, 1, 1, 2, 5, 3, 3, 32 + 5),      // risk-neutral SWAP 0-2 shape (n = 4, m = 3, J = 5)
-    FIBERO(3, 2, 1, 1), FIBERO(4, 2, 1, 1), FIBERO(4, 1, 1, 1), FIBERO(4, 1, 1, 2), FIBERO(6, 1, 1, 2), FIBERO(4, 3, 1, 1), FIBERO(2, 1, 1, 1),
-    FIBERHX(4, 2, 1, 1), FIBERHX(3, 2, 1, 1), FIBERHX(2, 2, 1, 1), FIBERHX(5, 2, 1, 1), FIBERHX(4, 3, 1, 1), FIBERHX(3, 3, 1, 1), FIBERHX(2, 3, 1, 1),
-    FIBERJAC(3, 2, 1, 1), FIBERJAC(4, 2, 1, 1), FIBERJAC(4, 1, 1, 2), FIBERJAC(6, 1, 1, 2),
-    FIBERG(4, 2, 1, 1), FIBERG(4, 1, 1, 1), FIBERG(4, 1, 1, 2), FIBERG(2, 1, 1, 1),
 };
 
 const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0) {
-    for (const Inst &i : kInst)
-        if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant &&
-            (i.glt == 0 || i.glt == GL)) return &i;
+    const Inst *parts[3] = {kInst, kInstB, kInstC};
+    const int counts[3] = {(int)(sizeof(kInst) / sizeof(kInst[0])), kInstBCount, kInstCCount};
+    for (int p = 0; p < 3; ++p)
+        for (int j = 0; j < counts[p]; ++j) {
+            const Inst &i = parts[p][j];
+            if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant &&
+                (i.glt == 0 || i.glt == GL)) return &i;
+        }
     return nullptr;
 }
 
