@@ -256,7 +256,10 @@ def main():
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+    roofline = {"bound": "fp64_fma",
+                "bound_note": "compute roofline in TFLOP/s (the contract's 'tensor' class), but on the FP64 FMA pipe: B200 has no faster "
+                              "FP64 tensor path (tensor_pipe below), and HBM carries ~1 KB per 1.4e8-flop evaluation (traffic)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": traffic, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "peak_no_operand_reuse": peak3, "frac_of_peak_no_operand_reuse": achieved / peak3 if peak3 else None,
                 "tensor_pipe": {"util": 0.0, "fp64_mma_peak": peak_dmma, "dense_to_nnz_flop_ratio": dense_ratio,
