@@ -26,8 +26,9 @@
 //
 // Reference lines: forward loop src/evalobjgrad.jl:698-753, infidelity :755-766, adjoint init :810-844/:2026-2042,
 // backward loop :859-921, steppers src/StormerVerlet.jl:255-303,:461-504, Neumann src/linear_solvers.jl:94-106,
-// controls src/bsplines.jl:211-304,:321-381, gradient src/evalobjgrad.jl:2567-2619.  The only algebraic regrouping
-// is S1*u + (h/2) S1*k1 = S1*(u + (h/2) k1)  (src/StormerVerlet.jl:483-484).
+// controls src/bsplines.jl:211-304,:321-381, gradient src/evalobjgrad.jl:2567-2619.  Algebraic regroupings (rounding-level
+// effect only, goldens still met at 1e-14..1e-13): S1*u + (h/2) S1*k1 = S1*(u + (h/2) k1)  (src/StormerVerlet.jl:483-484), and
+// the truncated Neumann sum evaluated in Horner form with (h/2) folded into the coefficients (see neumann()).
 #pragma once
 #include "jq_common.h"
 #include <type_traits>
@@ -172,9 +173,14 @@ struct SlotLane {
         UNROLL for (int k = 0; k < R; ++k) UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int e = 0; e < WQ; ++e)
             sc.c[k][qq][e] = q[level][qq] * ha[k][qq][e];
     }
-    __device__ __forceinline__ void s_from(const SC &sc, const double (&)[E], const Nbr &nb, double (&t)[E]) const {
+    __device__ __forceinline__ void s_scale(SC &sc, double f) const {
+        UNROLL for (int k = 0; k < R; ++k) UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int e = 0; e < WQ; ++e) sc.c[k][qq][e] *= f;
+    }
+    // t = S x  (ADD: t = add + S x)
+    template <bool ADD>
+    __device__ __forceinline__ void s_from(const SC &sc, const double (&)[E], const Nbr &nb, const double (&add)[E], double (&t)[E]) const {
         UNROLL for (int k = 0; k < R; ++k) {
-            UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = 0.0;
+            UNROLL for (int c = 0; c < C; ++c) t[k * C + c] = ADD ? add[k * C + c] : 0.0;
             UNROLL for (int qq = 0; qq < NC; ++qq)
                 UNROLL for (int e = 0; e < WQ; ++e) {
                     double xv[C];
@@ -186,7 +192,12 @@ struct SlotLane {
     __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
         Nbr nb;
         exchange(x, nb);
-        s_from(sc, x, nb, t);
+        s_from<false>(sc, x, nb, x, t);
+    }
+    __device__ __forceinline__ void s_pass_add(const SC &sc, const double (&x)[E], const double (&add)[E], double (&t)[E]) {
+        Nbr nb;
+        exchange(x, nb);
+        s_from<true>(sc, x, nb, add, t);
     }
 
     // f(e, Ae, De) is called once per element with Ae[q] = (Hsym_q x)_e, De[q] = (Hanti_q x)_e: the per-control
@@ -317,10 +328,17 @@ struct FiberLane {
                 sc.r[qq][1] = q[level][qq] * (AS ? rhs[qq][1] : rha[qq][1]);
             }
     }
-    __device__ __forceinline__ void s_from(const SC &sc, const double (&x)[E], const Nbr &nb, double (&t)[E]) const {
+    __device__ __forceinline__ void s_scale(SC &sc, double f) const {
+        UNROLL for (int k = 0; k < R - 1; ++k) { sc.lu[k] *= f; sc.ll[k] *= f; }
+        UNROLL for (int qq = 0; qq < NC; ++qq)
+            if (!((LMASK >> qq) & 1)) { sc.r[qq][0] *= f; sc.r[qq][1] *= f; }
+    }
+    // t = S x  (ADD: t = add + S x)
+    template <bool ADD>
+    __device__ __forceinline__ void s_from(const SC &sc, const double (&x)[E], const Nbr &nb, const double (&add)[E], double (&t)[E]) const {
         UNROLL for (int k = 0; k < R; ++k) {       // local part first: independent of the exchange
-            double a = 0.0;
-            if (k + 1 < R) a = sc.lu[k] * x[k + 1];
+            double a = ADD ? add[k] : 0.0;
+            if (k + 1 < R) a = ADD ? fma(sc.lu[k], x[k + 1], a) : sc.lu[k] * x[k + 1];
             if (k > 0) a = fma(sc.ll[k - 1], x[k - 1], a);
             t[k] = a;
         }
@@ -331,7 +349,12 @@ struct FiberLane {
     __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
         Nbr nb;
         exchange(x, nb);
-        s_from(sc, x, nb, t);
+        s_from<false>(sc, x, nb, x, t);
+    }
+    __device__ __forceinline__ void s_pass_add(const SC &sc, const double (&x)[E], const double (&add)[E], double (&t)[E]) {
+        Nbr nb;
+        exchange(x, nb);
+        s_from<true>(sc, x, nb, add, t);
     }
 
     template <bool WA, bool WD, class F>
@@ -422,19 +445,21 @@ __device__ __forceinline__ double kdiag(const LaneT &L, int e, double xe, double
     else return L.d0[e] * xe;
 }
 
-// X = sum_{j<=J} (h/2)^j S^j B   (src/linear_solvers.jl:94-106); B is consumed.  `sc` = S(level) prescaled.
-template <int JT, class LaneT>
-__device__ __forceinline__ void neumann(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
+// X = sum_{j<=J} (h/2)^j S^j B   (src/linear_solvers.jl:94-106), evaluated in Horner form  X <- B + ((h/2) S) X,  J times from
+// X = B -- the same polynomial in S applied to B (it is the reference's own Jacobi sweep, linear_solvers.jl:118-124, run for
+// exactly J sweeps), with the factor h/2 folded into the coefficients: one FMA per element and term less than accumulating
+// the terms one by one.  `sc` = S(level) prescaled by the control values; SCALED: already multiplied by h/2.  B is preserved.
+template <int JT, bool SCALED = false, class LaneT>
+__device__ __forceinline__ void neumann(LaneT &L, typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
     constexpr int E = LaneT::E;
+    if (!SCALED) L.s_scale(sc, 0.5 * h);
     UNROLL for (int e = 0; e < E; ++e) X[e] = B[e];
-    double coeff = 1.0;
     const int JJ = JT > 0 ? JT : J;          // JT > 0: number of Neumann terms known at compile time (fully unrolled)
 #pragma unroll
     for (int it = 0; it < JJ; ++it) {
         double T[E];
-        L.s_pass(sc, B, T);
-        coeff *= 0.5 * h;
-        UNROLL for (int e = 0; e < E; ++e) { B[e] = T[e]; X[e] = fma(coeff, T[e], X[e]); }
+        L.s_pass_add(sc, X, B, T);
+        UNROLL for (int e = 0; e < E; ++e) X[e] = T[e];
     }
 }
 
@@ -459,10 +484,10 @@ __device__ __forceinline__ void jacobi(LaneT &L, const typename LaneT::SC &sc, i
 }
 
 // linear_solver.solve of the steppers: JT >= 0 truncated Neumann series (JT > 0: compile-time J), JT < 0 Jacobi sweeps.
-template <int JT, class LaneT>
-__device__ __forceinline__ void solve(LaneT &L, const typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
+template <int JT, bool SCALED = false, class LaneT>
+__device__ __forceinline__ void solve(LaneT &L, typename LaneT::SC &sc, int J, double h, double (&B)[LaneT::E], double (&X)[LaneT::E]) {
     if constexpr (JT < 0) jacobi(L, sc, J, h, B, X);
-    else neumann<JT>(L, sc, J, h, B, X);
+    else neumann<JT, SCALED>(L, sc, J, h, B, X);
 }
 
 // src/StormerVerlet.jl:461-504.  u, v updated in place; v05 returned.
@@ -570,13 +595,17 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tred[qq * 5 + a] = tv3[qq * 3 + a]; }
     }
     L.s_prescale(1, sc);
-    {
+    double l1[E];
+    if constexpr (JT >= 0) {
+        L.s_scale(sc, 0.5 * h);
+        L.s_pass_add(sc, l2, r0, rhs);                                            // S05 nu + (h/2) S05 l2 + K1 X + hi1
+        solve<JT, true>(L, sc, J, h, rhs, l1);
+    } else {
         double tv[E];
         L.s_pass(sc, l2, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(0.5 * h, tv[e], r0[e]);   // S05 nu + (h/2) S05 l2 + K1 X + hi1
+        UNROLL for (int e = 0; e < E; ++e) rhs[e] = fma(0.5 * h, tv[e], r0[e]);
+        solve<JT>(L, sc, J, h, rhs, l1);
     }
-    double l1[E];
-    solve<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) nu[e] = fma(0.5 * h, l2[e] + l1[e], nu[e]);
     L.template pass_each<true, true>(nu, [&](int e, const double (&Ae)[NC + 1], const double (&De)[NC]) {
         double kk = kdiag(L, e, nu[e], Ae[NC]);
