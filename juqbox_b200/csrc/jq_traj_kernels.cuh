@@ -504,11 +504,7 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
     });
     typename LaneT::SC sc;
     L.s_prescale(1, sc);
-    {
-        double tv[E];
-        L.s_pass(sc, v, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhs[e] += tv[e];                                    // + S05 v
-    }
+    L.s_pass_add(sc, v, rhs, rhs);                                                             // + S05 v
     solve<JT>(L, sc, J, h, rhs, l1);
     UNROLL for (int e = 0; e < E; ++e) v05[e] = fma(0.5 * h, l1[e], v[e]);
     double k1v[E], s05v[E];
@@ -519,16 +515,12 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
             k1 = fma(L.p[2][qq], Ae[qq], k1);
             s = fma(L.q[1][qq], De[qq], s);
         }
-        k1v[e] = k1;                                   // K1 v05
+        k1v[e] = -k1;                                  // -K1 v05 (the sign rides on the FMA that consumes it)
         s05v[e] = s;                                   // S05 v05
         u[e] = fma(0.5 * h, s0u[e] - k0, u[e]);        // u + (h/2) kappa1,  kappa1 = S0 u - K0 v05
     });
     L.s_prescale(2, sc);
-    {
-        double tv[E];
-        L.s_pass(sc, u, tv);
-        UNROLL for (int e = 0; e < E; ++e) rhs[e] = tv[e] - k1v[e];                             // S1 (u + (h/2) kappa1) - K1 v05
-    }
+    L.s_pass_add(sc, u, k1v, rhs);                                                             // S1 (u + (h/2) kappa1) - K1 v05
     double k2[E];
     solve<JT>(L, sc, J, h, rhs, k2);
     UNROLL for (int e = 0; e < E; ++e) u[e] = fma(0.5 * h, k2[e], u[e]);
