@@ -173,24 +173,33 @@ def run_optimizer_multistart(prob: IpoptProblemMirror, pcof0s, maxIter: Optional
             b = rho * (yv * q).sum(1)
             q += (a - b)[:, None] * s
         d = -q
+        d[pg == 0.0] = 0.0                            # variables held at an active bound do not move
         bad = (d * pg).sum(1) >= 0                    # not a descent direction: steepest descent
         d[bad] = -pg[bad]
         if not S:
             d /= np.maximum(1.0, np.abs(d).max(axis=1))[:, None] * 4.0       # first step: a quarter of the box at most
-        slope = (d * pg).sum(1)
-        step = np.where(active, 1.0, 0.0)
+
+        def line_search(d, todo):
+            """Projected Armijo backtracking for the members in `todo`; returns the mask of members that found no step."""
+            step = np.where(todo, 1.0, 0.0)
+            todo = todo.copy()
+            for _bt in range(max_backtracks):
+                Yt = np.where(todo[:, None], np.clip(Y + step[:, None] * d, lo, hi), Ynew)
+                ft, _ = fg(Yt, need_grad=False)
+                acc = todo & (ft <= f + 1e-4 * (g * (Yt - Y)).sum(1)) & (np.abs(Yt - Y).max(axis=1) > 0)
+                Ynew[acc], fnew[acc] = Yt[acc], ft[acc]
+                todo &= ~acc
+                if not todo.any():
+                    break
+                step[todo] *= 0.5
+            return todo
+
         Ynew, fnew = Y.copy(), f.copy()
-        todo = active.copy()
-        for _bt in range(max_backtracks):
-            Yt = np.where(todo[:, None], np.clip(Y + step[:, None] * d, lo, hi), Ynew)
-            ft, _ = fg(Yt, need_grad=False)
-            acc = todo & (ft <= f + 1e-4 * step * slope)
-            Ynew[acc], fnew[acc] = Yt[acc], ft[acc]
-            todo &= ~acc
-            if not todo.any():
-                break
-            step[todo] *= 0.5
-        active &= ~todo                               # members whose line search failed stop here
+        failed = line_search(d, active)
+        if failed.any():                              # retry those members once along the projected steepest descent
+            dsd = np.where(failed[:, None], -pg / np.maximum(1.0, np.abs(pg).max(axis=1))[:, None], 0.0)
+            failed = line_search(dsd, failed)
+        active &= ~failed                             # members with no acceptable step stop here
         fchk, gnew = fg(Ynew)
         s, yv = Ynew - Y, gnew - g
         ok = (s * yv).sum(1) > 1e-12 * np.sqrt((s * s).sum(1) * (yv * yv).sum(1))

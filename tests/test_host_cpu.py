@@ -84,3 +84,42 @@ def test_tikhonov():
     pc = cfg.pcof0
     assert jq.tikhonov_pen(pc, cfg.params) == pytest.approx(0.01 * pc @ pc / len(pc))
     assert np.allclose(jq.tikhonov_grad(pc, cfg.params), 2 * 0.01 * pc / len(pc))
+
+
+def test_multistart_driver_logic_on_a_mock_evaluator():
+    """run_optimizer_multistart's host logic (projected L-BFGS in lock step, Armijo backtracking, box handling, Tikhonov term,
+    batch independence) on a stand-in for Working_Arrays.evaluate — an anisotropic quadratic bowl per member."""
+    import juqbox_b200 as jq
+    from juqbox_b200.optimize import IpoptProblemMirror
+    cfg, _ = golden_config("rabi")
+    p = cfg.params
+    p.tik0 = 0.05
+    n = 6
+    rng = np.random.default_rng(3)
+    centre = rng.uniform(-1, 1, n)
+    centre[0] = 5.0                                           # outside the box: the optimum sits on the bound
+    scale = np.array([1.0, 4.0, 0.5, 2.0, 8.0, 1.0])
+
+    class FakeWA:
+        calls = 0
+
+        def evaluate(self, X, shifts=None, weights=None, evaladjoint=True, out=None):
+            FakeWA.calls += 1
+            X = np.atleast_2d(X)
+            d = X - centre
+            r = {"infid": 0.5 * (scale * d * d).sum(1, keepdims=True), "leak": np.zeros((len(X), 1))}
+            if evaladjoint:
+                r["grad"] = (scale * d)[:, None, :]
+            return r
+
+    lo, hi = -2.0 * np.ones(n), 2.0 * np.ones(n)
+    prob = IpoptProblemMirror(p, FakeWA(), n, lo, hi, maxIter=60, lbfgsMax=6)
+    starts = rng.uniform(-2, 2, (5, n))
+    X, f, hist = jq.run_optimizer_multistart(prob, starts)
+    # exact minimiser of 0.5*sum(scale*(x-c)^2) + tik0*|x|^2/n inside the box
+    xs = np.clip(scale * centre / (scale + 2 * p.tik0 / n), lo, hi)
+    assert np.all(np.diff(hist, axis=0) <= 1e-15)
+    assert np.abs(X - xs).max() < 1e-5 and np.all(X <= hi + 1e-15) and np.all(X >= lo - 1e-15)
+    assert np.allclose(X[:, 0], 2.0)                          # the active bound
+    X1, f1, _ = jq.run_optimizer_multistart(prob, starts[2:3])
+    assert np.array_equal(X1[0], X[2]) and f1[0] == f[2]      # a member's iterates do not depend on the batch
