@@ -123,3 +123,65 @@ def test_multistart_driver_logic_on_a_mock_evaluator():
     assert np.allclose(X[:, 0], 2.0)                          # the active bound
     X1, f1, _ = jq.run_optimizer_multistart(prob, starts[2:3])
     assert np.array_equal(X1[0], X[2]) and f1[0] == f[2]      # a member's iterates do not depend on the batch
+
+
+class _QuadraticWA:
+    """Stand-in for Working_Arrays.evaluate: infidelity = quadratic bowl, leak = small quadratic, weights honoured."""
+
+    def __init__(self, centre, scale, objFuncType=1):
+        self.centre, self.scale, self.calls, self.objFuncType = centre, scale, 0, objFuncType
+
+    def evaluate(self, X, shifts=None, weights=None, evaladjoint=True, out=None):
+        self.calls += 1
+        X = np.atleast_2d(X)
+        d = X - self.centre
+        ns = 1 if shifts is None else len(shifts)
+        wsum = 1.0 if weights is None else float(np.sum(weights))
+        shape = (len(X),) if weights is not None else (len(X), ns)
+        infid = np.broadcast_to((0.5 * (self.scale * d * d).sum(1) * wsum).reshape(len(X), *([1] * (len(shape) - 1))), shape).copy()
+        leak = 1e-3 * infid
+        r = {"infid": infid, "leak": leak, "trace_infid": infid.copy()}
+        if evaladjoint:
+            g = (self.scale * d) * wsum
+            r["infidgrad"] = np.broadcast_to(g.reshape(len(X), *([1] * (len(shape) - 1)), -1), shape + (X.shape[1],)).copy()
+            r["leakgrad"] = 1e-3 * r["infidgrad"]
+            r["grad"] = r["infidgrad"] + r["leakgrad"]
+            if self.objFuncType == 1:                  # the library's convention: infidelgrad aliases totalgrad (evalobjgrad.jl:951)
+                r["infidgrad"], r["leakgrad"] = r["grad"], np.zeros_like(r["grad"])
+        return r
+
+
+@pytest.mark.parametrize("objFuncType", [1, 3])
+def test_ipopt_callback_layer_and_run_optimizer_on_a_mock_evaluator(objFuncType):
+    """eval_f_par / eval_grad_f_par / eval_g_par / eval_jac_g_par (src/ipopt_interface.jl:77-179): last-evaluation cache,
+    Tikhonov terms, objFuncType 3 constraint callbacks, convergence history, and the run_optimizer glue around them."""
+    import juqbox_b200 as jq
+    cfg, _ = golden_config("rabi")
+    p = cfg.params
+    p.tik0, p.objFuncType, p.leak_ubound = 0.02, objFuncType, 1.0
+    n = 6
+    rng = np.random.default_rng(8)
+    centre, scale = rng.uniform(-0.5, 0.5, n), np.array([1.0, 3.0, 0.5, 2.0, 5.0, 1.0])
+    wa = _QuadraticWA(centre, scale, objFuncType)
+    x = rng.uniform(-1, 1, n)
+    prob = jq.setup_ipopt_problem(p, wa, n, -np.ones(n), np.ones(n), maxIter=200, lbfgsMax=6, ipTol=1e-9)
+    f = jq.eval_f_par(x, p, wa)
+    quad = 0.5 * (scale * (x - centre) ** 2).sum()
+    tik = p.tik0 * (x @ x) / n
+    want = quad + tik if objFuncType == 3 else 1.001 * quad + tik        # objFuncType 3: leak is a constraint, not in f (:96-98)
+    assert abs(f - want) < 1e-14 and wa.calls == 1
+    gbuf = np.zeros(n)
+    jq.eval_grad_f_par(x, gbuf, p, wa)
+    assert wa.calls == 1                                               # served from the last-evaluation cache
+    wantg = scale * (x - centre) * (1.0 if objFuncType == 3 else 1.001) + 2 * p.tik0 * x / n
+    assert np.allclose(gbuf, wantg, atol=1e-14)
+    if objFuncType == 3:
+        gv = np.zeros(1)
+        jq.eval_g_par(x, gv, p, wa)
+        jac = np.zeros(n)
+        jq.eval_jac_g_par(x, np.zeros(0, np.int32), np.zeros(0, np.int32), jac, p, wa)
+        assert abs(gv[0] - 1e-3 * quad) < 1e-15 and np.allclose(jac, 1e-3 * scale * (x - centre), atol=1e-15) and wa.calls == 1
+    xo = jq.run_optimizer(prob, x)
+    xs = scale * centre / (scale * (1.0 if objFuncType == 3 else 1.001) + 2 * p.tik0 / n) * (1.0 if objFuncType == 3 else 1.001)
+    assert np.abs(xo - xs).max() < 1e-4, (xo, xs, prob.status)
+    assert len(p.objHist) >= 2 and p.objHist[-1] <= p.objHist[0]
