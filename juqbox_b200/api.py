@@ -131,7 +131,7 @@ class Working_Arrays:
         _lib.check(self._lib.jq_comm_destroy(self._handle))
 
     def set_kernel(self, kernel: int):
-        """0 = automatic, 1 = generic kernel, 2 = warp-slot kernel."""
+        """0 = automatic, 1 = generic kernel, 2 = slot layout, 3 = fibre layout, 4 = tile layout."""
         _lib.check(self._lib.jq_set_kernel(self._handle, int(kernel)))
 
     def query(self, what: int) -> float:

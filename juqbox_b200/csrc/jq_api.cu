@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -55,9 +56,10 @@ struct jq_handle {
     // host copies of the row-wise operators (for the planners)
     std::vector<int> rowptr, col;
     std::vector<double> val;
-    TrajPlan *slot = nullptr, *fiber = nullptr;
-    char slot_reason[256] = "", fiber_reason[256] = "";
+    TrajPlan *slot = nullptr, *fiber = nullptr, *tile = nullptr;
+    char slot_reason[256] = "", fiber_reason[256] = "", tile_reason[256] = "";
     int kernel_pref = 0;
+    bool prefer_tile = true;            // automatic mode: tile layout before the fibre layout
     // growable scratch
     double *d_scal = nullptr, *d_grad = nullptr, *d_igrad = nullptr;
     size_t cap_traj = 0, cap_grad = 0, cap_igrad = 0;
@@ -256,6 +258,10 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
     HostOps H{n, m, Nc, pb->nfreq, h->rowptr.data(), h->col.data(), h->val.data()};
     h->slot = jq_slot_plan_create(P, H, pb->wdiag, h->slot_reason, sizeof(h->slot_reason));
     h->fiber = jq_fiber_plan_create(P, H, pb->wdiag, h->fiber_reason, sizeof(h->fiber_reason));
+    {
+        const char *nt = getenv("JQ_TILE_NT");      // development: number of tiled directions of the tile layout (default 2)
+        h->tile = jq_tile_plan_create(P, H, pb->wdiag, nt ? atoi(nt) : 2, h->tile_reason, sizeof(h->tile_reason));
+    }
     *out = h;
     return 0;
 }
@@ -269,6 +275,7 @@ extern "C" int jq_destroy(jq_handle *h) {
     for (double *p : {h->d_scal, h->d_grad, h->d_igrad, h->d_in, h->d_out}) if (p) cudaFree(p);
     if (h->slot) jq_traj_plan_destroy(h->slot);
     if (h->fiber) jq_traj_plan_destroy(h->fiber);
+    if (h->tile) jq_traj_plan_destroy(h->tile);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -286,7 +293,8 @@ extern "C" int jq_update_target(jq_handle *h, const double *vr, const double *vi
 }
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
-    if (!h || kernel < 0 || kernel > 3) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0, 1, 2 or 3");
+    if (!h || kernel < 0 || kernel > 4) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0, 1, 2, 3 or 4");
+    if (kernel == 4 && !h->tile) return fail(JQ_ERR_ARG, "jq_set_kernel: no tile-layout instantiation for this problem (%s)", h->tile_reason);
     if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no slot-layout instantiation for this problem (%s)", h->slot_reason);
     if (kernel == 3 && !h->fiber) return fail(JQ_ERR_ARG, "jq_set_kernel: no fibre-layout instantiation for this problem (%s)", h->fiber_reason);
     h->kernel_pref = kernel;
@@ -393,6 +401,42 @@ __global__ void __launch_bounds__(32 * WS_LANES) jq_weighted_sum_kernel(int nsam
     }
 }
 
+
+// Launch the trajectory kernel for `A`: the register-resident layouts in order of preference (tile, fibre, slot), then the
+// generic kernel.  In automatic mode a layout that cannot serve this launch (no instantiation for the variant, shared-memory
+// layout does not fit, out of launch resources) hands over to the next one; an explicitly requested kernel fails instead.
+static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t st) {
+    TrajPlan *cands[3] = {nullptr, nullptr, nullptr};
+    int ncand = 0;
+    const int pref = h->kernel_pref;
+    if (pref == 4 || (pref == 0 && h->tile && h->prefer_tile)) cands[ncand++] = h->tile;
+    if (pref == 3 || (pref == 0 && h->fiber)) cands[ncand++] = h->fiber;
+    if (pref == 2 || (pref == 0 && h->slot)) cands[ncand++] = h->slot;
+    TrajPlan *plan = nullptr;
+    int ctas = 0, regs = 0, tpc = 1;
+    size_t smem = 0;
+    CU(cudaEventRecord(h->ev0, st));
+    for (int i = 0; i < ncand && !plan; ++i) {
+        cudaError_t e = jq_traj_launch(cands[i], h->P, A, st, &ctas, &regs, &smem, &tpc);
+        if (e == cudaSuccess) { plan = cands[i]; break; }
+        cudaGetLastError();                                   // clear the (non-sticky) launch error before trying the next kernel
+        const bool soft = e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources;
+        if (!soft || pref != 0) return fail(JQ_ERR_CUDA, "trajectory kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    if (!plan) {
+        if (pref > 1) return fail(JQ_ERR_ARG, "requested kernel is not available for this problem");
+        if (jq_generic_smem_bytes(h->P, A.Npar) > 227 * 1024)
+            return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory (n*m = %d)", h->n * h->m);
+        tpc = 1;
+        CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
+    }
+    CU(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    h->last_kernel = plan ? jq_traj_plan_kind(plan) : 1;
+    h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = tpc;
+    return 0;
+}
+
 static int check_batch_args(jq_handle *h, int nbatch, const double *pcof, int npar, int nsamples, const double *shift) {
     if (!h) return fail(JQ_ERR_ARG, "null handle");
     if (nbatch < 1 || !pcof) return fail(JQ_ERR_ARG, "need nbatch >= 1 and a pcof array");
@@ -424,35 +468,7 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = evaladjoint ? 1 : 0;
     A.pcof = pcof; A.shift = shift; A.scal = h->d_scal; A.grad = h->d_grad; A.infidgrad = h->P.objFuncType != 1 ? h->d_igrad : nullptr;
 
-    // candidates in order of preference; a register-resident kernel whose shared-memory layout does not fit
-    // (cudaErrorInvalidConfiguration, e.g. very long pcof vectors) hands over to the next one in automatic mode
-    TrajPlan *cands[2] = {nullptr, nullptr};
-    int ncand = 0;
-    if (h->kernel_pref == 3 || (h->kernel_pref == 0 && h->fiber)) cands[ncand++] = h->fiber;
-    if (h->kernel_pref == 2 || (h->kernel_pref == 0 && h->slot)) cands[ncand++] = h->slot;
-    TrajPlan *plan = nullptr;
-    int ctas = 0, regs = 0, tpc = 1;
-    size_t smem = 0;
-    CU(cudaEventRecord(h->ev0, st));
-    for (int i = 0; i < ncand && !plan; ++i) {
-        cudaError_t e = jq_traj_launch(cands[i], h->P, A, st, &ctas, &regs, &smem, &tpc);
-        if (e == cudaSuccess) { plan = cands[i]; break; }
-        if (e != cudaErrorInvalidConfiguration || h->kernel_pref != 0)
-            return fail(JQ_ERR_CUDA, "trajectory kernel launch failed: %s", cudaGetErrorString(e));
-        cudaGetLastError();
-    }
-    const bool use_slot = plan != nullptr;
-    if (!use_slot) {
-        if (h->kernel_pref > 1) return fail(JQ_ERR_ARG, "requested kernel is not available for this problem");
-        if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024)
-            return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory (n*m = %d)", h->n * h->m);
-        tpc = 1;
-        CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
-    }
-    CU(cudaEventRecord(h->ev1, st));
-    h->timed = true;
-    h->last_kernel = use_slot ? jq_traj_plan_kind(plan) : 1;
-    h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = tpc;
+    if ((rc = launch_trajectories(h, A, st)) != 0) return rc;
     const int nout = weights ? nbatch : (int)ntraj;
     const long long total = (long long)nout * (npar + 1);
     const int fb = 256, fg = (int)std::min<long long>((total + fb - 1) / fb, 148 * 8);
@@ -504,31 +520,8 @@ extern "C" int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof,
     A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = 0;
     A.pcof = d_pcof; A.shift = d_shift; A.scal = h->d_scal; A.grad = nullptr; A.infidgrad = nullptr;
     A.hist_r = h->d_out; A.hist_i = h->d_out + n_hist; A.save_every = save_every; A.nsave = nsave;
-    int ctas = 0, regs = 0;
-    size_t smem = 0;
-    // same kernel choice as jq_traceobjgrad_batch: fibre, slot, then generic
-    TrajPlan *cands[2] = {nullptr, nullptr};
-    int ncand = 0, tpc = 1;
-    if (h->kernel_pref == 3 || (h->kernel_pref == 0 && h->fiber)) cands[ncand++] = h->fiber;
-    if (h->kernel_pref == 2 || (h->kernel_pref == 0 && h->slot)) cands[ncand++] = h->slot;
-    TrajPlan *plan = nullptr;
-    CU(cudaEventRecord(h->ev0, st));
-    for (int i = 0; i < ncand && !plan; ++i) {
-        cudaError_t e = jq_traj_launch(cands[i], h->P, A, st, &ctas, &regs, &smem, &tpc);
-        if (e == cudaSuccess) { plan = cands[i]; break; }
-        if (e != cudaErrorInvalidConfiguration || h->kernel_pref != 0)
-            return fail(JQ_ERR_CUDA, "trajectory kernel launch failed: %s", cudaGetErrorString(e));
-        cudaGetLastError();
-    }
-    if (!plan) {
-        if (h->kernel_pref > 1) return fail(JQ_ERR_ARG, "requested kernel is not available for this problem");
-        if (jq_generic_smem_bytes(h->P, npar) > 227 * 1024) return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory");
-        tpc = 1;
-        CU(jq_generic_launch(h->P, A, st, &ctas, &regs, &smem));
-    }
-    CU(cudaEventRecord(h->ev1, st));
-    h->timed = true; h->last_kernel = plan ? jq_traj_plan_kind(plan) : 1; h->last_launches = 1; h->last_ctas = ctas; h->last_regs = regs;
-    h->last_smem = smem; h->last_tpc = tpc;
+    if ((rc = launch_trajectories(h, A, st)) != 0) return rc;      // same kernel choice as jq_traceobjgrad_batch
+    h->last_launches = 1;
     CU(cudaMemcpyAsync(hist_r, A.hist_r, n_hist * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hist_i, A.hist_i, n_hist * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -10,14 +10,15 @@ const Inst kInst[] = {
     FIBER(5, 2, 1, 1), FIBER(5, 3, 1, 1), FIBER(6, 2, 1, 1), FIBER(5, 1, 1, 2), FIBERO(5, 2, 1, 1),      // 5- and 6-level fastest subsystem
 };
 
-const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0) {
-    const Inst *parts[3] = {kInst, kInstB, kInstC};
-    const int counts[3] = {(int)(sizeof(kInst) / sizeof(kInst[0])), kInstBCount, kInstCCount};
-    for (int p = 0; p < 3; ++p)
+// jt = 0: the run-time-J instantiation; jt > 0: the one with exactly jt Neumann terms compiled in (if any).
+const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0, int jt = 0) {
+    const Inst *parts[4] = {kInst, kInstB, kInstC, kInstD};
+    const int counts[4] = {(int)(sizeof(kInst) / sizeof(kInst[0])), kInstBCount, kInstCCount, kInstDCount};
+    for (int p = 0; p < 4; ++p)
         for (int j = 0; j < counts[p]; ++j) {
             const Inst &i = parts[p][j];
             if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant &&
-                (i.glt == 0 || i.glt == GL)) return &i;
+                i.jt == jt && (i.glt == 0 || i.glt == GL)) return &i;
         }
     return nullptr;
 }
@@ -273,6 +274,79 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     return pl;
 }
 
+
+// Tile layout: every subsystem has 4 levels, control q is the ladder pair (a_q + a_q', a_q - a_q') of subsystem q (row stride
+// 4^q), Hconst diagonal.  NT tiled directions cut in mirrored halves, the others remote (see TileLane).
+TrajPlan *jq_tile_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, int NT, char *err, size_t errlen) {
+    const int n = H.n, m = H.m, Nc = H.Nc;
+    auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.solver != 1 || P.objFuncType != 1) return no("tile layout: only objFuncType 1 with the Neumann solver is instantiated");
+    if (Nc < 2 || Nc > 3) return no("tile layout: 2 or 3 controls");
+    if (NT < 2 || NT > Nc) return no("tile layout: bad number of tiled directions");
+    int n4 = 1;
+    for (int q = 0; q < Nc; ++q) n4 *= 4;
+    if (n != n4) return no("tile layout: every subsystem must have 4 levels");
+    std::vector<double> d0;
+    if (!h0_diagonal(H, d0)) return no("tile layout: Hconst has off-diagonal entries");
+    std::vector<double> sq((size_t)Nc * 3, 0.0);        // ladder coefficient between levels l and l+1 of subsystem q
+    for (int q = 0, stride = 1; q < Nc; ++q, stride *= 4) {
+        for (int o : {1 + q, 1 + Nc + q}) {
+            const int *rp = H.rowptr + o * (n + 1);
+            for (int r = 0; r < n; ++r)
+                for (int p = rp[r]; p < rp[r + 1]; ++p) {
+                    if (H.val[p] == 0.0) continue;
+                    const int c = H.col[p], lo = r < c ? r : c, hi = r < c ? c : r;
+                    if (hi - lo != stride || (lo / stride) % 4 == 3) return no("tile layout: control is not a ladder operator of its subsystem");
+                }
+        }
+        for (int l = 0; l < 3; ++l) sq[q * 3 + l] = value_at(H, 1 + q, l * stride, (l + 1) * stride);
+        for (int r = 0; r < n; ++r) {
+            const int l = (r / stride) % 4;
+            if (l == 3) continue;
+            const double s = sq[q * 3 + l];
+            if (value_at(H, 1 + q, r, r + stride) != s || value_at(H, 1 + q, r + stride, r) != s ||
+                value_at(H, 1 + Nc + q, r, r + stride) != s || value_at(H, 1 + Nc + q, r + stride, r) != -s)
+                return no("tile layout: control is not the (a + a', a - a') pair with level-only coefficients");
+        }
+    }
+    int NL = 1 << NT;
+    for (int q = NT; q < Nc; ++q) NL *= 4;
+    const int GL = pow2ceil(NL * m) > 32 ? 32 : pow2ceil(NL * m);
+    if (NL > 32) return no("tile layout: more than 32 lanes per column");
+    const int CPG = GL / NL, GPT = (m + CPG - 1) / CPG;
+    const int NU = Nc * H.Nfreq * 2, UPL = (NU + GL - 1) / GL;
+    if (UPL > 1) return no("tile layout: too many (control, frequency) pairs for the group size");
+    if (!find_inst(4, NT, 1, Nc, 0, 0, UPL, 0, GL, 0) && !find_inst(4, NT, 1, Nc, 0, 0, UPL, 0, GL, P.J)) return no("tile layout: no instantiation");
+    TrajPlan *pl = new TrajPlan();
+    pl->kind = 4; pl->R = NT; pl->C = 1; pl->NC = Nc; pl->WQ = 0; pl->LMASK = 0; pl->UPL = UPL; pl->AS = 1; pl->HX = 0;
+    pl->NL = NL; pl->NLR = n; pl->GL = GL; pl->GPT = GPT; pl->CPG = CPG;
+    pl->ngroups = TRAJ_WARPS * (32 / GL);
+    pl->TPC = pl->ngroups / GPT;
+    pl->exch_per_unit = 0;                         // shuffles only
+    if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
+    const int nrem = Nc - NT, per = 3 * NT + 2 * nrem;
+    std::vector<int> pi((size_t)NL * (nrem > 0 ? nrem : 1) * 2, 0);
+    std::vector<double> pd((size_t)NL * per, 0.0), d0p(n), wp(n);
+    for (int r = 0; r < n; ++r) { d0p[r] = d0[r]; wp[r] = wdiag[r]; }
+    for (int rho = 0; rho < NL; ++rho) {
+        double *c = pd.data() + (size_t)rho * per;
+        for (int d = 0; d < NT; ++d) {
+            const int hb = (rho >> d) & 1;
+            c[3 * d] = sq[d * 3 + (hb ? 2 : 0)];
+            c[3 * d + 1] = sq[d * 3 + 1];
+            c[3 * d + 2] = hb ? -1.0 : 1.0;
+        }
+        for (int r = 0, gs = 1; r < nrem; ++r, gs *= 4) {
+            const int g = ((rho >> NT) / gs) % 4, q = NT + r;
+            if (g > 0) { pi[((size_t)rho * nrem + r) * 2] = -(gs << NT); c[3 * NT + 2 * r] = sq[q * 3 + g - 1]; }
+            if (g < 3) { pi[((size_t)rho * nrem + r) * 2 + 1] = gs << NT; c[3 * NT + 2 * r + 1] = sq[q * 3 + g]; }
+        }
+    }
+    if (!upload_plan(pl, pi, pd, d0p, wp)) { jq_traj_plan_destroy(pl); return no("cudaMalloc failed for the tile plan"); }
+    err[0] = 0;
+    return pl;
+}
+
 void jq_traj_plan_destroy(TrajPlan *pl) {
     if (!pl) return;
     for (void *p : {(void *)pl->d_i, (void *)pl->d_d, (void *)pl->d_d0, (void *)pl->d_w}) if (p) cudaFree(p);
@@ -283,16 +357,27 @@ int jq_traj_plan_kind(const TrajPlan *pl) { return pl ? pl->kind : 0; }
 
 cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta) {
-    const char *venv = getenv("JQ_TRAJ_VARIANT");
-    if (P.objFuncType != 1) venv = "64";
-    if (P.solver != 1) venv = "128";
-    if (pl->HX) venv = "8";
-    const Inst *inst = (venv && pl->AS) ? find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, atoi(venv), pl->GL) : nullptr;
-    if ((P.solver != 1 || pl->HX) && !inst) return cudaErrorNotSupported;   // never substitute the Neumann series for Jacobi, or drop the drift couplings
-    if (!inst && !venv && pl->AS && P.objFuncType == 1)      // instantiations with the number of Neumann terms known at compile time
-        inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 32 + P.J, pl->GL);
-    if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, pl->AS ? 0 : 16);
-    if (!inst) return cudaErrorNotSupported;
+    // What the kernel must compute fixes the variant; exchange-mode twins (1, 512) are a development override for plain problems only.
+    int want = 0;
+    if (P.objFuncType != 1) want = 64;
+    else if (P.solver != 1) want = 128;
+    else if (pl->HX) want = 8;
+    else if (!pl->AS) want = 16;
+    if ((want == 64 || want == 128 || want == 8) && !pl->AS) return cudaErrorNotSupported;
+    const Inst *inst = nullptr;
+    if (want == 0) {
+        const char *xm = getenv("JQ_TRAJ_XMODE");
+        const int xv = xm ? atoi(xm) : 0;
+        if (xv == 1 || xv == 512) {
+            inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, xv, pl->GL, P.J);
+            if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, xv, pl->GL, 0);
+        }
+        if (!inst && P.J > 0)     // instantiation with the number of Neumann terms known at compile time
+            inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J);
+    }
+    if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, want, pl->GL, 0);
+    if (!inst) return cudaErrorNotSupported;       // never substitute: Neumann for Jacobi, one adjoint set for two, no drift couplings
+    if (inst->jt != 0 && inst->jt != P.J) return cudaErrorNotSupported;
     TrajParams S{};
     S.P = P; S.A = A;
     S.NL = pl->NL; S.NLR = pl->NLR; S.GL = pl->GL; S.GPT = pl->GPT; S.CPG = pl->CPG;

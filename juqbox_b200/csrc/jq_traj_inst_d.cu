@@ -1,0 +1,11 @@
+// Part of the instantiation table of the register-resident trajectory kernels (see jq_traj_kernels.cuh): tile layout.
+#include "jq_traj_kernels.cuh"
+
+const Inst kInstD[] = {
+    TILEJ(2, 2, 1, 4, 16),       // cnot2 example shape: 4 x 4 levels, 2 x 2 tiles, J = 4, 16-lane groups
+    TILEJ(2, 2, 1, 0, 0),        // 4 x 4 levels, run-time J and group size
+    TILEJ(3, 2, 1, 3, 32),       // cnot3 example shape: 4 x 4 x 4 levels, 2 x 2 tiles x remote third subsystem, J = 3
+    TILEJ(3, 2, 1, 0, 0),
+    TILEJ(3, 3, 1, 3, 32),       // cnot3 example shape with 2 x 2 x 2 tiles (8 elements per lane, one warp per trajectory)
+};
+const int kInstDCount = (int)(sizeof(kInstD) / sizeof(kInstD[0]));

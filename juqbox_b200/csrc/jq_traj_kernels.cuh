@@ -66,12 +66,15 @@ struct TrajPlan {
 };
 
 typedef void (*traj_kernel_t)(const TrajParams);
-// variant: 0 default, 16 general Hanti, 32+J compile-time J, 64 objFuncType 2/3; selectable for comparisons with the env
-// variable JQ_TRAJ_VARIANT: 1 warp-shuffle exchange (runtime J), 512 shared-memory twin of the cnot2 instantiation
-struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; };
+// variant (what the kernel computes / how it exchanges): 0 default, 8 exchange-coupled drift, 16 general Hanti, 64 objFuncType 2/3,
+// 128 Jacobi solver; 1 (warp-shuffle exchange) and 512 (shared-memory twin of the cnot2 instantiation) are exchange-mode
+// twins selectable for comparisons with the env variable JQ_TRAJ_XMODE.  jt: number of Neumann terms fixed at compile time
+// (0 = run-time J) -- its own field, never folded into `variant`.  glt: compile-time group size (0 = run-time).
+struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; int jt = 0; };
 // The instantiation table is split over jq_traj.cu / jq_traj_inst_b.cu / jq_traj_inst_c.cu so that they compile in parallel.
 extern const Inst kInstB[]; extern const int kInstBCount;
 extern const Inst kInstC[]; extern const int kInstCCount;
+extern const Inst kInstD[]; extern const int kInstDCount;
 
 namespace {
 
@@ -402,6 +405,142 @@ struct FiberLane {
     }
 };
 
+
+// Tile layout (kernel id 4): Kronecker ladder Hamiltonians whose subsystems all have 4 levels (the cnot2 and cnot3 examples).
+// The first NT subsystems ("tiled directions", control q <-> direction q, row stride 4^q) are cut in HALVES: a lane owns
+// 2 of the 4 levels of every tiled direction, E = 2^NT elements, element e = sum_d i_d 2^d with i_d the position inside the
+// half.  The upper half keeps its levels in MIRRORED order (i = 0 -> level 3, i = 1 -> level 2; lower half i = 0 -> level 0,
+// i = 1 -> level 1), so in every lane i = 1 is the level at the interface and i = 0 the outer level: the code is uniform,
+// each lane has exactly ONE neighbour lane per tiled direction (lane ^ 2^d) and needs only the interface face of its tile
+// (2^(NT-1) values) from it -- 4 doubles per product for the cnot2 shape where the fibre layout moves 8, and the in-lane
+// pair coupling needs no traffic at all.  Mirroring swaps "upper" and "lower" neighbour, i.e. flips the sign of the
+// antisymmetric product D = Hanti x of that direction; the sign sg[d] is folded into the lane's copy of q_d(t) (LOAD_LEVELS)
+// and applied to the lane's partial traces that contain D (dsign).  Controls NT..NC-1 are remote as in the fibre layout
+// (a lane per level, lower and upper neighbour lane, lane-uniform coefficients).  Exchange is by warp shuffle only.
+// Requires Hanti = upper(Hsym) - lower(Hsym) and a diagonal Hconst (the planner checks).
+template <int NC_, int NT_>
+struct TileLane {
+    static constexpr int NC = NC_, NT = NT_, E = 1 << NT_, HX = 0, R = NT_;
+    static constexpr bool SIGNED = true;
+    double cin[NT], cx[NT], sg[NT];          // in-lane pair coupling, cross-lane (interface) coupling, mirror sign
+    static constexpr int NREM = NC_ > NT_ ? NC_ - NT_ : 1;
+    int rpos[NREM][2];
+    double rhs[NREM][2];
+    double d0[E], w[E];
+    double p[3][NC], q[3][NC];
+    int lane, rho, colj, gdim;
+    int sGL, sbase; double stol;
+
+    __device__ __forceinline__ void setup(const TrajParams &S, double *, const Geo &g) {
+        lane = g.lane;
+        rho = g.lg % S.NL;
+        colj = g.gi * S.CPG + g.lg / S.NL;
+        gdim = rho >> NT;                                  // level index of the remote directions (row offset 4^NT * gdim)
+        const double *pd = S.plan_d + rho * (3 * NT + 2 * (NC - NT));
+        UNROLL for (int d = 0; d < NT; ++d) { cin[d] = pd[3 * d]; cx[d] = pd[3 * d + 1]; sg[d] = pd[3 * d + 2]; }
+        UNROLL for (int r = 0; r < NC - NT; ++r) {
+            UNROLL for (int e = 0; e < 2; ++e) {
+                rpos[r][e] = g.lane + S.plan_i[(rho * (NC - NT) + r) * 2 + e];
+                rhs[r][e] = pd[3 * NT + 2 * r + e];
+            }
+        }
+    }
+    __device__ __forceinline__ int row(int e) const {
+        int r = 0, st = 1;
+        UNROLL for (int d = 0; d < NT; ++d) {
+            const int i = (e >> d) & 1, hb = (rho >> d) & 1;
+            r += st * (hb ? 3 - i : i);
+            st *= 4;
+        }
+        return r + st * gdim;
+    }
+    __device__ __forceinline__ int col(int) const { return colj; }
+    __device__ __forceinline__ double dsign(int qq) const { return qq < NT ? sg[qq] : 1.0; }
+    __device__ __forceinline__ void sync_reset() {}
+
+    // index of element e inside the interface face of direction d (bit d removed)
+    static __device__ __forceinline__ constexpr int face(int e, int d) { return (e & ((1 << d) - 1)) | ((e >> (d + 1)) << d); }
+    struct Nbr { double t[NT][E / 2]; double r[NREM][2][E]; };
+    __device__ __forceinline__ void exchange(const double (&x)[E], Nbr &nb) const {
+        UNROLL for (int d = 0; d < NT; ++d)
+            UNROLL for (int e = 0; e < E; ++e)
+                if ((e >> d) & 1) nb.t[d][face(e, d)] = __shfl_xor_sync(0xffffffffu, x[e], 1 << d);
+        UNROLL for (int r = 0; r < NC - NT; ++r)
+            UNROLL for (int e = 0; e < E; ++e) {
+                nb.r[r][0][e] = __shfl_sync(0xffffffffu, x[e], rpos[r][0]);
+                nb.r[r][1][e] = __shfl_sync(0xffffffffu, x[e], rpos[r][1]);
+            }
+    }
+
+    struct SC { double a[NT], b[NT], r[NREM][2]; };
+    __device__ __forceinline__ void s_prescale(int level, SC &sc) const {          // q[level] already carries sg
+        UNROLL for (int d = 0; d < NT; ++d) { sc.a[d] = q[level][d] * cin[d]; sc.b[d] = q[level][d] * cx[d]; }
+        UNROLL for (int r = 0; r < NC - NT; ++r) { sc.r[r][0] = -q[level][NT + r] * rhs[r][0]; sc.r[r][1] = q[level][NT + r] * rhs[r][1]; }
+    }
+    __device__ __forceinline__ void s_scale(SC &sc, double f) const {
+        UNROLL for (int d = 0; d < NT; ++d) { sc.a[d] *= f; sc.b[d] *= f; }
+        UNROLL for (int r = 0; r < NC - NT; ++r) { sc.r[r][0] *= f; sc.r[r][1] *= f; }
+    }
+    template <bool ADD>
+    __device__ __forceinline__ void s_from(const SC &sc, const double (&x)[E], const Nbr &nb, const double (&add)[E], double (&t)[E]) const {
+        UNROLL for (int e = 0; e < E; ++e) {               // in-lane pair couplings first: independent of the exchange
+            double a = ADD ? add[e] : 0.0;
+            UNROLL for (int d = 0; d < NT; ++d) {
+                const double c = ((e >> d) & 1) ? -sc.a[d] : sc.a[d];
+                a = (!ADD && d == 0) ? c * x[e ^ (1 << d)] : fma(c, x[e ^ (1 << d)], a);
+            }
+            t[e] = a;
+        }
+        UNROLL for (int d = 0; d < NT; ++d)
+            UNROLL for (int e = 0; e < E; ++e)
+                if ((e >> d) & 1) t[e] = fma(sc.b[d], nb.t[d][face(e, d)], t[e]);
+        UNROLL for (int r = 0; r < NC - NT; ++r)
+            UNROLL for (int e = 0; e < E; ++e) t[e] = fma(sc.r[r][1], nb.r[r][1][e], fma(sc.r[r][0], nb.r[r][0][e], t[e]));
+    }
+    __device__ __forceinline__ void s_pass(const SC &sc, const double (&x)[E], double (&t)[E]) {
+        Nbr nb;
+        exchange(x, nb);
+        s_from<false>(sc, x, nb, x, t);
+    }
+    __device__ __forceinline__ void s_pass_add(const SC &sc, const double (&x)[E], const double (&add)[E], double (&t)[E]) {
+        Nbr nb;
+        exchange(x, nb);
+        s_from<true>(sc, x, nb, add, t);
+    }
+    // Ae[q] = (Hsym_q x)_e, De[q] = sg[q] * (Hanti_q x)_e  (the sign rides on q[.][q] and dsign)
+    template <bool WA, bool WD, class F>
+    __device__ __forceinline__ void each_from(const double (&x)[E], const Nbr &nb, F f) const {
+        UNROLL for (int e = 0; e < E; ++e) {
+            double Ae[NC + 1], De[NC];
+            Ae[NC] = 0.0;
+            UNROLL for (int d = 0; d < NT; ++d) {
+                const double pin = cin[d] * x[e ^ (1 << d)];
+                if ((e >> d) & 1) {
+                    const double xc = cx[d] * nb.t[d][face(e, d)];
+                    Ae[d] = xc + pin; De[d] = xc - pin;
+                } else {
+                    Ae[d] = pin; De[d] = pin;
+                }
+            }
+            UNROLL for (int r = 0; r < NC - NT; ++r) {
+                const double lo = rhs[r][0] * nb.r[r][0][e], up = rhs[r][1] * nb.r[r][1][e];
+                Ae[NT + r] = up + lo; De[NT + r] = up - lo;
+            }
+            f(e, Ae, De);
+        }
+    }
+    template <bool WA, bool WD, class F>
+    __device__ __forceinline__ void pass_each(const double (&x)[E], F f) {
+        Nbr nb;
+        exchange(x, nb);
+        each_from<WA, WD>(x, nb, f);
+    }
+};
+
+// Sign of the lane's antisymmetric products of control qq relative to Hanti_qq x (tile layout: mirrored halves); 1 elsewhere.
+template <class LaneT, class = void> struct LaneSigned : std::false_type {};
+template <class LaneT> struct LaneSigned<LaneT, std::enable_if_t<LaneT::SIGNED>> : std::true_type {};
+
 // ------------------------------------------------------------------------------------------------ steppers
 // Sum over the GL lanes of a group, result on every lane.  Power-of-two groups use the xor butterfly; other sizes
 // (single-fibre columns with m = 3) gather the GL values in lane order.
@@ -583,6 +722,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         // the three traces that only involve lr05 = X are complete: reduce them now, overlapped with the next products
         double tv3[NC * 3];
         UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tv3[qq * 3 + a] = Ta[qq][a];
+        if constexpr (LaneSigned<LaneT>::value) { UNROLL for (int qq = 0; qq < NC; ++qq) { tv3[qq * 3] *= L.dsign(qq); tv3[qq * 3 + 2] *= L.dsign(qq); } }
         group_sum_n(tv3, GL, gbase_lane);
         if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tred[qq * 5 + a] = tv3[qq * 3 + a]; }
     }
@@ -611,6 +751,7 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
     {
         double tv2[NC * 2];
         UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tv2[qq * 2 + a] = Tb[qq][a];
+        if constexpr (LaneSigned<LaneT>::value) { UNROLL for (int qq = 0; qq < NC; ++qq) tv2[qq * 2 + 1] *= L.dsign(qq); }
         group_sum_n(tv2, GL, gbase_lane);
         if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tred[qq * 5 + 3 + a] = tv2[qq * 2 + a]; }
     }
@@ -767,9 +908,13 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         const double *r1 = tabpq + ((2 * (ls) + 1) * S.TPC + tl) * 2 * NC, *r2 = tabpq + ((2 * (ls) + 2) * S.TPC + tl) * 2 * NC; \
         L.p[1][qq] = r1[2 * qq]; L.q[1][qq] = r1[2 * qq + 1];                                                        \
         L.p[2][qq] = r2[2 * qq]; L.q[2][qq] = r2[2 * qq + 1];                                                        \
+        if constexpr (LaneSigned<LaneT>::value) { L.q[1][qq] *= L.dsign(qq); L.q[2][qq] *= L.dsign(qq); }            \
     }
 #define LOAD_LEVEL0()                                                                                                \
-    UNROLL for (int qq = 0; qq < NC; ++qq) { L.p[2][qq] = tabpq[tl * 2 * NC + 2 * qq]; L.q[2][qq] = tabpq[tl * 2 * NC + 2 * qq + 1]; }
+    UNROLL for (int qq = 0; qq < NC; ++qq) {                                                                         \
+        L.p[2][qq] = tabpq[tl * 2 * NC + 2 * qq]; L.q[2][qq] = tabpq[tl * 2 * NC + 2 * qq + 1];                      \
+        if constexpr (LaneSigned<LaneT>::value) L.q[2][qq] *= L.dsign(qq);                                           \
+    }
 
     // ------------------------------------------------------------ forward sweep (src/evalobjgrad.jl:698-753)
     double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
@@ -906,13 +1051,14 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
 #define SLOTO(R, C, NC, WQ) {2, R, C, NC, WQ, 0, 1, 64, jq_traj_kernel<SlotLane<R, C, NC, WQ>, 1, 1, 0, 1>}   /* objFuncType 2/3 */
 #define FIBER(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL>}
 #define FIBERM(R, NC, LMASK, UPL, MINB) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB>}
-#define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>}   /* compile-time J */
-#define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 32 + JT, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size */
+#define FIBERJ(R, NC, LMASK, UPL, JT) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT>, 0, JT}   /* compile-time J */
+#define FIBERJG(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT>, GLT, JT}   /* compile-time J and group size */
 #define FIBERO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1>}   /* objFuncType 2/3 */
-#define FIBERJGM(R, NC, LMASK, UPL, JT, GLT, MINB, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB, JT, 0, GLT>, GLT}
-#define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, GLT>, GLT}   /* compile-time J and group size, exchange mode XM */
+#define FIBERJGM(R, NC, LMASK, UPL, JT, GLT, MINB, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, MINB, JT, 0, GLT>, GLT, JT}
+#define FIBERX(R, NC, LMASK, UPL, JT, GLT, XM, VAR) {3, R, 1, NC, 2, LMASK, UPL, VAR, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL, 1, JT, 0, GLT>, GLT, JT}   /* compile-time J and group size, exchange mode XM */
 #define FIBERHX(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 8, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, 0, ((1 << NC) - 1) & ~LMASK>, UPL>}   /* exchange-coupled drift */
 #define FIBERJAC(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 128, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, -1>}   /* Jacobi solver */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
+#define TILEJ(NC, NT, UPL, JT, GLT) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT>, GLT, JT}   /* tile layout */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
 }  // namespace

@@ -27,7 +27,7 @@ def _wa(cfg, kernel):
     return wa
 
 
-KERNELS = [1, 2, 3]
+KERNELS = [1, 2, 3, 4]
 GOLDEN_CASES = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq", "cnot2-jacobi", "cnot3"]
 
 
