@@ -5,13 +5,18 @@
 
 One "step" = one batched obj+grad evaluation (`jq_traceobjgrad_batch`) of B synthetic pcof candidates per GPU on the
 named BASELINE configuration (default: cnot2, "batched random pcof evaluations").  Ranks shard the candidates
-(weak scaling, no data-path collective); the risk-neutral leg in `extra` shards noise samples and does the one
-NCCL all-reduce per evaluation that the path really has.  Prints ONE JSON line on rank 0.
+(weak scaling, no data-path collective).  Prints ONE JSON line on rank 0.
 
   value     device-resident throughput: inputs already in HBM, CUDA events on the launching stream, max over ranks
   e2e       same metric through the host-pointer C-ABI call (pinned host buffers, H2D + D2H inside the timed region)
   roofline  algorithmic FP64 flops (SURVEY.md 8d formula) / kernel time, against the FP64 FMA peak measured in-run
   cpu_baseline   the CPU oracle (a port: the Julia reference cannot run in this image) on a bounded sample
+  extra.per_config (N = 1)   every named BASELINE shape — rabi, cnot1, cnot2, cnot3, risk-neutral 9-node quadrature x B
+            candidates, the 1001-point epsilon sweep — with evals/s, roofline fractions and ITS OWN bounded CPU baseline
+  extra.single_eval_latency (N = 1)   one pcof per call, the reference's real call pattern (Ipopt callback)
+  extra.risk_neutral_sample_sharded   noise samples sharded over the ranks + the path's one NCCL all-reduce per evaluation:
+            weak (16384 samples per GPU) and strong (16384 samples in total; the 1001-point sweep) scaling, and a parity
+            self-check of the sharded + all-reduced result against one rank evaluating every sample (<= 1e-12)
   --impl reference   the same oracle with every host thread, as the reference arm
 """
 from __future__ import annotations
@@ -28,6 +33,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+WORKLOADS = ["rabi", "cnot1", "cnot2", "cnot3", "risk_neutral"]
+# candidates per GPU per step: multiples of the resident-CTA wave of the kernel that serves the shape
+DEFAULT_BATCH = {"rabi": 262144, "cnot1": 32768, "cnot2": 16384, "cnot3": 2368, "risk_neutral": 4096}
+KERNEL_NAMES = {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>", 4: "jq_traj_kernel<TileLane>"}
 
 
 def alg_flops_per_eval(p, npar, dense=False):
@@ -106,17 +116,26 @@ def cpu_baseline_run(cfg, pcof, shifts, nthreads, budget_s):
     return ncand * nsamp / dt, ncand * nsamp, dt
 
 
+def ncu_summary(workload):
+    """Per-launch DRAM traffic and executed-FP64-flop fraction from the committed `ncu --set full` captures (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(workload)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cnot2", choices=["rabi", "cnot1", "cnot2", "cnot3", "risk_neutral"])
+    ap.add_argument("--workload", default="cnot2", choices=WORKLOADS)
     ap.add_argument("--batch", type=int, default=0, help="pcof candidates per GPU per step (0 = per-workload default)")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 slot layout, 3 fibre layout")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 slot layout, 3 fibre layout, 4 tile layout")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--per-config-cpu-budget", type=float, default=2.5, help="seconds of CPU work per extra.per_config baseline")
     args = ap.parse_args()
     if args.impl != "reference" and args.warmup < 3:
         args.warmup = 3          # timing rules: at least 3 warm-up steps; the JSON line reports the value actually used
@@ -128,8 +147,7 @@ def main():
 
     from juqbox_b200 import configs
     cfg = configs.example(args.workload)
-    default_batch = {"rabi": 262144, "cnot1": 32768, "cnot2": 16384, "cnot3": 1024, "risk_neutral": 4096}[args.workload]
-    B = args.batch or default_batch
+    B = args.batch or DEFAULT_BATCH[args.workload]
     shifts_h = configs.noise_shift(cfg.params.Ntot, cfg.nodes) if args.workload == "risk_neutral" else None
     nsamp = 1 if shifts_h is None else len(shifts_h)
     npar = cfg.nCoeff
@@ -186,6 +204,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    launches = 0                                         # kernels of this library launched inside timed regions
     wa = jq.Working_Arrays(cfg.params, npar, device=local_rank)
     wa.set_kernel(args.kernel)
     pc_h = configs.synthetic_pcof(cfg, B, seed_offset=rank)
@@ -216,7 +235,7 @@ def main():
         e1.record(stream)
         kernel_ms.append(wa.last_kernel_ms)      # library's own events around the trajectory kernel (synchronises)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    launches += 2 * args.steps
     total_ms = max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs))
     evals_per_step = world * B * nsamp
     value = evals_per_step * args.steps / (total_ms * 1e-3)
@@ -238,6 +257,8 @@ def main():
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches += 2 * args.steps
     e2e_val = evals_per_step * args.steps / e2e_s
     h2d = pc_pin.nbytes + (shifts_h.nbytes if shifts_h is not None else 0)
     d2h = sum(r[k].nbytes for k in ("infid", "leak", "trace_infid", "grad"))       # objFuncType 1: infidgrad aliases grad
@@ -249,29 +270,29 @@ def main():
     achieved = flops_eval * B * nsamp / (kern_ms * 1e-3) / 1e12
     peak_dmma = _lib.fp64_peak_tflops(local_rank, tensor=True)
     dense_ratio = alg_flops_per_eval(cfg.params, npar, dense=True) / flops_eval
-    traffic = None                                  # DRAM bytes per launch from the committed ncu --set full capture
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_dram_traffic.json"))).get(args.workload)
-        if tj and tj["evals_per_launch"] == B * nsamp and used_kernel == 3:
-            traffic = tj["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    ns = ncu_summary(args.workload)
+    same_launch = bool(ns and ns.get("evals_per_launch") == B * nsamp and ns.get("kernel") == used_kernel)
     roofline = {"bound": "fp64_fma",
                 "bound_note": "compute roofline in TFLOP/s (the contract's 'tensor' class), but on the FP64 FMA pipe: B200 has no faster "
                               "FP64 tensor path (tensor_pipe below), and HBM carries ~1 KB per 1.4e8-flop evaluation (traffic)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic, "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                "traffic": ns["dram_bytes_per_launch"] if same_launch else None,
+                "peak_source": "jq_fp64_peak DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
+                               "against ncu's dfma peak_sustained (64/clk/SM x 148 SMs x sm_mhz) the fraction is frac_vs_ncu_sustained_peak",
+                "frac_vs_ncu_sustained_peak": (achieved / (2 * 64 * 148 * clocks["sm_mhz"] * 1e-6)) if clocks and clocks.get("sm_mhz") else None,
+                "executed_fp64_frac_ncu": ns.get("executed_fp64_flop_frac") if ns else None,
                 "peak_no_operand_reuse": peak3, "frac_of_peak_no_operand_reuse": achieved / peak3 if peak3 else None,
                 "tensor_pipe": {"util": 0.0, "fp64_mma_peak": peak_dmma, "dense_to_nnz_flop_ratio": dense_ratio,
                                 "nnz_equivalent_ceiling": peak_dmma / dense_ratio if dense_ratio else None,
                                 "note": "FP64 MMA (mma.sync m16n8k16) peak measured in this run; a dense contraction executes "
                                         "dense_to_nnz_flop_ratio x the structural flops, so its ceiling in this line's units is "
                                         "nnz_equivalent_ceiling TFLOP/s; the path stays on the DFMA pipe when that is below `achieved`"},
-                "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>"}[used_kernel],
+                "alg_flops_per_eval": flops_eval, "kernel_ms": kern_ms, "kernel": KERNEL_NAMES[used_kernel],
                 "hbm_alg_bytes_per_launch": 8 * (B * npar + nsamp * cfg.params.Ntot + B * nsamp * (4 + npar))}
 
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
+    nthr = 1
     if rank == 0 and world == 1:
         from oracle import max_threads
         v1, ne1, dt1 = cpu_baseline_run(cfg, pc_h, shifts_h, 1, args.cpu_budget * 0.4)
@@ -281,42 +302,162 @@ def main():
                "sample": f"{neN} obj+grad evaluations from the same batch in {dtN:.1f}s on {nthr} threads (pthread pool over trajectories)",
                "single_thread": {"value": v1, "cores": 1, "sample": f"{ne1} evaluations in {dt1:.1f}s"}}
 
-    # ---- extra: risk-neutral evaluation with the sample shard + NCCL all-reduce (the path's one exchange step)
-    extra = {}
-    if not args.no_extra:
-        rn = configs.example("risk_neutral")
-        S = 16384                                            # noise samples per GPU (weak scaling)
-        # uniform additive noise on +-ep_max/2 (BASELINE config 5), midpoint rule: node k of world*S, weight 1/(world*S)
-        ep_max = 2 * np.pi * 2e-2
-        nodes = (np.arange(S * world) + 0.5) / (S * world) * ep_max - 0.5 * ep_max
-        weights = np.full(S * world, 1.0 / (S * world))
-        sl = slice(rank * S, (rank + 1) * S)
-        wr = jq.Working_Arrays(rn.params, rn.nCoeff, device=local_rank)
-        if world > 1:
-            wr.comm_init(rank, world)                        # the library's own NCCL communicator (jq_comm_init)
-        pcr = torch.from_numpy(configs.synthetic_pcof(rn, 1)).to(dev)
-        shr = torch.from_numpy(configs.noise_shift(rn.params.Ntot, nodes[sl])).to(dev)
-        wtr = torch.from_numpy(np.ascontiguousarray(weights[sl])).to(dev)
-        o = None
-
-        def rn_step():
-            nonlocal o
-            # weighted partial sums on the device, then ONE grouped ncclAllReduce(sum) of 3 + Npar doubles inside the call
-            o = wr.evaluate_device(pcr, shr, wtr, True, out=o, stream=stream)
-        for _ in range(3):
-            rn_step()
+    def time_launches(fn, reps):
+        """CUDA-event time per call of `fn` on `stream`, max over ranks, after one warm-up call."""
+        fn()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        for _ in range(args.steps):
-            rn_step()
+        for _ in range(reps):
+            fn()
         b.record(stream)
         barrier()
-        ms = max_over_ranks(a.elapsed_time(b))
-        extra["risk_neutral_sample_sharded"] = {
-            "samples_per_gpu": S, "evals_per_sec": world * S * args.steps / (ms * 1e-3), "ms_per_risk_neutral_evaluation": ms / args.steps,
-            "allreduce_doubles": 3 + rn.nCoeff, "collective": "ncclAllReduce(sum, f64) inside jq_traceobjgrad_batch_device" if world > 1 else "none (1 GPU)",
-            "objective": float(o["infid"][0].item() + o["leak"][0].item())}
+        return max_over_ranks(a.elapsed_time(b)) / reps
+
+    extra = {}
+    # ---- extra.per_config: every named shape at 1 GPU with its own CPU baseline (north_star: "each named problem shape ...
+    #      CPU path timed in the same run")
+    if not args.no_extra and world == 1:
+        per = {}
+        legs = [(n, None) for n in WORKLOADS] + [("risk_neutral", "sweep1001")]
+        for name, variant in legs:
+            c = configs.example(name)
+            Bc = DEFAULT_BATCH[name]
+            sh = wts = None
+            label = name
+            if name == "risk_neutral" and variant is None:
+                sh = configs.noise_shift(c.params.Ntot, c.nodes)             # 9 Gauss-Legendre nodes (swap-02-risk-neutral.jl:45-49)
+                label = "risk_neutral_9node"
+            elif variant == "sweep1001":
+                eps = np.linspace(-2 * np.pi * 3e-2, 2 * np.pi * 3e-2, 1001)   # examples/Risk_Neutral/run_all.jl:70-72
+                sh = configs.noise_shift(c.params.Ntot, eps)
+                Bc, label = 1, "risk_neutral_sweep1001"
+            ns_c = 1 if sh is None else len(sh)
+            pch = configs.synthetic_pcof(c, Bc)
+            w2 = jq.Working_Arrays(c.params, c.nCoeff, device=local_rank)
+            pcd = torch.from_numpy(pch).to(dev)
+            shd = torch.from_numpy(sh).to(dev) if sh is not None else None
+            o2 = None
+
+            def leg():
+                nonlocal o2
+                o2 = w2.evaluate_device(pcd, shd, None, True, out=o2, stream=stream)
+            reps = 2 if name == "cnot3" else 3
+            leg()
+            kms = []
+            for _ in range(reps):
+                flush.fill_(1)
+                leg()
+                kms.append(w2.last_kernel_ms)
+            launches += 2 * reps
+            kms = float(np.mean(kms))
+            fl = alg_flops_per_eval(c.params, c.nCoeff)
+            ev = Bc * ns_c / (kms * 1e-3)
+            vC, neC, dtC = cpu_baseline_run(c, pch, sh, nthr, args.per_config_cpu_budget)
+            nsum = ncu_summary(label) or ncu_summary(name)
+            per[label] = {"candidates": Bc, "noise_samples": ns_c, "n": c.params.Ntot, "m": c.params.N, "nsteps": c.params.nsteps,
+                          "kernel": KERNEL_NAMES[w2.last_kernel], "kernel_ms": kms, "evals_per_sec": ev,
+                          "state_steps_per_sec": ev * 3 * c.params.nsteps, "alg_tflops": ev * fl / 1e12,
+                          "frac": ev * fl / 1e12 / peak, "executed_fp64_frac_ncu": nsum.get("executed_fp64_flop_frac") if nsum else None,
+                          "cpu_baseline": {"value": vC, "unit": "evals/s", "cores": nthr, "kind": "port",
+                                           "sample": f"{neC} evaluations in {dtC:.1f}s"},
+                          "speedup_vs_cpu_all_threads": ev / vC}
+            w2.close()
+        extra["per_config"] = per
+
+        # ---- one pcof per call: the reference's own call pattern (eval_f_g_grad! from an Ipopt callback)
+        lat = {}
+        for name in ("cnot2", "cnot3", "risk_neutral"):
+            c = configs.example(name)
+            sh = configs.noise_shift(c.params.Ntot, c.nodes) if name == "risk_neutral" else None
+            wts = c.weights if name == "risk_neutral" else None
+            w2 = jq.Working_Arrays(c.params, c.nCoeff, device=local_rank)
+            p1 = configs.synthetic_pcof(c, 1)
+            w2.evaluate(p1, sh, wts)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                w2.evaluate(p1, sh, wts)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            launches += 6
+            from oracle import oracle_traceobjgrad
+            t0 = time.perf_counter()
+            oracle_traceobjgrad(c.params, p1, sh, nthreads=min(nthr, 1 if sh is None else len(sh)))
+            cpu_ms = (time.perf_counter() - t0) * 1e3
+            lat[name] = {"trajectories": 1 if sh is None else len(sh), "kernel": KERNEL_NAMES[w2.last_kernel], "kernel_ms": w2.last_kernel_ms,
+                         "host_call_ms": min(ts), "cpu_ms": cpu_ms, "cpu_threads": min(nthr, 1 if sh is None else len(sh))}
+            w2.close()
+        extra["single_eval_latency"] = lat
+
+    # ---- extra: risk-neutral evaluation with the sample shard + NCCL all-reduce (the path's one exchange step)
+    if not args.no_extra:
+        rn = configs.example("risk_neutral")
+        ep_max = 2 * np.pi * 2e-2
+        wr = jq.Working_Arrays(rn.params, rn.nCoeff, device=local_rank)
+        if world > 1:
+            wr.comm_init(rank, world)                        # the library's own NCCL communicator (jq_comm_init)
+        pcr_h = configs.synthetic_pcof(rn, 1)
+        pcr = torch.from_numpy(pcr_h).to(dev)
+
+        def sharded_leg(nodes, weights, reps):
+            """Each rank evaluates its contiguous shard of (nodes, weights); the call ends with the library's one grouped
+            ncclAllReduce(sum) of 3 + Npar doubles.  Returns (ms per risk-neutral evaluation, result dict of this rank)."""
+            per_rank = -(-len(nodes) // world)
+            sl = slice(rank * per_rank, min(len(nodes), (rank + 1) * per_rank))
+            shr = torch.from_numpy(configs.noise_shift(rn.params.Ntot, nodes[sl])).to(dev)
+            wtr = torch.from_numpy(np.ascontiguousarray(weights[sl])).to(dev)
+            res = {}
+
+            def f():
+                res["o"] = wr.evaluate_device(pcr, shr, wtr, True, out=res.get("o"), stream=stream)
+            ms = time_launches(f, reps)
+            return ms, res["o"]
+
+        def midpoint(S):
+            # uniform additive noise on +-ep_max/2 (BASELINE config 5), midpoint rule: node k of S, weight 1/S
+            return (np.arange(S) + 0.5) / S * ep_max - 0.5 * ep_max, np.full(S, 1.0 / S)
+
+        S = 16384                                            # noise samples per GPU (weak scaling)
+        nodes, weights = midpoint(S * world)
+        ms, o = sharded_leg(nodes, weights, args.steps)
+        launches += 2 * args.steps
+        rnleg = {"samples_per_gpu": S, "evals_per_sec": world * S / (ms * 1e-3), "ms_per_risk_neutral_evaluation": ms,
+                 "allreduce_doubles": 3 + rn.nCoeff,
+                 "collective": "ncclAllReduce(sum, f64) inside jq_traceobjgrad_batch_device" if world > 1 else "none (1 GPU)",
+                 "objective": float(o["infid"][0].item() + o["leak"][0].item())}
+        if rank == 0 and world == 1:
+            vC, neC, dtC = cpu_baseline_run(rn, pcr_h, configs.noise_shift(rn.params.Ntot, nodes[:1024]), nthr, args.per_config_cpu_budget)
+            rnleg["cpu_baseline"] = {"value": vC, "unit": "evals/s", "cores": nthr, "kind": "port",
+                                     "sample": f"{neC} sample evaluations (first 1024 nodes, one pcof) in {dtC:.1f}s"}
+            rnleg["speedup_vs_cpu_all_threads"] = rnleg["evals_per_sec"] / vC
+        # strong scaling: the same 16384 samples in total, and the reference's own 1001-point epsilon sweep
+        nodes_s, weights_s = midpoint(S)
+        ms_s, _ = sharded_leg(nodes_s, weights_s, args.steps)
+        eps = np.linspace(-2 * np.pi * 3e-2, 2 * np.pi * 3e-2, 1001)
+        ms_w, _ = sharded_leg(eps, np.full(1001, 1.0 / 1001), args.steps)
+        launches += 4 * args.steps
+        rnleg["strong_scaling"] = {"samples_total_16384": {"ms_per_evaluation": ms_s, "evals_per_sec": S / (ms_s * 1e-3)},
+                                   "sweep_1001": {"ms_per_evaluation": ms_w, "evals_per_sec": 1001 / (ms_w * 1e-3)},
+                                   "note": "total work fixed, samples split in contiguous shards over the ranks; one all-reduce per evaluation"}
+        # parity self-check of the exchange step: sharded + all-reduced vs every sample on this rank alone (no communicator)
+        if world > 1:
+            Sp = 64 * world
+            nodes_p, weights_p = midpoint(Sp)
+            weights_p = weights_p * (1.0 + 0.25 * np.cos(np.arange(Sp)))          # non-uniform weights
+            _, o_sh = sharded_leg(nodes_p, weights_p, 1)
+            w1 = jq.Working_Arrays(rn.params, rn.nCoeff, device=local_rank)
+            o_all = w1.evaluate_device(pcr, torch.from_numpy(configs.noise_shift(rn.params.Ntot, nodes_p)).to(dev),
+                                       torch.from_numpy(weights_p).to(dev), True, stream=stream)
+            torch.cuda.synchronize()
+            g_sh, g_all = o_sh["grad"][0].cpu().numpy(), o_all["grad"][0].cpu().numpy()
+            f_sh = float(o_sh["infid"][0].item() + o_sh["leak"][0].item())
+            f_all = float(o_all["infid"][0].item() + o_all["leak"][0].item())
+            err = max(abs(f_sh - f_all) / abs(f_all), float(np.linalg.norm(g_sh - g_all) / np.linalg.norm(g_all)))
+            err = max_over_ranks(err)
+            rnleg["nccl_parity"] = {"ok": bool(err <= 1e-12), "max_rel_err_over_ranks": err, "samples": Sp, "tolerance": 1e-12,
+                                    "what": "objective and gradient: sample shards + ncclAllReduce vs one rank evaluating all samples"}
+            w1.close()
+        extra["risk_neutral_sample_sharded"] = rnleg
         wr.close()
 
     if rank == 0:
@@ -325,7 +466,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
                 "state_steps_per_sec": value * 3 * cfg.params.nsteps,
                 "e2e": {"value": e2e_val, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(2 * args.steps), "roofline": roofline, "clocks": clocks, "extra": extra}
+                "gpu_launches": int(launches), "gpu_launches_note": "trajectory kernel + finalize/weighted-sum kernel per evaluation, all legs of this run",
+                "roofline": roofline, "clocks": clocks, "extra": extra}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

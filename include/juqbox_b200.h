@@ -53,7 +53,9 @@ typedef struct jq_problem {
     int32_t nfreq;         /* size(Cfreq, 2)                            (:169)               */
     int32_t neumann_terms; /* linear_solver.max_iter: Neumann terms, or the Jacobi sweep limit (linear_solvers.jl:41,46) */
     int32_t obj_func_type; /* objFuncType: 1 = infidelity+leak, 2/3 = also return infidelity-only gradient (:848-855) */
-    int32_t pfid_type;     /* pFidType; only 2 is built (hard-wired by the reference constructor, :164) */
+    int32_t pfid_type;     /* pFidType 1, 2, 3 or 4 (:755-763, :2026-2059); 2 is the reference constructor's value (:164).  With 3 every
+                              pcof vector carries the global phase as an extra last entry and every gradient has one more entry
+                              (:589-596, :923-945): npar below is then 2*(ncoupled+nuncoupled)*nfreq*D1 + 1 */
     int32_t linear_solver; /* linear_solver.solver_id: 0 or 1 = NEUMANN_SOLVER, 2 = JACOBI_SOLVER (linear_solvers.jl:4-5) */
     int64_t nsteps;
     double T;
@@ -61,11 +63,20 @@ typedef struct jq_problem {
     const double *vtarget_r; /* n*m, params.Utarget_r */
     const double *vtarget_i; /* n*m, params.Utarget_i */
     const double *wdiag;     /* n, diagonal of params.wmat_real (Diagonal weights only) */
-    const double *cfreq;     /* ncoupled*nfreq, params.Cfreq column-major: (c,f) at c + ncoupled*f */
+    const double *cfreq;     /* (ncoupled+nuncoupled)*nfreq, params.Cfreq[1:Nctrl,:] column-major: (c,f) at c + Nctrl*f */
     jq_operator h0;          /* params.Hconst */
     const jq_operator *hsym; /* ncoupled */
     const jq_operator *hanti;/* ncoupled */
     double solver_tol;       /* linear_solver.tol (Jacobi only; already multiplied by sqrt(nrhs), linear_solvers.jl:40) */
+    /* --- SURVEY.md 8f rank 3; all zero / NULL = the core path --- */
+    double global_phase;     /* params.globalPhase (pFidType 1 and 4) */
+    const double *wmat_real; /* n*n column-major dense params.wmat_real when use_custom_forbidden (:214-232), else NULL: Diagonal(wdiag) */
+    const double *wmat_imag; /* n*n column-major params.wmat_imag, or NULL (zero) */
+    int32_t nuncoupled;      /* length(Hunc_ops): uncoupled (lab-frame) controls, two splines each as KS! reads them (:2372-2387) */
+    int32_t reserved0;
+    const jq_operator *hunc;      /* nuncoupled, each symmetric or antisymmetric */
+    const int32_t *unc_is_symm;   /* nuncoupled: params.isSymm (:186-199) */
+    const double *unc_rfreq;      /* nuncoupled: params.Rfreq[q] in GHz: f_q(t) = 2 (p cos(2 pi Rfreq t) - q sin(2 pi Rfreq t)) */
 } jq_problem;
 
 /* Replaces Working_Arrays(params, nCoeff) (src/evalobjgrad.jl:405): copies the problem to the GPU `device`,
@@ -101,6 +112,31 @@ int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const double *pco
                                  const double *h0_diag_shift, const double *weights, int32_t evaladjoint,
                                  double *infid, double *leak, double *trace_infid, double *grad,
                                  double *infidgrad, double *leakgrad, void *cuda_stream);
+
+/* Fused Ipopt-callback entry: one call serves eval_f_par AND eval_grad_f_par (src/ipopt_interface.jl:77-148), plus eval_g_par /
+ * eval_jac_g_par for objFuncType 3 (:104-179).  Everything those callbacks do per evaluation happens behind this call:
+ *   - the last-evaluation cache: trajectories run only if ||pcof - last_pcof||_2 > 1e-15 (the reference's own test, :84,:131),
+ *     otherwise the stored results are returned without touching the GPU;
+ *   - eval_f_g_grad! (:24-70): the nsamples noise samples of ONE pcof in one launch, weighted sums on the device (and the
+ *     all-reduce over sample shards if a communicator is attached); weights == NULL with nsamples == 1 means weight 1;
+ *   - Tikhonov on the device (tikhonov_pen / tikhonov_grad!, src/evalobjgrad.jl:2291-2351):
+ *       f      = last_infidelity (+ last_leak if objFuncType == 1) + tik0 * ||pcof - prior||^2 / npar          (:89-98)
+ *       grad_f = last_infidelity_grad + 2 tik0 (pcof - prior) / npar   (the total gradient when objFuncType == 1, :136-141)
+ *     prior == NULL means usingPriorCoeffs == false;
+ *   - infid / leak: last_infidelity and last_leak (eval_g_par's g[1]); leakgrad: last_leak_grad (eval_jac_g_par), written
+ *     only for objFuncType != 1.  Any output pointer may be NULL.  *evaluated = 1 if trajectories ran, 0 on a cache hit.
+ * The cache is keyed on pcof like the reference's (nodes/weights are fixed per optimisation); jq_update_target,
+ * jq_cache_invalidate and a changed nsamples or tik0-independent input (shift/weights pointers' contents are compared) reset it.
+ * Host pointers, blocking. */
+int jq_eval_f_grad(jq_handle *h, const double *pcof, int32_t npar, int32_t nsamples, const double *h0_diag_shift,
+                   const double *weights, double tik0, const double *prior, double *f, double *grad_f, double *infid,
+                   double *leak, double *leakgrad, int32_t *evaluated);
+int jq_cache_invalidate(jq_handle *h);
+
+/* Layout self-description for bindings that mirror the structs by hand (julia/JuqboxB200.jl, ctypes): what = 0 ABI version,
+ * 1 sizeof(jq_problem), 2 sizeof(jq_operator), 3 offsetof(jq_problem, nsteps), 4 offsetof(T), 5 offsetof(uinit), 6 offsetof(h0),
+ * 7 offsetof(hsym), 8 offsetof(solver_tol), 9 offsetof(jq_operator, nnz), 10 offsetof(jq_operator, nzval); -1 otherwise. */
+int64_t jq_abi_info(int32_t what);
 
 /* Forward propagation with state history: eval_forward(U0 = Uinit, pcof, params; saveEndOnly=false, saveEvery)
  * (src/evalobjgrad.jl:2727-2873) and the history that traceobjgrad(verbose=true, evaladjoint=false) returns

@@ -22,15 +22,20 @@ class jq_problem(C.Structure):
                 ("linear_solver", C.c_int32), ("nsteps", C.c_int64), ("T", C.c_double),
                 ("uinit", C.c_void_p), ("vtarget_r", C.c_void_p), ("vtarget_i", C.c_void_p), ("wdiag", C.c_void_p),
                 ("cfreq", C.c_void_p), ("h0", jq_operator), ("hsym", C.POINTER(jq_operator)),
-                ("hanti", C.POINTER(jq_operator)), ("solver_tol", C.c_double)]
+                ("hanti", C.POINTER(jq_operator)), ("solver_tol", C.c_double),
+                ("global_phase", C.c_double), ("wmat_real", C.c_void_p), ("wmat_imag", C.c_void_p),
+                ("nuncoupled", C.c_int32), ("reserved0", C.c_int32), ("hunc", C.POINTER(jq_operator)),
+                ("unc_is_symm", C.c_void_p), ("unc_rfreq", C.c_void_p)]
 
 
 JQ_DENSE, JQ_CSC = 0, 1
 JQ_ERR_PCOF_LENGTH = -2
 
-EXPORTS = ["jq_create", "jq_destroy", "jq_update_target", "jq_traceobjgrad_batch", "jq_traceobjgrad_batch_device", "jq_eval_forward", "jq_eval_controls",
+EXPORTS = ["jq_create", "jq_destroy", "jq_update_target", "jq_traceobjgrad_batch", "jq_traceobjgrad_batch_device", "jq_eval_f_grad",
+           "jq_cache_invalidate", "jq_eval_forward", "jq_eval_controls",
            "jq_set_kernel", "jq_query", "jq_fp64_peak", "jq_fp64_peak_3op", "jq_fp64_peak_dmma", "jq_comm_unique_id", "jq_comm_init", "jq_comm_destroy",
-           "jq_last_error", "jq_version"]
+           "jq_abi_info", "jq_last_error", "jq_version"]
+ABI_VERSION = 2
 
 _lib = None
 
@@ -49,13 +54,12 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if build_if_missing:
+    if build_if_missing and _build.needs_build():
         try:
-            if _build.needs_build():
-                _build.build_library()
-        except Exception as e:  # stale or missing and cannot rebuild
-            if not os.path.exists(path):
-                raise JuqboxCudaError(f"libjuqbox_b200.so is missing and could not be built: {e}") from e
+            _build.build_library()
+        except Exception as e:
+            # never load a stale binary silently: its structs may no longer match the ctypes definitions above
+            raise JuqboxCudaError(f"libjuqbox_b200.so is {'stale' if os.path.exists(path) else 'missing'} and could not be rebuilt: {e}") from e
     if not os.path.exists(path):
         raise JuqboxCudaError(f"{path} not found: run `python -m juqbox_b200.build` (there is no CPU fallback)")
     lib = C.CDLL(path)
@@ -75,8 +79,17 @@ def load(build_if_missing: bool = True):
     lib.jq_comm_unique_id.argtypes = [vp]
     lib.jq_comm_init.argtypes = [vp, i32, i32, vp]
     lib.jq_comm_destroy.argtypes = [vp]
-    for name in EXPORTS[:-2]:
+    lib.jq_eval_f_grad.argtypes = [vp, dp, i32, i32, dp, dp, C.c_double, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int32)]
+    lib.jq_cache_invalidate.argtypes = [vp]
+    lib.jq_abi_info.argtypes = [i32]
+    lib.jq_abi_info.restype = C.c_int64
+    for name in EXPORTS[:-3]:
         getattr(lib, name).restype = C.c_int
+    # the hand-written struct mirrors above must match the binary (guards against a stale or foreign .so)
+    got = (lib.jq_abi_info(0), lib.jq_abi_info(1), lib.jq_abi_info(2))
+    want = (ABI_VERSION, C.sizeof(jq_problem), C.sizeof(jq_operator))
+    if got != want:
+        raise JuqboxCudaError(f"{path}: ABI mismatch (version, sizeof(jq_problem), sizeof(jq_operator)) = {got}, this package expects {want}")
     lib.jq_last_error.restype = C.c_char_p
     lib.jq_version.restype = C.c_char_p
     _lib = lib

@@ -43,9 +43,10 @@ class Working_Arrays:
         self._lib = lib
         self.params = params
         self.nCoeff = int(nCoeff)
-        nsig = 2 * params.Ncoupled
-        if nCoeff % (nsig * params.Nfreq) != 0 or nCoeff < 3 * nsig:
-            raise ValueError(f"pcof must have an even number of elements >= {3 * nsig}, not {nCoeff}")
+        nsig = 2 * (params.Ncoupled + params.Nunc)
+        nspl = nCoeff - (1 if params.pFidType == 3 else 0)      # pFidType 3: the last entry is the global phase (:591-596)
+        if nspl % (nsig * params.Nfreq) != 0 or nspl < 3 * nsig:
+            raise ValueError(f"pcof must have an even number of elements >= {3 * nsig}, not {nspl}")
         if device is None:
             import os
             device = int(os.environ.get("LOCAL_RANK", "0")) if "JUQBOX_B200_USE_LOCAL_RANK" in os.environ else 0
@@ -54,6 +55,25 @@ class Working_Arrays:
         self._handle = C.c_void_p()
         pb = self._describe(params)
         _lib.check(lib.jq_create(C.byref(pb), C.c_int(device), C.byref(self._handle)))
+        self._snapshot = self._fingerprint(params)
+
+    # The reference re-reads `params` on every traceobjgrad call; the device handle copies it once.  Fields the kernels
+    # depend on are fingerprinted so that a later edit (estimate_Neumann, params.nsteps = ..., a new Hconst) is an error
+    # instead of being silently ignored.  Utarget is the one supported mutation (update_target).
+    @staticmethod
+    def _fingerprint(p):
+        import hashlib
+        hsh = hashlib.sha1()
+        for a in [p.Hconst, p.Uinit, p.wmat_real, p.Cfreq] + list(p.Hsym_ops) + list(p.Hanti_ops) + list(p.Hunc_ops) + \
+                ([p.wmat_imag] if p.wmat_imag is not None else []):
+            hsh.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        return (p.T, p.nsteps, p.linear_solver.max_iter, p.linear_solver.solver_id, p.linear_solver.tol, p.objFuncType, p.pFidType,
+                p.globalPhase, tuple(p.Rfreq[:p.Nunc]), hsh.hexdigest())
+
+    def _check_params(self):
+        if self._fingerprint(self.params) != self._snapshot:
+            raise RuntimeError("params changed after Working_Arrays was created (T, nsteps, linear_solver, objFuncType, Hconst, "
+                               "operators, weights or Cfreq): create a new Working_Arrays (only Utarget can be updated in place)")
 
     # -- problem descriptor -------------------------------------------------------------------
     def _ptr(self, a):
@@ -82,14 +102,29 @@ class Working_Arrays:
         pb.uinit = self._ptr(np.asfortranarray(p.Uinit, dtype=np.float64))
         pb.vtarget_r = self._ptr(np.asfortranarray(p.Utarget_r, dtype=np.float64))
         pb.vtarget_i = self._ptr(np.asfortranarray(p.Utarget_i, dtype=np.float64))
-        pb.wdiag = self._ptr(_f64(p.wmat_real))
-        pb.cfreq = self._ptr(np.asfortranarray(p.Cfreq[:p.Ncoupled, :], dtype=np.float64))
+        wr = np.asarray(p.wmat_real, dtype=np.float64)
+        if wr.ndim == 2:                       # custom forbidden states: dense real / imaginary weights (src/evalobjgrad.jl:214-232)
+            pb.wdiag = self._ptr(_f64(np.diag(wr)))
+            pb.wmat_real = self._ptr(np.asfortranarray(wr))
+            if p.wmat_imag is not None and np.any(p.wmat_imag):
+                pb.wmat_imag = self._ptr(np.asfortranarray(p.wmat_imag, dtype=np.float64))
+        else:
+            pb.wdiag = self._ptr(_f64(wr))
+        pb.cfreq = self._ptr(np.asfortranarray(p.Cfreq[:p.Ncoupled + p.Nunc, :], dtype=np.float64))
+        pb.global_phase = float(p.globalPhase)
         pb.h0 = self._op(p.Hconst, p.use_sparse)
-        OpArr = _lib.jq_operator * p.Ncoupled
+        OpArr = _lib.jq_operator * max(p.Ncoupled, 1)
         hs = OpArr(*[self._op(h, p.use_sparse) for h in p.Hsym_ops])
         ha = OpArr(*[self._op(h, p.use_sparse) for h in p.Hanti_ops])
         self._keep += [hs, ha]
         pb.hsym, pb.hanti = hs, ha
+        pb.nuncoupled = p.Nunc
+        if p.Nunc:
+            hu = (_lib.jq_operator * p.Nunc)(*[self._op(h, p.use_sparse) for h in p.Hunc_ops])
+            self._keep.append(hu)
+            pb.hunc = hu
+            pb.unc_is_symm = self._ptr(np.ascontiguousarray(p.isSymm, dtype=np.int32))
+            pb.unc_rfreq = self._ptr(_f64(np.asarray(p.Rfreq, dtype=np.float64)[:p.Nunc]))
         return pb
 
     # -- lifecycle ----------------------------------------------------------------------------
@@ -108,7 +143,7 @@ class Working_Arrays:
         """Push params.Utarget_r/i to the device after change_target (src/evalobjgrad.jl:1492)."""
         p = self.params
         vr, vi = np.asfortranarray(p.Utarget_r, dtype=np.float64), np.asfortranarray(p.Utarget_i, dtype=np.float64)
-        _lib.check(self._lib.jq_update_target(self._handle, vr.ctypes.data_as(C.c_void_p), vi.ctypes.data_as(C.c_void_p)))
+        _lib.check(self._lib.jq_update_target(self._handle, vr.ctypes.data_as(C.c_void_p), vi.ctypes.data_as(C.c_void_p)))      # also resets the cache
 
     def comm_init(self, rank: int, nranks: int, unique_id: bytes = None):
         """Attach an NCCL communicator (jq_comm_init).  With torch.distributed initialised, the 128-byte unique id is
@@ -156,6 +191,7 @@ class Working_Arrays:
         With objFuncType == 1 `infidgrad` is the same array as `grad` (the reference's infidelgrad aliases totalgrad,
         src/evalobjgrad.jl:951) and `leakgrad` is a read-only zero view: only one gradient crosses the bus."""
         p = self.params
+        self._check_params()
         pcof = _f64(np.atleast_2d(pcof))
         nbatch, npar = pcof.shape
         nsamples = 1
@@ -203,11 +239,14 @@ class Working_Arrays:
         """Forward sweep with state history (jq_eval_forward).  Returns (hist, infid, leak): hist complex
         [nbatch, nsamples, nsave, N, Ntot] — for one trajectory hist[b, s].transpose(2, 1, 0) is Julia's Ntot x N x nsave."""
         p = self.params
+        self._check_params()
         pcof = _f64(np.atleast_2d(pcof))
         nbatch, npar = pcof.shape
         nsamples, sp = 1, None
         if shifts is not None:
             shifts = _f64(np.atleast_2d(shifts))
+            if shifts.shape[1] != p.Ntot:
+                raise ValueError("shifts must be [nsamples, Ntot]")
             nsamples, sp = shifts.shape[0], shifts.ctypes.data_as(C.c_void_p)
         if save_every < 1 or p.nsteps % save_every != 0:
             raise ValueError(f"nsteps must be divisible by saveEvery. nsteps={p.nsteps}, saveEvery={save_every}")
@@ -220,10 +259,42 @@ class Working_Arrays:
                                              infid.ctypes.data_as(C.c_void_p), leak.ctypes.data_as(C.c_void_p)))
         return hr + 1j * hi, infid, leak
 
+    def eval_f_grad(self, pcof, shifts=None, weights=None, tik0: float = 0.0, prior=None):
+        """The fused Ipopt-callback entry (jq_eval_f_grad): objective with Tikhonov, its gradient, infidelity, leak and leak
+        gradient of ONE pcof in one call, with the last-pcof cache inside the handle.  Returns a dict; `evaluated` is False
+        when the call was served from the cache."""
+        p = self.params
+        self._check_params()
+        pcof = _f64(np.ravel(pcof))
+        npar = len(pcof)
+        nsamples, sp, wp, pp = 1, None, None, None
+        if shifts is not None:
+            shifts = _f64(np.atleast_2d(shifts))
+            if shifts.shape[1] != p.Ntot:
+                raise ValueError("shifts must be [nsamples, Ntot]")
+            nsamples, sp = shifts.shape[0], shifts.ctypes.data_as(C.c_void_p)
+        if weights is not None:
+            weights = _f64(np.atleast_1d(weights))
+            if len(weights) != nsamples:
+                raise ValueError("weights must have one entry per sample")
+            wp = weights.ctypes.data_as(C.c_void_p)
+        if prior is not None:
+            prior = _f64(np.ravel(prior))
+            if len(prior) != npar:
+                raise ValueError("prior must have the length of pcof")
+            pp = prior.ctypes.data_as(C.c_void_p)
+        f, infid, leak = C.c_double(), C.c_double(), C.c_double()
+        ev = C.c_int32()
+        grad, lgrad = np.zeros(npar), np.zeros(npar if p.objFuncType != 1 else 0)
+        _lib.check(self._lib.jq_eval_f_grad(self._handle, pcof.ctypes.data_as(C.c_void_p), npar, nsamples, sp, wp, float(tik0), pp,
+                                            C.byref(f), grad.ctypes.data_as(C.c_void_p), C.byref(infid), C.byref(leak),
+                                            lgrad.ctypes.data_as(C.c_void_p) if len(lgrad) else None, C.byref(ev)))
+        return {"f": f.value, "grad_f": grad, "infid": infid.value, "leak": leak.value, "leakgrad": lgrad, "evaluated": bool(ev.value)}
+
     def controls(self, pcof, times):
         """p_q(t), q_q(t) of every coupled control at `times` (jq_eval_controls).  Returns p, q of shape [Ncoupled, ntimes]."""
         pcof, times = _f64(np.ravel(pcof)), _f64(np.ravel(times))
-        p = np.zeros((self.params.Ncoupled, len(times)))
+        p = np.zeros((self.params.Ncoupled + self.params.Nunc, len(times)))
         q = np.zeros_like(p)
         _lib.check(self._lib.jq_eval_controls(self._handle, pcof.ctypes.data_as(C.c_void_p), len(pcof), len(times),
                                               times.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p)))
@@ -233,9 +304,20 @@ class Working_Arrays:
         """Batched evaluation on torch CUDA tensors (no host copies, asynchronous on `stream` or torch's current
         stream).  pcof [nbatch, npar], shifts [nsamples, n], weights [nsamples]; returns dict of CUDA tensors."""
         import torch
-        assert pcof.is_cuda and pcof.dtype == torch.float64 and pcof.is_contiguous()
+        self._check_params()
+
+        def ok(t, shape, what):
+            if not (t.is_cuda and t.device.index == self.device and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == shape):
+                raise ValueError(f"{what} must be a contiguous float64 CUDA tensor of shape {shape} on device {self.device}")
+        if pcof.dim() != 2:
+            raise ValueError("pcof must be [nbatch, npar]")
+        ok(pcof, tuple(pcof.shape), "pcof")
         nbatch, npar = pcof.shape
         nsamples = 1 if shifts is None else shifts.shape[0]
+        if shifts is not None:
+            ok(shifts, (nsamples, self.params.Ntot), "shifts")
+        if weights is not None:
+            ok(weights, (nsamples,), "weights")
         shape = (nbatch,) if weights is not None else (nbatch, nsamples)
         if out is None:
             out = {k: torch.empty(shape, dtype=torch.float64, device=pcof.device) for k in ("infid", "leak", "trace_infid")}
@@ -247,7 +329,9 @@ class Working_Arrays:
         st = stream if stream is not None else torch.cuda.current_stream(pcof.device)
 
         def dp(t):
-            return C.c_void_p(t.data_ptr()) if t is not None else None
+            if t is None:
+                return None
+            return C.c_void_p(t.data_ptr() if t.numel() else pcof.data_ptr())      # empty sample shard: any valid non-null pointer
         _lib.check(self._lib.jq_traceobjgrad_batch_device(
             self._handle, nbatch, dp(pcof), npar, nsamples, dp(shifts), dp(weights), int(bool(evaladjoint)),
             dp(out["infid"]), dp(out["leak"]), dp(out["trace_infid"]), dp(out.get("grad")), dp(out.get("infidgrad")),
@@ -328,8 +412,23 @@ def _stale(pcof, params):
     return len(params.last_pcof) != len(pcof) or np.linalg.norm(pcof - params.last_pcof) > 1.0e-15
 
 
+def _fused(pcof, params, wa, nodes, weights):
+    """One jq_eval_f_grad call: cache test, sample loop, weighted sums and Tikhonov behind the C ABI.
+    Keeps the scalar last-evaluation fields of `params` that intermediate_par reads (src/ipopt_interface.jl:67-68,212-228)."""
+    nodes, weights = np.atleast_1d(np.asarray(nodes, float)), np.atleast_1d(np.asarray(weights, float))
+    r = wa.eval_f_grad(pcof, noise_shift(params.Ntot, nodes), weights, params.tik0, params.priorCoeffs if params.usingPriorCoeffs else None)
+    params.last_pcof = np.array(pcof, dtype=np.float64)
+    params.last_infidelity, params.last_leak = r["infid"], r["leak"]
+    params.lastTraceInfidelity, params.lastLeakIntegral = r["infid"], r["leak"]
+    return r
+
+
 def eval_f_par(pcof, params, wa, nodes=(0.0,), weights=(1.0,)):
+    """eval_f_par (src/ipopt_interface.jl:77-100).  With a device handle this is ONE fused C-ABI call (jq_eval_f_grad) shared with
+    eval_grad_f_par through the handle's cache; a `wa` without `eval_f_grad` (host mocks) takes the reference's own steps."""
     pcof = np.asarray(pcof, dtype=np.float64)
+    if hasattr(wa, "eval_f_grad"):
+        return _fused(pcof, params, wa, nodes, weights)["f"]
     if _stale(pcof, params):
         eval_f_g_grad(pcof, params, wa, nodes, weights, True)
     f = params.last_infidelity + params.last_leak if params.objFuncType == 1 else params.last_infidelity
@@ -338,6 +437,9 @@ def eval_f_par(pcof, params, wa, nodes=(0.0,), weights=(1.0,)):
 
 def eval_g_par(pcof, g, params, wa, nodes=(0.0,), weights=(1.0,)):
     pcof = np.asarray(pcof, dtype=np.float64)
+    if hasattr(wa, "eval_f_grad"):
+        g[0] = _fused(pcof, params, wa, nodes, weights)["leak"]
+        return g[0]
     if _stale(pcof, params):
         eval_f_g_grad(pcof, params, wa, nodes, weights, True)
     g[0] = params.last_leak
@@ -346,9 +448,12 @@ def eval_g_par(pcof, g, params, wa, nodes=(0.0,), weights=(1.0,)):
 
 def eval_grad_f_par(pcof, grad_f, params, wa, nodes=(0.0,), weights=(1.0,)):
     pcof = np.asarray(pcof, dtype=np.float64)
-    if _stale(pcof, params):
-        eval_f_g_grad(pcof, params, wa, nodes, weights, True)
-    grad_f[:] = params.last_infidelity_grad + tikhonov_grad(pcof, params)
+    if hasattr(wa, "eval_f_grad"):
+        grad_f[:] = _fused(pcof, params, wa, nodes, weights)["grad_f"]
+    else:
+        if _stale(pcof, params):
+            eval_f_g_grad(pcof, params, wa, nodes, weights, True)
+        grad_f[:] = params.last_infidelity_grad + tikhonov_grad(pcof, params)
     if params.save_pcof_hist:
         params.pcof_hist.append(pcof.copy())
 
@@ -359,6 +464,12 @@ def eval_jac_g_par(pcof, rows, cols, jac_g, params, wa, nodes=(0.0,), weights=(1
         if len(rows) > 0:
             rows[:] = 1
             cols[:] = np.arange(1, len(pcof) + 1)
+        return
+    if hasattr(wa, "eval_f_grad"):
+        r = _fused(pcof, params, wa, nodes, weights)
+        if r["evaluated"]:
+            return                  # the reference returns without filling jac_g when it had to re-evaluate (:169-173)
+        jac_g[:] = r["leakgrad"]
         return
     if _stale(pcof, params):
         eval_f_g_grad(pcof, params, wa, nodes, weights, True)

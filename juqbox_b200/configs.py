@@ -37,7 +37,7 @@ class Config:
     @property
     def nCoeff(self) -> int:
         p = self.params
-        return 2 * p.Ncoupled * p.Nfreq * self.D1
+        return 2 * (p.Ncoupled + p.Nunc) * p.Nfreq * self.D1
 
 
 def lowering(nt: int) -> np.ndarray:
@@ -287,6 +287,31 @@ def _ex_rabi() -> Config:
     return Config("rabi", p, pc, D1, [maxpar])
 
 
+def _ex_rabi_lab(T: float = 100.0, Pmin: int = 100) -> Config:
+    # examples/rabi-lab.jl: the single-qubit pi-pulse in the LAB frame, one UNCOUPLED control a + a' with two splines (p, q):
+    # f(t) = 2 (p(t) cos(2 pi fa t) - q(t) sin(2 pi fa t))  (KS!, src/evalobjgrad.jl:2372-2387); target not rotated (:79-80)
+    N, Ng, Ntot = 2, 0, 2
+    fa, xa = 5.0, 2 * 0.1099
+    theta, aOmega = np.pi / 4, np.pi / 100.0
+    ut = np.eye(Ntot, N, dtype=complex)
+    ut[0, 0] = math.cos(aOmega * T)
+    ut[1, 0] = -(math.sin(theta) + 1j * math.cos(theta)) * math.sin(aOmega * T)
+    ut[0, 1] = (math.sin(theta) - 1j * math.cos(theta)) * math.sin(aOmega * T)
+    ut[1, 1] = math.cos(aOmega * T)
+    num = np.diag(np.arange(Ntot, dtype=float))
+    H0 = 2 * np.pi * (fa * num - 0.5 * xa * (num @ num - num))
+    a = lowering(Ntot)
+    maxpar = aOmega
+    nsteps = calculate_timestep(T, H0, [a + a.T], [np.zeros((Ntot, Ntot))], [maxpar], Pmin)
+    p = objparams([N], [Ng], T, nsteps, Uinit=np.eye(Ntot, N), Utarget=ut, Cfreq=np.zeros((1, 1)), Rfreq=[fa],
+                  Hconst=H0, Hunc_ops=[a + a.T])
+    D1 = 3
+    pc = np.zeros(2 * D1)
+    pc[:D1] = aOmega * math.cos(theta)
+    pc[D1:] = aOmega * math.sin(theta)
+    return Config("rabi_lab", p, pc, D1, [maxpar])
+
+
 def _ex_cnot1() -> Config:
     # examples/cnot1-setup.jl (Integrator_id = 2 there; built here with Stormer-Verlet)
     N, Ng = 4, 2
@@ -445,7 +470,7 @@ def example(name: str, **kw) -> Config:
     """One of the five BASELINE.json configurations (keyword arguments: the knobs the example script itself exposes,
     e.g. example("cnot2", T=100.0))."""
     return {"rabi": _ex_rabi, "cnot1": _ex_cnot1, "cnot2": _ex_cnot2, "cnot3": _ex_cnot3,
-            "risk_neutral": _ex_risk_neutral}[name](**kw)
+            "risk_neutral": _ex_risk_neutral, "rabi_lab": _ex_rabi_lab}[name](**kw)
 
 
 def synthetic_pcof(cfg: Config, nbatch: int, seed_offset: int = 0) -> np.ndarray:

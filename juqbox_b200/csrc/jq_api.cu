@@ -6,7 +6,9 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -48,7 +50,7 @@ struct jq_handle {
     int comm_rank = 0, comm_size = 1;
     int device = 0;
     DevProblem P{};
-    int n = 0, m = 0, Nc = 0, Nfreq = 0;
+    int n = 0, m = 0, Nc = 0, Nfreq = 0, pfid = 2;       // Nc: coupled + uncoupled controls
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void *> owned;          // device allocations freed at destroy
@@ -65,6 +67,10 @@ struct jq_handle {
     size_t cap_traj = 0, cap_grad = 0, cap_igrad = 0;
     double *d_in = nullptr;  size_t cap_in = 0;    // staged host inputs
     double *d_out = nullptr; size_t cap_out = 0;   // staged host outputs
+    // last-evaluation cache of the fused callback entry (jq_eval_f_grad; src/ipopt_interface.jl:27-31)
+    bool cache_valid = false;
+    std::vector<double> c_pcof, c_shift, c_w, c_igrad, c_lgrad;
+    double c_infid = 0.0, c_leak = 0.0;
     // last-evaluation facts
     int last_kernel = 0, last_launches = 0, last_ctas = 0, last_regs = 0, last_tpc = 1;
     size_t last_smem = 0;
@@ -195,15 +201,19 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
     if (!pb || !out) return fail(JQ_ERR_ARG, "jq_create: null argument");
     *out = nullptr;
     if (pb->n < 1 || pb->m < 1 || pb->m > pb->n) return fail(JQ_ERR_ARG, "jq_create: need 1 <= m <= n (n=%d, m=%d)", pb->n, pb->m);
-    if (pb->ncoupled < 1) return fail(JQ_ERR_ARG, "jq_create: ncoupled must be >= 1 (uncoupled-only controls are not on this path)");
+    if (pb->ncoupled < 0 || pb->nuncoupled < 0 || pb->ncoupled + pb->nuncoupled < 1)
+        return fail(JQ_ERR_ARG, "jq_create: need at least one control Hamiltonian (ncoupled + nuncoupled >= 1)");
+    if (pb->ncoupled + pb->nuncoupled > JQ_MAX_CTRL) return fail(JQ_ERR_ARG, "jq_create: at most %d control Hamiltonians", JQ_MAX_CTRL);
     if (pb->nfreq < 1 || pb->nsteps < 1 || !(pb->T > 0.0) || pb->neumann_terms < 0)
         return fail(JQ_ERR_ARG, "jq_create: need nfreq >= 1, nsteps >= 1, T > 0, neumann_terms >= 0");
     if (pb->linear_solver < 0 || pb->linear_solver > 2)
         return fail(JQ_ERR_ARG, "jq_create: linear_solver must be NEUMANN_SOLVER (1) or JACOBI_SOLVER (2), got %d", pb->linear_solver);
-    if (pb->pfid_type != 2) return fail(JQ_ERR_ARG, "jq_create: only pFidType == 2 is built (got %d)", pb->pfid_type);
+    if (pb->pfid_type < 1 || pb->pfid_type > 4) return fail(JQ_ERR_ARG, "jq_create: pFidType must be 1, 2, 3 or 4 (got %d)", pb->pfid_type);
     if (pb->obj_func_type < 1 || pb->obj_func_type > 3) return fail(JQ_ERR_ARG, "jq_create: objFuncType must be 1, 2 or 3");
-    if (!pb->uinit || !pb->vtarget_r || !pb->vtarget_i || !pb->wdiag || !pb->cfreq || !pb->hsym || !pb->hanti)
+    if (!pb->uinit || !pb->vtarget_r || !pb->vtarget_i || !pb->wdiag || !pb->cfreq || (pb->ncoupled > 0 && (!pb->hsym || !pb->hanti)))
         return fail(JQ_ERR_ARG, "jq_create: null problem array");
+    if (pb->nuncoupled > 0 && (!pb->hunc || !pb->unc_is_symm || !pb->unc_rfreq)) return fail(JQ_ERR_ARG, "jq_create: null uncoupled-control array");
+    if (pb->wmat_imag && !pb->wmat_real) return fail(JQ_ERR_ARG, "jq_create: wmat_imag needs wmat_real");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(JQ_ERR_CUDA, "jq_create: no CUDA device (there is no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(JQ_ERR_ARG, "jq_create: device %d out of range (%d devices)", device, ndev);
@@ -211,11 +221,25 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
 
     jq_handle *h = new jq_handle();
     h->device = device;
-    const int n = pb->n, m = pb->m, Nc = pb->ncoupled;
-    h->n = n; h->m = m; h->Nc = Nc; h->Nfreq = pb->nfreq;
+    // Controls as the kernels see them: the coupled pairs first, then one entry per uncoupled control with its operator in the
+    // Hsym slot (symmetric, added to K) or in the Hanti slot (antisymmetric, added to S) and an empty partner (KS!, :2372-2387).
+    const int n = pb->n, m = pb->m, Nc = pb->ncoupled + pb->nuncoupled;
+    h->n = n; h->m = m; h->Nc = Nc; h->Nfreq = pb->nfreq; h->pfid = pb->pfid_type;
+    const jq_operator empty{JQ_DENSE, 0, nullptr, nullptr, nullptr};
+    std::vector<double> zeros((size_t)n * n, 0.0);
+    jq_operator zero_op = empty;
+    zero_op.nnz = (int64_t)n * n; zero_op.nzval = zeros.data();
     int rc = append_rows(pb->h0, n, true, h->rowptr, h->col, h->val, "Hconst");
-    for (int q = 0; q < Nc && rc == 0; ++q) rc = append_rows(pb->hsym[q], n, false, h->rowptr, h->col, h->val, "Hsym_ops");
-    for (int q = 0; q < Nc && rc == 0; ++q) rc = append_rows(pb->hanti[q], n, false, h->rowptr, h->col, h->val, "Hanti_ops");
+    for (int q = 0; q < Nc && rc == 0; ++q) {
+        const bool unc = q >= pb->ncoupled;
+        const int u = q - pb->ncoupled;
+        rc = append_rows(!unc ? pb->hsym[q] : (pb->unc_is_symm[u] ? pb->hunc[u] : zero_op), n, false, h->rowptr, h->col, h->val, unc ? "Hunc_ops" : "Hsym_ops");
+    }
+    for (int q = 0; q < Nc && rc == 0; ++q) {
+        const bool unc = q >= pb->ncoupled;
+        const int u = q - pb->ncoupled;
+        rc = append_rows(!unc ? pb->hanti[q] : (pb->unc_is_symm[u] ? zero_op : pb->hunc[u]), n, false, h->rowptr, h->col, h->val, unc ? "Hunc_ops" : "Hanti_ops");
+    }
     if (rc) { delete h; return rc; }
     std::vector<int> h0diag(n);
     for (int r = 0; r < n; ++r)
@@ -224,6 +248,12 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
 
     DevProblem &P = h->P;
     P.n = n; P.m = m; P.Nc = Nc; P.Nfreq = pb->nfreq; P.J = pb->neumann_terms; P.objFuncType = pb->obj_func_type;
+    P.pFidType = pb->pfid_type; P.globalPhase = pb->global_phase; P.any_unc = pb->nuncoupled > 0;
+    for (int q = 0; q < JQ_MAX_CTRL; ++q) { P.ctrl_kind[q] = 0; P.ctrl_rfreq[q] = 0.0; }
+    for (int u = 0; u < pb->nuncoupled; ++u) {
+        P.ctrl_kind[pb->ncoupled + u] = pb->unc_is_symm[u] ? 1 : 2;
+        P.ctrl_rfreq[pb->ncoupled + u] = pb->unc_rfreq[u];
+    }
     P.solver = pb->linear_solver == 2 ? 2 : 1; P.tol = pb->solver_tol;
     P.nsteps = pb->nsteps; P.T = pb->T;
     double *tmp = nullptr;
@@ -244,6 +274,9 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
     P.vtr = h->d_vtr; P.vti = h->d_vti;
     UP(pb->wdiag, n, P.wdiag);
     UP(pb->cfreq, Nc * pb->nfreq, P.cfreq);
+    P.wreal = P.wimag = nullptr;
+    if (pb->wmat_real) UP(pb->wmat_real, (size_t)n * n, P.wreal);
+    if (pb->wmat_imag) UP(pb->wmat_imag, (size_t)n * n, P.wimag);
     UP(h->val.data(), h->val.size(), P.val);
     UPI(h->rowptr.data(), h->rowptr.size(), P.rowptr);
     UPI(h->col.data(), h->col.size(), P.col);
@@ -259,8 +292,8 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
     h->slot = jq_slot_plan_create(P, H, pb->wdiag, h->slot_reason, sizeof(h->slot_reason));
     h->fiber = jq_fiber_plan_create(P, H, pb->wdiag, h->fiber_reason, sizeof(h->fiber_reason));
     {
-        const char *nt = getenv("JQ_TILE_NT");      // development: number of tiled directions of the tile layout (default 2)
-        h->tile = jq_tile_plan_create(P, H, pb->wdiag, nt ? atoi(nt) : 2, h->tile_reason, sizeof(h->tile_reason));
+        const char *nt = getenv("JQ_TILE_NT");      // development: number of tiled directions of the tile layout (default: all)
+        h->tile = jq_tile_plan_create(P, H, pb->wdiag, nt ? atoi(nt) : Nc, h->tile_reason, sizeof(h->tile_reason));
     }
     *out = h;
     return 0;
@@ -289,7 +322,31 @@ extern "C" int jq_update_target(jq_handle *h, const double *vr, const double *vi
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(h->d_vtr, vr, sizeof(double) * h->n * h->m, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->d_vti, vi, sizeof(double) * h->n * h->m, cudaMemcpyHostToDevice));
+    h->cache_valid = false;
     return 0;
+}
+
+extern "C" int jq_cache_invalidate(jq_handle *h) {
+    if (!h) return fail(JQ_ERR_ARG, "jq_cache_invalidate: null handle");
+    h->cache_valid = false;
+    return 0;
+}
+
+extern "C" int64_t jq_abi_info(int32_t what) {
+    switch (what) {
+    case 0: return 2;                                   // ABI version (2: jq_eval_f_grad, jq_abi_info, pFidType / dense weights / uncoupled controls)
+    case 1: return (int64_t)sizeof(jq_problem);
+    case 2: return (int64_t)sizeof(jq_operator);
+    case 3: return (int64_t)offsetof(jq_problem, nsteps);
+    case 4: return (int64_t)offsetof(jq_problem, T);
+    case 5: return (int64_t)offsetof(jq_problem, uinit);
+    case 6: return (int64_t)offsetof(jq_problem, h0);
+    case 7: return (int64_t)offsetof(jq_problem, hsym);
+    case 8: return (int64_t)offsetof(jq_problem, solver_tol);
+    case 9: return (int64_t)offsetof(jq_operator, nnz);
+    case 10: return (int64_t)offsetof(jq_operator, nzval);
+    default: return -1;
+    }
 }
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
@@ -437,17 +494,20 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
     return 0;
 }
 
-static int check_batch_args(jq_handle *h, int nbatch, const double *pcof, int npar, int nsamples, const double *shift) {
+static int check_batch_args(jq_handle *h, int nbatch, const double *pcof, int npar, int nsamples, const double *shift,
+                            bool empty_shard_ok = false) {
     if (!h) return fail(JQ_ERR_ARG, "null handle");
     if (nbatch < 1 || !pcof) return fail(JQ_ERR_ARG, "need nbatch >= 1 and a pcof array");
     const int nsig = 2 * h->Nc;
+    npar -= h->pfid == 3 ? 1 : 0;              // pFidType 3: the last entry is the global phase (src/evalobjgrad.jl:591-596)
     if (npar % nsig != 0 || npar < 3 * nsig)   // src/evalobjgrad.jl:604-606
         return fail(JQ_ERR_PCOF_LENGTH, "pcof must have an even number of elements >= %d, not %d", 3 * nsig, npar);
     if (npar % (nsig * h->Nfreq) != 0 || npar / (nsig * h->Nfreq) < 3)   // src/bsplines.jl:177-181 (and k >= 3 needs D1 >= 3)
-        return fail(JQ_ERR_PCOF_LENGTH, "Inconsistent number of coefficients and size of parameter vector (nCoeff = %d, Nfreq = %d, Ncoupled = %d)", npar, h->Nfreq, h->Nc);
-    if (nsamples < 1) return fail(JQ_ERR_ARG, "nsamples must be >= 1");
+        return fail(JQ_ERR_PCOF_LENGTH, "Inconsistent number of coefficients and size of parameter vector (nCoeff = %d, Nfreq = %d, Ncoupled + Nunc = %d)", npar, h->Nfreq, h->Nc);
+    // an empty sample shard (more ranks than quadrature nodes) contributes zeros and still joins the all-reduce
+    if (nsamples < (empty_shard_ok ? 0 : 1)) return fail(JQ_ERR_ARG, "nsamples must be >= 1 (0 only with weights: an empty sample shard)");
     if ((long long)nbatch * nsamples > 0x7fffffffLL) return fail(JQ_ERR_ARG, "nbatch * nsamples exceeds 2^31 - 1 trajectories per call");
-    if (!shift && nsamples != 1) return fail(JQ_ERR_ARG, "nsamples > 1 needs h0_diag_shift");
+    if (!shift && nsamples > 1) return fail(JQ_ERR_ARG, "nsamples > 1 needs h0_diag_shift");
     return 0;
 }
 
@@ -455,7 +515,7 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
                                             const double *shift, const double *weights, int32_t evaladjoint, double *infid,
                                             double *leak, double *trace_infid, double *grad, double *infidgrad, double *leakgrad,
                                             void *cuda_stream) {
-    int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift);
+    int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift, weights != nullptr);
     if (rc) return rc;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -464,11 +524,15 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     if (evaladjoint && (rc = grow(&h->d_grad, &h->cap_grad, ntraj * npar)) != 0) return rc;
     if (evaladjoint && h->P.objFuncType != 1 && (rc = grow(&h->d_igrad, &h->cap_igrad, ntraj * npar)) != 0) return rc;
 
+    // npar is the caller's vector length: the spline coefficients, plus the global phase as last entry for pFidType 3; gradients
+    // have the same length, so the finalize kernels just see npar columns
+    const int nspl = npar - (h->pfid == 3 ? 1 : 0);
     LaunchArgs A{};
-    A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = evaladjoint ? 1 : 0;
+    A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = nspl; A.D1 = nspl / (2 * h->Nc * h->Nfreq); A.evaladjoint = evaladjoint ? 1 : 0;
+    A.pstride = npar; A.gstride = npar;
     A.pcof = pcof; A.shift = shift; A.scal = h->d_scal; A.grad = h->d_grad; A.infidgrad = h->P.objFuncType != 1 ? h->d_igrad : nullptr;
 
-    if ((rc = launch_trajectories(h, A, st)) != 0) return rc;
+    if (ntraj > 0 && (rc = launch_trajectories(h, A, st)) != 0) return rc;
     const int nout = weights ? nbatch : (int)ntraj;
     const long long total = (long long)nout * (npar + 1);
     const int fb = 256, fg = (int)std::min<long long>((total + fb - 1) / fb, 148 * 8);
@@ -483,18 +547,117 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     if (h->comm && weights && h->comm_size > 1) {
         // the path's one exchange step: weighted sums over the sample shards of all ranks (sum, FP64), one grouped call
         const size_t nb = (size_t)nbatch, ng = (size_t)nbatch * npar;
-        NC(g_nccl.GroupStart());
-        if (infid) NC(g_nccl.AllReduce(infid, infid, nb, 8 /*ncclDouble*/, 0 /*ncclSum*/, h->comm, st));
-        if (leak) NC(g_nccl.AllReduce(leak, leak, nb, 8, 0, h->comm, st));
-        if (trace_infid) NC(g_nccl.AllReduce(trace_infid, trace_infid, nb, 8, 0, h->comm, st));
+        // every call between GroupStart and GroupEnd is attempted and the group is always closed, so an error on one rank
+        // cannot leave the communicator inside an open group
+        int nrc = g_nccl.GroupStart();
+        auto red = [&](double *buf, size_t cnt) { if (buf && nrc == 0) nrc = g_nccl.AllReduce(buf, buf, cnt, 8 /*ncclDouble*/, 0 /*ncclSum*/, h->comm, st); };
+        red(infid, nb); red(leak, nb); red(trace_infid, nb);
         if (A.evaladjoint) {
-            if (grad) NC(g_nccl.AllReduce(grad, grad, ng, 8, 0, h->comm, st));
-            if (infidgrad) NC(g_nccl.AllReduce(infidgrad, infidgrad, ng, 8, 0, h->comm, st));
-            if (leakgrad && h->P.objFuncType != 1) NC(g_nccl.AllReduce(leakgrad, leakgrad, ng, 8, 0, h->comm, st));
+            red(grad, ng); red(infidgrad, ng);
+            if (h->P.objFuncType != 1) red(leakgrad, ng);
         }
-        NC(g_nccl.GroupEnd());
+        const int erc = g_nccl.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        if (nrc != 0) return fail(JQ_ERR_CUDA, "ncclAllReduce of the weighted sample sums: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "nccl error");
         h->last_launches = 3;
     }
+    return 0;
+}
+
+
+// Tikhonov + packing of the fused callback entry: out = [f, infid, leak, grad_f[npar], leakgrad[npar], infidgrad[npar]]; one block, the
+// squared norm summed in a fixed order (thread-strided partials, then thread order) so that f is bit-reproducible.
+__global__ void __launch_bounds__(256) jq_tikhonov_kernel(int npar, int objFuncType, double tik0, const double *pcof, const double *prior,
+                                                          const double *infid, const double *leak, const double *igrad, const double *lgrad, double *out) {
+    __shared__ double part[256];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < npar; k += blockDim.x) {
+        const double d = prior ? pcof[k] - prior[k] : pcof[k];
+        s += d * d;
+        out[3 + k] = igrad[k] + (2.0 * tik0 / npar) * d;                   // src/evalobjgrad.jl:2339-2349, ipopt_interface.jl:136-141
+        out[3 + npar + k] = objFuncType != 1 ? lgrad[k] : 0.0;
+        out[3 + 2 * npar + k] = igrad[k];                                  // last_infidelity_grad as the reference stores it (cache)
+    }
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double pen = 0.0;
+        for (int j = 0; j < blockDim.x; ++j) pen += part[j];
+        const double f = objFuncType == 1 ? infid[0] + leak[0] : infid[0];  // ipopt_interface.jl:89-93
+        out[0] = f + tik0 * pen / npar;                                    // :96-98, evalobjgrad.jl:2291-2316
+        out[1] = infid[0];
+        out[2] = leak[0];
+    }
+}
+
+extern "C" int jq_eval_f_grad(jq_handle *h, const double *pcof, int32_t npar, int32_t nsamples, const double *shift, const double *weights,
+                              double tik0, const double *prior, double *f, double *grad_f, double *infid, double *leak, double *leakgrad,
+                              int32_t *evaluated) {
+    int rc = check_batch_args(h, 1, pcof, npar, nsamples, shift, weights != nullptr);
+    if (rc) return rc;
+    const size_t n_shift = shift ? (size_t)nsamples * h->n : 0, n_w = weights ? (size_t)nsamples : 0;
+    // the reference's cache test (src/ipopt_interface.jl:84): norm(pcof - last_pcof) > 1e-15; shards / weights compared exactly
+    bool hit = h->cache_valid && h->c_pcof.size() == (size_t)npar && h->c_shift.size() == n_shift && h->c_w.size() == n_w;
+    if (hit) {
+        double d2 = 0.0;
+        for (int k = 0; k < npar; ++k) { const double d = pcof[k] - h->c_pcof[k]; d2 += d * d; }
+        hit = !(sqrt(d2) > 1.0e-15) && (n_shift == 0 || memcmp(shift, h->c_shift.data(), n_shift * sizeof(double)) == 0) &&
+              (n_w == 0 || memcmp(weights, h->c_w.data(), n_w * sizeof(double)) == 0);
+    }
+    if (evaluated) *evaluated = hit ? 0 : 1;
+    if (!hit) {
+        CU(cudaSetDevice(h->device));
+        h->cache_valid = false;
+        const bool two = h->P.objFuncType != 1;
+        const size_t n_in = (size_t)npar + n_shift + (n_w ? n_w : 1) + (prior ? npar : 0);
+        const size_t n_out = 3 + (size_t)npar * (two ? 3 : 1) + 3 + 3 * (size_t)npar;
+        if ((rc = grow(&h->d_in, &h->cap_in, n_in)) != 0) return rc;
+        if ((rc = grow(&h->d_out, &h->cap_out, n_out)) != 0) return rc;
+        cudaStream_t st = h->stream;
+        double *d_pcof = h->d_in, *d_shift = shift ? d_pcof + npar : nullptr, *d_w = d_pcof + npar + n_shift;
+        double *d_prior = prior ? d_w + (n_w ? n_w : 1) : nullptr;
+        CU(cudaMemcpyAsync(d_pcof, pcof, (size_t)npar * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (n_shift) CU(cudaMemcpyAsync(d_shift, shift, n_shift * sizeof(double), cudaMemcpyHostToDevice, st));
+        const double one = 1.0;
+        if (n_w) CU(cudaMemcpyAsync(d_w, weights, n_w * sizeof(double), cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpyAsync(d_w, &one, sizeof(double), cudaMemcpyHostToDevice, st));      // no weights: the single sample has weight 1
+        if (prior) CU(cudaMemcpyAsync(d_prior, prior, (size_t)npar * sizeof(double), cudaMemcpyHostToDevice, st));
+        double *o_infid = h->d_out, *o_leak = o_infid + 1, *o_tinf = o_leak + 1, *o_g = o_tinf + 1;
+        double *o_ig = two ? o_g + npar : nullptr, *o_lg = two ? o_ig + npar : nullptr;
+        double *o_pack = o_g + (size_t)npar * (two ? 3 : 1);
+        rc = jq_traceobjgrad_batch_device(h, 1, d_pcof, npar, nsamples, d_shift, d_w, 1, o_infid, o_leak, o_tinf, o_g, o_ig, o_lg, st);
+        if (rc) return rc;
+        jq_tikhonov_kernel<<<1, 256, 0, st>>>(npar, h->P.objFuncType, tik0, d_pcof, d_prior, o_infid, o_leak, two ? o_ig : o_g, o_lg, o_pack);
+        CU(cudaGetLastError());
+        h->last_launches += 1;
+        std::vector<double> pack(3 + 3 * (size_t)npar);
+        CU(cudaMemcpyAsync(pack.data(), o_pack, pack.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // store what the reference stores (last_infidelity, last_leak, last_infidelity_grad, last_leak_grad): the Tikhonov terms are
+        // re-applied on a cache hit because tik0 / prior are inputs of every call
+        h->c_pcof.assign(pcof, pcof + npar);
+        h->c_shift.assign(shift ? shift : pcof, shift ? shift + n_shift : pcof);
+        h->c_w.assign(weights ? weights : pcof, weights ? weights + n_w : pcof);
+        h->c_infid = pack[1]; h->c_leak = pack[2];
+        h->c_lgrad.assign(pack.begin() + 3 + npar, pack.begin() + 3 + 2 * (size_t)npar);
+        h->c_igrad.assign(pack.begin() + 3 + 2 * (size_t)npar, pack.end());
+        h->cache_valid = true;
+        if (f) *f = pack[0];
+        if (infid) *infid = pack[1];
+        if (leak) *leak = pack[2];
+        if (grad_f) memcpy(grad_f, pack.data() + 3, (size_t)npar * sizeof(double));
+        if (leakgrad && two) memcpy(leakgrad, pack.data() + 3 + npar, (size_t)npar * sizeof(double));
+        return 0;
+    }
+    // cache hit: no launch, no transfer
+    double pen = 0.0;
+    for (int k = 0; k < npar; ++k) { const double d = prior ? pcof[k] - prior[k] : pcof[k]; pen += d * d; }
+    if (f) *f = (h->P.objFuncType == 1 ? h->c_infid + h->c_leak : h->c_infid) + tik0 * pen / npar;
+    if (infid) *infid = h->c_infid;
+    if (leak) *leak = h->c_leak;
+    if (grad_f)
+        for (int k = 0; k < npar; ++k) grad_f[k] = h->c_igrad[k] + (2.0 * tik0 / npar) * (prior ? pcof[k] - prior[k] : pcof[k]);
+    if (leakgrad && h->P.objFuncType != 1) memcpy(leakgrad, h->c_lgrad.data(), (size_t)npar * sizeof(double));
     return 0;
 }
 
@@ -516,8 +679,10 @@ extern "C" int jq_eval_forward(jq_handle *h, int32_t nbatch, const double *pcof,
     double *d_pcof = h->d_in, *d_shift = shift ? h->d_in + n_pcof : nullptr;
     CU(cudaMemcpyAsync(d_pcof, pcof, n_pcof * sizeof(double), cudaMemcpyHostToDevice, st));
     if (shift) CU(cudaMemcpyAsync(d_shift, shift, n_shift * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int nspl = npar - (h->pfid == 3 ? 1 : 0);
     LaunchArgs A{};
-    A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = npar; A.D1 = npar / (2 * h->Nc * h->Nfreq); A.evaladjoint = 0;
+    A.ntraj = (int)ntraj; A.nsamples = nsamples; A.Npar = nspl; A.D1 = nspl / (2 * h->Nc * h->Nfreq); A.evaladjoint = 0;
+    A.pstride = npar; A.gstride = npar;
     A.pcof = d_pcof; A.shift = d_shift; A.scal = h->d_scal; A.grad = nullptr; A.infidgrad = nullptr;
     A.hist_r = h->d_out; A.hist_i = h->d_out + n_hist; A.save_every = save_every; A.nsave = nsave;
     if ((rc = launch_trajectories(h, A, st)) != 0) return rc;      // same kernel choice as jq_traceobjgrad_batch
@@ -545,7 +710,7 @@ extern "C" int jq_eval_controls(jq_handle *h, const double *pcof, int32_t npar, 
     cudaStream_t st = h->stream;
     CU(cudaMemcpyAsync(h->d_in, pcof, (size_t)npar * sizeof(double), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->d_in + npar, times, (size_t)ntimes * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(jq_controls_launch(h->P, npar / (2 * h->Nc * h->Nfreq), h->d_in, ntimes, h->d_in + npar, h->d_out, h->d_out + nout, st));
+    CU(jq_controls_launch(h->P, (npar - (h->pfid == 3 ? 1 : 0)) / (2 * h->Nc * h->Nfreq), h->d_in, ntimes, h->d_in + npar, h->d_out, h->d_out + nout, st));
     CU(cudaMemcpyAsync(p, h->d_out, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(q, h->d_out + nout, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -555,20 +720,20 @@ extern "C" int jq_eval_controls(jq_handle *h, const double *pcof, int32_t npar, 
 extern "C" int jq_traceobjgrad_batch(jq_handle *h, int32_t nbatch, const double *pcof, int32_t npar, int32_t nsamples,
                                      const double *shift, const double *weights, int32_t evaladjoint, double *infid, double *leak,
                                      double *trace_infid, double *grad, double *infidgrad, double *leakgrad) {
-    int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift);
+    int rc = check_batch_args(h, nbatch, pcof, npar, nsamples, shift, weights != nullptr);
     if (rc) return rc;
     CU(cudaSetDevice(h->device));
     const size_t ntraj = (size_t)nbatch * nsamples, nout = weights ? (size_t)nbatch : ntraj;
     const size_t n_pcof = (size_t)nbatch * npar, n_shift = shift ? (size_t)nsamples * h->n : 0, n_w = weights ? (size_t)nsamples : 0;
-    if ((rc = grow(&h->d_in, &h->cap_in, n_pcof + n_shift + n_w)) != 0) return rc;
+    if ((rc = grow(&h->d_in, &h->cap_in, n_pcof + n_shift + n_w + 1)) != 0) return rc;      // + 1: a valid weights pointer for an empty shard
     const bool want_g = evaladjoint && grad, want_ig = evaladjoint && infidgrad, want_lg = evaladjoint && leakgrad && h->P.objFuncType != 1;
     const size_t n_outs = 3 * nout + (size_t)(want_g + want_ig + want_lg) * nout * npar;
     if ((rc = grow(&h->d_out, &h->cap_out, n_outs)) != 0) return rc;
     cudaStream_t st = h->stream;
     double *d_pcof = h->d_in, *d_shift = shift ? h->d_in + n_pcof : nullptr, *d_w = weights ? h->d_in + n_pcof + n_shift : nullptr;
     CU(cudaMemcpyAsync(d_pcof, pcof, n_pcof * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (shift) CU(cudaMemcpyAsync(d_shift, shift, n_shift * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (weights) CU(cudaMemcpyAsync(d_w, weights, n_w * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (shift && n_shift) CU(cudaMemcpyAsync(d_shift, shift, n_shift * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (weights && n_w) CU(cudaMemcpyAsync(d_w, weights, n_w * sizeof(double), cudaMemcpyHostToDevice, st));
     double *o_infid = h->d_out, *o_leak = o_infid + nout, *o_tinf = o_leak + nout, *cur = o_tinf + nout;
     double *o_g = nullptr, *o_ig = nullptr, *o_lg = nullptr;
     if (want_g) { o_g = cur; cur += nout * npar; }

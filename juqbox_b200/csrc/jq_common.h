@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define JQ_MAX_CTRL 8
+
 // Problem data as the kernels see it (device pointers).  Operators are row-wise CSR, one per
 // o in {0: Hconst (diagonal included even if zero), 1..Nc: Hsym_q, Nc+1..2Nc: Hanti_q}.
 struct DevProblem {
@@ -16,16 +18,27 @@ struct DevProblem {
     const int *col;
     const double *val;
     const int *h0diag;     // n: position of H0[i,i] inside col/val (always present)
+    // --- SURVEY 8f rank 3 ---
+    int pFidType;          // 1, 2, 3 or 4 (src/evalobjgrad.jl:755-763); 3: the global phase is the last entry of every pcof vector
+    double globalPhase;    // params.globalPhase (pFidType 1 and 4)
+    const double *wreal, *wimag;   // dense n x n column-major weights (custom forbidden states) or nullptr -> Diagonal(wdiag)
+    // Controls 0..Nc-1 are uniform for the kernels: (Hsym_q, Hanti_q, p_q(t), q_q(t)).  An UNCOUPLED control (KS!, :2372-2387) is
+    // entered as kind 1 (symmetric Hunc: Hsym = Hunc, Hanti = 0, p = f, q = 0) or kind 2 (antisymmetric: Hanti = Hunc, q = f),
+    // with f(t) = 2 (p_spline cos(2 pi rfreq t) - q_spline sin(2 pi rfreq t)); kind 0 = coupled.
+    int ctrl_kind[JQ_MAX_CTRL];
+    double ctrl_rfreq[JQ_MAX_CTRL];
+    int any_unc;
 };
 
 // Per-launch arguments common to both kernels.
 struct LaunchArgs {
     int ntraj, nsamples, Npar, D1, evaladjoint;
-    const double *pcof;    // [nbatch][Npar]
+    int pstride, gstride;  // row stride of pcof and of grad / infidgrad: Npar, or Npar + 1 when the global phase rides along (pFidType 3)
+    const double *pcof;    // [nbatch][pstride]
     const double *shift;   // [nsamples][n] or nullptr
     double *scal;          // [ntraj][4]: infid, leak, trace_infid, spare
-    double *grad;          // [ntraj][Npar] total gradient
-    double *infidgrad;     // [ntraj][Npar] (objFuncType != 1) or nullptr
+    double *grad;          // [ntraj][gstride] total gradient
+    double *infidgrad;     // [ntraj][gstride] (objFuncType != 1) or nullptr
     // forward-history output (generic kernel only): state after every save_every-th step, [ntraj][nsave][n*m]
     double *hist_r, *hist_i;   // Re(psi) = vr, Im(psi) = -vi  (src/evalobjgrad.jl:679-680,750-751)
     int save_every;

@@ -22,8 +22,20 @@ struct Ctx {
     double *lrn, *lin, *lr05n, *li0n;
     double *rhs, *scr, *k1, *k2, *l1, *l2;
     double *pcof, *grad, *igrad, *ctrl, *shift, *red;
-    double dtknot;
+    double dtknot, tinv;
 };
+
+// Dense forbidden-state weights (src/evalobjgrad.jl:214-232): (W x)[i, j] for a column-major n x n W read through L1.
+__device__ __forceinline__ double wapply(const Ctx &c, const double *W, const double *x, int i, int j) {
+    const double *xc = x + j * c.n;
+    double s = 0.0;
+    for (int k = 0; k < c.n; ++k) s += W[i + (size_t)k * c.n] * xc[k];
+    return s;
+}
+// (wmat_real x)[i, j] for either form of the weights
+__device__ __forceinline__ double wreal_apply(const Ctx &c, const double *x, int e, int i, int j) {
+    return c.P->wreal ? wapply(c, c.P->wreal, x, i, j) : c.P->wdiag[i] * x[e];
+}
 
 __device__ __forceinline__ double op_apply(const Ctx &c, int o, const double *x, int i, int j) {
     const int *rp = c.P->rowptr + o * (c.n + 1);
@@ -79,7 +91,18 @@ __device__ void eval_controls(const Ctx &c, double t, double dt) {
     for (int idx = threadIdx.x; idx < 3 * nf; idx += GEN_THREADS) {
         const int level = idx / nf, func = idx % nf;
         const double tt = level == 0 ? t : (level == 1 ? t + 0.5 * dt : t + dt);
-        c.ctrl[idx] = bcarrier2(c, tt, func);
+        const int kind = c.P->ctrl_kind[func >> 1];
+        if (kind == 0) {
+            c.ctrl[idx] = bcarrier2(c, tt, func);
+        } else {                               // uncoupled control (KS!, src/evalobjgrad.jl:2372-2387): f = 2 (p cos - q sin) goes to K or to S
+            double v = 0.0;
+            if ((func & 1) == (kind == 2)) {
+                double sr, cr;
+                sincos(2.0 * M_PI * c.P->ctrl_rfreq[func >> 1] * tt, &sr, &cr);
+                v = 2.0 * (bcarrier2(c, tt, func & ~1) * cr - bcarrier2(c, tt, func | 1) * sr);
+            }
+            c.ctrl[idx] = v;
+        }
     }
     __syncthreads();
 }
@@ -142,9 +165,11 @@ __device__ void state_step(const Ctx &c, double h) {
 
 // src/StormerVerlet.jl:255-303 (forcing) / :365-406 (no forcing).  Forcing with diagonal W:
 // hr0 = W vr0 / T, hi0 = hi1 = W vi05 / T, hr1 = W vr / T  (src/evalobjgrad.jl:862,882-888).
+// General weights (:882-888): hr0 = Wr vr0 / T, hi0 = Wr vi05 / T, hr1 = (Wr vr + Wi vi05) / T, hi1 = hi0 - Wi vr / T.
 __device__ void adjoint_step(const Ctx &c, double *mu, double *nu, double *X, double h, bool forcing, double tinv) {
+    const double *Wi = c.P->wimag;
     FOR_E {
-        double f = forcing ? tinv * c.P->wdiag[i] * c.vr0[e] : 0.0;
+        double f = forcing ? tinv * wreal_apply(c, c.vr0, e, i, j) : 0.0;
         c.rhs[e] = applyS(c, 0, mu, i, j) - applyK(c, 1, nu, i, j) + f;
     }
     __syncthreads();
@@ -152,12 +177,13 @@ __device__ void adjoint_step(const Ctx &c, double *mu, double *nu, double *X, do
     FOR_E { mu[e] += 0.5 * h * c.k2[e]; X[e] = mu[e]; }
     __syncthreads();
     FOR_E {
-        double f = forcing ? tinv * c.P->wdiag[i] * c.vi05[e] : 0.0;
+        double f = forcing ? tinv * wreal_apply(c, c.vi05, e, i, j) : 0.0;
         c.l2[e] = applyK(c, 0, X, i, j) + applyS(c, 1, nu, i, j) + f;
     }
     __syncthreads();
     FOR_E {
-        double f = forcing ? tinv * c.P->wdiag[i] * c.vi05[e] : 0.0;
+        double f = forcing ? tinv * wreal_apply(c, c.vi05, e, i, j) : 0.0;
+        if (forcing && Wi) f -= tinv * wapply(c, Wi, c.vr, i, j);
         c.rhs[e] = applyS(c, 1, nu, i, j) + 0.5 * h * applyS(c, 1, c.l2, i, j) + applyK(c, 2, X, i, j) + f;
     }
     __syncthreads();
@@ -165,7 +191,8 @@ __device__ void adjoint_step(const Ctx &c, double *mu, double *nu, double *X, do
     FOR_E nu[e] += 0.5 * h * (c.l2[e] + c.l1[e]);
     __syncthreads();
     FOR_E {
-        double f = forcing ? tinv * c.P->wdiag[i] * c.vr[e] : 0.0;
+        double f = forcing ? tinv * wreal_apply(c, c.vr, e, i, j) : 0.0;
+        if (forcing && Wi) f += tinv * wapply(c, Wi, c.vi05, i, j);
         c.k1[e] = applyS(c, 2, X, i, j) - applyK(c, 1, nu, i, j) + f;
     }
     __syncthreads();
@@ -207,14 +234,25 @@ __device__ void grad_step(const Ctx &c, const double *lr05, const double *li, co
         }
         block_sum(c, T, 5);
         // threads (f, alpha) scatter into the 3 knots of each of the 3 time points; deterministic order
+        const int kind = c.P->ctrl_kind[q];
         for (int idx = threadIdx.x; idx < 2 * c.Nfreq; idx += GEN_THREADS) {
             const int fr = idx >> 1, alpha = idx & 1;
             const int base = 2 * q * c.Nfreq * c.D1 + fr * 2 * c.D1 + alpha * c.D1 - 1;
             const double om = c.P->cfreq[q + c.Nc * fr];
             for (int tp = 0; tp < 3; ++tp) {
                 const double tt = tp == 0 ? t0 : (tp == 1 ? t0 + dt : t0 + 0.5 * dt);
-                const double Pc = tp == 2 ? T[3] : -T[1];                       // multiplies grad p
-                const double Qc = tp == 0 ? -T[0] : (tp == 1 ? -T[2] : -T[4]);  // multiplies grad q
+                double Pc = tp == 2 ? T[3] : -T[1];                       // multiplies grad p
+                double Qc = tp == 0 ? -T[0] : (tp == 1 ? -T[2] : -T[4]);  // multiplies grad q
+                if (kind != 0) {
+                    // uncoupled control: the K-type (kind 1) or S-type (kind 2) trace combination multiplies grad f,
+                    // f = 2 (p cos(w t) - q sin(w t))  ->  d/dp: 2 cos, d/dq: -2 sin  (exact gradient of KS!'s model; the
+                    // reference's adjoint_grad_calc! :2621-2654 omits these factors, see oracle header)
+                    const double C0 = kind == 1 ? Pc : Qc;
+                    double sr, cr;
+                    sincos(2.0 * M_PI * c.P->ctrl_rfreq[q] * tt, &sr, &cr);
+                    Pc = 2.0 * cr * C0;
+                    Qc = -2.0 * sr * C0;
+                }
                 double sn, cs;
                 sincos(om * tt, &sn, &cs);
                 const double X = alpha == 0 ? Pc * cs + Qc * sn : Qc * cs - Pc * sn;
@@ -251,6 +289,7 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
     c.n = P.n; c.m = P.m; c.len = P.n * P.m; c.Nc = P.Nc; c.Nfreq = P.Nfreq; c.J = P.J;
     c.Npar = A.Npar; c.D1 = A.D1;
     c.dtknot = P.T / (A.D1 - 2);
+    c.tinv = 1.0 / P.T;
     double *p = sm;
     double **blk[] = {&c.vr, &c.vi, &c.vi05, &c.vr0, &c.lr, &c.li, &c.lr05, &c.li0, &c.lrn, &c.lin, &c.lr05n, &c.li0n,
                       &c.rhs, &c.scr, &c.k1, &c.k2, &c.l1, &c.l2};
@@ -268,7 +307,8 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
     const double tinv = 1.0 / P.T;
     for (int traj = blockIdx.x; traj < A.ntraj; traj += gridDim.x) {
         const int b = traj / A.nsamples, s = traj % A.nsamples;
-        for (int k = threadIdx.x; k < c.Npar; k += GEN_THREADS) { c.pcof[k] = A.pcof[(size_t)b * c.Npar + k]; c.grad[k] = 0.0; if (P.objFuncType != 1) c.igrad[k] = 0.0; }
+        for (int k = threadIdx.x; k < c.Npar; k += GEN_THREADS) { c.pcof[k] = A.pcof[(size_t)b * A.pstride + k]; c.grad[k] = 0.0; if (P.objFuncType != 1) c.igrad[k] = 0.0; }
+        const double phase = P.pFidType == 3 ? A.pcof[(size_t)b * A.pstride + c.Npar] : P.globalPhase;   // src/evalobjgrad.jl:591-596
         for (int k = threadIdx.x; k < c.n; k += GEN_THREADS) c.shift[k] = A.shift ? A.shift[(size_t)s * c.n + k] : 0.0;
         FOR_E { c.vr[e] = P.uinit[e]; c.vi[e] = 0.0; c.vi05[e] = 0.0; }
         __syncthreads();
@@ -278,12 +318,24 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
         double *hr = A.hist_r ? A.hist_r + (size_t)traj * A.nsave * c.len : nullptr;
         double *hi = A.hist_i ? A.hist_i + (size_t)traj * A.nsave * c.len : nullptr;
         if (hr) FOR_E { hr[e] = c.vr[e]; hi[e] = -c.vi[e]; }
+        const bool densew = P.wreal != nullptr;
         for (long long step = 0; step < P.nsteps; ++step) {
-            FOR_E pen += P.wdiag[i] * c.vr[e] * c.vr[e];                           // penalf2aTrap(vr)
-            eval_controls(c, t, dt);
+            if (!densew) { FOR_E pen += P.wdiag[i] * c.vr[e] * c.vr[e]; }          // penalf2aTrap(vr)
+            else {
+                FOR_E { pen += c.vr[e] * wapply(c, P.wreal, c.vr, i, j); c.vr0[e] = c.vr[e]; }   // dense penalf2aTrap (:2210-2223); vr0 for penalf2imag
+            }
+            eval_controls(c, t, dt);                                               // (its barrier also orders the vr0 copy)
             state_step(c, dt);
             t = t + dt;
-            FOR_E pen += P.wdiag[i] * (c.vr[e] * c.vr[e] + 2.0 * c.vi05[e] * c.vi05[e]);  // penalf2a(vr, vi05)
+            if (!densew) { FOR_E pen += P.wdiag[i] * (c.vr[e] * c.vr[e] + 2.0 * c.vi05[e] * c.vi05[e]); }  // penalf2a(vr, vi05)
+            else {
+                // dense penalf2a (:2183-2197) and -2 penalf2imag(vr0, vi05, wmat_imag) = -2 tr(vi05' Wi vr0) (:716-718,:2226-2228)
+                FOR_E {
+                    pen += c.vr[e] * wapply(c, P.wreal, c.vr, i, j) + 2.0 * c.vi05[e] * wapply(c, P.wreal, c.vi05, i, j);
+                    if (P.wimag) pen -= 2.0 * c.vi05[e] * wapply(c, P.wimag, c.vr0, i, j);
+                }
+                __syncthreads();                                                   // vr0 is rewritten at the top of the next step
+            }
             if (hr && (step + 1) % A.save_every == 0) {                                      // src/evalobjgrad.jl:2847-2849
                 const size_t o = (size_t)((step + 1) / A.save_every) * c.len;
                 FOR_E { hr[o + e] = c.vr[e]; hi[o + e] = -c.vi[e]; }
@@ -292,17 +344,28 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
         double re, im, pv[1] = {pen};
         block_sum(c, pv, 1);
         trace_fid(c, &re, &im);
-        const double infid = 1.0 - (re * re + im * im);
+        double sph, cph;
+        sincos(phase, &sph, &cph);
+        const int pfid = P.pFidType;
+        const double abs2 = re * re + im * im;
+        // src/evalobjgrad.jl:755-763: type 1: 1 + |s|^2 - 2 Re(s e^{-i phase}); type 2: 1 - |s|^2; types 3, 4: 1 - tracefidreal(v, e^{i phase} Vtg) = 1 - (Re s cos(phase) - Im s sin(phase))
+        const double infid = pfid == 1 ? 1.0 + abs2 - 2.0 * (re * cph + im * sph) : pfid == 2 ? 1.0 - abs2 : 1.0 - (re * cph - im * sph);
         const double leak = 0.5 * dt * tinv * pv[0];
         if (threadIdx.x == 0) {
             double *o = A.scal + (size_t)traj * 4;
-            o[0] = infid; o[1] = leak; o[2] = infid; o[3] = 0.0;
+            o[0] = infid; o[1] = leak; o[2] = 1.0 - abs2; o[3] = 0.0;      // traceInfidelity is always 1 - |s|^2 (:792)
         }
         if (!A.evaladjoint) { __syncthreads(); continue; }
 
         // ---------------- backward sweep ----------------
+        // terminal condition (init_adjoint!, :2026-2059).  Types 1 and 2 share the formula, type 1 on scomplex0 = e^{i phase} - s
+        // (:825-826; the reference's init_adjoint! has no branch for type 1 and leaves lambda(T) stale — see the oracle header);
+        // types 3, 4: lambda_r = Re(rot) / 2N, lambda_i = -Im(rot) / 2N with rot = e^{i phase} (Vtr + i Vti).
+        const double rs_ = pfid == 1 ? cph - re : re, is_ = pfid == 1 ? sph - im : im;
         FOR_E {
-            const double lr = (re * P.vtr[e] + im * P.vti[e]) / c.m, li = (im * P.vtr[e] - re * P.vti[e]) / c.m;
+            double lr, li;
+            if (pfid <= 2) { lr = (rs_ * P.vtr[e] + is_ * P.vti[e]) / c.m; li = (is_ * P.vtr[e] - rs_ * P.vti[e]) / c.m; }
+            else { lr = 0.5 * (cph * P.vtr[e] - sph * P.vti[e]) / c.m; li = -0.5 * (sph * P.vtr[e] + cph * P.vti[e]) / c.m; }
             c.lr[e] = lr; c.lr05[e] = lr; c.li[e] = li; c.li0[e] = li;
             if (P.objFuncType != 1) { c.lrn[e] = lr; c.lr05n[e] = lr; c.lin[e] = li; c.li0n[e] = li; }
         }
@@ -326,8 +389,15 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
             __syncthreads();
         }
         for (int k = threadIdx.x; k < c.Npar; k += GEN_THREADS) {
-            A.grad[(size_t)traj * c.Npar + k] = dt * c.grad[k];
-            if (P.objFuncType != 1 && A.infidgrad) A.infidgrad[(size_t)traj * c.Npar + k] = dt * c.igrad[k];
+            A.grad[(size_t)traj * A.gstride + k] = dt * c.grad[k];
+            if (P.objFuncType != 1 && A.infidgrad) A.infidgrad[(size_t)traj * A.gstride + k] = dt * c.igrad[k];
+        }
+        if (pfid == 3 && threadIdx.x == 0) {
+            // primObjGradPhase = -tracefidreal(vfinal, Re(i rot), Im(i rot)) = Re(s) sin(phase) + Im(s) cos(phase) (:923-945),
+            // appended to the total and to the infidelity gradient (leakgrad's last entry is their difference, 0)
+            const double pg = re * sph + im * cph;
+            A.grad[(size_t)traj * A.gstride + c.Npar] = pg;
+            if (P.objFuncType != 1 && A.infidgrad) A.infidgrad[(size_t)traj * A.gstride + c.Npar] = pg;
         }
         __syncthreads();
     }

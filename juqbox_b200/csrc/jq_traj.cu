@@ -63,6 +63,7 @@ int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.wreal || P.any_unc) return no("dense forbidden-state weights / uncoupled controls run on the generic kernel");
     if (P.solver != 1) return no("Jacobi solver (data-dependent sweep count) runs on the generic kernel");
     if (n > 128) return no("n > 128");
     std::vector<double> d0;
@@ -131,6 +132,7 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
 TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.wreal || P.any_unc) return no("dense forbidden-state weights / uncoupled controls run on the generic kernel");
     std::vector<double> d0;
     std::vector<OffDiag> h0off;
     const bool h0diag = h0_diagonal(H, d0, &h0off);
@@ -280,6 +282,7 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
 TrajPlan *jq_tile_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, int NT, char *err, size_t errlen) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
+    if (P.wreal || P.any_unc) return no("dense forbidden-state weights / uncoupled controls run on the generic kernel");
     if (P.solver != 1 || P.objFuncType != 1) return no("tile layout: only objFuncType 1 with the Neumann solver is instantiated");
     if (Nc < 2 || Nc > 3) return no("tile layout: 2 or 3 controls");
     if (NT < 2 || NT > Nc) return no("tile layout: bad number of tiled directions");
@@ -368,7 +371,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     if (want == 0) {
         const char *xm = getenv("JQ_TRAJ_XMODE");
         const int xv = xm ? atoi(xm) : 0;
-        if (xv == 1 || xv == 512) {
+        if (xv > 0) {
             inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, xv, pl->GL, P.J);
             if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, xv, pl->GL, 0);
         }
@@ -388,7 +391,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     const int npts = 2 * TRAJ_CH + 1, NC = pl->NC;
     // warps per CTA: 4 normally; fewer when the per-CTA gradient windows / pcof staging of very long coefficient
     // vectors would not fit in shared memory (the kernel only uses blockDim.x and the counts below)
-    int nw = TRAJ_WARPS, TPC = 0, ngroups = 0;
+    int nw = inst->nw, TPC = 0, ngroups = 0;
     size_t bytes = 0;
     for (; nw >= 1; nw >>= 1) {
         ngroups = nw * S.GPW;

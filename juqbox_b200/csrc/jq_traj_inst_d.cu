@@ -2,10 +2,10 @@
 #include "jq_traj_kernels.cuh"
 
 const Inst kInstD[] = {
-    TILEJ(2, 2, 1, 4, 16),       // cnot2 example shape: 4 x 4 levels, 2 x 2 tiles, J = 4, 16-lane groups
-    TILEJ(2, 2, 1, 0, 0),        // 4 x 4 levels, run-time J and group size
-    TILEJ(3, 2, 1, 3, 32),       // cnot3 example shape: 4 x 4 x 4 levels, 2 x 2 tiles x remote third subsystem, J = 3
-    TILEJ(3, 2, 1, 0, 0),
-    TILEJ(3, 3, 1, 3, 32),       // cnot3 example shape with 2 x 2 x 2 tiles (8 elements per lane, one warp per trajectory)
+    TILEJ(2, 2, 1, 4, 16),                 // cnot2 example shape: 4 x 4 levels, 2 x 2 tiles, J = 4, 16-lane groups (two trajectories per warp)
+    TILEJ(2, 2, 1, 0, 0),                  // 4 x 4 levels, run-time J and group size
+    TILEJW(3, 3, 1, 3, 32, 8, 1, 0),       // cnot3 example shape: 4 x 4 x 4 levels, 2 x 2 x 2 tiles (one warp per trajectory), J = 3, 8 warps per CTA
+    TILEJW(3, 3, 1, 0, 0, 8, 1, 0),        // 4 x 4 x 4 levels, run-time J and group size
+    TILEJ(3, 2, 1, 0, 0),                  // 2 x 2 tiles x remote third subsystem (JQ_TILE_NT=2; 4 elements per lane, no spills, slower)
 };
 const int kInstDCount = (int)(sizeof(kInstD) / sizeof(kInstD[0]));

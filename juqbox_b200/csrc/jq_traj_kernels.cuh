@@ -70,7 +70,7 @@ typedef void (*traj_kernel_t)(const TrajParams);
 // 128 Jacobi solver; 1 (warp-shuffle exchange) and 512 (shared-memory twin of the cnot2 instantiation) are exchange-mode
 // twins selectable for comparisons with the env variable JQ_TRAJ_XMODE.  jt: number of Neumann terms fixed at compile time
 // (0 = run-time J) -- its own field, never folded into `variant`.  glt: compile-time group size (0 = run-time).
-struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; int jt = 0; };
+struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; int jt = 0; int nw = TRAJ_WARPS; };
 // The instantiation table is split over jq_traj.cu / jq_traj_inst_b.cu / jq_traj_inst_c.cu so that they compile in parallel.
 extern const Inst kInstB[]; extern const int kInstBCount;
 extern const Inst kInstC[]; extern const int kInstCCount;
@@ -483,14 +483,11 @@ struct TileLane {
     }
     template <bool ADD>
     __device__ __forceinline__ void s_from(const SC &sc, const double (&x)[E], const Nbr &nb, const double (&add)[E], double (&t)[E]) const {
-        UNROLL for (int e = 0; e < E; ++e) {               // in-lane pair couplings first: independent of the exchange
-            double a = ADD ? add[e] : 0.0;
-            UNROLL for (int d = 0; d < NT; ++d) {
+        UNROLL for (int d = 0; d < NT; ++d)                // in-lane pair couplings first: independent of the exchange;
+            UNROLL for (int e = 0; e < E; ++e) {           // direction outer / element inner: neighbouring FMAs share the coefficient register
                 const double c = ((e >> d) & 1) ? -sc.a[d] : sc.a[d];
-                a = (!ADD && d == 0) ? c * x[e ^ (1 << d)] : fma(c, x[e ^ (1 << d)], a);
+                t[e] = d == 0 ? (ADD ? fma(c, x[e ^ 1], add[e]) : c * x[e ^ 1]) : fma(c, x[e ^ (1 << d)], t[e]);
             }
-            t[e] = a;
-        }
         UNROLL for (int d = 0; d < NT; ++d)
             UNROLL for (int e = 0; e < E; ++e)
                 if ((e >> d) & 1) t[e] = fma(sc.b[d], nb.t[d][face(e, d)], t[e]);
@@ -855,8 +852,8 @@ __device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, con
 
 // OBJ = 1: objFuncType 2/3 — a second adjoint set without forcing gives the infidelity-only gradient
 // (src/evalobjgrad.jl:848-855, :905-918; step_no_forcing! src/StormerVerlet.jl:365-406).
-template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0>
-__global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
+template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0, int NW = TRAJ_WARPS>
+__global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     extern __shared__ double sm[];
     const DevProblem &P = S.P;
@@ -890,7 +887,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
     // stage this CTA's pcof vectors and zero the per-group gradient accumulators
     for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += blockDim.x) {
         const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
-        sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * Npar + k] : 0.0;
+        sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * A.pstride + k] : 0.0;
     }
     for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += blockDim.x) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
 
@@ -972,20 +969,40 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         rs += red[gg * 4]; is += red[gg * 4 + 1]; pens += red[gg * 4 + 2];
     }
     rs /= m; is /= m;
-    const double infid = 1.0 - (rs * rs + is * is);
+    // primary objective by pFidType (src/evalobjgrad.jl:755-763) with s = rs + i is: 1: 1 + |s|^2 - 2 Re(s e^{-i phase});
+    // 2: 1 - |s|^2; 3, 4: 1 - tracefidreal(v, e^{i phase} Vtg) = 1 - (rs cos(phase) - is sin(phase)).  pFidType 3 carries the
+    // phase as the last entry of the pcof vector (:591-596).
+    const int pfid = P.pFidType;
+    double sph = 0.0, cph = 1.0;
+    if (pfid != 2) sincos(pfid == 3 ? A.pcof[(size_t)((live_t ? traj : 0) / A.nsamples) * A.pstride + Npar] : P.globalPhase, &sph, &cph);
+    const double abs2 = rs * rs + is * is;
+    const double infid = pfid == 1 ? 1.0 + abs2 - 2.0 * (rs * cph + is * sph) : pfid == 2 ? 1.0 - abs2 : 1.0 - (rs * cph - is * sph);
     if (live_t && g.gi == 0 && g.lg == 0) {
         double *o = A.scal + (size_t)traj * 4;
-        o[0] = infid; o[1] = 0.5 * dt * pens; o[2] = infid; o[3] = 0.0;   // w already carries 1/T
+        o[0] = infid; o[1] = 0.5 * dt * pens; o[2] = 1.0 - abs2; o[3] = 0.0;   // w already carries 1/T; traceInfidelity = 1 - |s|^2 (:792)
+        if (pfid == 3 && A.evaladjoint) {        // gradient with respect to the global phase (:923-945), last entry of both gradients
+            const double pg = rs * sph + is * cph;
+            A.grad[(size_t)traj * A.gstride + Npar] = pg;
+            if (OBJ) A.infidgrad[(size_t)traj * A.gstride + Npar] = pg;
+        }
     }
     if (!A.evaladjoint) return;
 
     // ------------------------------------------------------------ backward sweep (src/evalobjgrad.jl:810-921)
+    // terminal condition (init_adjoint!, :2026-2059): types 1 and 2 share the formula, type 1 on scomplex0 = e^{i phase} - s (:825-826);
+    // types 3, 4: lambda_r = Re(rot) / 2N, lambda_i = -Im(rot) / 2N, rot = e^{i phase} (Vtr + i Vti)
+    const double rs_ = pfid == 1 ? cph - rs : rs, is_ = pfid == 1 ? sph - is : is;
     double lr[E], li[E], vr0[E];
     UNROLL for (int e = 0; e < E; ++e) {
         const size_t ix = L.row(e) + (size_t)n * L.col(e);
         const double tr_ = ok[e] ? P.vtr[ix] : 0.0, ti_ = ok[e] ? P.vti[ix] : 0.0;
-        lr[e] = (rs * tr_ + is * ti_) / m;     // init_adjoint!, src/evalobjgrad.jl:2029-2042
-        li[e] = (is * tr_ - rs * ti_) / m;
+        if (pfid <= 2) {
+            lr[e] = (rs_ * tr_ + is_ * ti_) / m;     // init_adjoint!, src/evalobjgrad.jl:2029-2042
+            li[e] = (is_ * tr_ - rs_ * ti_) / m;
+        } else {
+            lr[e] = 0.5 * (cph * tr_ - sph * ti_) / m;
+            li[e] = -0.5 * (sph * tr_ + cph * ti_) / m;
+        }
     }
     double lrn[OBJ ? E : 1], lin[OBJ ? E : 1];
     if constexpr (OBJ != 0) { UNROLL for (int e = 0; e < E; ++e) { lrn[e] = lr[e]; lin[e] = li[e]; } }
@@ -1038,11 +1055,11 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
         if (tg >= A.ntraj) continue;
         double gs = 0.0;
         for (int j = 0; j < S.GPT; ++j) gs += sm[S.o_gsm + (tr * S.GPT + j) * Npar + k];
-        A.grad[(size_t)tg * Npar + k] = dt * gs;
+        A.grad[(size_t)tg * A.gstride + k] = dt * gs;
         if (OBJ) {
             double g2 = 0.0;
             for (int j = 0; j < S.GPT; ++j) g2 += sm[S.o_gsm2 + (tr * S.GPT + j) * Npar + k];
-            A.infidgrad[(size_t)tg * Npar + k] = dt * g2;
+            A.infidgrad[(size_t)tg * A.gstride + k] = dt * g2;
         }
     }
 }
@@ -1060,5 +1077,6 @@ __global__ void __launch_bounds__(TRAJ_THREADS, MINB) jq_traj_kernel(const __gri
 #define FIBERJAC(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 128, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, -1>}   /* Jacobi solver */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define TILEJ(NC, NT, UPL, JT, GLT) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT>, GLT, JT}   /* tile layout */
+#define TILEJW(NC, NT, UPL, JT, GLT, NW, MINB, VAR) {4, NT, 1, NC, 0, 0, UPL, VAR, jq_traj_kernel<TileLane<NC, NT>, UPL, MINB, JT, 0, GLT, NW>, GLT, JT, NW}   /* tile layout, NW warps per CTA */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
 }  // namespace

@@ -200,6 +200,8 @@ class objparams:
     wmatScale: float = 1.0
     use_sparse: bool = False
     use_custom_forbidden: bool = False
+    forb_states: Optional[np.ndarray] = None      # Ntot x nforb complex columns (src/evalobjgrad.jl:155,214-232)
+    forb_weights: Sequence[float] = ()
     linear_solver: Optional[lsolver_object] = None
     Integrator: int = Stormer_Verlet
 
@@ -217,16 +219,11 @@ class objparams:
         self.Nfreq = self.Cfreq.shape[1]
         self.Ncoupled = len(self.Hsym_ops)
         self.Nunc = len(self.Hunc_ops)
-        if self.Nunc != 0:
-            # uncoupled controls are outside the B200 hot path
-            raise NotImplementedError("uncoupled controls (Hunc_ops) are not on the B200 hot path")
-        if self.use_custom_forbidden:
-            raise NotImplementedError("custom (dense) forbidden-state weights are not on the B200 hot path")
         if self.Integrator != Stormer_Verlet:
             raise NotImplementedError("only Integrator = Stormer_Verlet is built for B200")
         assert len(self.Hanti_ops) == self.Ncoupled
-        assert len(self.Rfreq) >= self.Ncoupled
-        assert self.Cfreq.shape[0] >= self.Ncoupled
+        assert len(self.Rfreq) >= self.Ncoupled + self.Nunc
+        assert self.Cfreq.shape[0] >= self.Ncoupled + self.Nunc
         self.Uinit = np.asarray(self.Uinit, dtype=float)
         Ut = np.asarray(self.Utarget, dtype=complex)
         assert self.Uinit.shape == (Ntot, self.N)
@@ -236,14 +233,39 @@ class objparams:
         self.Hconst = np.asarray(self.Hconst, dtype=float)
         self.Hsym_ops = [np.asarray(h, dtype=float) for h in self.Hsym_ops]
         self.Hanti_ops = [np.asarray(h, dtype=float) for h in self.Hanti_ops]
-        for h in [self.Hconst] + self.Hsym_ops + self.Hanti_ops:
+        self.Hunc_ops = [np.asarray(h, dtype=float) for h in self.Hunc_ops]
+        for h in [self.Hconst] + self.Hsym_ops + self.Hanti_ops + self.Hunc_ops:
             assert h.shape == (Ntot, Ntot)
+        # symmetry of the uncoupled control Hamiltonians (src/evalobjgrad.jl:186-199): symmetric -> added to K, antisymmetric -> to S
+        self.isSymm = []
+        for h in self.Hunc_ops:
+            if np.array_equal(h, h.T):
+                self.isSymm.append(True)
+            elif np.linalg.norm(h + h.T) < 1e-15:
+                self.isSymm.append(False)
+            else:
+                raise ValueError("Uncoupled Hamiltonian is not symmetric or anti-symmetric. This functionality is not currently supported.")
+        self.unc_grad_literal = 0   # oracle only: 1 = the reference's adjoint_grad_calc! lines for uncoupled controls as written
         if self.linear_solver is None:
             self.linear_solver = lsolver_object(nrhs=self.N)
-        self.pFidType = 2          # hard-wired in the reference constructor (:164)
+        self.pFidType = 2          # the reference constructor's value (:164); a mutable field: 1, 3, 4 select evalobjgrad.jl:755-763
+        self.globalPhase = 0.0     # (:100,:334) used by pFidType 1 and 4; pFidType 3 reads it from the last entry of pcof (:591-596)
         self.tik0 = 0.01           # default Tikhonov coefficient (:202)
         self.use_bcarrier = True   # (:208)
         self.wmat_real = self.wmatScale * wmatsetup(self.Ne, self.Ng)  # diagonal, stored as a vector
+        self.wmat_imag = None
+        if self.use_custom_forbidden:
+            # user-specified forbidden states: dense W = sum_k w_k f_k f_k^dagger split in real / imaginary parts (:214-232)
+            F = np.asarray(self.forb_states, dtype=complex)
+            if F.ndim != 2 or F.shape[0] != Ntot:
+                raise ValueError("Forbidden states array is an incorrect size. Make sure guard levels are accounted for!")
+            wts = np.asarray(self.forb_weights, dtype=float)
+            assert len(wts) == F.shape[1]
+            W = np.zeros((Ntot, Ntot), dtype=complex)
+            for k in range(F.shape[1]):
+                W += wts[k] * np.outer(F[:, k], np.conj(F[:, k]))     # W[i,j] += w conj(f_j) f_i
+            self.wmat_real = np.ascontiguousarray(W.real)
+            self.wmat_imag = np.ascontiguousarray(W.imag)
         self.quiet = False
         self.usingPriorCoeffs = False
         self.priorCoeffs = np.zeros(0)

@@ -22,7 +22,11 @@ class _Problem(C.Structure):
                 ("Uinit", C.c_void_p), ("Vtr", C.c_void_p), ("Vti", C.c_void_p), ("wdiag", C.c_void_p),
                 ("Cfreq", C.c_void_p), ("H0", C.c_void_p), ("Hsym", C.c_void_p), ("Hanti", C.c_void_p),
                 ("colptr", C.c_void_p), ("rowval", C.c_void_p), ("nzval", C.c_void_p),
-                ("solver", C.c_int), ("tol", C.c_double)]
+                ("solver", C.c_int), ("tol", C.c_double),
+                # extensions (parity unpinned by the reference, see the header of traceobjgrad_oracle.c)
+                ("pFidType", C.c_int), ("globalPhase", C.c_double), ("wmat_real", C.c_void_p), ("wmat_imag", C.c_void_p),
+                ("Nunc", C.c_int), ("Hunc", C.c_void_p), ("isSymm", C.c_void_p), ("Rfreq", C.c_void_p),
+                ("unc_grad_literal", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -74,17 +78,32 @@ def _problem(params, keep):
     P.nsteps, P.T = params.nsteps, params.T
     P.solver, P.tol = params.linear_solver.solver_id, params.linear_solver.tol
     P.Uinit, P.Vtr, P.Vti = ptr(_f(params.Uinit)), ptr(_f(params.Utarget_r)), ptr(_f(params.Utarget_i))
-    P.wdiag = ptr(np.ascontiguousarray(params.wmat_real, dtype=np.float64))
-    P.Cfreq = ptr(_f(params.Cfreq[:Nc, :]))
+    Nunc = int(getattr(params, "Nunc", 0))
+    wr = np.asarray(params.wmat_real, dtype=np.float64)
+    if wr.ndim == 2:                               # custom forbidden states: dense real / imaginary weights
+        P.wdiag = ptr(np.ascontiguousarray(np.diag(wr)))
+        P.wmat_real = ptr(_f(wr))
+        P.wmat_imag = ptr(_f(params.wmat_imag))
+    else:
+        P.wdiag = ptr(np.ascontiguousarray(wr))
+    P.Cfreq = ptr(_f(params.Cfreq[:Nc + Nunc, :]))
+    P.pFidType, P.globalPhase = int(getattr(params, "pFidType", 2)), float(getattr(params, "globalPhase", 0.0))
+    P.Nunc, P.unc_grad_literal = Nunc, int(getattr(params, "unc_grad_literal", 0))
+    hunc = list(getattr(params, "Hunc_ops", []))
+    if Nunc:
+        P.isSymm = ptr(np.ascontiguousarray(params.isSymm, dtype=np.int32))
+        P.Rfreq = ptr(np.ascontiguousarray(np.asarray(params.Rfreq, dtype=np.float64)[:Nunc]))
+        if not params.use_sparse:
+            P.Hunc = ptr(np.concatenate([_f(h).ravel(order="F") for h in hunc]))
     if params.use_sparse:
-        parts = [_csc(h) for h in [params.Hconst] + list(params.Hsym_ops) + list(params.Hanti_ops)]
+        parts = [_csc(h) for h in [params.Hconst] + list(params.Hsym_ops) + list(params.Hanti_ops) + hunc]
         P.colptr = ptr(np.concatenate([p[0] for p in parts]))
         P.rowval = ptr(np.concatenate([p[1] for p in parts] + [np.zeros(1, np.int64)]))
         P.nzval = ptr(np.concatenate([p[2] for p in parts] + [np.zeros(1)]))
     else:
         P.H0 = ptr(_f(params.Hconst))
-        P.Hsym = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hsym_ops]))
-        P.Hanti = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hanti_ops]))
+        P.Hsym = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hsym_ops] + [np.zeros(1)]))
+        P.Hanti = ptr(np.concatenate([_f(h).ravel(order="F") for h in params.Hanti_ops] + [np.zeros(1)]))
     return P
 
 
@@ -116,7 +135,7 @@ def oracle_eval_controls(params, pcof, times):
     P = _problem(params, keep)
     pcof = np.ascontiguousarray(pcof, dtype=np.float64)
     times = np.ascontiguousarray(times, dtype=np.float64)
-    p = np.zeros((params.Ncoupled, len(times)))
+    p = np.zeros((params.Ncoupled + int(getattr(params, "Nunc", 0)), len(times)))
     q = np.zeros_like(p)
     lib.jqo_eval_controls.restype = C.c_int
     rc = lib.jqo_eval_controls(C.byref(P), C.c_int(len(pcof)), pcof.ctypes.data_as(C.c_void_p), C.c_int(len(times)),
@@ -135,7 +154,9 @@ def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nth
     lib = _lib()
     pcof = np.ascontiguousarray(np.atleast_2d(np.asarray(pcof, dtype=np.float64)))
     nbatch, Npar = pcof.shape
-    n, m, Nc = params.Ntot, params.N, params.Ncoupled
+    ext = 1 if int(getattr(params, "pFidType", 2)) == 3 else 0      # pFidType 3: last entry = global phase, gradients one longer
+    Npar -= ext
+    n, m, Nc = params.Ntot, params.N, params.Ncoupled + int(getattr(params, "Nunc", 0))
     keep = []
 
     def ptr(a):
@@ -151,9 +172,9 @@ def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nth
         nsamples = 1
     ntraj = nbatch * nsamples
     out = np.zeros((ntraj, 4))
-    grad = np.zeros((ntraj, Npar))
-    infidgrad = np.zeros((ntraj, Npar))
-    leakgrad = np.zeros((ntraj, Npar))
+    grad = np.zeros((ntraj, Npar + ext))
+    infidgrad = np.zeros((ntraj, Npar + ext))
+    leakgrad = np.zeros((ntraj, Npar + ext))
     rc = lib.jqo_traceobjgrad_batch(C.byref(P), C.c_int(Npar), C.c_int(nbatch), ptr(pcof), C.c_int(nsamples),
                                     ptr(shifts) if shifts is not None else None, C.c_int(int(evaladjoint)),
                                     C.c_int(nthreads), ptr(out), ptr(grad), ptr(infidgrad), ptr(leakgrad))
@@ -161,5 +182,5 @@ def oracle_traceobjgrad(params, pcof, shifts=None, evaladjoint: bool = True, nth
         raise ValueError("pcof must have an even number of elements >= %d, not %d" % (3 * 2 * Nc, Npar))
     shp = (nbatch, nsamples)
     return {"objf": out[:, 0].reshape(shp), "infid": out[:, 1].reshape(shp), "leak": out[:, 2].reshape(shp),
-            "trace_infid": out[:, 3].reshape(shp), "grad": grad.reshape(shp + (Npar,)),
-            "infidgrad": infidgrad.reshape(shp + (Npar,)), "leakgrad": leakgrad.reshape(shp + (Npar,))}
+            "trace_infid": out[:, 3].reshape(shp), "grad": grad.reshape(shp + (Npar + ext,)),
+            "infidgrad": infidgrad.reshape(shp + (Npar + ext,)), "leakgrad": leakgrad.reshape(shp + (Npar + ext,))}

@@ -26,6 +26,19 @@
  *   penalf2a / penalf2aTrap ........ evalobjgrad.jl:2170-2208
  *   risk-neutral H0 shift .......... ipopt_interface.jl:41-44 (passed in as a diagonal vector)
  *
+ * Extensions beyond the golden-pinned core — PARITY UNPINNED BY THE REFERENCE: no reference test or
+ * golden exercises them (pFidType is hard-wired to 2 by the constructor, evalobjgrad.jl:164; cnot-lab-ref.jld2 is not in the CI
+ * list and its case script cannot build a bcparams with this revision, bsplines.jl:177-181 vs test/cases/cnot-lab-setup.jl:116).
+ * They are restated from the cited lines and pinned by central finite differences of the restated objective (tests/):
+ *   pFidType 1/3/4 + globalPhase ... objective evalobjgrad.jl:755-763; terminal condition :2026-2059; phase gradient :923-945.
+ *       pFidType 1: init_adjoint! has NO branch for it (lambda(T) is left stale, i.e. undefined); the intended terminal condition
+ *       (the pFidType-2 formula applied to scomplex0 = exp(i phase) - s, which :825-826 computes for exactly that purpose) is used.
+ *   dense wmat_real / wmat_imag .... penalf2a / penalf2aTrap / penalf2imag dense methods :2183-2233; forcing :862,:882-888.
+ *   uncoupled controls ............. KS! :2372-2387 (TWO splines p, q per control, ft = 2(p cos(2 pi Rfreq t) - q sin(...)), added to
+ *       K if isSymm else to S).  adjoint_grad_calc! :2621-2654 indexes ONE spline per uncoupled control (qu = 2Nc-1+q) and omits
+ *       d ft / d(p,q): it is not the gradient of KS!'s model.  unc_grad_literal = 0 (default): exact gradient of KS!'s model
+ *       (the same trace combinations, multiplied by d ft/dp = 2cos, d ft/dq = -2sin); unc_grad_literal = 1: the literal lines.
+ *
  * Deliberate deviations (none changes a result beyond round-off):
  *   - sparse KS! uses a precomputed position map instead of `A[row,j] +=` lookups (faster than the
  *     reference, so the timed CPU baseline is, if anything, too fast);
@@ -33,6 +46,7 @@
  *
  * Layout: all matrices column-major (Julia), CSC 0-based.
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -52,6 +66,13 @@ typedef struct {
 typedef struct {
     /* problem */
     int n, m, Nc, Nfreq, D1, J, objFuncType, sparse;
+    int Nunc, NcT;    /* uncoupled controls; NcT = Nc + Nunc = rows of Cfreq and number of (p, q) spline pairs */
+    const int *isSymm;
+    const double *Rfreq;
+    int unc_grad_literal;
+    int pFidType;
+    double globalPhase;
+    const double *wreal, *wimag;   /* dense n x n weights (col-major) or NULL: Diagonal(wdiag), zero imaginary part */
     int solver;       /* 1 = Neumann (J terms), 2 = Jacobi (J = max_iter, tol) — linear_solvers.jl:4-5 */
     double tol;
     double *jac_scaled; /* Jacobi: the S.*=coeff copy */
@@ -61,10 +82,10 @@ typedef struct {
     const double *Uinit, *Vtr, *Vti, *wdiag, *Cfreq;
     /* dense operators (col-major n*n), hsym/hanti: Nc consecutive matrices */
     double *H0d;
-    const double *Hsymd, *Hantid;
+    const double *Hsymd, *Hantid, *Huncd;
     /* sparse operators */
-    csc_t H0s, *Hsyms, *Hantis;
-    int64_t **mapK_h0, **mapK_sym, **mapS_anti; /* nz position maps into K / S patterns */
+    csc_t H0s, *Hsyms, *Hantis, *Huncs;
+    int64_t **mapK_h0, **mapK_sym, **mapS_anti, **map_unc; /* nz position maps into K / S patterns */
     /* working arrays (Working_Arrays, evalobjgrad.jl:359-442) */
     double *K0d, *S0d, *K05d, *S05d, *K1d, *S1d;
     csc_t K0s, S0s, K05s, S05s, K1s, S1s;
@@ -105,7 +126,7 @@ static double bcarrier2(double t, const ws_t *w, int func) {
         b = 9.0 / 8 - 4.5 * tau + 4.5 * tau * tau;
         fbs1 += p[offset1 + k - 2] * b;
         fbs2 += p[offset2 + k - 2] * b;
-        double om = w->Cfreq[osc + w->Nc * (freq - 1)];
+        double om = w->Cfreq[osc + w->NcT * (freq - 1)];
         if (q_func == 1)
             f += fbs1 * sin(om * t) + fbs2 * cos(om * t);
         else
@@ -126,7 +147,7 @@ static void gradbcarrier2(double t, const ws_t *w, int func, double *g) {
     for (int freq = 1; freq <= Nfreq; freq++) {
         int64_t offset1 = 2 * osc * Nfreq * D1 + (freq - 1) * 2 * D1;
         int64_t offset2 = offset1 + D1;
-        double om = w->Cfreq[osc + w->Nc * (freq - 1)];
+        double om = w->Cfreq[osc + w->NcT * (freq - 1)];
         double s = sin(om * t), c = cos(om * t);
         for (int seg = 0; seg < 3; seg++) {
             double tc = dtknot * ((double)(k - seg) - 1.5);
@@ -246,6 +267,12 @@ static void KS(ws_t *w, int level, double t) {
             axpy(nn, pt, w->Hsymd + q * nn, K);
             axpy(nn, qt, w->Hantid + q * nn, S);
         }
+        for (int q = 0; q < w->Nunc; q++) {                      /* evalobjgrad.jl:2372-2387 */
+            int qs = 2 * Nc + 2 * q, qa = qs + 1;
+            double pt = bcarrier2(t, w, qs), qt = bcarrier2(t, w, qa);
+            double ft = 2 * (pt * cos(2 * M_PI * w->Rfreq[q] * t) - qt * sin(2 * M_PI * w->Rfreq[q] * t));
+            axpy(nn, ft, w->Huncd + q * nn, w->isSymm[q] ? K : S);
+        }
     } else {
         csc_t *K = level == 0 ? &w->K0s : level == 1 ? &w->K05s : &w->K1s;
         csc_t *S = level == 0 ? &w->S0s : level == 1 ? &w->S05s : &w->S1s;
@@ -256,6 +283,13 @@ static void KS(ws_t *w, int level, double t) {
             double pt = bcarrier2(t, w, 2 * q), qt = bcarrier2(t, w, 2 * q + 1);
             for (int64_t p = 0; p < w->Hsyms[q].nnz; p++) K->nzval[w->mapK_sym[q][p]] += pt * w->Hsyms[q].nzval[p];
             for (int64_t p = 0; p < w->Hantis[q].nnz; p++) S->nzval[w->mapS_anti[q][p]] += qt * w->Hantis[q].nzval[p];
+        }
+        for (int q = 0; q < w->Nunc; q++) {                      /* evalobjgrad.jl:2408-2424 */
+            int qs = 2 * Nc + 2 * q, qa = qs + 1;
+            double pt = bcarrier2(t, w, qs), qt = bcarrier2(t, w, qa);
+            double ft = 2 * (pt * cos(2 * M_PI * w->Rfreq[q] * t) - qt * sin(2 * M_PI * w->Rfreq[q] * t));
+            csc_t *A = w->isSymm[q] ? K : S;
+            for (int64_t p = 0; p < w->Huncs[q].nnz; p++) A->nzval[w->map_unc[q][p]] += ft * w->Huncs[q].nzval[p];
         }
     }
 }
@@ -342,15 +376,28 @@ static double tracefidabs2(const ws_t *w, const double *vr, const double *vi) {
     tracefidcomplex(w, vr, vi, &re, &im);
     return re * re + im * im;
 }
-/* evalobjgrad.jl:2199-2208 */
+/* dense-weight helpers: sum_ij A[i,j] (W B)[i,j] */
+static double quadform(const ws_t *w, const double *A, const double *W, const double *B) {
+    double f = 0.0;
+    int n = w->n;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < w->m; j++) {
+            double a = A[i + (int64_t)j * n];
+            for (int k = 0; k < n; k++) f += a * W[i + (int64_t)k * n] * B[k + (int64_t)j * n];
+        }
+    return f;
+}
+/* evalobjgrad.jl:2199-2208 (Diagonal), :2210-2223 (dense) */
 static double penalf2aTrap(const ws_t *w, const double *vr) {
+    if (w->wreal) return quadform(w, vr, w->wreal, vr);
     double f = 0.0;
     for (int j = 0; j < w->m; j++)
         for (int i = 0; i < w->n; i++) { double x = vr[i + (int64_t)j * w->n]; f += w->wdiag[i] * x * x; }
     return f;
 }
-/* evalobjgrad.jl:2170-2180 */
+/* evalobjgrad.jl:2170-2180 (Diagonal), :2183-2197 (dense) */
 static double penalf2a(const ws_t *w, const double *vr, const double *vi) {
+    if (w->wreal) return quadform(w, vr, w->wreal, vr) + 2.0 * quadform(w, vi, w->wreal, vi);
     double f = 0.0;
     for (int j = 0; j < w->m; j++)
         for (int i = 0; i < w->n; i++) {
@@ -359,12 +406,20 @@ static double penalf2a(const ws_t *w, const double *vr, const double *vi) {
         }
     return f;
 }
-/* tr(A' * H * C): evalobjgrad.jl:2114-2131 (dense), :2135-2154 (sparse) */
+/* penalf2imag(vr0, vi05, wmat_imag) = tr(vi05' Wi vr0), evalobjgrad.jl:2226-2233 (0 for a Diagonal wmat_imag) */
+static double penalf2imag(const ws_t *w, const double *vr, const double *vi) {
+    return w->wimag ? quadform(w, vi, w->wimag, vr) : 0.0;
+}
+/* C = alpha * W * B + beta * C for the dense weights (mul!(h, wmat, v, tinv, beta), evalobjgrad.jl:862,882-888) */
+static void wmul(const ws_t *w, double *C, const double *W, const double *B, double alpha, double beta) {
+    gemm_d(w->n, w->m, W, B, alpha, beta, C);
+}
+/* tr(A' * H * C): evalobjgrad.jl:2114-2131 (dense), :2135-2154 (sparse).  anti: 0 Hsym_q, 1 Hanti_q, 2 Hunc_q */
 static double adjoint_trace(const ws_t *w, const double *A, int q, int anti, const double *C) {
     int n = w->n, m = w->m;
     double trace = 0.0;
     if (!w->sparse) {
-        const double *B = (anti ? w->Hantid : w->Hsymd) + (int64_t)q * n * n;
+        const double *B = (anti == 2 ? w->Huncd : anti ? w->Hantid : w->Hsymd) + (int64_t)q * n * n;
         for (int j = 0; j < m; j++)
             for (int i = 0; i < n; i++) {
                 double Btmp = 0.0;
@@ -372,7 +427,7 @@ static double adjoint_trace(const ws_t *w, const double *A, int q, int anti, con
                 trace += A[i + (int64_t)j * n] * Btmp;
             }
     } else {
-        const csc_t *B = anti ? &w->Hantis[q] : &w->Hsyms[q];
+        const csc_t *B = anti == 2 ? &w->Huncs[q] : anti ? &w->Hantis[q] : &w->Hsyms[q];
         for (int j = 0; j < m; j++)
             for (int i = 0; i < n; i++) {
                 double mat_temp = 0.0;
@@ -414,6 +469,34 @@ static void adjoint_grad_calc(ws_t *w, const double *vr0, const double *vi05, co
         axpy(Npar, -tt, gi, grad_step);
         tt = adjoint_trace(w, vi05, q, 1, li0);
         axpy(Npar, -tt, gi, grad_step);
+    }
+    for (int q = 0; q < w->Nunc; q++) {
+        /* trace combinations of evalobjgrad.jl:2621-2654: a K-type operator (isSymm) has coefficient c0 at t0 and t0+dt and c1
+         * at t0+dt/2; an S-type one has three different ones */
+        double c[3];   /* multiplies grad ft at t0, t0+dt, t0+dt/2 */
+        if (w->isSymm[q]) {
+            double tmp = adjoint_trace(w, vi05, q, 2, lr05);
+            c[0] = -tmp; c[1] = -tmp;
+            c[2] = adjoint_trace(w, vr, q, 2, li) + adjoint_trace(w, vr0, q, 2, li0);
+        } else {
+            c[0] = -adjoint_trace(w, vr0, q, 2, lr05);
+            c[1] = -adjoint_trace(w, vr, q, 2, lr05);
+            c[2] = -(adjoint_trace(w, vi05, q, 2, li) + adjoint_trace(w, vi05, q, 2, li0));
+        }
+        const double tp[3] = {t0, t0 + dt, t0 + 0.5 * dt};
+        if (w->unc_grad_literal) {                     /* the reference's lines as written: one spline, index 2Nc-1+q (1-based q) */
+            int qu = 2 * w->Nc - 1 + (q + 1);
+            for (int k = 0; k < 3; k++) { gradbcarrier2(tp[k], w, qu, gr); axpy(Npar, c[k], gr, grad_step); }
+        } else {                                       /* exact gradient of KS!'s ft = 2 (p cos - q sin) */
+            int qs = 2 * w->Nc + 2 * q, qa = qs + 1;
+            for (int k = 0; k < 3; k++) {
+                double cr = cos(2 * M_PI * w->Rfreq[q] * tp[k]), sr = sin(2 * M_PI * w->Rfreq[q] * tp[k]);
+                gradbcarrier2(tp[k], w, qs, gr);
+                gradbcarrier2(tp[k], w, qa, gi);
+                axpy(Npar, 2.0 * cr * c[k], gr, grad_step);
+                axpy(Npar, -2.0 * sr * c[k], gi, grad_step);
+            }
+        }
     }
 }
 
@@ -472,6 +555,16 @@ typedef struct {
     const double *nzval;
     int solver;   /* 0/1 Neumann, 2 Jacobi */
     double tol;   /* Jacobi tolerance (already scaled by sqrt(nrhs), linear_solvers.jl:40) */
+    /* --- extensions; all-zero = the golden-pinned core --- */
+    int pFidType;            /* 0 or 2: pFidType 2; 1, 3, 4 as in evalobjgrad.jl:755-763.  pFidType 3: every pcof vector carries the global
+                                phase as an extra LAST entry (stride Npar + 1) and every gradient an extra last entry (:589-596,:923-945) */
+    double globalPhase;      /* params.globalPhase (pFidType 1 and 4) */
+    const double *wmat_real, *wmat_imag;   /* dense n x n col-major weights, or NULL (Diagonal(wdiag), no imaginary part) */
+    int Nunc;                /* uncoupled controls: Cfreq then has Nc + Nunc rows, pcof 2 (Nc + Nunc) Nfreq D1 entries */
+    const double *Hunc;      /* dense: Nunc matrices; sparse: the CSC list continues with Hunc.. after Hanti.. */
+    const int *isSymm;       /* Nunc */
+    const double *Rfreq;     /* Nunc */
+    int unc_grad_literal;
 } jqo_problem;
 
 static void ws_init(ws_t *w, const jqo_problem *P, int Npar) {
@@ -482,17 +575,20 @@ static void ws_init(ws_t *w, const jqo_problem *P, int Npar) {
     w->solver = P->solver == 2 ? 2 : 1; w->tol = P->tol;
     w->Uinit = P->Uinit; w->Vtr = P->Vtr; w->Vti = P->Vti; w->wdiag = P->wdiag; w->Cfreq = P->Cfreq;
     w->Npar = Npar;
-    w->D1 = Npar / (2 * Nc * P->Nfreq);
+    w->Nunc = P->Nunc; w->NcT = Nc + P->Nunc; w->isSymm = P->isSymm; w->Rfreq = P->Rfreq; w->unc_grad_literal = P->unc_grad_literal;
+    w->pFidType = P->pFidType == 0 ? 2 : P->pFidType; w->globalPhase = P->globalPhase;
+    w->wreal = P->wmat_real; w->wimag = P->wmat_imag;
+    w->D1 = Npar / (2 * w->NcT * P->Nfreq);
     w->dtknot = P->T / (w->D1 - 2);
     int64_t nn = (int64_t)n * n, len = (int64_t)n * m;
     if (!P->sparse) {
         w->H0d = (double *)malloc(sizeof(double) * nn);
         memcpy(w->H0d, P->H0, sizeof(double) * nn);
-        w->Hsymd = P->Hsym; w->Hantid = P->Hanti;
+        w->Hsymd = P->Hsym; w->Hantid = P->Hanti; w->Huncd = P->Hunc;
         double **mats[6] = {&w->K0d, &w->S0d, &w->K05d, &w->S05d, &w->K1d, &w->S1d};
         for (int i = 0; i < 6; i++) *mats[i] = (double *)calloc(nn, sizeof(double));
     } else {
-        int nop = 1 + 2 * Nc;
+        int nop = 1 + 2 * Nc + P->Nunc;
         csc_t *ops = (csc_t *)calloc(nop, sizeof(csc_t));
         int64_t off = 0;
         for (int o = 0; o < nop; o++) {
@@ -509,13 +605,15 @@ static void ws_init(ws_t *w, const jqo_problem *P, int Npar) {
         int64_t *m0 = csc_map(&w->H0s, &ops[0]);
         for (int64_t p = 0; p < ops[0].nnz; p++) w->H0s.nzval[m0[p]] = ops[0].nzval[p];
         free(m0);
-        w->Hsyms = ops + 1; w->Hantis = ops + 1 + Nc;
-        const csc_t **kops = (const csc_t **)malloc(sizeof(csc_t *) * (1 + Nc));
-        const csc_t **sops = (const csc_t **)malloc(sizeof(csc_t *) * (Nc > 0 ? Nc : 1));
+        w->Hsyms = ops + 1; w->Hantis = ops + 1 + Nc; w->Huncs = ops + 1 + 2 * Nc;
+        const csc_t **kops = (const csc_t **)malloc(sizeof(csc_t *) * (1 + Nc + P->Nunc));
+        const csc_t **sops = (const csc_t **)malloc(sizeof(csc_t *) * (Nc + P->Nunc + 1));
         kops[0] = &w->H0s;
-        for (int q = 0; q < Nc; q++) { kops[1 + q] = &w->Hsyms[q]; sops[q] = &w->Hantis[q]; }
-        csc_union(&w->K0s, n, kops, 1 + Nc, 1);
-        csc_union(&w->S0s, n, sops, Nc, 0);
+        int nk = 1, nsop = 0;
+        for (int q = 0; q < Nc; q++) { kops[nk++] = &w->Hsyms[q]; sops[nsop++] = &w->Hantis[q]; }
+        for (int q = 0; q < P->Nunc; q++) { if (P->isSymm[q]) kops[nk++] = &w->Huncs[q]; else sops[nsop++] = &w->Huncs[q]; }
+        csc_union(&w->K0s, n, kops, nk, 1);
+        csc_union(&w->S0s, n, sops, nsop, 0);
         csc_copy_pattern(&w->K05s, &w->K0s); csc_copy_pattern(&w->K1s, &w->K0s);
         csc_copy_pattern(&w->S05s, &w->S0s); csc_copy_pattern(&w->S1s, &w->S0s);
         w->mapK_h0 = (int64_t **)malloc(sizeof(int64_t *));
@@ -523,6 +621,8 @@ static void ws_init(ws_t *w, const jqo_problem *P, int Npar) {
         w->mapK_sym = (int64_t **)malloc(sizeof(int64_t *) * Nc);
         w->mapS_anti = (int64_t **)malloc(sizeof(int64_t *) * Nc);
         for (int q = 0; q < Nc; q++) { w->mapK_sym[q] = csc_map(&w->K0s, &w->Hsyms[q]); w->mapS_anti[q] = csc_map(&w->S0s, &w->Hantis[q]); }
+        w->map_unc = (int64_t **)malloc(sizeof(int64_t *) * (P->Nunc + 1));
+        for (int q = 0; q < P->Nunc; q++) w->map_unc[q] = csc_map(P->isSymm[q] ? &w->K0s : &w->S0s, &w->Huncs[q]);
         free(kops); free(sops);
     }
     double **blocks[] = {&w->lambdar, &w->lambdar0, &w->lambdai, &w->lambdai0, &w->lambdar05, &w->lambdar_n, &w->lambdar0_n,
@@ -541,8 +641,9 @@ static void ws_free(ws_t *w) {
     } else {
         csc_t *ops = w->Hsyms - 1;
         for (int q = 0; q < Nc; q++) { free(w->mapK_sym[q]); free(w->mapS_anti[q]); }
-        free(w->mapK_h0[0]); free(w->mapK_h0); free(w->mapK_sym); free(w->mapS_anti);
-        for (int o = 0; o < 1 + 2 * Nc; o++) csc_free(&ops[o]);
+        for (int q = 0; q < w->Nunc; q++) free(w->map_unc[q]);
+        free(w->mapK_h0[0]); free(w->mapK_h0); free(w->mapK_sym); free(w->mapS_anti); free(w->map_unc);
+        for (int o = 0; o < 1 + 2 * Nc + w->Nunc; o++) csc_free(&ops[o]);
         free(ops);
         csc_free(&w->H0s); csc_free(&w->K0s); csc_free(&w->S0s); csc_free(&w->K05s); csc_free(&w->S05s); csc_free(&w->K1s); csc_free(&w->S1s);
     }
@@ -569,6 +670,8 @@ static void shift_h0(ws_t *w, const double *shift, double sign) {
 static void traceobjgrad(ws_t *w, const double *pcof, int evaladjoint, double *out, double *grad, double *infidelgrad_out,
                          double *leakgrad_out) {
     int n = w->n, m = w->m, Npar = w->Npar;
+    const int pFid = w->pFidType;
+    const double phase = pFid == 3 ? pcof[Npar] : w->globalPhase;   /* evalobjgrad.jl:591-596: the last entry is the global phase */
     int64_t len = (int64_t)n * m, nsteps = w->nsteps;
     double T = w->T, tinv = 1.0 / T;
     w->pcof = pcof;
@@ -587,10 +690,24 @@ static void traceobjgrad(ws_t *w, const double *pcof, int evaladjoint, double *o
         KS(w, 2, t + dt);
         t = step_state(w, t, vr, vi, vi05, dt);
         double forbidden = tinv * penalf2a(w, vr, vi05);
-        double forbidden_imag1 = 0.0; /* penalf2imag with Diagonal wmat_imag, evalobjgrad.jl:2231-2233 */
+        double forbidden_imag1 = tinv * penalf2imag(w, vr0, vi05); /* 0 with a Diagonal wmat_imag, evalobjgrad.jl:2226-2233 */
         objfv = objfv + dt * 0.5 * (forbidden0 + forbidden - 2.0 * forbidden_imag1);
     }
-    double primaryobjf = 1.0 - tracefidabs2(w, vr, vi); /* pFidType == 2 */
+    double primaryobjf, s_re, s_im;
+    tracefidcomplex(w, vr, vi, &s_re, &s_im);
+    const double cph = cos(phase), sph = sin(phase);
+    if (pFid == 1)          /* 1 + |s|^2 - 2 Re(s exp(-i phase)), evalobjgrad.jl:755-757 */
+        primaryobjf = 1.0 + tracefidabs2(w, vr, vi) - 2.0 * (s_re * cph + s_im * sph);
+    else if (pFid == 2)
+        primaryobjf = 1.0 - tracefidabs2(w, vr, vi);
+    else {                  /* 1 - tracefidreal(vr, -vi, Re rot, Im rot), rot = exp(i phase) (Vtr + i Vti), :760-762 */
+        double tr = 0.0;
+        for (int64_t i = 0; i < len; i++) {
+            double rr = cph * w->Vtr[i] - sph * w->Vti[i], ri = sph * w->Vtr[i] + cph * w->Vti[i];
+            tr += vr[i] * rr + (-vi[i]) * ri;
+        }
+        primaryobjf = 1.0 - tr / m;
+    }
     double secondaryobjf = objfv;
     objfv = primaryobjf + secondaryobjf;
     double traceInfidelity = 1.0 - tracefidabs2(w, vr, vi);
@@ -603,11 +720,24 @@ static void traceobjgrad(ws_t *w, const double *pcof, int evaladjoint, double *o
     dt = -dt;
     double rs, is;
     tracefidcomplex(w, vr, vi, &rs, &is);
-    for (int64_t i = 0; i < len; i++) { /* init_adjoint!, pFidType == 2 */
-        double rtmp = (rs * w->Vtr[i] + is * w->Vti[i]) / m;
-        lr[i] = rtmp; lr0[i] = rtmp; lr05[i] = rtmp;
-        double itmp = (is * w->Vtr[i] - rs * w->Vti[i]) / m;
-        li[i] = itmp; li0[i] = itmp;
+    if (pFid == 1) { rs = cph - rs; is = sph - is; }     /* scomplex0 = exp(i phase) - scomplex0, evalobjgrad.jl:825-826 */
+    double phasegrad = 0.0;
+    if (pFid == 1 || pFid == 2) {
+        for (int64_t i = 0; i < len; i++) { /* init_adjoint!, pFidType == 2 branch (:2029-2042); also the intended one for pFidType 1 */
+            double rtmp = (rs * w->Vtr[i] + is * w->Vti[i]) / m;
+            lr[i] = rtmp; lr0[i] = rtmp; lr05[i] = rtmp;
+            double itmp = (is * w->Vtr[i] - rs * w->Vti[i]) / m;
+            li[i] = itmp; li0[i] = itmp;
+        }
+    } else {
+        for (int64_t i = 0; i < len; i++) { /* init_adjoint!, pFidType 3 / 4 (:2043-2057) */
+            double rr = cph * w->Vtr[i] - sph * w->Vti[i], ri = sph * w->Vtr[i] + cph * w->Vti[i];
+            double rtmp = 0.5 * rr / m, itmp = -0.5 * ri / m;
+            lr[i] = rtmp; lr0[i] = rtmp; lr05[i] = rtmp;
+            li[i] = itmp; li0[i] = itmp;
+            /* primObjGradPhase = -tracefidreal(vfinalr, vfinali, Re(i rot), Im(i rot)), :923-928; vfinali = -vi */
+            phasegrad -= (vr[i] * (-ri) + (-vi[i]) * rr) / m;
+        }
     }
     if (w->objFuncType != 1) {
         memcpy(w->lambdar_n, lr, sizeof(double) * len); memcpy(w->lambdar0_n, lr0, sizeof(double) * len);
@@ -616,13 +746,21 @@ static void traceobjgrad(ws_t *w, const double *pcof, int evaladjoint, double *o
         memset(w->infidelgrad, 0, sizeof(double) * Npar);
     }
     for (int64_t step = nsteps - 1; step >= 0; step--) {
-        for (int j = 0; j < m; j++) for (int i = 0; i < n; i++) w->hr0[i + (int64_t)j * n] = tinv * w->wdiag[i] * vr[i + (int64_t)j * n];
+        if (w->wreal) wmul(w, w->hr0, w->wreal, vr, tinv, 0.0);      /* mul!(hr0, wmat_real, vr, tinv, 0.0), :862 */
+        else for (int j = 0; j < m; j++) for (int i = 0; i < n; i++) w->hr0[i + (int64_t)j * n] = tinv * w->wdiag[i] * vr[i + (int64_t)j * n];
         double t0 = t;
         memcpy(vr0, vr, sizeof(double) * len);
         KS(w, 0, t);
         KS(w, 1, t + 0.5 * dt);
         KS(w, 2, t + dt);
         t = step_state(w, t, vr, vi, vi05, dt);
+        if (w->wreal) {                                              /* evalobjgrad.jl:882-888 */
+            wmul(w, w->hi0, w->wreal, vi05, tinv, 0.0);
+            wmul(w, w->hr1, w->wreal, vr, tinv, 0.0);
+            if (w->wimag) wmul(w, w->hr1, w->wimag, vi05, tinv, 1.0);
+            memcpy(w->hi1, w->hi0, sizeof(double) * len);
+            if (w->wimag) wmul(w, w->hi1, w->wimag, vr, -tinv, 1.0);
+        } else
         for (int j = 0; j < m; j++)
             for (int i = 0; i < n; i++) {
                 int64_t e = i + (int64_t)j * n;
@@ -644,11 +782,12 @@ static void traceobjgrad(ws_t *w, const double *pcof, int evaladjoint, double *o
         }
     }
     memcpy(grad, w->gradobjfadj, sizeof(double) * Npar);
+    if (pFid == 3) grad[Npar] = phasegrad;                       /* totalgrad[Psize+1] = primObjGradPhase, :931-934 */
     if (w->objFuncType != 1) {
-        if (infidelgrad_out) memcpy(infidelgrad_out, w->infidelgrad, sizeof(double) * Npar);
-        if (leakgrad_out) for (int i = 0; i < Npar; i++) leakgrad_out[i] = w->gradobjfadj[i] - w->infidelgrad[i];
+        if (infidelgrad_out) { memcpy(infidelgrad_out, w->infidelgrad, sizeof(double) * Npar); if (pFid == 3) infidelgrad_out[Npar] = phasegrad; }
+        if (leakgrad_out) { for (int i = 0; i < Npar; i++) leakgrad_out[i] = w->gradobjfadj[i] - w->infidelgrad[i]; if (pFid == 3) leakgrad_out[Npar] = 0.0; }
     } else if (infidelgrad_out) {
-        memcpy(infidelgrad_out, w->gradobjfadj, sizeof(double) * Npar); /* infidelgrad = totalgrad, :951 */
+        memcpy(infidelgrad_out, grad, sizeof(double) * (Npar + (pFid == 3))); /* infidelgrad = totalgrad, :951 */
     }
 }
 
@@ -671,15 +810,16 @@ static void *worker(void *arg) {
     int Npar = jb->Npar;
     ws_t w;
     ws_init(&w, P, Npar);
-    double *gtmp = (double *)calloc(Npar, sizeof(double));
+    const int ext = P->pFidType == 3 ? 1 : 0;           /* pcof / gradient stride Npar + 1: the global phase rides along */
+    double *gtmp = (double *)calloc(Npar + 1, sizeof(double));
     for (;;) {
         int64_t tr = (int64_t)atomic_fetch_add(jb->next, 1);
         if (tr >= jb->ntraj) break;
         int64_t b = tr / jb->nsamples, s = tr % jb->nsamples;
         const double *sh = jb->shift ? jb->shift + s * P->n : NULL;
         shift_h0(&w, sh, +1.0);
-        traceobjgrad(&w, jb->pcof + b * Npar, jb->evaladjoint, jb->out + tr * 4, jb->grad ? jb->grad + tr * Npar : gtmp,
-                     jb->infidelgrad ? jb->infidelgrad + tr * Npar : NULL, jb->leakgrad ? jb->leakgrad + tr * Npar : NULL);
+        traceobjgrad(&w, jb->pcof + b * (Npar + ext), jb->evaladjoint, jb->out + tr * 4, jb->grad ? jb->grad + tr * (Npar + ext) : gtmp,
+                     jb->infidelgrad ? jb->infidelgrad + tr * (Npar + ext) : NULL, jb->leakgrad ? jb->leakgrad + tr * (Npar + ext) : NULL);
         shift_h0(&w, sh, -1.0);
     }
     free(gtmp);
@@ -689,7 +829,8 @@ static void *worker(void *arg) {
 
 int jqo_traceobjgrad_batch(const jqo_problem *P, int Npar, int nbatch, const double *pcof, int nsamples, const double *shift,
                            int evaladjoint, int nthreads, double *out, double *grad, double *infidelgrad, double *leakgrad) {
-    if (P->Nc < 1 || Npar % (2 * P->Nc * P->Nfreq) != 0 || Npar < 3 * 2 * P->Nc) return -1; /* evalobjgrad.jl:604-606 */
+    const int NcT = P->Nc + P->Nunc;
+    if (NcT < 1 || Npar % (2 * NcT * P->Nfreq) != 0 || Npar < 3 * 2 * NcT) return -1; /* evalobjgrad.jl:604-606 */
     if (nsamples < 1) nsamples = 1;
     atomic_llong next = 0;
     job_t jb = {P, Npar, nsamples, evaladjoint, (int64_t)nbatch * nsamples, pcof, shift, out, grad, infidelgrad, leakgrad, &next};
@@ -708,7 +849,7 @@ int jqo_traceobjgrad_batch(const jqo_problem *P, int Npar, int nbatch, const dou
  * verbose=true history of traceobjgrad, :676-680,:748-752): hist_r/hist_i [nsteps/save_every + 1][n*m] = vr, -vi. */
 int jqo_forward_history(const jqo_problem *P, int Npar, const double *pcof, const double *shift, int save_every,
                         double *hist_r, double *hist_i, double *out) {
-    if (P->Nc < 1 || Npar % (2 * P->Nc * P->Nfreq) != 0 || Npar < 3 * 2 * P->Nc) return -1;
+    if (P->Nc + P->Nunc < 1 || Npar % (2 * (P->Nc + P->Nunc) * P->Nfreq) != 0 || Npar < 3 * 2 * (P->Nc + P->Nunc)) return -1;
     if (save_every < 1 || P->nsteps % save_every != 0) return -2;
     ws_t w;
     ws_init(&w, P, Npar);
@@ -740,13 +881,14 @@ int jqo_forward_history(const jqo_problem *P, int Npar, const double *pcof, cons
 /* evalctrl (plotstatectrl.jl:246-276): p_q(t), q_q(t) for every coupled control at the given times.
  * p, q: [Nc][ntimes].  Only the fields of the problem that the control functions read are used. */
 int jqo_eval_controls(const jqo_problem *P, int Npar, const double *pcof, int ntimes, const double *times, double *p, double *q) {
-    if (Npar % (2 * P->Nc * P->Nfreq) != 0 || Npar / (2 * P->Nc * P->Nfreq) < 3) return -2;
+    const int NcT = P->Nc + P->Nunc;
+    if (Npar % (2 * NcT * P->Nfreq) != 0 || Npar / (2 * NcT * P->Nfreq) < 3) return -2;
     ws_t w;
     memset(&w, 0, sizeof(w));
-    w.Nc = P->Nc; w.Nfreq = P->Nfreq; w.Cfreq = P->Cfreq; w.T = P->T; w.Npar = Npar; w.pcof = pcof;
-    w.D1 = Npar / (2 * P->Nc * P->Nfreq);
+    w.Nc = P->Nc; w.NcT = NcT; w.Nfreq = P->Nfreq; w.Cfreq = P->Cfreq; w.T = P->T; w.Npar = Npar; w.pcof = pcof;
+    w.D1 = Npar / (2 * NcT * P->Nfreq);
     w.dtknot = P->T / (w.D1 - 2);
-    for (int c = 0; c < P->Nc; c++)
+    for (int c = 0; c < NcT; c++)
         for (int i = 0; i < ntimes; i++) {
             p[(int64_t)c * ntimes + i] = bcarrier2(times[i], &w, 2 * c);
             q[(int64_t)c * ntimes + i] = bcarrier2(times[i], &w, 2 * c + 1);
