@@ -164,12 +164,14 @@ int jq_comm_unique_id(void *id128);
 int jq_comm_init(jq_handle *h, int32_t rank, int32_t nranks, const void *id128);
 int jq_comm_destroy(jq_handle *h);
 
-/* Kernel selection, for tests and profiling: 0 = automatic (3, else 2, else 1), 1 = generic (one CTA per trajectory,
- * any operators), 2 = register-resident kernel, slot layout (sparse rows with <= 2 entries per row and control),
- * 3 = register-resident kernel, fibre layout (Kronecker ladder structure).  2 and 3 fail with JQ_ERR_ARG if the
- * problem has no instantiation. */
+/* Kernel selection, for tests and profiling: 0 = automatic, 1 = generic (any operators, dense weights, uncoupled controls),
+ * 2 = register-resident kernel, slot layout (sparse rows with <= 2 entries per row and control), 3 = fibre layout (Kronecker
+ * ladder structure), 4 = tile layout (all subsystems with 4 levels: mirrored half-tiles, shuffle-only exchange), 5 = the tile
+ * layout with the fewest elements per lane (latency layout).  Automatic: launches of at most 2 x #SM trajectories take 5 (then
+ * 3 for three subsystems); otherwise 4, 3, 2, 1 in that order, each handing over when it has no instantiation for the problem.
+ * 2 ... 5 fail with JQ_ERR_ARG if the problem has no instantiation. */
 int jq_set_kernel(jq_handle *h, int32_t kernel);
-/* what: 0 = kernel actually used by the last evaluation (1/2/3), 1 = CUDA-event time of the last evaluation's
+/* what: 0 = kernel actually used by the last evaluation (1 ... 5), 1 = CUDA-event time of the last evaluation's
  * trajectory kernel in ms (synchronises), 2 = number of kernels launched by the last evaluation,
  * 3 = trajectories resident per CTA, 4 = CTAs launched, 5 = registers per thread, 6 = dynamic smem bytes per CTA. */
 int jq_query(jq_handle *h, int32_t what, double *value);

@@ -10,8 +10,13 @@
 #   traceobjgrad(pcof0, params, wa, verbose, evaladjoint)  src/evalobjgrad.jl:504   -> new method on Working_Arrays_B200
 #   eval_f_g_grad!(pcof, params, wa, nodes, weights, ..)   src/ipopt_interface.jl:24 -> new method: ONE batched ccall
 #                                                                                     instead of the nquad loop
-# eval_f_par / eval_grad_f_par / eval_g_par / eval_jac_g_par take `wa` untyped (src/ipopt_interface.jl:77-179) and
-# need no change: they dispatch to the methods below through `wa`.
+# eval_f_par / eval_grad_f_par / eval_g_par / eval_jac_g_par take `wa` untyped (src/ipopt_interface.jl:77-179); the methods at
+# the end of this file specialise them on Working_Arrays_B200 so that each Ipopt callback is ONE ccall (jq_eval_f_grad: cache
+# test, sample loop, weighted sums and Tikhonov behind the ABI).  Without those four methods the generic ones still work:
+# they dispatch to eval_f_g_grad! below through `wa`.
+#
+# Layout pin: tests/c_abi_harness.c (gcc) asserts sizeof(jq_problem) == 208, sizeof(jq_operator) == 40 and the field offsets
+# the two structs below produce; at run time compare with jq_abi_info (jq_check_layout()).
 
 const libjq = get(ENV, "JUQBOX_B200_LIB", "libjuqbox_b200.so")
 
@@ -33,6 +38,20 @@ struct JqProblem             # == jq_problem
     hsym::Ptr{JqOperator}
     hanti::Ptr{JqOperator}
     solver_tol::Float64
+    global_phase::Float64                    # params.globalPhase (pFidType 1 and 4)
+    wmat_real::Ptr{Float64}                  # dense Ntot x Ntot weights (use_custom_forbidden) or C_NULL
+    wmat_imag::Ptr{Float64}
+    nuncoupled::Int32; reserved0::Int32
+    hunc::Ptr{JqOperator}
+    unc_is_symm::Ptr{Int32}
+    unc_rfreq::Ptr{Float64}
+end
+
+function jq_check_layout()
+    info(k) = ccall((:jq_abi_info, libjq), Int64, (Int32,), k)
+    (info(1) == sizeof(JqProblem) && info(2) == sizeof(JqOperator) && info(3) == fieldoffset(JqProblem, 9) &&
+     info(6) == fieldoffset(JqProblem, 16) && info(8) == fieldoffset(JqProblem, 19)) ||
+        error("juqbox_b200: struct layout of JuqboxB200.jl does not match the library (ABI version ", info(0), ")")
 end
 
 jq_error() = unsafe_string(ccall((:jq_last_error, libjq), Cstring, ()))
@@ -56,21 +75,31 @@ function jq_operator(A::SparseMatrixCSC{Float64,Int64}, keep)
 end
 
 function Working_Arrays_B200(params::objparams, nCoeff::Int64; device::Int = 0)
-    @assert params.Nunc == 0 "uncoupled controls stay on the CPU path"
     @assert params.linear_solver.solver_id in (NEUMANN_SOLVER, JACOBI_SOLVER) "Neumann and Jacobi solvers are built for B200"
     @assert params.Integrator_id == Stormer_Verlet
-    @assert isa(params.wmat_real, Diagonal) "custom forbidden-state weights stay on the CPU path"
+    jq_check_layout()
     keep = Any[]
     Ntot = params.N + params.Nguard
-    Cf = Array{Float64,2}(params.Cfreq[1:params.Ncoupled, :])
+    Nctrl = params.Ncoupled + params.Nunc
+    Cf = Array{Float64,2}(params.Cfreq[1:Nctrl, :])
     wd = Vector{Float64}(diag(params.wmat_real))
+    dense_w = !isa(params.wmat_real, Diagonal)                     # use_custom_forbidden (src/evalobjgrad.jl:214-232)
+    wr = dense_w ? Array{Float64,2}(params.wmat_real) : zeros(0, 0)
+    wi = dense_w ? Array{Float64,2}(params.wmat_imag) : zeros(0, 0)
     hs = [jq_operator(h, keep) for h in params.Hsym_ops]
     ha = [jq_operator(h, keep) for h in params.Hanti_ops]
-    append!(keep, (Cf, wd, hs, ha, params.Uinit, params.Utarget_r, params.Utarget_i))
+    hu = [jq_operator(h, keep) for h in params.Hunc_ops]           # two splines per uncoupled control, as KS! reads them (:2372-2387)
+    sy = Int32[s ? 1 : 0 for s in params.isSymm]
+    rf = Vector{Float64}(params.Rfreq[1:params.Nunc])
+    append!(keep, (Cf, wd, wr, wi, hs, ha, hu, sy, rf, params.Uinit, params.Utarget_r, params.Utarget_i))
     pb = JqProblem(Ntot, params.N, params.Ncoupled, params.Nfreq, params.linear_solver.max_iter, params.objFuncType,
                    params.pFidType, params.linear_solver.solver_id, params.nsteps, params.T, pointer(params.Uinit), pointer(params.Utarget_r),
-                   pointer(params.Utarget_i), pointer(wd), pointer(Cf), jq_operator(params.Hconst, keep), pointer(hs), pointer(ha),
-                   params.linear_solver.tol)
+                   pointer(params.Utarget_i), pointer(wd), pointer(Cf), jq_operator(params.Hconst, keep),
+                   params.Ncoupled > 0 ? pointer(hs) : Ptr{JqOperator}(C_NULL), params.Ncoupled > 0 ? pointer(ha) : Ptr{JqOperator}(C_NULL),
+                   params.linear_solver.tol, params.globalPhase, dense_w ? pointer(wr) : Ptr{Float64}(C_NULL),
+                   dense_w ? pointer(wi) : Ptr{Float64}(C_NULL), Int32(params.Nunc), Int32(0),
+                   params.Nunc > 0 ? pointer(hu) : Ptr{JqOperator}(C_NULL), params.Nunc > 0 ? pointer(sy) : Ptr{Int32}(C_NULL),
+                   params.Nunc > 0 ? pointer(rf) : Ptr{Float64}(C_NULL))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep pb jq_check(ccall((:jq_create, libjq), Cint, (Ref{JqProblem}, Cint, Ref{Ptr{Cvoid}}), pb, device, h))
     wa = Working_Arrays_B200(h[], nCoeff, Any[])
@@ -158,4 +187,66 @@ function eval_forward(pcof0::Array{Float64,1}, params::objparams, wa::Working_Ar
                    (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                    wa.handle, 1, pcof0, length(pcof0), 1, C_NULL, saveEvery, hr, hi, C_NULL, C_NULL))
     return hr .+ im .* hi
+end
+
+
+# ---- the four Ipopt callbacks as ONE ccall each (src/ipopt_interface.jl:77-179): jq_eval_f_grad keeps the last-pcof cache, runs
+# eval_f_g_grad!'s sample loop as one launch and adds the Tikhonov terms on the device.  params.last_* scalars are kept for
+# intermediate_par (:212-228).
+function jq_shifts(params::objparams, nodes::AbstractArray)
+    n = params.N + params.Nguard
+    shifts = zeros(n, length(nodes))
+    for i in 1:length(nodes), j in 2:n
+        shifts[j, i] = 0.01 * nodes[i] * (10.0^(j - 2))          # src/ipopt_interface.jl:43
+    end
+    return shifts
+end
+
+function jq_eval_f_grad(pcof::Vector{Float64}, params::objparams, wa::Working_Arrays_B200, nodes::AbstractArray, weights::AbstractArray)
+    Npar = length(pcof)
+    shifts = jq_shifts(params, nodes)
+    w = Vector{Float64}(weights)
+    f = Ref{Float64}(0.0); infid = Ref{Float64}(0.0); leak = Ref{Float64}(0.0); ev = Ref{Int32}(0)
+    grad = zeros(Npar)
+    lgrad = params.objFuncType != 1 ? zeros(Npar) : zeros(0)
+    prior = params.usingPriorCoeffs ? Vector{Float64}(params.priorCoeffs) : zeros(0)
+    jq_check(ccall((:jq_eval_f_grad, libjq), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64},
+                    Ref{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}, Ptr{Float64}, Ref{Int32}),
+                   wa.handle, pcof, Npar, length(nodes), shifts, w, params.tik0,
+                   params.usingPriorCoeffs ? pointer(prior) : Ptr{Float64}(C_NULL), f, grad, infid, leak,
+                   params.objFuncType != 1 ? pointer(lgrad) : Ptr{Float64}(C_NULL), ev))
+    params.last_pcof .= pcof
+    params.last_infidelity = infid[]; params.last_leak = leak[]
+    params.lastTraceInfidelity = infid[]; params.lastLeakIntegral = leak[]
+    return f[], grad, leak[], lgrad, ev[] != 0
+end
+
+eval_f_par(pcof::Vector{Float64}, params::objparams, wa::Working_Arrays_B200, nodes::AbstractArray = [0.0], weights::AbstractArray = [1.0]) =
+    jq_eval_f_grad(pcof, params, wa, nodes, weights)[1]
+
+function eval_grad_f_par(pcof::Vector{Float64}, grad_f::Vector{Float64}, params::objparams, wa::Working_Arrays_B200,
+                         nodes::AbstractArray = [0.0], weights::AbstractArray = [1.0])
+    grad_f .= jq_eval_f_grad(pcof, params, wa, nodes, weights)[2]
+    params.save_pcof_hist && push!(params.pcof_hist, copy(pcof))
+end
+
+function eval_g_par(pcof::Vector{Float64}, g::Vector{Float64}, params::objparams, wa::Working_Arrays_B200,
+                    nodes::AbstractArray = [0.0], weights::AbstractArray = [1.0])
+    g[1] = jq_eval_f_grad(pcof, params, wa, nodes, weights)[3]
+    return g[1]
+end
+
+function eval_jac_g_par(pcof::Vector{Float64}, rows::Vector{Int32}, cols::Vector{Int32}, jac_g::Union{Nothing,Vector{Float64}},
+                        params::objparams, wa::Working_Arrays_B200, nodes::AbstractArray = [0.0], weights::AbstractArray = [1.0])
+    if jac_g === nothing
+        for i in 1:(length(rows) > 0 ? length(pcof) : 0)
+            rows[i] = 1; cols[i] = i
+        end
+        return
+    end
+    _, _, _, lgrad, evaluated = jq_eval_f_grad(pcof, params, wa, nodes, weights)
+    evaluated && return            # the reference returns without filling jac_g when it had to re-evaluate (:169-173)
+    jac_g .= lgrad
+    return
 end

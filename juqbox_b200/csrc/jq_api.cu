@@ -58,7 +58,8 @@ struct jq_handle {
     // host copies of the row-wise operators (for the planners)
     std::vector<int> rowptr, col;
     std::vector<double> val;
-    TrajPlan *slot = nullptr, *fiber = nullptr, *tile = nullptr;
+    TrajPlan *slot = nullptr, *fiber = nullptr, *tile = nullptr, *tile_lat = nullptr;     // tile_lat: fewest elements per lane (small batches)
+    int lat_ntraj = 0;                  // automatic mode: launches with at most this many trajectories use the latency layout
     char slot_reason[256] = "", fiber_reason[256] = "", tile_reason[256] = "";
     int kernel_pref = 0;
     bool prefer_tile = true;            // automatic mode: tile layout before the fibre layout
@@ -294,6 +295,17 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
     {
         const char *nt = getenv("JQ_TILE_NT");      // development: number of tiled directions of the tile layout (default: all)
         h->tile = jq_tile_plan_create(P, H, pb->wdiag, nt ? atoi(nt) : Nc, h->tile_reason, sizeof(h->tile_reason));
+        // Latency layout: a trajectory spread over as many lanes as the warp-local exchange allows (one element per lane for two
+        // subsystems, two for three).  A lone evaluation (the reference's own call pattern, one pcof per Ipopt callback) is bound
+        // by the instruction stream of ONE lane, so fewer elements per lane is what shortens it; throughput layouts win once the
+        // SMs are full.
+        char why[256];
+        const char *lnt = getenv("JQ_TILE_LAT_NT");
+        h->tile_lat = jq_tile_plan_create(P, H, pb->wdiag, lnt ? atoi(lnt) : (Nc == 2 ? 0 : 1), why, sizeof(why));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const char *lt = getenv("JQ_LAT_NTRAJ");
+        h->lat_ntraj = lt ? atoi(lt) : 2 * sms;
     }
     *out = h;
     return 0;
@@ -309,6 +321,7 @@ extern "C" int jq_destroy(jq_handle *h) {
     if (h->slot) jq_traj_plan_destroy(h->slot);
     if (h->fiber) jq_traj_plan_destroy(h->fiber);
     if (h->tile) jq_traj_plan_destroy(h->tile);
+    if (h->tile_lat) jq_traj_plan_destroy(h->tile_lat);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -350,7 +363,8 @@ extern "C" int64_t jq_abi_info(int32_t what) {
 }
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
-    if (!h || kernel < 0 || kernel > 4) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0, 1, 2, 3 or 4");
+    if (!h || kernel < 0 || kernel > 5) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0 ... 5");
+    if (kernel == 5 && !h->tile_lat) return fail(JQ_ERR_ARG, "jq_set_kernel: no latency (tile) layout for this problem");
     if (kernel == 4 && !h->tile) return fail(JQ_ERR_ARG, "jq_set_kernel: no tile-layout instantiation for this problem (%s)", h->tile_reason);
     if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no slot-layout instantiation for this problem (%s)", h->slot_reason);
     if (kernel == 3 && !h->fiber) return fail(JQ_ERR_ARG, "jq_set_kernel: no fibre-layout instantiation for this problem (%s)", h->fiber_reason);
@@ -463,11 +477,14 @@ __global__ void __launch_bounds__(32 * WS_LANES) jq_weighted_sum_kernel(int nsam
 // generic kernel.  In automatic mode a layout that cannot serve this launch (no instantiation for the variant, shared-memory
 // layout does not fit, out of launch resources) hands over to the next one; an explicitly requested kernel fails instead.
 static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t st) {
-    TrajPlan *cands[3] = {nullptr, nullptr, nullptr};
+    TrajPlan *cands[4] = {nullptr, nullptr, nullptr, nullptr};
     int ncand = 0;
     const int pref = h->kernel_pref;
+    const bool small = A.ntraj <= h->lat_ntraj;
+    if (pref == 5 || (pref == 0 && h->tile_lat && small)) cands[ncand++] = h->tile_lat;
+    if (pref == 0 && small && h->fiber && h->tile && h->Nc >= 3) cands[ncand++] = h->fiber;     // three subsystems: the fibre layout (4 elements per lane) before the 8-element tiles
     if (pref == 4 || (pref == 0 && h->tile && h->prefer_tile)) cands[ncand++] = h->tile;
-    if (pref == 3 || (pref == 0 && h->fiber)) cands[ncand++] = h->fiber;
+    if (pref == 3 || (pref == 0 && h->fiber && !(ncand && cands[ncand - 1] == h->fiber) && !(ncand > 1 && cands[ncand - 2] == h->fiber))) cands[ncand++] = h->fiber;
     if (pref == 2 || (pref == 0 && h->slot)) cands[ncand++] = h->slot;
     TrajPlan *plan = nullptr;
     int ctas = 0, regs = 0, tpc = 1;
@@ -489,7 +506,7 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
     }
     CU(cudaEventRecord(h->ev1, st));
     h->timed = true;
-    h->last_kernel = plan ? jq_traj_plan_kind(plan) : 1;
+    h->last_kernel = plan ? (plan == h->tile_lat ? 5 : jq_traj_plan_kind(plan)) : 1;
     h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = tpc;
     return 0;
 }

@@ -285,7 +285,7 @@ TrajPlan *jq_tile_plan_create(const DevProblem &P, const HostOps &H, const doubl
     if (P.wreal || P.any_unc) return no("dense forbidden-state weights / uncoupled controls run on the generic kernel");
     if (P.solver != 1 || P.objFuncType != 1) return no("tile layout: only objFuncType 1 with the Neumann solver is instantiated");
     if (Nc < 2 || Nc > 3) return no("tile layout: 2 or 3 controls");
-    if (NT < 2 || NT > Nc) return no("tile layout: bad number of tiled directions");
+    if (NT < 0 || NT > Nc) return no("tile layout: bad number of tiled directions");
     int n4 = 1;
     for (int q = 0; q < Nc; ++q) n4 *= 4;
     if (n != n4) return no("tile layout: every subsystem must have 4 levels");

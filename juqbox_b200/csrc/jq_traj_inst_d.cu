@@ -6,6 +6,8 @@ const Inst kInstD[] = {
     TILEJ(2, 2, 1, 0, 0),                  // 4 x 4 levels, run-time J and group size
     TILEJW(3, 3, 1, 3, 32, 8, 1, 0),       // cnot3 example shape: 4 x 4 x 4 levels, 2 x 2 x 2 tiles (one warp per trajectory), J = 3, 8 warps per CTA
     TILEJW(3, 3, 1, 0, 0, 8, 1, 0),        // 4 x 4 x 4 levels, run-time J and group size
+    TILEJ(2, 0, 1, 4, 32), TILEJ(2, 0, 1, 0, 0),   // latency layout for small batches: one element per lane, 64 lanes per 4 x 4 x 4-column trajectory
+    TILEJ(3, 1, 1, 3, 32), TILEJ(3, 1, 1, 0, 0),   // 4 x 4 x 4 levels: first subsystem in halves, 2 elements per lane, one warp per column
     TILEJ(3, 2, 1, 0, 0),                  // 2 x 2 tiles x remote third subsystem (JQ_TILE_NT=2; 4 elements per lane, no spills, slower)
 };
 const int kInstDCount = (int)(sizeof(kInstD) / sizeof(kInstD[0]));

@@ -422,7 +422,8 @@ template <int NC_, int NT_>
 struct TileLane {
     static constexpr int NC = NC_, NT = NT_, E = 1 << NT_, HX = 0, R = NT_;
     static constexpr bool SIGNED = true;
-    double cin[NT], cx[NT], sg[NT];          // in-lane pair coupling, cross-lane (interface) coupling, mirror sign
+    static constexpr int NT1 = NT_ > 0 ? NT_ : 1, EH = NT_ > 0 ? (1 << NT_) / 2 : 1;      // array extents (NT = 0: one element per lane, all directions remote)
+    double cin[NT1], cx[NT1], sg[NT1];       // in-lane pair coupling, cross-lane (interface) coupling, mirror sign
     static constexpr int NREM = NC_ > NT_ ? NC_ - NT_ : 1;
     int rpos[NREM][2];
     double rhs[NREM][2];
@@ -460,7 +461,7 @@ struct TileLane {
 
     // index of element e inside the interface face of direction d (bit d removed)
     static __device__ __forceinline__ constexpr int face(int e, int d) { return (e & ((1 << d) - 1)) | ((e >> (d + 1)) << d); }
-    struct Nbr { double t[NT][E / 2]; double r[NREM][2][E]; };
+    struct Nbr { double t[NT1][EH]; double r[NREM][2][E]; };
     __device__ __forceinline__ void exchange(const double (&x)[E], Nbr &nb) const {
         UNROLL for (int d = 0; d < NT; ++d)
             UNROLL for (int e = 0; e < E; ++e)
@@ -472,7 +473,7 @@ struct TileLane {
             }
     }
 
-    struct SC { double a[NT], b[NT], r[NREM][2]; };
+    struct SC { double a[NT1], b[NT1], r[NREM][2]; };
     __device__ __forceinline__ void s_prescale(int level, SC &sc) const {          // q[level] already carries sg
         UNROLL for (int d = 0; d < NT; ++d) { sc.a[d] = q[level][d] * cin[d]; sc.b[d] = q[level][d] * cx[d]; }
         UNROLL for (int r = 0; r < NC - NT; ++r) { sc.r[r][0] = -q[level][NT + r] * rhs[r][0]; sc.r[r][1] = q[level][NT + r] * rhs[r][1]; }
@@ -483,6 +484,7 @@ struct TileLane {
     }
     template <bool ADD>
     __device__ __forceinline__ void s_from(const SC &sc, const double (&x)[E], const Nbr &nb, const double (&add)[E], double (&t)[E]) const {
+        if constexpr (NT == 0) { UNROLL for (int e = 0; e < E; ++e) t[e] = ADD ? add[e] : 0.0; }
         UNROLL for (int d = 0; d < NT; ++d)                // in-lane pair couplings first: independent of the exchange;
             UNROLL for (int e = 0; e < E; ++e) {           // direction outer / element inner: neighbouring FMAs share the coefficient register
                 const double c = ((e >> d) & 1) ? -sc.a[d] : sc.a[d];

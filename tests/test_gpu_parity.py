@@ -27,7 +27,7 @@ def _wa(cfg, kernel):
     return wa
 
 
-KERNELS = [1, 2, 3, 4]
+KERNELS = [1, 2, 3, 4, 5]
 GOLDEN_CASES = ["rabi", "swap02", "cnot2", "flux", "cnot2-leakieq", "cnot2-jacobi", "cnot3"]
 
 
@@ -333,12 +333,12 @@ def test_jacobi_solver_tolerance_exit_vs_oracle():
 @pytest.mark.parametrize("Ne,Ng,kw,kernel", [
     ([2], [1], {}, 3), ([3], [2], {}, 3), ([5], [3], {}, 2), ([2, 2], [0, 0], {}, 3), ([3, 3], [2, 2], {}, 3),
     ([3, 2], [2, 1], {}, 3), ([2, 2, 2], [1, 1, 1], {}, 3), ([2, 2], [2, 2], {"exchange": 0.02}, 3), ([3, 2], [1, 1], {"exchange": 0.05}, 3),
-    ([2, 2, 2], [1, 1, 1], {"exchange": 0.02}, 1), ([2, 2], [2, 2], {"Nfreq": 3}, 4), ([2, 2], [2, 2], {}, 4),
-    ([2, 2, 1], [2, 2, 3], {"T": 6.0}, 4),
+    ([2, 2, 2], [1, 1, 1], {"exchange": 0.02}, 1), ([2, 2], [2, 2], {"Nfreq": 3}, 5), ([2, 2], [2, 2], {}, 5),
+    ([2, 2, 1], [2, 2, 3], {"T": 6.0}, 5),
 ])
 def test_other_shapes_auto_kernel_vs_oracle(Ne, Ng, kw, kernel):
     """Shapes beyond the named configs (tools/kernel_coverage.py): the auto-selected kernel is the expected one and
-    matches the oracle.  All-4-level qudits go to the tile layout (kernel 4).  Exchange couplings a_0' a_q + a_0 a_q' in the drift ride on the fibre kernel's neighbour fetches; a
+    matches the oracle.  All-4-level qudits go to the tile layout (kernel 4; its latency variant, kernel 5, for a 3-candidate batch).  Exchange couplings a_0' a_q + a_0 a_q' in the drift ride on the fibre kernel's neighbour fetches; a
     coupling between two remote subsystems (three qudits) must fall back to the generic kernel, not be mis-planned."""
     import juqbox_b200 as jq
     from juqbox_b200 import configs
