@@ -282,6 +282,18 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
     UPI(h->rowptr.data(), h->rowptr.size(), P.rowptr);
     UPI(h->col.data(), h->col.size(), P.col);
     UPI(h0diag.data(), n, P.h0diag);
+    {   // packed copy of the operator table for the generic kernel's bulk copy
+        const size_t nrp = h->rowptr.size(), nnz = h->col.size();
+        const size_t off_col = nrp * sizeof(int), off_val = (off_col + nnz * sizeof(int) + 15) & ~(size_t)15;
+        const size_t total = (off_val + nnz * sizeof(double) + 15) & ~(size_t)15;
+        std::vector<unsigned char> blob(total, 0);
+        memcpy(blob.data(), h->rowptr.data(), nrp * sizeof(int));
+        memcpy(blob.data() + off_col, h->col.data(), nnz * sizeof(int));
+        memcpy(blob.data() + off_val, h->val.data(), nnz * sizeof(double));
+        unsigned char *dblob = nullptr;
+        if ((rc = upload(h, blob.data(), total, &dblob)) != 0) { jq_destroy(h); return rc; }
+        P.csr_blob = dblob; P.csr_bytes = (int)total; P.csr_off_col = (int)off_col; P.csr_off_val = (int)off_val;
+    }
 #undef UP
 #undef UPI
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||

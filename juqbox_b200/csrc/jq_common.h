@@ -18,6 +18,10 @@ struct DevProblem {
     const int *col;
     const double *val;
     const int *h0diag;     // n: position of H0[i,i] inside col/val (always present)
+    // the same table as ONE 16-byte aligned blob [rowptr | col | pad | val] (byte offsets below), the source of the generic
+    // kernel's TMA bulk copy into shared memory; csr_bytes is a multiple of 16
+    const void *csr_blob;
+    int csr_bytes, csr_off_col, csr_off_val;
     // --- SURVEY 8f rank 3 ---
     int pFidType;          // 1, 2, 3 or 4 (src/evalobjgrad.jl:755-763); 3: the global phase is the last entry of every pcof vector
     double globalPhase;    // params.globalPhase (pFidType 1 and 4)

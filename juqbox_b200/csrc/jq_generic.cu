@@ -8,14 +8,26 @@
 // condition :810-844 / :2026-2042, backward loop :859-921, steppers src/StormerVerlet.jl:255-303,:365-406,:461-504,
 // Neumann src/linear_solvers.jl:94-106, controls src/bsplines.jl:211-304,:321-381, gradient :2567-2619.
 // K(t) and S(t) are never assembled: K(t)x = H0 x + sum_q p_q(t) Hsym_q x,  S(t)x = sum_q q_q(t) Hanti_q x.
+//
+// Work decomposition: a GROUP of TPT threads (32, 64, 128 or 256: the smallest that covers n*m, one element per thread where
+// possible) owns one trajectory; a CTA of GEN_THREADS threads runs GEN_THREADS / TPT groups side by side, each looping over its
+// own trajectories and synchronising only with itself (__syncwarp for one-warp groups, a named barrier per group otherwise).
+// Operators: the whole row-wise CSR table (row pointers, columns, values of Hconst, Hsym_q, Hanti_q) is staged into shared
+// memory ONCE per CTA with a 1-D TMA bulk copy (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) when it fits next to
+// the state blocks; otherwise the products read it through L1.
 #include "jq_common.h"
 
-#define GEN_THREADS 128
+#define GEN_THREADS 256
 
 namespace {
 
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 struct Ctx {
     const DevProblem *P;
+    int gtid, tpt, bar, gwarps;          // thread in group, threads per group, named-barrier id of the group, warps per group
+    const int *rp, *cl;                  // row pointers / columns / values of the operator table: shared memory or global
+    const double *vl;
     int n, m, len, Nc, Nfreq, D1, Npar, J;
     double *vr, *vi, *vi05, *vr0;
     double *lr, *li, *lr05, *li0;
@@ -37,11 +49,16 @@ __device__ __forceinline__ double wreal_apply(const Ctx &c, const double *x, int
     return c.P->wreal ? wapply(c, c.P->wreal, x, i, j) : c.P->wdiag[i] * x[e];
 }
 
+// all threads of the group (the trajectory's n x m blocks live in the group's shared memory)
+__device__ __forceinline__ void gsync(const Ctx &c) {
+    if (c.tpt == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(c.bar), "r"(c.tpt) : "memory");
+}
 __device__ __forceinline__ double op_apply(const Ctx &c, int o, const double *x, int i, int j) {
-    const int *rp = c.P->rowptr + o * (c.n + 1);
+    const int *rp = c.rp + o * (c.n + 1);
     const double *xc = x + j * c.n;
     double s = 0.0;
-    for (int p = rp[i]; p < rp[i + 1]; ++p) s += c.P->val[p] * xc[c.P->col[p]];
+    for (int p = rp[i]; p < rp[i + 1]; ++p) s += c.vl[p] * xc[c.cl[p]];
     return s;
 }
 __device__ __forceinline__ double applyK(const Ctx &c, int level, const double *x, int i, int j) {
@@ -88,7 +105,7 @@ __device__ double bcarrier2(const Ctx &c, double t, int func) {
 
 __device__ void eval_controls(const Ctx &c, double t, double dt) {
     const int nf = 2 * c.Nc;
-    for (int idx = threadIdx.x; idx < 3 * nf; idx += GEN_THREADS) {
+    for (int idx = c.gtid; idx < 3 * nf; idx += c.tpt) {
         const int level = idx / nf, func = idx % nf;
         const double tt = level == 0 ? t : (level == 1 ? t + 0.5 * dt : t + dt);
         const int kind = c.P->ctrl_kind[func >> 1];
@@ -104,10 +121,12 @@ __device__ void eval_controls(const Ctx &c, double t, double dt) {
             c.ctrl[idx] = v;
         }
     }
-    __syncthreads();
+    gsync(c);
 }
 
-#define FOR_E for (int e = threadIdx.x, i = e % c.n, j = e / c.n; e < c.len; e += GEN_THREADS, i = e % c.n, j = e / c.n)
+// element loop of the group: e = gtid, gtid + tpt, ...; (i, j) = (row, column) advanced without divisions
+#define FOR_E for (int e = c.gtid, i = c.gtid % c.n, j = c.gtid / c.n, di_ = c.tpt % c.n, dj_ = c.tpt / c.n; e < c.len; \
+                   e += c.tpt, i += di_, j += dj_ + (i >= c.n ? 1 : 0), i -= (i >= c.n ? c.n : 0))
 
 // X = sum_{j<=J} (h/2)^j S^j B ; B destroyed, T scratch (src/linear_solvers.jl:94-106)
 __device__ void neumann(const Ctx &c, int level, double h, double *B, double *T, double *X) {
@@ -116,7 +135,7 @@ __device__ void neumann(const Ctx &c, int level, double h, double *B, double *T,
     for (int it = 0; it < c.J; ++it) {
         coeff *= 0.5 * h;
         FOR_E { double tv = applyS(c, level, B, i, j); T[e] = tv; X[e] += coeff * tv; }
-        __syncthreads();
+        gsync(c);
         double *sw = B; B = T; T = sw;
     }
 }
@@ -127,13 +146,13 @@ __device__ void neumann(const Ctx &c, int level, double h, double *B, double *T,
 __device__ void block_sum(const Ctx &c, double *v, int cnt);
 __device__ void jacobi(const Ctx &c, int level, double h, const double *B, double *T, double *X) {
     FOR_E X[e] = B[e];
-    __syncthreads();
+    gsync(c);
     for (int it = 0; it < c.J; ++it) {
         double err[1] = {0.0};
         FOR_E { double tv = B[e] + 0.5 * h * applyS(c, level, X, i, j); double d = tv - X[e]; err[0] += d * d; T[e] = tv; }
         block_sum(c, err, 1);                 // also orders the T writes before the copy below
         FOR_E X[e] = T[e];
-        __syncthreads();
+        gsync(c);
         if (sqrt(err[0]) < c.P->tol) break;   // uniform across the CTA: block_sum broadcasts
     }
 }
@@ -147,20 +166,20 @@ __device__ __forceinline__ void solve(const Ctx &c, int level, double h, double 
 __device__ void state_step(const Ctx &c, double h) {
     double *u = c.vr, *v = c.vi, *v05 = c.vi05;
     FOR_E c.rhs[e] = applyK(c, 1, u, i, j) + applyS(c, 1, v, i, j);
-    __syncthreads();
+    gsync(c);
     solve(c, 1, h, c.rhs, c.scr, c.l1);
     FOR_E v05[e] = v[e] + 0.5 * h * c.l1[e];
-    __syncthreads();
+    gsync(c);
     FOR_E c.k1[e] = applyS(c, 0, u, i, j) - applyK(c, 0, v05, i, j);
-    __syncthreads();
+    gsync(c);
     FOR_E c.rhs[e] = applyS(c, 2, u, i, j) + 0.5 * h * applyS(c, 2, c.k1, i, j) - applyK(c, 2, v05, i, j);
-    __syncthreads();
+    gsync(c);
     FOR_E u[e] += 0.5 * h * c.k1[e];
     solve(c, 2, h, c.rhs, c.scr, c.k2);
     FOR_E u[e] += 0.5 * h * c.k2[e];
-    __syncthreads();
+    gsync(c);
     FOR_E { c.l2[e] = applyK(c, 1, u, i, j) + applyS(c, 1, v05, i, j); v[e] += 0.5 * h * (c.l1[e] + c.l2[e]); }
-    __syncthreads();
+    gsync(c);
 }
 
 // src/StormerVerlet.jl:255-303 (forcing) / :365-406 (no forcing).  Forcing with diagonal W:
@@ -172,49 +191,51 @@ __device__ void adjoint_step(const Ctx &c, double *mu, double *nu, double *X, do
         double f = forcing ? tinv * wreal_apply(c, c.vr0, e, i, j) : 0.0;
         c.rhs[e] = applyS(c, 0, mu, i, j) - applyK(c, 1, nu, i, j) + f;
     }
-    __syncthreads();
+    gsync(c);
     solve(c, 0, h, c.rhs, c.scr, c.k2);
     FOR_E { mu[e] += 0.5 * h * c.k2[e]; X[e] = mu[e]; }
-    __syncthreads();
+    gsync(c);
     FOR_E {
         double f = forcing ? tinv * wreal_apply(c, c.vi05, e, i, j) : 0.0;
         c.l2[e] = applyK(c, 0, X, i, j) + applyS(c, 1, nu, i, j) + f;
     }
-    __syncthreads();
+    gsync(c);
     FOR_E {
         double f = forcing ? tinv * wreal_apply(c, c.vi05, e, i, j) : 0.0;
         if (forcing && Wi) f -= tinv * wapply(c, Wi, c.vr, i, j);
         c.rhs[e] = applyS(c, 1, nu, i, j) + 0.5 * h * applyS(c, 1, c.l2, i, j) + applyK(c, 2, X, i, j) + f;
     }
-    __syncthreads();
+    gsync(c);
     solve(c, 1, h, c.rhs, c.scr, c.l1);
     FOR_E nu[e] += 0.5 * h * (c.l2[e] + c.l1[e]);
-    __syncthreads();
+    gsync(c);
     FOR_E {
         double f = forcing ? tinv * wreal_apply(c, c.vr, e, i, j) : 0.0;
         if (forcing && Wi) f += tinv * wapply(c, Wi, c.vi05, i, j);
         c.k1[e] = applyS(c, 2, X, i, j) - applyK(c, 1, nu, i, j) + f;
     }
-    __syncthreads();
+    gsync(c);
     FOR_E mu[e] += 0.5 * h * c.k1[e];
-    __syncthreads();
+    gsync(c);
 }
 
-// Sum `cnt` (<= 8) per-thread values over the CTA; result broadcast to every thread.
+// Sum `cnt` (<= 8) per-thread values over the group; result broadcast to every thread of the group.
 __device__ void block_sum(const Ctx &c, double *v, int cnt) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = c.gtid >> 5;
     for (int k = 0; k < cnt; ++k) {
         double x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) c.red[w * 8 + k] = x;
+        if (c.gwarps == 1) v[k] = x;
+        else if (lane == 0) c.red[w * 8 + k] = x;
     }
-    __syncthreads();
+    if (c.gwarps == 1) return;
+    gsync(c);
     for (int k = 0; k < cnt; ++k) {
         double x = 0.0;
-        for (int ww = 0; ww < GEN_THREADS / 32; ++ww) x += c.red[ww * 8 + k];
+        for (int ww = 0; ww < c.gwarps; ++ww) x += c.red[ww * 8 + k];
         v[k] = x;
     }
-    __syncthreads();
+    gsync(c);
 }
 
 // One step's contribution to the gradient (src/evalobjgrad.jl:2567-2619), scaled by dt at the end of the sweep.
@@ -235,7 +256,7 @@ __device__ void grad_step(const Ctx &c, const double *lr05, const double *li, co
         block_sum(c, T, 5);
         // threads (f, alpha) scatter into the 3 knots of each of the 3 time points; deterministic order
         const int kind = c.P->ctrl_kind[q];
-        for (int idx = threadIdx.x; idx < 2 * c.Nfreq; idx += GEN_THREADS) {
+        for (int idx = c.gtid; idx < 2 * c.Nfreq; idx += c.tpt) {
             const int fr = idx >> 1, alpha = idx & 1;
             const int base = 2 * q * c.Nfreq * c.D1 + fr * 2 * c.D1 + alpha * c.D1 - 1;
             const double om = c.P->cfreq[q + c.Nc * fr];
@@ -268,7 +289,7 @@ __device__ void grad_step(const Ctx &c, const double *lr05, const double *li, co
             }
         }
     }
-    __syncthreads();
+    gsync(c);
 }
 
 __device__ void trace_fid(const Ctx &c, double *re, double *im) {
@@ -282,15 +303,48 @@ __device__ void trace_fid(const Ctx &c, double *re, double *im) {
     *im = v[1] / c.m;
 }
 
-__global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, LaunchArgs A) {
-    extern __shared__ double sm[];
+// Geometry of one launch (host-computed): threads per group, groups per CTA, doubles of shared memory per group, and whether
+// the operator table is staged into shared memory.
+struct GenGeom { int tpt, gpc, per_group, stage; };
+
+__global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, LaunchArgs A, GenGeom G) {
+    extern __shared__ __align__(16) double sm[];
     Ctx c;
     c.P = &P;
     c.n = P.n; c.m = P.m; c.len = P.n * P.m; c.Nc = P.Nc; c.Nfreq = P.Nfreq; c.J = P.J;
     c.Npar = A.Npar; c.D1 = A.D1;
     c.dtknot = P.T / (A.D1 - 2);
     c.tinv = 1.0 / P.T;
-    double *p = sm;
+    c.tpt = G.tpt; c.gwarps = G.tpt / 32;
+    const int grp = threadIdx.x / G.tpt;
+    c.gtid = threadIdx.x % G.tpt;
+    c.bar = 1 + grp;                                   // named barrier of this group (0 is __syncthreads)
+    // ---- operator table: one TMA bulk copy into shared memory per CTA (cp.async.bulk + mbarrier), or global memory through L1
+    c.rp = P.rowptr; c.cl = P.col; c.vl = P.val;
+    size_t off = 0;                                    // doubles
+    if (G.stage) {
+        unsigned char *blob = reinterpret_cast<unsigned char *>(sm);
+        unsigned long long *mbar = reinterpret_cast<unsigned long long *>(blob + P.csr_bytes);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(P.csr_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(blob)), "l"(P.csr_blob), "r"(P.csr_bytes), "r"(smem_u32(mbar)) : "memory");
+        }
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(smem_u32(mbar)) : "memory");
+        c.rp = reinterpret_cast<const int *>(blob);
+        c.cl = reinterpret_cast<const int *>(blob + P.csr_off_col);
+        c.vl = reinterpret_cast<const double *>(blob + P.csr_off_val);
+        off = (P.csr_bytes + 16) / sizeof(double);
+    }
+    double *p = sm + off + (size_t)grp * G.per_group;
     double **blk[] = {&c.vr, &c.vi, &c.vi05, &c.vr0, &c.lr, &c.li, &c.lr05, &c.li0, &c.lrn, &c.lin, &c.lr05n, &c.li0n,
                       &c.rhs, &c.scr, &c.k1, &c.k2, &c.l1, &c.l2};
     for (int b = 0; b < 18; ++b) {
@@ -303,15 +357,16 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
     c.ctrl = p; p += 6 * c.Nc;
     c.shift = p; p += c.n;
     c.red = p;
+    if (grp >= G.gpc) return;                          // threads beyond the last whole group (none with the host's geometry)
 
     const double tinv = 1.0 / P.T;
-    for (int traj = blockIdx.x; traj < A.ntraj; traj += gridDim.x) {
+    for (int traj = blockIdx.x * G.gpc + grp; traj < A.ntraj; traj += gridDim.x * G.gpc) {      // persistent: groups loop over trajectories
         const int b = traj / A.nsamples, s = traj % A.nsamples;
-        for (int k = threadIdx.x; k < c.Npar; k += GEN_THREADS) { c.pcof[k] = A.pcof[(size_t)b * A.pstride + k]; c.grad[k] = 0.0; if (P.objFuncType != 1) c.igrad[k] = 0.0; }
+        for (int k = c.gtid; k < c.Npar; k += c.tpt) { c.pcof[k] = A.pcof[(size_t)b * A.pstride + k]; c.grad[k] = 0.0; if (P.objFuncType != 1) c.igrad[k] = 0.0; }
         const double phase = P.pFidType == 3 ? A.pcof[(size_t)b * A.pstride + c.Npar] : P.globalPhase;   // src/evalobjgrad.jl:591-596
-        for (int k = threadIdx.x; k < c.n; k += GEN_THREADS) c.shift[k] = A.shift ? A.shift[(size_t)s * c.n + k] : 0.0;
+        for (int k = c.gtid; k < c.n; k += c.tpt) c.shift[k] = A.shift ? A.shift[(size_t)s * c.n + k] : 0.0;
         FOR_E { c.vr[e] = P.uinit[e]; c.vi[e] = 0.0; c.vi05[e] = 0.0; }
-        __syncthreads();
+        gsync(c);
 
         // ---------------- forward sweep ----------------
         double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
@@ -334,7 +389,7 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
                     pen += c.vr[e] * wapply(c, P.wreal, c.vr, i, j) + 2.0 * c.vi05[e] * wapply(c, P.wreal, c.vi05, i, j);
                     if (P.wimag) pen -= 2.0 * c.vi05[e] * wapply(c, P.wimag, c.vr0, i, j);
                 }
-                __syncthreads();                                                   // vr0 is rewritten at the top of the next step
+                gsync(c);                                                   // vr0 is rewritten at the top of the next step
             }
             if (hr && (step + 1) % A.save_every == 0) {                                      // src/evalobjgrad.jl:2847-2849
                 const size_t o = (size_t)((step + 1) / A.save_every) * c.len;
@@ -351,11 +406,11 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
         // src/evalobjgrad.jl:755-763: type 1: 1 + |s|^2 - 2 Re(s e^{-i phase}); type 2: 1 - |s|^2; types 3, 4: 1 - tracefidreal(v, e^{i phase} Vtg) = 1 - (Re s cos(phase) - Im s sin(phase))
         const double infid = pfid == 1 ? 1.0 + abs2 - 2.0 * (re * cph + im * sph) : pfid == 2 ? 1.0 - abs2 : 1.0 - (re * cph - im * sph);
         const double leak = 0.5 * dt * tinv * pv[0];
-        if (threadIdx.x == 0) {
+        if (c.gtid == 0) {
             double *o = A.scal + (size_t)traj * 4;
             o[0] = infid; o[1] = leak; o[2] = 1.0 - abs2; o[3] = 0.0;      // traceInfidelity is always 1 - |s|^2 (:792)
         }
-        if (!A.evaladjoint) { __syncthreads(); continue; }
+        if (!A.evaladjoint) { gsync(c); continue; }
 
         // ---------------- backward sweep ----------------
         // terminal condition (init_adjoint!, :2026-2059).  Types 1 and 2 share the formula, type 1 on scomplex0 = e^{i phase} - s
@@ -371,7 +426,7 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
         }
         t = P.T;
         dt = -dt;
-        __syncthreads();
+        gsync(c);
         for (long long step = P.nsteps - 1; step >= 0; --step) {
             const double t0 = t;
             FOR_E c.vr0[e] = c.vr[e];
@@ -386,29 +441,55 @@ __global__ void __launch_bounds__(GEN_THREADS) jq_generic_kernel(DevProblem P, L
                 grad_step(c, c.lr05n, c.lin, c.li0n, t0, dt, c.igrad);
                 FOR_E c.li0n[e] = c.lin[e];
             }
-            __syncthreads();
+            gsync(c);
         }
-        for (int k = threadIdx.x; k < c.Npar; k += GEN_THREADS) {
+        for (int k = c.gtid; k < c.Npar; k += c.tpt) {
             A.grad[(size_t)traj * A.gstride + k] = dt * c.grad[k];
             if (P.objFuncType != 1 && A.infidgrad) A.infidgrad[(size_t)traj * A.gstride + k] = dt * c.igrad[k];
         }
-        if (pfid == 3 && threadIdx.x == 0) {
+        if (pfid == 3 && c.gtid == 0) {
             // primObjGradPhase = -tracefidreal(vfinal, Re(i rot), Im(i rot)) = Re(s) sin(phase) + Im(s) cos(phase) (:923-945),
             // appended to the total and to the infidelity gradient (leakgrad's last entry is their difference, 0)
             const double pg = re * sph + im * cph;
             A.grad[(size_t)traj * A.gstride + c.Npar] = pg;
             if (P.objFuncType != 1 && A.infidgrad) A.infidgrad[(size_t)traj * A.gstride + c.Npar] = pg;
         }
-        __syncthreads();
+        gsync(c);
     }
 }
 
 }  // namespace
 
-size_t jq_generic_smem_bytes(const DevProblem &P, int Npar) {
+// doubles of shared memory per trajectory group
+static size_t per_group_doubles(const DevProblem &P, int Npar) {
     const size_t len = (size_t)P.n * P.m;
     const size_t nblk = P.objFuncType == 1 ? 14 : 18;
-    return sizeof(double) * (nblk * len + Npar * (P.objFuncType == 1 ? 2 : 3) + 6 * P.Nc + P.n + (GEN_THREADS / 32) * 8);
+    size_t d = nblk * len + (size_t)Npar * (P.objFuncType == 1 ? 2 : 3) + 6 * P.Nc + P.n + (GEN_THREADS / 32) * 8;
+    return (d + 1) & ~(size_t)1;                       // keep every group's region 16-byte aligned
+}
+
+static GenGeom generic_geometry(const DevProblem &P, int Npar, size_t *bytes) {
+    const size_t len = (size_t)P.n * P.m, limit = 227 * 1024;
+    GenGeom G{};
+    G.tpt = len <= 32 ? 32 : len <= 64 ? 64 : len <= 128 ? 128 : 256;
+    G.gpc = GEN_THREADS / G.tpt;
+    G.per_group = (int)per_group_doubles(P, Npar);
+    const size_t blob = P.csr_blob ? (size_t)P.csr_bytes + 16 : 0;      // + mbarrier
+    while (G.gpc > 1 && (size_t)G.gpc * G.per_group * sizeof(double) > limit) G.gpc >>= 1;
+    size_t need = (size_t)G.gpc * G.per_group * sizeof(double);
+    G.stage = blob != 0 && need + blob <= limit;
+    // staging beats more groups per CTA only if the groups still fit: give up groups down to half before giving up staging
+    if (!G.stage && blob != 0 && G.gpc > 1 && (size_t)(G.gpc / 2) * G.per_group * sizeof(double) + blob <= limit) {
+        G.gpc /= 2;
+        need = (size_t)G.gpc * G.per_group * sizeof(double);
+        G.stage = 1;
+    }
+    *bytes = need + (G.stage ? blob : 0);
+    return G;
+}
+
+size_t jq_generic_smem_bytes(const DevProblem &P, int Npar) {          // minimum: one group, operators through L1
+    return per_group_doubles(P, Npar) * sizeof(double);
 }
 
 // evalctrl (src/plotstatectrl.jl:246-276): the control functions of every coupled control on an arbitrary time grid,
@@ -434,7 +515,8 @@ cudaError_t jq_controls_launch(const DevProblem &P, int D1, const double *pcof, 
 }
 
 cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem) {
-    const size_t bytes = jq_generic_smem_bytes(P, A.Npar);
+    size_t bytes = 0;
+    const GenGeom G = generic_geometry(P, A.Npar, &bytes);
     cudaError_t e = cudaFuncSetAttribute(jq_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
@@ -443,10 +525,11 @@ cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStre
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jq_generic_kernel, GEN_THREADS, bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, jq_generic_kernel, G.tpt * G.gpc, bytes);
     if (occ < 1) occ = 1;
-    int grid = A.ntraj < sms * occ ? A.ntraj : sms * occ;   // persistent: CTAs loop over trajectories
-    jq_generic_kernel<<<grid, GEN_THREADS, bytes, st>>>(P, A);
+    const int want = (A.ntraj + G.gpc - 1) / G.gpc;
+    int grid = want < sms * occ ? want : sms * occ;   // persistent: groups loop over trajectories
+    jq_generic_kernel<<<grid, G.tpt * G.gpc, bytes, st>>>(P, A, G);
     if (nctas) *nctas = grid;
     if (regs) *regs = fa.numRegs;
     if (smem) *smem = bytes;

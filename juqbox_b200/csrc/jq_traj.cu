@@ -11,14 +11,14 @@ const Inst kInst[] = {
 };
 
 // jt = 0: the run-time-J instantiation; jt > 0: the one with exactly jt Neumann terms compiled in (if any).
-const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0, int jt = 0) {
+const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0, int jt = 0, int nw = 0) {
     const Inst *parts[4] = {kInst, kInstB, kInstC, kInstD};
     const int counts[4] = {(int)(sizeof(kInst) / sizeof(kInst[0])), kInstBCount, kInstCCount, kInstDCount};
     for (int p = 0; p < 4; ++p)
         for (int j = 0; j < counts[p]; ++j) {
             const Inst &i = parts[p][j];
             if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant &&
-                i.jt == jt && (i.glt == 0 || i.glt == GL)) return &i;
+                i.jt == jt && (i.glt == 0 || i.glt == GL) && (nw == 0 || i.nw == nw)) return &i;
         }
     return nullptr;
 }
@@ -242,7 +242,12 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
     pl->ngroups = TRAJ_WARPS * (32 / GL);
     pl->TPC = pl->ngroups / GPT;
     pl->exch_per_unit = 4 * R * 32;           // 2 parities x 2 fibres per round
-    if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
+    if (pl->TPC < 1) {
+        // a trajectory wider than 4 warps (e.g. 45 x 12): the 8-warp instantiations, plain problems only
+        const bool plain = AS && !HX && P.objFuncType == 1 && P.solver == 1;
+        if (GPT <= 8 && plain && find_inst(3, R, 1, Nc, 2, LMASK, UPL, 0, GL, 0, 8)) { pl->nw = 8; pl->ngroups = 8 * (32 / GL); pl->TPC = pl->ngroups / GPT; }
+        else { delete pl; return no("a trajectory does not fit in one CTA"); }
+    }
     const int perq = 4 * (R - 1) + 4 + (HX ? 2 * (R - 1) : 0), per = Nc * perq;
     std::vector<int> pi((size_t)NL * Nc * 2, 0);
     std::vector<double> pd((size_t)NL * per, 0.0), d0p((size_t)NL * R, 0.0), wp((size_t)NL * R, 0.0);
@@ -368,7 +373,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     else if (!pl->AS) want = 16;
     if ((want == 64 || want == 128 || want == 8) && !pl->AS) return cudaErrorNotSupported;
     const Inst *inst = nullptr;
-    if (want == 0) {
+    if (want == 0 && !pl->nw) {
         const char *xm = getenv("JQ_TRAJ_XMODE");
         const int xv = xm ? atoi(xm) : 0;
         if (xv > 0) {
@@ -378,6 +383,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
         if (!inst && P.J > 0)     // instantiation with the number of Neumann terms known at compile time
             inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J);
     }
+    if (pl->nw) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, want, pl->GL, 0, pl->nw);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, want, pl->GL, 0);
     if (!inst) return cudaErrorNotSupported;       // never substitute: Neumann for Jacobi, one adjoint set for two, no drift couplings
     if (inst->jt != 0 && inst->jt != P.J) return cudaErrorNotSupported;

@@ -61,6 +61,7 @@ struct TrajPlan {
     int kind;                                // 2 slot, 3 fibre
     int R, C, NC, WQ, LMASK, UPL, AS, HX = 0;
     int NL, GL, GPT, TPC, ngroups, CPG, NLR, exch_per_unit;
+    int nw = 0;                              // warps per CTA the plan needs (0: the instantiation's own)
     int *d_i = nullptr;
     double *d_d = nullptr, *d_d0 = nullptr, *d_w = nullptr;
 };
@@ -1080,5 +1081,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define TILEJ(NC, NT, UPL, JT, GLT) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT>, GLT, JT}   /* tile layout */
 #define TILEJW(NC, NT, UPL, JT, GLT, NW, MINB, VAR) {4, NT, 1, NC, 0, 0, UPL, VAR, jq_traj_kernel<TileLane<NC, NT>, UPL, MINB, JT, 0, GLT, NW>, GLT, JT, NW}   /* tile layout, NW warps per CTA */
+#define FIBERW(R, NC, LMASK, UPL, NW) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 0, 0, NW>, 0, 0, NW}   /* NW warps per CTA: trajectories wider than 4 warps */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
 }  // namespace
