@@ -313,11 +313,14 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
         // SMs are full.
         char why[256];
         const char *lnt = getenv("JQ_TILE_LAT_NT");
-        h->tile_lat = jq_tile_plan_create(P, H, pb->wdiag, lnt ? atoi(lnt) : (Nc == 2 ? 0 : 1), why, sizeof(why));
+        const char *lp = getenv("JQ_LAT_PIPE");        // development: 0 = latency layout without the pipelined roles
+        const int pipe = lp ? atoi(lp) : 1;
+        h->tile_lat = jq_tile_plan_create(P, H, pb->wdiag, lnt ? atoi(lnt) : (Nc == 2 ? 0 : 1), why, sizeof(why), pipe);
+        if (!h->tile_lat && pipe) h->tile_lat = jq_fiber_plan_create(P, H, pb->wdiag, why, sizeof(why), 1);     // single-fibre shapes: same layout, pipelined roles
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const char *lt = getenv("JQ_LAT_NTRAJ");
-        h->lat_ntraj = lt ? atoi(lt) : 2 * sms;
+        h->lat_ntraj = lt ? atoi(lt) : sms;            // one trajectory per SM: beyond that the throughput layouts win (measured)
     }
     *out = h;
     return 0;
@@ -376,7 +379,7 @@ extern "C" int64_t jq_abi_info(int32_t what) {
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
     if (!h || kernel < 0 || kernel > 5) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0 ... 5");
-    if (kernel == 5 && !h->tile_lat) return fail(JQ_ERR_ARG, "jq_set_kernel: no latency (tile) layout for this problem");
+    if (kernel == 5 && !h->tile_lat) return fail(JQ_ERR_ARG, "jq_set_kernel: no latency layout for this problem");
     if (kernel == 4 && !h->tile) return fail(JQ_ERR_ARG, "jq_set_kernel: no tile-layout instantiation for this problem (%s)", h->tile_reason);
     if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no slot-layout instantiation for this problem (%s)", h->slot_reason);
     if (kernel == 3 && !h->fiber) return fail(JQ_ERR_ARG, "jq_set_kernel: no fibre-layout instantiation for this problem (%s)", h->fiber_reason);

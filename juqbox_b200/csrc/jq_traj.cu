@@ -11,14 +11,14 @@ const Inst kInst[] = {
 };
 
 // jt = 0: the run-time-J instantiation; jt > 0: the one with exactly jt Neumann terms compiled in (if any).
-const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0, int jt = 0, int nw = 0) {
+const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0, int jt = 0, int nw = 0, int pipe = 0) {
     const Inst *parts[4] = {kInst, kInstB, kInstC, kInstD};
     const int counts[4] = {(int)(sizeof(kInst) / sizeof(kInst[0])), kInstBCount, kInstCCount, kInstDCount};
     for (int p = 0; p < 4; ++p)
         for (int j = 0; j < counts[p]; ++j) {
             const Inst &i = parts[p][j];
             if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant &&
-                i.jt == jt && (i.glt == 0 || i.glt == GL) && (nw == 0 || i.nw == nw)) return &i;
+                i.jt == jt && (i.glt == 0 || i.glt == GL) && (nw == 0 || i.nw == nw) && (i.pipe != 0) == (pipe != 0)) return &i;
         }
     return nullptr;
 }
@@ -129,7 +129,7 @@ TrajPlan *jq_slot_plan_create(const DevProblem &P, const HostOps &H, const doubl
 // Fibre layout: find R such that control q is either "local" (couples only rows r, r+-1 inside a block of R
 // consecutive rows) or "remote" (couples row k of fibre rho only to row k of <= 2 other fibres, with a coefficient
 // that does not depend on k).  True for Kronecker ladder operators with the first subsystem of size R.
-TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen) {
+TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, char *err, size_t errlen, int pipe) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
     if (P.wreal || P.any_unc) return no("dense forbidden-state weights / uncoupled controls run on the generic kernel");
@@ -276,6 +276,14 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
             }
         }
     }
+    if (pipe) {      // pipelined roles: single-fibre columns only (no exchange buffer), plain problems; NW = warps that hold one group set
+        const int nwp = (GPT * GL + 31) / 32;
+        const bool plain = AS && !HX && P.objFuncType == 1 && P.solver == 1 && LMASK == (1 << Nc) - 1;
+        if (!plain || !(find_inst(3, R, 1, Nc, 2, LMASK, UPL, 0, GL, P.J, nwp, 1) || find_inst(3, R, 1, Nc, 2, LMASK, UPL, 0, GL, 0, nwp, 1))) {
+            delete pl; return no("no pipelined fibre instantiation for this shape");
+        }
+        pl->pipe = 1; pl->nw = nwp; pl->ngroups = nwp * (32 / GL); pl->TPC = pl->ngroups / GPT;
+    }
     if (!upload_plan(pl, pi, pd, d0p, wp)) { jq_traj_plan_destroy(pl); return no("cudaMalloc failed for the fibre plan"); }
     err[0] = 0;
     return pl;
@@ -284,7 +292,7 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &P, const HostOps &H, const doub
 
 // Tile layout: every subsystem has 4 levels, control q is the ladder pair (a_q + a_q', a_q - a_q') of subsystem q (row stride
 // 4^q), Hconst diagonal.  NT tiled directions cut in mirrored halves, the others remote (see TileLane).
-TrajPlan *jq_tile_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, int NT, char *err, size_t errlen) {
+TrajPlan *jq_tile_plan_create(const DevProblem &P, const HostOps &H, const double *wdiag, int NT, char *err, size_t errlen, int pipe) {
     const int n = H.n, m = H.m, Nc = H.Nc;
     auto no = [&](const char *why) { snprintf(err, errlen, "%s", why); return (TrajPlan *)nullptr; };
     if (P.wreal || P.any_unc) return no("dense forbidden-state weights / uncoupled controls run on the generic kernel");
@@ -324,13 +332,15 @@ TrajPlan *jq_tile_plan_create(const DevProblem &P, const HostOps &H, const doubl
     const int CPG = GL / NL, GPT = (m + CPG - 1) / CPG;
     const int NU = Nc * H.Nfreq * 2, UPL = (NU + GL - 1) / GL;
     if (UPL > 1) return no("tile layout: too many (control, frequency) pairs for the group size");
-    if (!find_inst(4, NT, 1, Nc, 0, 0, UPL, 0, GL, 0) && !find_inst(4, NT, 1, Nc, 0, 0, UPL, 0, GL, P.J)) return no("tile layout: no instantiation");
+    const int nwp = pipe ? (GPT * GL + 31) / 32 : 0;
+    if (!find_inst(4, NT, 1, Nc, 0, 0, UPL, 0, GL, 0, nwp, pipe) && !find_inst(4, NT, 1, Nc, 0, 0, UPL, 0, GL, P.J, nwp, pipe)) return no("tile layout: no instantiation");
     TrajPlan *pl = new TrajPlan();
     pl->kind = 4; pl->R = NT; pl->C = 1; pl->NC = Nc; pl->WQ = 0; pl->LMASK = 0; pl->UPL = UPL; pl->AS = 1; pl->HX = 0;
     pl->NL = NL; pl->NLR = n; pl->GL = GL; pl->GPT = GPT; pl->CPG = CPG;
     pl->ngroups = TRAJ_WARPS * (32 / GL);
     pl->TPC = pl->ngroups / GPT;
     pl->exch_per_unit = 0;                         // shuffles only
+    if (pipe) { pl->pipe = 1; pl->nw = nwp; pl->ngroups = nwp * (32 / GL); pl->TPC = pl->ngroups / GPT; }
     if (pl->TPC < 1) { delete pl; return no("a trajectory does not fit in one CTA"); }
     const int nrem = Nc - NT, per = 3 * NT + 2 * nrem;
     std::vector<int> pi((size_t)NL * (nrem > 0 ? nrem : 1) * 2, 0);
@@ -373,7 +383,12 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     else if (!pl->AS) want = 16;
     if ((want == 64 || want == 128 || want == 8) && !pl->AS) return cudaErrorNotSupported;
     const Inst *inst = nullptr;
-    if (want == 0 && !pl->nw) {
+    if (pl->pipe) {
+        if (want != 0 || P.nsteps > 0x7ffffff0LL) return cudaErrorNotSupported;      // the hand-over counters are ints
+        inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J, pl->nw, 1);
+        if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, 0, pl->nw, 1);
+        if (!inst) return cudaErrorNotSupported;
+    } else if (want == 0 && !pl->nw) {
         const char *xm = getenv("JQ_TRAJ_XMODE");
         const int xv = xm ? atoi(xm) : 0;
         if (xv > 0) {
@@ -383,7 +398,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
         if (!inst && P.J > 0)     // instantiation with the number of Neumann terms known at compile time
             inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J);
     }
-    if (pl->nw) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, want, pl->GL, 0, pl->nw);
+    if (pl->nw && !inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, want, pl->GL, 0, pl->nw);
     if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, want, pl->GL, 0);
     if (!inst) return cudaErrorNotSupported;       // never substitute: Neumann for Jacobi, one adjoint set for two, no drift couplings
     if (inst->jt != 0 && inst->jt != P.J) return cudaErrorNotSupported;
@@ -399,6 +414,8 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     // vectors would not fit in shared memory (the kernel only uses blockDim.x and the counts below)
     int nw = inst->nw, TPC = 0, ngroups = 0;
     size_t bytes = 0;
+    const int pipe = inst->pipe;
+    const int Eper = pl->kind == 4 ? (1 << pl->R) : pl->kind == 3 ? pl->R : pl->R * pl->C;      // elements per lane
     for (; nw >= 1; nw >>= 1) {
         ngroups = nw * S.GPW;
         TPC = ngroups / pl->GPT;
@@ -408,16 +425,20 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
         S.o_exch = take(pl->exch_per_unit * (pl->kind == 2 ? ngroups : nw));
         S.o_pcof = take(TPC * S.NparS);
         S.o_gsm = take(ngroups * A.Npar);
-        S.o_times = take(npts);
+        S.o_times = take(npts);                              // control table: one contiguous block per role
         S.o_tabb = take(3 * npts);
         S.o_tabph = take(2 * npts * NC * P.Nfreq);
         S.o_tabpq = take(npts * TPC * 2 * NC);
-        S.o_red = take(ngroups * 4);
         S.o_tabk = take((npts + 1) / 2);
+        S.tab_role_stride = o - S.o_times;
+        if (pipe) take((TRAJ_TABS - 1) * S.tab_role_stride);   // the other table buffers of the table warp's ring
+        S.o_red = take(ngroups * 4);
         S.o_tred = take(ngroups * NC * 5);
         S.o_gsm2 = take(P.objFuncType != 1 ? ngroups * A.Npar : 0);
+        S.o_ring = take(pipe ? TRAJ_RING * (3 * Eper + 5 * NC) * nw * 32 : 0);      // state hand-over ring, then the trace ring
+        S.o_mbar = take(pipe ? 2 * nw + (3 * nw + 2) / 2 + 1 : 0);       // int counters: 4 per warp triple, 1 per consumer warp, 1 for the tables
         bytes = (size_t)o * sizeof(double);
-        if (bytes <= 227 * 1024) break;
+        if (bytes <= 227 * 1024 || pipe) break;              // pipelined instantiations have a fixed number of warps
     }
     if (nw < 1) return cudaErrorInvalidConfiguration;       // does not fit even with one warp per CTA: caller falls back
     S.TPC = TPC; S.ngroups = ngroups;
@@ -428,7 +449,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     e = cudaFuncGetAttributes(&fa, inst->fn);
     if (e != cudaSuccess) return e;
     const int grid = (A.ntraj + TPC - 1) / TPC;
-    inst->fn<<<grid, nw * 32, bytes, st>>>(S);
+    inst->fn<<<grid, (pipe == 1 ? 3 * nw + 1 : pipe == 2 ? 2 * nw : nw) * 32, bytes, st>>>(S);
     if (nctas) *nctas = grid;
     if (regs) *regs = fa.numRegs;
     if (smem) *smem = bytes;

@@ -40,6 +40,8 @@
 #define TRAJ_WARPS 4
 #define TRAJ_THREADS (TRAJ_WARPS * 32)
 #define TRAJ_CH 16   // steps per control-table chunk
+#define TRAJ_RING 4  // pipelined instantiations: hand-over slots between the state role and the adjoint role
+#define TRAJ_TABS 4  // pipelined instantiations: control-table buffers the table warp runs ahead with
 
 struct TrajParams {
     DevProblem P;
@@ -55,13 +57,16 @@ struct TrajParams {
     int exch_per_unit;                       // doubles of exchange buffer per group (slot) / per warp (fibre)
     int NparS;                               // shared-memory row stride of the staged pcof vectors (odd: no bank conflicts)
     int GPW;                                 // groups per warp (32 / GL, rounded down: GL need not be a power of two)
+    // pipelined (PIPE) instantiations: state-role and adjoint-role warps of one CTA
+    int o_ring, o_mbar, tab_role_stride;     // ring of (vr0, vi05, vr) hand-overs, its mbarriers, distance between the two roles' control tables
 };
 
 struct TrajPlan {
     int kind;                                // 2 slot, 3 fibre
     int R, C, NC, WQ, LMASK, UPL, AS, HX = 0;
     int NL, GL, GPT, TPC, ngroups, CPG, NLR, exch_per_unit;
-    int nw = 0;                              // warps per CTA the plan needs (0: the instantiation's own)
+    int nw = 0;                              // warps per CTA (per role) the plan needs (0: the instantiation's own)
+    int pipe = 0;                            // pipelined state / adjoint roles (latency plans)
     int *d_i = nullptr;
     double *d_d = nullptr, *d_d0 = nullptr, *d_w = nullptr;
 };
@@ -71,7 +76,7 @@ typedef void (*traj_kernel_t)(const TrajParams);
 // 128 Jacobi solver; 1 (warp-shuffle exchange) and 512 (shared-memory twin of the cnot2 instantiation) are exchange-mode
 // twins selectable for comparisons with the env variable JQ_TRAJ_XMODE.  jt: number of Neumann terms fixed at compile time
 // (0 = run-time J) -- its own field, never folded into `variant`.  glt: compile-time group size (0 = run-time).
-struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; int jt = 0; int nw = TRAJ_WARPS; };
+struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; int jt = 0; int nw = TRAJ_WARPS; int pipe = 0; };
 // The instantiation table is split over jq_traj.cu / jq_traj_inst_b.cu / jq_traj_inst_c.cu so that they compile in parallel.
 extern const Inst kInstB[]; extern const int kInstBCount;
 extern const Inst kInstC[]; extern const int kInstCCount;
@@ -675,10 +680,13 @@ __device__ __forceinline__ void state_step(LaneT &L, int J, double h, double (&u
 //   T[q][0] = tr(vr0,Ha,lr05)  T[q][1] = tr(vi05,Hs,lr05)  T[q][2] = tr(vr,Ha,lr05)
 //   T[q][3] = tr(vr,Hs,li)+tr(vr0,Hs,li0)                   T[q][4] = tr(vi05,Ha,li)+tr(vi05,Ha,li0)
 // The group-reduced traces are left in shared memory at tred[q*5 + a] (written by lane 0 of the group).
-template <int JT, bool FORCING, class LaneT>
+// DEFER: the lane's partial traces are returned in tpart[q*5 + a] instead of being reduced over the group (pipelined
+// instantiations hand them to the gradient role).
+template <int JT, bool FORCING, class LaneT, bool DEFER = false>
 __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (&mu)[LaneT::E], double (&nu)[LaneT::E],
                                              const double (&vr0)[LaneT::E], const double (&vi05)[LaneT::E],
-                                             const double (&vr)[LaneT::E], double *tred, int GL, int gbase_lane, bool writer) {
+                                             const double (&vr)[LaneT::E], double *tred, int GL, int gbase_lane, bool writer,
+                                             double *tpart = nullptr) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     double rhs[E], s05n[E], Tb[NC][2];
     typename LaneT::SC sc;
@@ -723,8 +731,11 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         double tv3[NC * 3];
         UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tv3[qq * 3 + a] = Ta[qq][a];
         if constexpr (LaneSigned<LaneT>::value) { UNROLL for (int qq = 0; qq < NC; ++qq) { tv3[qq * 3] *= L.dsign(qq); tv3[qq * 3 + 2] *= L.dsign(qq); } }
-        group_sum_n(tv3, GL, gbase_lane);
-        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tred[qq * 5 + a] = tv3[qq * 3 + a]; }
+        if constexpr (DEFER) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tpart[qq * 5 + a] = tv3[qq * 3 + a]; }
+        else {
+            group_sum_n(tv3, GL, gbase_lane);
+            if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 3; ++a) tred[qq * 5 + a] = tv3[qq * 3 + a]; }
+        }
     }
     L.s_prescale(1, sc);
     double l1[E];
@@ -752,20 +763,45 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
         double tv2[NC * 2];
         UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tv2[qq * 2 + a] = Tb[qq][a];
         if constexpr (LaneSigned<LaneT>::value) { UNROLL for (int qq = 0; qq < NC; ++qq) tv2[qq * 2 + 1] *= L.dsign(qq); }
-        group_sum_n(tv2, GL, gbase_lane);
-        if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tred[qq * 5 + 3 + a] = tv2[qq * 2 + a]; }
+        if constexpr (DEFER) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tpart[qq * 5 + 3 + a] = tv2[qq * 2 + a]; }
+        else {
+            group_sum_n(tv2, GL, gbase_lane);
+            if (writer) { UNROLL for (int qq = 0; qq < NC; ++qq) UNROLL for (int a = 0; a < 2; ++a) tred[qq * 5 + 3 + a] = tv2[qq * 2 + a]; }
+        }
     }
-    __syncwarp();
+    if constexpr (!DEFER) __syncwarp();
 }
 
-// Fill the control table for `nst` steps starting at time t (all threads of the CTA).
-template <int NC>
-__device__ void fill_table(const TrajParams &S, double *sm, double t, double dt, int nst, double dtknot) {
-    double *times = sm + S.o_times, *tabb = sm + S.o_tabb, *tabph = sm + S.o_tabph, *tabpq = sm + S.o_tabpq;
-    int *tabk = reinterpret_cast<int *>(sm + S.o_tabk);
+// ---- pipelined instantiations: hand-over between the state role and the adjoint role of one CTA through two step counters per
+// warp pair in shared memory (volatile accesses + __threadfence_block; measured: mbarrier try_wait wake-ups cost ~1 us per hand-over,
+// more than the step they synchronise)
+__device__ __forceinline__ void pipe_post(volatile int *cnt, int value, int lane) {      // after the warp's shared-memory traffic
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); *cnt = value; }
+}
+__device__ __forceinline__ void pipe_wait(volatile int *cnt, int at_least) {
+    while (*cnt < at_least) {}
+    __threadfence_block();
+}
+// SYNC 0: all threads of the CTA; 1: the calling warp; 2: the nthr threads of the gradient role (named barrier 2)
+template <int SYNC>
+__device__ __forceinline__ void role_sync(int, int nthr) {
+    if constexpr (SYNC == 1) __syncwarp();
+    else if constexpr (SYNC == 2) asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory");
+    else __syncthreads();
+}
+
+// Fill the control table for `nst` steps starting at time t: all threads of the CTA into the table at offset 0 (PIPE = 0), or the
+// 32 lanes of the table warp (PIPE = 1) / the rnthr threads of the gradient role (PIPE = 2) into the table buffer at offset `toff`.
+template <int NC, int PIPE = 0>
+__device__ void fill_table(const TrajParams &S, double *sm, double t, double dt, int nst, double dtknot, int toff = 0, int rtid = 0, int rnthr = 0) {
+    const int role = 0;
+    if (PIPE == 0) { rtid = threadIdx.x; rnthr = blockDim.x; toff = 0; }
+    double *times = sm + S.o_times + toff, *tabb = sm + S.o_tabb + toff, *tabph = sm + S.o_tabph + toff, *tabpq = sm + S.o_tabpq + toff;
+    int *tabk = reinterpret_cast<int *>(sm + S.o_tabk + toff);
     const int npts = 2 * nst + 1, Nfreq = S.P.Nfreq, D1 = S.A.D1;
-    __syncthreads();                       // the previous chunk's table is no longer in use
-    if (threadIdx.x == 0) {
+    role_sync<PIPE>(role, rnthr);          // the previous chunk's table is no longer in use
+    if (rtid == 0) {
         double tt = t;
         times[0] = tt;
         for (int i = 0; i < nst; ++i) {    // same recurrence as the reference: t + 0.5 dt, then t = t + dt
@@ -774,9 +810,9 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
             times[2 * i + 2] = tt;
         }
     }
-    __syncthreads();
+    role_sync<PIPE>(role, rnthr);
     const double width = 3.0 * dtknot;
-    for (int idx = threadIdx.x; idx < npts * (NC * Nfreq + 1); idx += blockDim.x) {
+    for (int idx = rtid; idx < npts * (NC * Nfreq + 1); idx += rnthr) {
         const int i = idx / (NC * Nfreq + 1), j = idx % (NC * Nfreq + 1);
         const double tt = times[i];
         if (j == NC * Nfreq) {             // src/bsplines.jl:224-253
@@ -797,9 +833,9 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
             tabph[2 * (i * NC * Nfreq + j) + 1] = sn;
         }
     }
-    __syncthreads();
+    role_sync<PIPE>(role, rnthr);
     const double *pcof = sm + S.o_pcof;
-    for (int idx = threadIdx.x; idx < npts * S.TPC * NC; idx += blockDim.x) {
+    for (int idx = rtid; idx < npts * S.TPC * NC; idx += rnthr) {
         const int i = idx / (S.TPC * NC), rem = idx % (S.TPC * NC), tr = rem / NC, qq = rem % NC;
         const int k = tabk[i];
         const double b0 = tabb[3 * i], b1 = tabb[3 * i + 1], b2 = tabb[3 * i + 2];
@@ -816,7 +852,7 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
         tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq] = pv;
         tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq + 1] = qv;
     }
-    __syncthreads();
+    role_sync<PIPE>(role, rnthr);
 }
 
 // Gradient scatter role: (control, frequency, alpha) with a 3-knot register window.
@@ -855,14 +891,32 @@ __device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, con
 
 // OBJ = 1: objFuncType 2/3 — a second adjoint set without forcing gives the infidelity-only gradient
 // (src/evalobjgrad.jl:848-855, :905-918; step_no_forcing! src/StormerVerlet.jl:365-406).
-template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0, int NW = TRAJ_WARPS>
-__global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
+//
+// PIPE = 1 (latency instantiations, small launches): the CTA has 3 NW warps in three ROLES with the same lane layout, plus one
+// table warp that computes the control tables (B-spline values, carrier phases, p_q, q_q of the next TRAJ_CH steps) ahead of all of
+// them into a ring of TRAJ_TABS buffers, so no role ever stops for the table (measured: ~20% of a lone trajectory's time).  The state
+// role runs the forward sweep and then recomputes the states backwards, handing (vr0, vi05, vr) of every step to its twin lane in
+// the adjoint role through a TRAJ_RING-slot ring in shared memory (two step counters per warp pair); the adjoint role runs the
+// adjoint steps one or more steps behind and hands its lane-partial traces to the gradient role, which does the group
+// reductions and the B-spline scatter.  A single trajectory has no other parallelism beyond its n x m elements: the recomputed
+// state does not depend on the adjoint, and the gradient accumulation feeds nothing back, so the backward sweep costs the
+// longest of the three per-step chains instead of their sum.  Same arithmetic on the same values as PIPE = 0.
+template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0, int NW = TRAJ_WARPS, int PIPE_ = 0>
+__global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW : NW) * 32, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
+    constexpr bool PIPE = PIPE_ != 0;
+    // PIPE_ = 1: roles state | adjoint | gradient + one table warp; PIPE_ = 2 (shapes whose register budget allows 8 warps only):
+    // state and adjoint in one role, and the gradient role also produces the control tables in the slack of its own steps
+    constexpr int NR = PIPE_ == 1 ? 3 : PIPE_ == 2 ? 2 : 1, R_ADJ = PIPE_ == 1 ? 1 : 0, R_GRAD = NR - 1;
     extern __shared__ double sm[];
     const DevProblem &P = S.P;
     const LaunchArgs &A = S.A;
     Geo g;
     g.lane = threadIdx.x & 31; g.warp = threadIdx.x >> 5;
+    const int role = PIPE ? g.warp / NW : 0;                 // 0: state role (and everything when PIPE = 0), 1: adjoint role, 2: gradient role, 3: table warp
+    const int pwarp = g.warp;                                // warp in the CTA
+    if constexpr (PIPE) g.warp = role < NR ? g.warp - role * NW : 0;
+    const int rtid = PIPE ? (int)threadIdx.x - role * NW * 32 : (int)threadIdx.x, rnthr = PIPE ? NW * 32 : (int)blockDim.x;
     const int GL = GLT > 0 ? GLT : S.GL;       // GLT: group size known at compile time (reductions unroll and overlap)
     g.lg = g.lane % GL;
     const int gw = g.lane / GL;                              // group inside the warp; lanes past GPW*GL are idle
@@ -893,6 +947,48 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
         sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * A.pstride + k] : 0.0;
     }
     for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += blockDim.x) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
+    volatile int *pcnt = reinterpret_cast<volatile int *>(sm + S.o_mbar);     // [warp][states produced, consumed, traces produced, consumed]
+    volatile int *cdone = pcnt + NW * 4, *tabs_ready = cdone + NR * NW;        // chunks finished per consumer warp; table chunks produced
+    const int nch = (int)((P.nsteps + TRAJ_CH - 1) / TRAJ_CH);                // global chunk ids: forward c, backward nch + c
+    if constexpr (PIPE) {
+        if (threadIdx.x < NW * 4) pcnt[threadIdx.x] = 0;
+        if (threadIdx.x < NR * NW) cdone[threadIdx.x] = threadIdx.x < NW ? 0 : nch;     // only the state role consumes forward tables
+        if (threadIdx.x == 0) *tabs_ready = 0;
+        __syncthreads();                                     // pcof staged and counters cleared before the roles part ways
+    }
+    // table production (PIPE): chunk k of the forward (k < nch) or backward sweep into buffer k % TRAJ_TABS, by the table warp
+    // (PIPE_ = 1) or by all warps of the gradient role (PIPE_ = 2), once every consumer warp has finished chunk k - TRAJ_TABS
+    double ptt = 0.0, pdt = P.T / (double)P.nsteps;
+    int kprod = 0;
+    const int ktotal = A.evaladjoint ? 2 * nch : nch;
+    auto produce_table = [&]() {
+        if constexpr (!PIPE) return;
+        const int k = kprod++;
+        if (k == nch) { ptt = P.T; pdt = -pdt; }
+        const long long s0 = (long long)(k < nch ? k : k - nch) * TRAJ_CH;
+        const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+        constexpr int NCONS = PIPE_ == 1 ? NR * NW : NW;                              // PIPE_ = 2: the gradient role trails its own tables by construction
+        if (g.lane < NCONS) pipe_wait(cdone + g.lane, k - TRAJ_TABS + 1);             // buffer k % TRAJ_TABS no longer in use
+        __syncwarp();
+        if constexpr (PIPE_ == 1) fill_table<NC, 1>(S, sm, ptt, pdt, nst, dtknot, (k % TRAJ_TABS) * S.tab_role_stride, g.lane, 32);
+        else if constexpr (PIPE_ == 2) fill_table<NC, 2>(S, sm, ptt, pdt, nst, dtknot, (k % TRAJ_TABS) * S.tab_role_stride, rtid, rnthr);
+        for (int i = 0; i < nst; ++i) ptt = ptt + pdt;                                // the consumers' own recurrence
+        if (PIPE_ == 1 || g.warp == 0) pipe_post(tabs_ready, k + 1, g.lane);
+    };
+    if constexpr (PIPE_ == 1) {
+        if (role == NR) {               // table warp: runs ahead of every role; the roles meet at named barrier 1, which does not count it
+            while (kprod < ktotal) produce_table();
+            return;
+        }
+    }
+    if constexpr (PIPE_ == 2) {
+        if (role == R_GRAD) { while (kprod < nch) produce_table(); }                  // forward sweep: the gradient role has nothing else to do
+    }
+    // every thread of the CTA (PIPE: of the trajectory roles)
+    auto consumer_sync = [&]() {
+        if constexpr (PIPE) asm volatile("bar.sync 1, %0;" ::"r"(NR * NW * 32) : "memory");
+        else __syncthreads();
+    };
 
     double vr[E], vi[E], vi05[E];
     UNROLL for (int e = 0; e < E; ++e) {
@@ -900,7 +996,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
         vi[e] = 0.0;
         vi05[e] = 0.0;
     }
-    const double *tabpq = sm + S.o_tabpq;
+    const double *tabpq = sm + S.o_tabpq;                     // PIPE: re-pointed at the chunk's table buffer
 
 #define LOAD_LEVELS(ls)                                                                                              \
     UNROLL for (int qq = 0; qq < NC; ++qq) {                                                                         \
@@ -935,7 +1031,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
     auto forward_sweep = [&](auto with_hist) {
         for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
             const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
-            fill_table<NC>(S, sm, t, dt, nst, dtknot);
+            if constexpr (PIPE) {
+                const int gk = (int)(s0 / TRAJ_CH);
+                pipe_wait(tabs_ready, gk + 1);
+                tabpq = sm + S.o_tabpq + (gk % TRAJ_TABS) * S.tab_role_stride;
+            } else fill_table<NC>(S, sm, t, dt, nst, dtknot);
             LOAD_LEVEL0();
             for (int ls = 0; ls < nst; ++ls) {
                 LOAD_LEVELS(ls);
@@ -945,9 +1045,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
                 t = t + dt;
                 if constexpr (decltype(with_hist)::value) { if (--hcount == 0) { hcount = A.save_every; save_state(); } }
             }
+            if constexpr (PIPE) pipe_post(cdone + pwarp, (int)(s0 / TRAJ_CH) + 1, g.lane);
         }
     };
-    if (hist) forward_sweep(std::true_type{});
+    if (PIPE && role != 0) {}                                // the adjoint and gradient roles wait at the barrier below
+    else if (hist) forward_sweep(std::true_type{});
     else forward_sweep(std::false_type{});
     // infidelity (pFidType 2) and leak: group partials -> shared -> per-trajectory sums in group order
     double *red = sm + S.o_red;
@@ -962,9 +1064,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
         double rip[3] = {re, im, pen};
         group_sum_n(rip, GL, gbase_lane);
         re = rip[0]; im = rip[1]; pen = rip[2];
-        __syncthreads();
-        if (lane_on && g.lg == 0) { red[g.group * 4] = re; red[g.group * 4 + 1] = im; red[g.group * 4 + 2] = pen; }
-        __syncthreads();
+        consumer_sync();
+        if (lane_on && g.lg == 0 && role == 0) { red[g.group * 4] = re; red[g.group * 4 + 1] = im; red[g.group * 4 + 2] = pen; }
+        consumer_sync();
     }
     double rs = 0.0, is = 0.0, pens = 0.0;
     for (int j = 0; j < S.GPT; ++j) {
@@ -980,7 +1082,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
     if (pfid != 2) sincos(pfid == 3 ? A.pcof[(size_t)((live_t ? traj : 0) / A.nsamples) * A.pstride + Npar] : P.globalPhase, &sph, &cph);
     const double abs2 = rs * rs + is * is;
     const double infid = pfid == 1 ? 1.0 + abs2 - 2.0 * (rs * cph + is * sph) : pfid == 2 ? 1.0 - abs2 : 1.0 - (rs * cph - is * sph);
-    if (live_t && g.gi == 0 && g.lg == 0) {
+    if (live_t && g.gi == 0 && g.lg == 0 && role == 0) {
         double *o = A.scal + (size_t)traj * 4;
         o[0] = infid; o[1] = 0.5 * dt * pens; o[2] = 1.0 - abs2; o[3] = 0.0;   // w already carries 1/T; traceInfidelity = 1 - |s|^2 (:792)
         if (pfid == 3 && A.evaladjoint) {        // gradient with respect to the global phase (:923-945), last entry of both gradients
@@ -1014,7 +1116,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
     Updater U[UPL], U2[OBJ ? UPL : 1];
     UNROLL for (int j = 0; j < UPL; ++j) {
         const int u = g.lg + j * GL;
-        U[j].on = lane_on && u < NU;
+        U[j].on = lane_on && u < NU && (!PIPE || role == R_GRAD);
         U[j].uq = U[j].on ? u / (2 * Nfreq) : 0;
         U[j].uf = U[j].on ? (u >> 1) % Nfreq : 0;
         U[j].ua = u & 1;
@@ -1030,30 +1132,91 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
 
     t = P.T;
     dt = -dt;
-    for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
-        const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
-        fill_table<NC>(S, sm, t, dt, nst, dtknot);
-        LOAD_LEVEL0();
-        for (int ls = 0; ls < nst; ++ls) {
-            LOAD_LEVELS(ls);
-            UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
-            state_step<JT>(L, J, dt, vr, vi, vi05);
-            adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
-            grad_scatter<NC, UPL>(U, gsm, tred, tabb, tabph, tabk, ls, Nfreq);
-            if constexpr (OBJ != 0) {
-                adjoint_step<JT, false>(L, J, dt, lrn, lin, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);
-                grad_scatter<NC, UPL>(U2, gsm2, tred, tabb, tabph, tabk, ls, Nfreq);
+    if constexpr (!PIPE) {
+        for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
+            const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+            fill_table<NC>(S, sm, t, dt, nst, dtknot);
+            LOAD_LEVEL0();
+            for (int ls = 0; ls < nst; ++ls) {
+                LOAD_LEVELS(ls);
+                UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
+                state_step<JT>(L, J, dt, vr, vi, vi05);
+                adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
+                grad_scatter<NC, UPL>(U, gsm, tred, tabb, tabph, tabk, ls, Nfreq);
+                if constexpr (OBJ != 0) {
+                    adjoint_step<JT, false>(L, J, dt, lrn, lin, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);
+                    grad_scatter<NC, UPL>(U2, gsm2, tred, tabb, tabph, tabk, ls, Nfreq);
+                }
+                t = t + dt;
             }
-            t = t + dt;
+        }
+    } else {
+        // hand-over ring: slot = step % TRAJ_RING; element k of (vr0, vi05, vr) of this lane at ring[(slot * 3E + k) * rnthr + rtid]
+        double *ring = sm + S.o_ring;
+        volatile int *produced = pcnt + g.warp * 4, *consumed = produced + 1, *tproduced = produced + 2, *tconsumed = produced + 3;
+        double *tring = ring + (size_t)TRAJ_RING * 3 * E * rnthr;      // lane-partial traces: [slot][NC * 5][rnthr]
+        int step = 0;
+        for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
+            const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+            const int gk = nch + (int)(s0 / TRAJ_CH);
+            if constexpr (PIPE_ == 2) {
+                if (role == R_GRAD) { while (kprod < ktotal && kprod < gk + 3) produce_table(); }     // stay two chunks ahead of the own steps
+            }
+            pipe_wait(tabs_ready, gk + 1);
+            {
+                const int toff = (gk % TRAJ_TABS) * S.tab_role_stride;
+                tabpq = sm + S.o_tabpq + toff; tabb = sm + S.o_tabb + toff; tabph = sm + S.o_tabph + toff;
+                tabk = reinterpret_cast<const int *>(sm + S.o_tabk + toff);
+            }
+            LOAD_LEVEL0();
+            for (int ls = 0; ls < nst; ++ls, ++step) {
+                LOAD_LEVELS(ls);
+                const int slot = step % TRAJ_RING;
+                double *rs_ = ring + (size_t)slot * 3 * E * rnthr + rtid;
+                double *ts_ = tring + (size_t)slot * NC * 5 * rnthr + rtid;
+                if (role == 0) {
+                    UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
+                    state_step<JT>(L, J, dt, vr, vi, vi05);
+                    if constexpr (PIPE_ == 1) {
+                        pipe_wait(consumed, step - TRAJ_RING + 1);                 // the slot's previous content has been read
+                        UNROLL for (int e = 0; e < E; ++e) { rs_[e * rnthr] = vr0[e]; rs_[(E + e) * rnthr] = vi05[e]; rs_[(2 * E + e) * rnthr] = vr[e]; }
+                        pipe_post(produced, step + 1, g.lane);
+                    }
+                }
+                if (role == R_ADJ) {
+                    if constexpr (PIPE_ == 1) {
+                        pipe_wait(produced, step + 1);
+                        UNROLL for (int e = 0; e < E; ++e) { vr0[e] = rs_[e * rnthr]; vi05[e] = rs_[(E + e) * rnthr]; vr[e] = rs_[(2 * E + e) * rnthr]; }
+                        pipe_post(consumed, step + 1, g.lane);
+                    }
+                    double tp[NC * 5];
+                    adjoint_step<JT, true, LaneT, true>(L, J, dt, lr, li, vr0, vi05, vr, nullptr, GL, gbase_lane, false, tp);
+                    pipe_wait(tconsumed, step - TRAJ_RING + 1);
+                    UNROLL for (int k = 0; k < NC * 5; ++k) ts_[k * rnthr] = tp[k];
+                    pipe_post(tproduced, step + 1, g.lane);
+                }
+                if (role == R_GRAD) {
+                    pipe_wait(tproduced, step + 1);
+                    double tp[NC * 5];
+                    UNROLL for (int k = 0; k < NC * 5; ++k) tp[k] = ts_[k * rnthr];
+                    pipe_post(tconsumed, step + 1, g.lane);
+                    group_sum_n(tp, GL, gbase_lane);
+                    if (lane_on && g.lg == 0) { UNROLL for (int k = 0; k < NC * 5; ++k) tred[k] = tp[k]; }
+                    __syncwarp();
+                    grad_scatter<NC, UPL>(U, gsm, tred, tabb, tabph, tabk, ls, Nfreq);
+                }
+                t = t + dt;
+            }
+            pipe_post(cdone + pwarp, gk + 1, g.lane);
         }
     }
     UNROLL for (int j = 0; j < UPL; ++j) {
         if (U[j].on) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; gsm[U[j].gbase + U[j].kw - 1] += U[j].acc1; gsm[U[j].gbase + U[j].kw - 2] += U[j].acc2; }
         if constexpr (OBJ != 0) if (U2[j].on) { gsm2[U2[j].gbase + U2[j].kw] += U2[j].acc0; gsm2[U2[j].gbase + U2[j].kw - 1] += U2[j].acc1; gsm2[U2[j].gbase + U2[j].kw - 2] += U2[j].acc2; }
     }
-    __syncthreads();
+    consumer_sync();
     // total gradient of each resident trajectory = dt * sum of its groups' partial gradients, in group order
-    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += (PIPE ? NR * NW * 32 : (int)blockDim.x)) {
         const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
         if (tg >= A.ntraj) continue;
         double gs = 0.0;
@@ -1080,6 +1243,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) jq_traj_kernel(const __grid_con
 #define FIBERJAC(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 128, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, -1>}   /* Jacobi solver */
 #define FIBERG(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 16, jq_traj_kernel<FiberLane<R, NC, LMASK, 0>, UPL>}   /* general Hanti (AS = 0) */
 #define TILEJ(NC, NT, UPL, JT, GLT) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT>, GLT, JT}   /* tile layout */
+#define TILEP(NC, NT, UPL, JT, GLT, NW) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT, NW, 1>, GLT, JT, NW, 1}   /* tile layout, pipelined roles (2 NW warps) */
+#define TILEP2(NC, NT, UPL, JT, GLT, NW) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT, NW, 2>, GLT, JT, NW, 2}   /* roles (state + adjoint) | (gradient + tables) */
+#define FIBERP(R, NC, LMASK, UPL, JT, GLT, NW) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT, NW, 1>, GLT, JT, NW, 1}   /* single-fibre layout, pipelined roles */
 #define TILEJW(NC, NT, UPL, JT, GLT, NW, MINB, VAR) {4, NT, 1, NC, 0, 0, UPL, VAR, jq_traj_kernel<TileLane<NC, NT>, UPL, MINB, JT, 0, GLT, NW>, GLT, JT, NW}   /* tile layout, NW warps per CTA */
 #define FIBERW(R, NC, LMASK, UPL, NW) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 0, 0, NW>, 0, 0, NW}   /* NW warps per CTA: trajectories wider than 4 warps */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */

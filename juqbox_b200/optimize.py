@@ -107,7 +107,7 @@ def run_optimizer(prob: IpoptProblemMirror, pcof0, baseName: str = ""):
 
 
 def run_optimizer_multistart(prob: IpoptProblemMirror, pcof0s, maxIter: Optional[int] = None, lbfgsMax: Optional[int] = None,
-                             gtol: float = 1e-7, max_backtracks: int = 12):
+                             gtol: float = 1e-7, max_backtracks: int = 12, ls_batch: int = 4):
     """Many independent optimisations advanced in lock step (north star: "batched candidate pcof vectors for multi-start
     or line search").  Start vectors pcof0s [B, nCoeff]; every objective/gradient request of all B members is ONE
     jq_traceobjgrad_batch call, so B starts cost about as much wall time as one while the GPU has idle SMs.
@@ -116,7 +116,9 @@ def run_optimizer_multistart(prob: IpoptProblemMirror, pcof0s, maxIter: Optional
     pairs, box-scaled variables as in run_optimizer) with Armijo backtracking; the objective is infidelity + leak +
     Tikhonov (eval_f_par's objective, src/ipopt_interface.jl:77-100), with the risk-neutral nodes/weights of `prob`.
     Returns (pcofs [B, nCoeff], objective [B], history [iters + 1, B]).  A member's iterates do not depend on which other
-    members share the batch.
+    members share the batch.  The Armijo backtracking is batched too: `ls_batch` trial steps (1, 1/2, 1/4, ...) of every member
+    that still searches go into ONE objective-only launch and the first acceptable one is taken, so an iteration usually costs two
+    launches (trial steps, then objective + gradient at the accepted point) instead of up to `max_backtracks` + 1.
     """
     from .api import tikhonov_grad, tikhonov_pen
     from .configs import noise_shift
@@ -142,6 +144,12 @@ def run_optimizer_multistart(prob: IpoptProblemMirror, pcof0s, maxIter: Optional
             return f, None
         g = r["grad"].reshape(B, n) + np.array([tikhonov_grad(x, p) for x in Xc])
         return f, g * scale
+
+    def f_only(Yrows):
+        """Objective of arbitrary many points (trial steps): one objective-only launch."""
+        Xc = Yrows * scale
+        r = wa.evaluate(Xc, shifts, w, evaladjoint=False)
+        return (r["infid"] + r["leak"]).reshape(len(Xc)) + np.array([tikhonov_pen(x, p) for x in Xc])
 
     Y = X / scale
     f, g = fg(Y)
@@ -180,18 +188,25 @@ def run_optimizer_multistart(prob: IpoptProblemMirror, pcof0s, maxIter: Optional
             d /= np.maximum(1.0, np.abs(d).max(axis=1))[:, None] * 4.0       # first step: a quarter of the box at most
 
         def line_search(d, todo):
-            """Projected Armijo backtracking for the members in `todo`; returns the mask of members that found no step."""
-            step = np.where(todo, 1.0, 0.0)
+            """Projected Armijo backtracking for the members in `todo`; returns the mask of members that found no step.  Trial
+            steps are evaluated `ls_batch` at a time in one launch; the smallest power of 1/2 that satisfies Armijo wins, exactly
+            as in the one-trial-per-launch loop."""
             todo = todo.copy()
-            for _bt in range(max_backtracks):
-                Yt = np.where(todo[:, None], np.clip(Y + step[:, None] * d, lo, hi), Ynew)
-                ft, _ = fg(Yt, need_grad=False)
-                acc = todo & (ft <= f + 1e-4 * (g * (Yt - Y)).sum(1)) & (np.abs(Yt - Y).max(axis=1) > 0)
-                Ynew[acc], fnew[acc] = Yt[acc], ft[acc]
-                todo &= ~acc
-                if not todo.any():
-                    break
-                step[todo] *= 0.5
+            k0 = 0
+            while k0 < max_backtracks and todo.any():
+                ks = np.arange(k0, min(k0 + ls_batch, max_backtracks))
+                idx = np.nonzero(todo)[0]
+                # [member, trial, n] trial points of the searching members; the other members ride along unchanged (fg needs B rows)
+                Yt = np.clip(Y[idx, None, :] + (0.5 ** ks)[None, :, None] * d[idx, None, :], lo, hi)
+                ft = f_only(Yt.reshape(-1, n)).reshape(len(idx), len(ks))
+                ok_ = (ft <= f[idx, None] + 1e-4 * (g[idx, None, :] * (Yt - Y[idx, None, :])).sum(2)) & \
+                      (np.abs(Yt - Y[idx, None, :]).max(axis=2) > 0)
+                first = np.where(ok_.any(axis=1), ok_.argmax(axis=1), -1)
+                hit = first >= 0
+                Ynew[idx[hit]] = Yt[hit, first[hit]]
+                fnew[idx[hit]] = ft[hit, first[hit]]
+                todo[idx[hit]] = False
+                k0 += len(ks)
             return todo
 
         Ynew, fnew = Y.copy(), f.copy()
