@@ -168,7 +168,7 @@ int jq_comm_destroy(jq_handle *h);
  * 2 = register-resident kernel, slot layout (sparse rows with <= 2 entries per row and control), 3 = fibre layout (Kronecker
  * ladder structure), 4 = tile layout (all subsystems with 4 levels: mirrored half-tiles, shuffle-only exchange), 5 = the tile
  * layout with the fewest elements per lane and pipelined state / adjoint / gradient roles (latency layout; also the single-qudit
- * shapes).  Automatic: launches of at most #SM trajectories take 5 (then
+ * shapes).  Automatic: launches that fit one latency CTA per SM take 5 (then
  * 3 for three subsystems); otherwise 4, 3, 2, 1 in that order, each handing over when it has no instantiation for the problem.
  * 2 ... 5 fail with JQ_ERR_ARG if the problem has no instantiation. */
 int jq_set_kernel(jq_handle *h, int32_t kernel);

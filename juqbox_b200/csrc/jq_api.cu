@@ -53,6 +53,9 @@ struct jq_handle {
     int n = 0, m = 0, Nc = 0, Nfreq = 0, pfid = 2;       // Nc: coupled + uncoupled controls
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_done = nullptr;      // end of the last evaluation: calls on another stream wait for it (shared scratch buffers)
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
     std::vector<void *> owned;          // device allocations freed at destroy
     double *d_vtr = nullptr, *d_vti = nullptr;
     // host copies of the row-wise operators (for the planners)
@@ -297,7 +300,7 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
 #undef UP
 #undef UPI
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
-        cudaEventCreate(&h->ev1) != cudaSuccess) {
+        cudaEventCreate(&h->ev1) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess) {
         jq_destroy(h);
         return fail(JQ_ERR_CUDA, "jq_create: stream/event creation failed");
     }
@@ -320,7 +323,8 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const char *lt = getenv("JQ_LAT_NTRAJ");
-        h->lat_ntraj = lt ? atoi(lt) : sms;            // one trajectory per SM: beyond that the throughput layouts win (measured)
+        // one latency CTA per SM: beyond that the throughput layouts win (measured)
+        h->lat_ntraj = lt ? atoi(lt) : sms * (h->tile_lat ? jq_traj_plan_tpc(h->tile_lat) : 1);
     }
     *out = h;
     return 0;
@@ -339,6 +343,7 @@ extern "C" int jq_destroy(jq_handle *h) {
     if (h->tile_lat) jq_traj_plan_destroy(h->tile_lat);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -552,6 +557,9 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t ntraj = (size_t)nbatch * nsamples;
+    // the handle's scratch (d_scal, d_grad, d_igrad) is shared by every call: a call on a different stream than the previous one
+    // (host-pointer entry = the handle's own stream, device entry = the caller's) first waits for that one to finish
+    if (h->have_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->ev_done, 0));
     if ((rc = grow(&h->d_scal, &h->cap_traj, ntraj * 4)) != 0) return rc;
     if (evaladjoint && (rc = grow(&h->d_grad, &h->cap_grad, ntraj * npar)) != 0) return rc;
     if (evaladjoint && h->P.objFuncType != 1 && (rc = grow(&h->d_igrad, &h->cap_igrad, ntraj * npar)) != 0) return rc;
@@ -593,6 +601,8 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
         if (nrc != 0) return fail(JQ_ERR_CUDA, "ncclAllReduce of the weighted sample sums: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "nccl error");
         h->last_launches = 3;
     }
+    CU(cudaEventRecord(h->ev_done, st));
+    h->last_stream = st; h->have_last = true;
     return 0;
 }
 

@@ -70,5 +70,6 @@ TrajPlan *jq_fiber_plan_create(const DevProblem &Pdev, const HostOps &H, const d
 TrajPlan *jq_tile_plan_create(const DevProblem &Pdev, const HostOps &H, const double *wdiag_host, int NT, char *err, size_t errlen, int pipe = 0);
 void jq_traj_plan_destroy(TrajPlan *);
 int jq_traj_plan_kind(const TrajPlan *);
+int jq_traj_plan_tpc(const TrajPlan *);      // trajectories per CTA
 cudaError_t jq_traj_launch(TrajPlan *plan, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta);

@@ -372,6 +372,7 @@ void jq_traj_plan_destroy(TrajPlan *pl) {
 }
 
 int jq_traj_plan_kind(const TrajPlan *pl) { return pl ? pl->kind : 0; }
+int jq_traj_plan_tpc(const TrajPlan *pl) { return pl ? pl->TPC : 0; }
 
 cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta) {

@@ -19,7 +19,7 @@ def main():
     import juqbox_b200 as jq
     from juqbox_b200 import _lib, configs
     from bench import alg_flops_per_eval
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     dev = torch.device("cuda", 0)
     peak = _lib.fp64_peak_tflops(0)
     rows = []
@@ -30,7 +30,7 @@ def main():
         flops = alg_flops_per_eval(cfg.params, cfg.nCoeff)
         wa = jq.Working_Arrays(cfg.params, cfg.nCoeff, device=0)
         sh = torch.from_numpy(shifts).to(dev) if shifts is not None else None
-        batches = [1, 64, 1024, 16384] if name != "cnot3" else [1, 64, 1024, 4096]
+        batches = [1, 64, 1024, 16384] if name != "cnot3" else [1, 148, 1184, 2368, 4736]
         if name == "rabi":
             batches.append(262144)
         for B in batches:

@@ -2,7 +2,7 @@
 
     python tools/kernel_coverage.py [--batch 2048]          (needs a GPU; the oracle is the checker)
 
-Prints one markdown row per shape: auto-selected kernel (1 generic, 2 slot, 3 fibre), why the register-resident
+Prints one markdown row per shape: auto-selected kernel (1 generic, 2 slot, 3 fibre, 4 tile, 5 latency layout), why the register-resident
 kernels declined (if they did), relative gradient error vs the CPU oracle on two candidates, evals/s on `batch`.
 """
 import argparse
@@ -45,7 +45,7 @@ def main():
         k = wa.last_kernel
         why = ""
         if k == 1:
-            for kid in (3, 2):
+            for kid in (4, 3, 2):
                 try:
                     wa.set_kernel(kid)
                 except Exception as e:                       # the library's reason string

@@ -41,8 +41,8 @@ for r in rows[hdr_i + 1:]:
             pass
 ts = sum(smp.values())
 print(f"total warp instructions {tot:.4g}, samples {ts:.0f}")
-print(f"{'op':10s} {'executed%':>9s} {'reuse%':>7s} {'samples%':>9s}  top stalls")
+print(f"{'op':10s} {'executed%':>9s} {'samples%':>9s}  top stalls (% of all samples)")
 for op, n in sorted(ex.items(), key=lambda kv: -kv[1])[:22]:
     st = sorted(stalls[op].items(), key=lambda kv: -kv[1])[:3]
-    print(f"{op:10s} {100 * n / tot:9.2f} {100 * reuse[op] / n if n else 0:7.1f} {100 * smp[op] / ts if ts else 0:9.2f}  " +
+    print(f"{op:10s} {100 * n / tot:9.2f} {100 * smp[op] / ts if ts else 0:9.2f}  " +
           ", ".join(f"{k[6:]} {100 * v / ts:.1f}" for k, v in st if v))

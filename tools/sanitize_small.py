@@ -18,12 +18,12 @@ for name, T, nsteps in (("risk_neutral", 3.0, 40), ("cnot2", 2.0, 40), ("cnot3",
     for obj in (1, 3):
         cfg.params.objFuncType = obj
         wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
-        for k in (1, 2, 3):
+        for k in (1, 2, 3, 4, 5):
             try:
                 wa.set_kernel(k)
-            except Exception:
+                r = wa.evaluate(pc, sh)
+            except Exception:      # no instantiation of this layout for the shape / objFuncType
                 continue
-            r = wa.evaluate(pc, sh)
             res[(obj, k)] = r["grad"]
         wa.close()
     ref = res[(1, 1)]
@@ -37,10 +37,10 @@ cfg.params.T, cfg.params.nsteps = 2.0, 40
 pc = configs.synthetic_pcof(cfg, 3) * 20
 wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
 hists = {}
-for k in (1, 2, 3):
+for k in (1, 2, 3, 4, 5):
     wa.set_kernel(k)
     hists[k] = wa.forward_history(pc, save_every=4)[0]
-assert np.abs(hists[3] - hists[1]).max() < 1e-12 and np.abs(hists[2] - hists[1]).max() < 1e-12
+assert all(np.abs(hists[k] - hists[1]).max() < 1e-12 for k in hists)
 wa.set_kernel(0)
 p, q = wa.controls(pc[0], np.linspace(0, cfg.params.T, 77))
 wa.close()
@@ -53,5 +53,36 @@ pc = configs.synthetic_pcof(cfg, 2) * 20
 tot = wa.evaluate(pc, sh, w)
 per = wa.evaluate(pc, sh)
 assert np.allclose(tot["grad"], (per["grad"] * w[None, :, None]).sum(1), rtol=1e-12, atol=1e-16)
+wa.close()
+# round 2: fused callback entry, pFidType 3, dense forbidden-state weights and uncoupled controls on the generic kernel (TMA-staged
+# operator table, several trajectory groups per CTA)
+r = wa = None
+cfg = configs.example("risk_neutral")
+cfg.params.T, cfg.params.nsteps = 3.0, 40
+wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
+pc = configs.synthetic_pcof(cfg, 1)[0] * 20
+sh = configs.noise_shift(cfg.params.Ntot, cfg.nodes)
+a = wa.eval_f_grad(pc, sh, cfg.weights, tik0=0.01)
+b = wa.eval_f_grad(pc, sh, cfg.weights, tik0=0.01)
+assert a["evaluated"] and not b["evaluated"]
+wa.close()
+cfg.params.pFidType = 3
+wa = jq.Working_Arrays(cfg.params, cfg.nCoeff + 1)
+pcs = np.concatenate([configs.synthetic_pcof(cfg, 4) * 20, np.linspace(-1, 1, 4)[:, None]], axis=1)
+for k in (1, 3, 5):
+    wa.set_kernel(k)
+    wa.evaluate(pcs)
+wa.close()
+from juqbox_b200.params import objparams
+lab = configs.example("rabi_lab", T=2.0, Pmin=20)
+wa = jq.Working_Arrays(lab.params, lab.nCoeff)
+wa.evaluate(np.tile(lab.pcof0, (7, 1)) * np.linspace(0.5, 2, 7)[:, None])
+wa.close()
+p = configs.example("risk_neutral").params
+F = np.random.default_rng(0).standard_normal((p.Ntot, 2)) + 1j * np.random.default_rng(1).standard_normal((p.Ntot, 2))
+pd = objparams(p.Ne, p.Ng, 3.0, 40, Uinit=p.Uinit, Utarget=p.Utarget_r + 1j * p.Utarget_i, Cfreq=p.Cfreq, Rfreq=p.Rfreq, Hconst=p.Hconst,
+               Hsym_ops=p.Hsym_ops, Hanti_ops=p.Hanti_ops, use_custom_forbidden=True, forb_states=F / np.linalg.norm(F, axis=0), forb_weights=[0.5, 0.1])
+wa = jq.Working_Arrays(pd, 48)
+wa.evaluate(configs.synthetic_pcof(configs.example("risk_neutral"), 9) * 20)
 wa.close()
 print("sanitize_small OK")
