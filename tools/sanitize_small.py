@@ -70,7 +70,10 @@ cfg.params.pFidType = 3
 wa = jq.Working_Arrays(cfg.params, cfg.nCoeff + 1)
 pcs = np.concatenate([configs.synthetic_pcof(cfg, 4) * 20, np.linspace(-1, 1, 4)[:, None]], axis=1)
 for k in (1, 3, 5):
-    wa.set_kernel(k)
+    try:
+        wa.set_kernel(k)
+    except Exception:      # JQ_LAT_PIPE=0: single-qudit shapes have no latency layout without the pipelined roles
+        continue
     wa.evaluate(pcs)
 wa.close()
 from juqbox_b200.params import objparams
