@@ -437,7 +437,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
         S.o_tred = take(ngroups * NC * 5);
         S.o_gsm2 = take(P.objFuncType != 1 ? ngroups * A.Npar : 0);
         S.o_ring = take(pipe ? TRAJ_RING * (3 * Eper + 5 * NC) * nw * 32 : 0);      // state hand-over ring, then the trace ring
-        S.o_mbar = take(pipe ? 2 * nw + (3 * nw + 2) / 2 + 1 : 0);       // int counters: 4 per warp triple, 1 per consumer warp, 1 for the tables
+        S.o_cnt = take(pipe ? 2 * nw + (3 * nw + 2) / 2 + 1 : 0);       // int counters: 4 per warp triple, 1 per consumer warp, 1 for the tables
         bytes = (size_t)o * sizeof(double);
         if (bytes <= 227 * 1024 || pipe) break;              // pipelined instantiations have a fixed number of warps
     }

@@ -58,7 +58,7 @@ struct TrajParams {
     int NparS;                               // shared-memory row stride of the staged pcof vectors (odd: no bank conflicts)
     int GPW;                                 // groups per warp (32 / GL, rounded down: GL need not be a power of two)
     // pipelined (PIPE) instantiations: state-role and adjoint-role warps of one CTA
-    int o_ring, o_mbar, tab_role_stride;     // ring of (vr0, vi05, vr) hand-overs, its mbarriers, distance between the two roles' control tables
+    int o_ring, o_cnt, tab_role_stride;      // rings of (vr0, vi05, vr) and of lane-partial traces, the int step / chunk counters, size of one control-table buffer
 };
 
 struct TrajPlan {
@@ -773,34 +773,34 @@ __device__ __forceinline__ void adjoint_step(LaneT &L, int J, double h, double (
 }
 
 // ---- pipelined instantiations: hand-over between the state role and the adjoint role of one CTA through two step counters per
-// warp pair in shared memory (volatile accesses + __threadfence_block; measured: mbarrier try_wait wake-ups cost ~1 us per hand-over,
-// more than the step they synchronise)
+// warp pair in shared memory (st.release.cta / ld.acquire.cta; an mbarrier try_wait version was no faster, and its wake-ups are
+// coarser than the step they synchronise)
 __device__ __forceinline__ void pipe_post(volatile int *cnt, int value, int lane) {      // after the warp's shared-memory traffic
     __syncwarp();
-    if (lane == 0) { __threadfence_block(); *cnt = value; }
+    if (lane == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(const_cast<int *>(cnt))), "r"(value) : "memory");
 }
 __device__ __forceinline__ void pipe_wait(volatile int *cnt, int at_least) {
-    while (*cnt < at_least) {}
-    __threadfence_block();
+    const unsigned a = (unsigned)__cvta_generic_to_shared(const_cast<int *>(cnt));
+    int v;
+    do { asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); } while (v < at_least);
 }
 // SYNC 0: all threads of the CTA; 1: the calling warp; 2: the nthr threads of the gradient role (named barrier 2)
 template <int SYNC>
-__device__ __forceinline__ void role_sync(int, int nthr) {
+__device__ __forceinline__ void role_sync(int nthr) {
     if constexpr (SYNC == 1) __syncwarp();
     else if constexpr (SYNC == 2) asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory");
     else __syncthreads();
 }
 
-// Fill the control table for `nst` steps starting at time t: all threads of the CTA into the table at offset 0 (PIPE = 0), or the
-// 32 lanes of the table warp (PIPE = 1) / the rnthr threads of the gradient role (PIPE = 2) into the table buffer at offset `toff`.
-template <int NC, int PIPE = 0>
+// Fill the control table for `nst` steps starting at time t: all threads of the CTA into the table at offset 0 (SYNC = 0), or the
+// 32 lanes of the table warp (SYNC = 1) / the rnthr threads of the gradient role (SYNC = 2) into the table buffer at offset `toff`.
+template <int NC, int SYNC = 0>
 __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt, int nst, double dtknot, int toff = 0, int rtid = 0, int rnthr = 0) {
-    const int role = 0;
-    if (PIPE == 0) { rtid = threadIdx.x; rnthr = blockDim.x; toff = 0; }
+    if (SYNC == 0) { rtid = threadIdx.x; rnthr = blockDim.x; toff = 0; }
     double *times = sm + S.o_times + toff, *tabb = sm + S.o_tabb + toff, *tabph = sm + S.o_tabph + toff, *tabpq = sm + S.o_tabpq + toff;
     int *tabk = reinterpret_cast<int *>(sm + S.o_tabk + toff);
     const int npts = 2 * nst + 1, Nfreq = S.P.Nfreq, D1 = S.A.D1;
-    role_sync<PIPE>(role, rnthr);          // the previous chunk's table is no longer in use
+    role_sync<SYNC>(rnthr);          // the previous chunk's table is no longer in use
     if (rtid == 0) {
         double tt = t;
         times[0] = tt;
@@ -810,7 +810,7 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
             times[2 * i + 2] = tt;
         }
     }
-    role_sync<PIPE>(role, rnthr);
+    role_sync<SYNC>(rnthr);
     const double width = 3.0 * dtknot;
     for (int idx = rtid; idx < npts * (NC * Nfreq + 1); idx += rnthr) {
         const int i = idx / (NC * Nfreq + 1), j = idx % (NC * Nfreq + 1);
@@ -833,7 +833,7 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
             tabph[2 * (i * NC * Nfreq + j) + 1] = sn;
         }
     }
-    role_sync<PIPE>(role, rnthr);
+    role_sync<SYNC>(rnthr);
     const double *pcof = sm + S.o_pcof;
     for (int idx = rtid; idx < npts * S.TPC * NC; idx += rnthr) {
         const int i = idx / (S.TPC * NC), rem = idx % (S.TPC * NC), tr = rem / NC, qq = rem % NC;
@@ -852,7 +852,7 @@ __device__ void fill_table(const TrajParams &S, double *sm, double t, double dt,
         tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq] = pv;
         tabpq[(i * S.TPC + tr) * 2 * NC + 2 * qq + 1] = qv;
     }
-    role_sync<PIPE>(role, rnthr);
+    role_sync<SYNC>(rnthr);
 }
 
 // Gradient scatter role: (control, frequency, alpha) with a 3-knot register window.
@@ -947,7 +947,7 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
         sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * A.pstride + k] : 0.0;
     }
     for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += blockDim.x) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
-    volatile int *pcnt = reinterpret_cast<volatile int *>(sm + S.o_mbar);     // [warp][states produced, consumed, traces produced, consumed]
+    volatile int *pcnt = reinterpret_cast<volatile int *>(sm + S.o_cnt);     // [warp][states produced, consumed, traces produced, consumed]
     volatile int *cdone = pcnt + NW * 4, *tabs_ready = cdone + NR * NW;        // chunks finished per consumer warp; table chunks produced
     const int nch = (int)((P.nsteps + TRAJ_CH - 1) / TRAJ_CH);                // global chunk ids: forward c, backward nch + c
     if constexpr (PIPE) {
