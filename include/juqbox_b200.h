@@ -170,9 +170,12 @@ int jq_comm_destroy(jq_handle *h);
  * layout with the fewest elements per lane and pipelined state / adjoint / gradient roles (latency layout; also the single-qudit
  * shapes).  Automatic: launches that fit one latency CTA per SM take 5 (then
  * 3 for three subsystems); otherwise 4, 3, 2, 1 in that order, each handing over when it has no instantiation for the problem.
- * 2 ... 5 fail with JQ_ERR_ARG if the problem has no instantiation. */
+ * 6 = dense-operator kernel on the FP64 tensor-core path (mma.sync f64; unstructured operators, the noise samples of a candidate
+ * batched as columns of one contraction); automatic mode takes it when no register-resident layout applies, n >= 8 and the
+ * operators are at least 20% filled.
+ * 2 ... 6 fail with JQ_ERR_ARG if the problem has no instantiation. */
 int jq_set_kernel(jq_handle *h, int32_t kernel);
-/* what: 0 = kernel actually used by the last evaluation (1 ... 5), 1 = CUDA-event time of the last evaluation's
+/* what: 0 = kernel actually used by the last evaluation (1 ... 6), 1 = CUDA-event time of the last evaluation's
  * trajectory kernel in ms (synchronises), 2 = number of kernels launched by the last evaluation,
  * 3 = trajectories resident per CTA, 4 = CTAs launched, 5 = registers per thread, 6 = dynamic smem bytes per CTA. */
 int jq_query(jq_handle *h, int32_t what, double *value);

@@ -166,7 +166,8 @@ class Working_Arrays:
         _lib.check(self._lib.jq_comm_destroy(self._handle))
 
     def set_kernel(self, kernel: int):
-        """0 = automatic, 1 = generic kernel, 2 = slot layout, 3 = fibre layout, 4 = tile layout."""
+        """0 = automatic, 1 = generic kernel, 2 = slot layout, 3 = fibre layout, 4 = tile layout, 5 = latency layout (pipelined roles),
+        6 = dense-operator kernel on FP64 tensor cores."""
         _lib.check(self._lib.jq_set_kernel(self._handle, int(kernel)))
 
     def query(self, what: int) -> float:

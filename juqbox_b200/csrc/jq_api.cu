@@ -62,6 +62,9 @@ struct jq_handle {
     std::vector<int> rowptr, col;
     std::vector<double> val;
     TrajPlan *slot = nullptr, *fiber = nullptr, *tile = nullptr, *tile_lat = nullptr;     // tile_lat: fewest elements per lane (small batches)
+    bool dense_ok = false;              // the dense (FP64 MMA) kernel can serve this problem
+    bool dense_auto = false;            // ... and the operators are dense enough for it to beat the row-wise generic kernel
+    char dense_reason[128] = "";
     int lat_ntraj = 0;                  // automatic mode: launches with at most this many trajectories use the latency layout
     char slot_reason[256] = "", fiber_reason[256] = "", tile_reason[256] = "";
     int kernel_pref = 0;
@@ -297,6 +300,19 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
         if ((rc = upload(h, blob.data(), total, &dblob)) != 0) { jq_destroy(h); return rc; }
         P.csr_blob = dblob; P.csr_bytes = (int)total; P.csr_off_col = (int)off_col; P.csr_off_val = (int)off_val;
     }
+    P.dense_ops = nullptr;
+    if (n <= 64) {   // dense row-major copies for the tensor-core kernel
+        int n8 = 0, ldk = 0;
+        jq_dense_padding(n, &n8, &ldk);
+        std::vector<double> dn((size_t)(1 + 2 * Nc) * n8 * ldk, 0.0);
+        for (int o = 0; o < 1 + 2 * Nc; ++o)
+            for (int r = 0; r < n; ++r)
+                for (int p2 = h->rowptr[(size_t)o * (n + 1) + r]; p2 < h->rowptr[(size_t)o * (n + 1) + r + 1]; ++p2)
+                    dn[((size_t)o * n8 + r) * ldk + h->col[p2]] += h->val[p2];
+        double *ddn = nullptr;
+        if ((rc = upload(h, dn.data(), dn.size(), &ddn)) != 0) { jq_destroy(h); return rc; }
+        P.dense_ops = ddn;
+    }
 #undef UP
 #undef UPI
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev0) != cudaSuccess ||
@@ -324,6 +340,12 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const char *lt = getenv("JQ_LAT_NTRAJ");
         // one latency CTA per SM: beyond that the throughput layouts win (measured)
+        h->dense_ok = jq_dense_supported(P, h->dense_reason, sizeof(h->dense_reason));
+        // a dense contraction executes n^2 multiply-adds per product and column whatever the sparsity: worth it from ~20% fill
+        // (measured: 5%-filled ladder operators with remote exchange run 1.6x faster on the row-wise generic kernel)
+        size_t nnz = 0;
+        for (double v : h->val) nnz += v != 0.0;
+        h->dense_auto = h->dense_ok && n >= 8 && (double)nnz >= 0.2 * (double)(1 + 2 * Nc) * n * n;
         h->lat_ntraj = lt ? atoi(lt) : sms * (h->tile_lat ? jq_traj_plan_tpc(h->tile_lat) : 1);
     }
     *out = h;
@@ -383,7 +405,8 @@ extern "C" int64_t jq_abi_info(int32_t what) {
 }
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
-    if (!h || kernel < 0 || kernel > 5) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0 ... 5");
+    if (!h || kernel < 0 || kernel > 6) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0 ... 6");
+    if (kernel == 6 && !h->dense_ok) return fail(JQ_ERR_ARG, "jq_set_kernel: the dense (tensor-core) kernel cannot serve this problem (%s)", h->dense_reason);
     if (kernel == 5 && !h->tile_lat) return fail(JQ_ERR_ARG, "jq_set_kernel: no latency layout for this problem");
     if (kernel == 4 && !h->tile) return fail(JQ_ERR_ARG, "jq_set_kernel: no tile-layout instantiation for this problem (%s)", h->tile_reason);
     if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no slot-layout instantiation for this problem (%s)", h->slot_reason);
@@ -517,7 +540,17 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
         const bool soft = e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources;
         if (!soft || pref != 0) return fail(JQ_ERR_CUDA, "trajectory kernel launch failed: %s", cudaGetErrorString(e));
     }
-    if (!plan) {
+    bool dense = false;
+    if (!plan && (pref == 6 || (pref == 0 && h->dense_auto && !A.hist_r))) {
+        // unstructured operators: the products are real contractions -> FP64 tensor-core kernel, samples of a candidate batched
+        cudaError_t e = jq_dense_launch(h->P, A, st, &ctas, &regs, &smem, &tpc);
+        if (e == cudaSuccess) dense = true;
+        else {
+            cudaGetLastError();
+            if (pref == 6) return fail(JQ_ERR_CUDA, "dense kernel launch failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (!plan && !dense) {
         if (pref > 1) return fail(JQ_ERR_ARG, "requested kernel is not available for this problem");
         if (jq_generic_smem_bytes(h->P, A.Npar) > 227 * 1024)
             return fail(JQ_ERR_ARG, "problem too large for the generic kernel's shared memory (n*m = %d)", h->n * h->m);
@@ -526,7 +559,7 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
     }
     CU(cudaEventRecord(h->ev1, st));
     h->timed = true;
-    h->last_kernel = plan ? (plan == h->tile_lat ? 5 : jq_traj_plan_kind(plan)) : 1;
+    h->last_kernel = plan ? (plan == h->tile_lat ? 5 : jq_traj_plan_kind(plan)) : dense ? 6 : 1;
     h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = tpc;
     return 0;
 }

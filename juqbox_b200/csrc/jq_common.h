@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
 
 #define JQ_MAX_CTRL 8
 
@@ -22,6 +24,8 @@ struct DevProblem {
     // kernel's TMA bulk copy into shared memory; csr_bytes is a multiple of 16
     const void *csr_blob;
     int csr_bytes, csr_off_col, csr_off_val;
+    const double *dense_ops;   // the same operators as dense row-major matrices [H0, Hsym.., Hanti..], zero padded to n8 x ldk each
+                               // (jq_dense_padding; n <= 64, else nullptr): the dense kernel's MMA A operands
     // --- SURVEY 8f rank 3 ---
     int pFidType;          // 1, 2, 3 or 4 (src/evalobjgrad.jl:755-763); 3: the global phase is the last entry of every pcof vector
     double globalPhase;    // params.globalPhase (pFidType 1 and 4)
@@ -54,6 +58,11 @@ size_t jq_generic_smem_bytes(const DevProblem &P, int Npar);
 cudaError_t jq_generic_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem);
 cudaError_t jq_controls_launch(const DevProblem &P, int D1, const double *pcof, int ntimes, const double *times, double *p, double *q,
                                cudaStream_t st);
+
+// ---- dense-operator kernel on the FP64 tensor-core path (jq_dense.cu): one CTA per (candidate, tile of samples) ----
+bool jq_dense_supported(const DevProblem &P, char *why, size_t len);
+void jq_dense_padding(int n, int *n8, int *ldk);      // layout of DevProblem::dense_ops: [1 + 2 Nc][n8][ldk], zero padded
+cudaError_t jq_dense_launch(const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs, size_t *smem, int *traj_per_cta);
 
 // Host copy of the operators in row-wise form, used by the planners.
 struct HostOps {

@@ -157,3 +157,49 @@ def test_fused_entry_risk_neutral_and_empty_shard():
     e = wa.evaluate(pc, np.zeros((0, cfg.params.Ntot)), np.zeros(0))
     assert e["infid"][0] == 0.0 and e["leak"][0] == 0.0 and not np.any(e["grad"])
     wa.close()
+
+
+def _dense_problem(n, m, Nc=2, Nfreq=2, nsteps=240, seed=12, pfid=2):
+    from juqbox_b200.params import objparams
+    rng = np.random.default_rng(seed)
+    sym = lambda a: (a + a.T) / 2
+    H0 = sym(rng.standard_normal((n, n))) * 0.3
+    Hs = [sym(rng.standard_normal((n, n))) / np.sqrt(n) for _ in range(Nc)]
+    Ha = [(lambda a: (a - a.T) / 2)(rng.standard_normal((n, n))) / np.sqrt(n) for _ in range(Nc)]
+    Vt = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))[0][:, :m]
+    p = objparams([m], [n - m], 3.0, nsteps, Uinit=np.eye(n, m), Utarget=Vt, Cfreq=rng.standard_normal((Nc, Nfreq)), Rfreq=[1.0, 2.0],
+                  Hconst=H0, Hsym_ops=Hs, Hanti_ops=Ha)
+    p.pFidType, p.globalPhase = pfid, 0.4
+    return p, 2 * Nc * Nfreq * 5
+
+
+@pytest.mark.parametrize("n,m,nsamples,pfid", [(12, 4, 1, 2), (24, 6, 11, 2), (9, 3, 5, 3), (33, 5, 3, 4)])
+def test_dense_tensor_core_kernel_vs_oracle_and_generic(n, m, nsamples, pfid):
+    """Unstructured dense operators: the FP64-MMA kernel (kernel id 6) batches the noise samples of a candidate as columns of one
+    contraction (ragged last tile: 11 = 8 + 3 samples); it must agree with the oracle and with the generic kernel, and the automatic
+    selection must pick it for n >= 8."""
+    import juqbox_b200 as jq
+    from oracle import oracle_traceobjgrad
+    p, npar = _dense_problem(n, m, pfid=pfid)
+    rng = np.random.default_rng(4)
+    pcs = rng.uniform(-0.2, 0.2, (3, npar))
+    if pfid == 3:
+        pcs = np.concatenate([pcs, [[0.3], [-0.9], [1.7]]], axis=1)
+    shifts = None if nsamples == 1 else rng.uniform(-0.05, 0.05, (nsamples, n))
+    o = oracle_traceobjgrad(p, pcs, shifts, nthreads=8)
+    wa = jq.Working_Arrays(p, pcs.shape[1])
+    for want in (0, 6, 1):
+        wa.set_kernel(want)
+        r = wa.evaluate(pcs, shifts)
+        assert wa.last_kernel == (want or 6)
+        for key in ("infid", "leak", "trace_infid"):
+            assert np.all(np.abs(r[key] - o[key]) <= TOL * np.maximum(np.abs(o[key]), 1e-6)), (want, key)
+        for b in range(3):
+            for s in range(nsamples):
+                assert _rel(r["grad"][b, s], o["grad"][b, s]) < TOL, (want, b, s, _rel(r["grad"][b, s], o["grad"][b, s]))
+    if nsamples > 1:                       # weighted sums through the same kernel
+        w = rng.uniform(0.1, 1.0, nsamples)
+        wa.set_kernel(0)
+        rw = wa.evaluate(pcs, shifts, w)
+        assert _rel(rw["grad"], (o["grad"] * w[None, :, None]).sum(1)) < TOL
+    wa.close()

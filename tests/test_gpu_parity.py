@@ -462,12 +462,14 @@ def test_random_dense_operators_fall_back_to_generic_and_match_oracle(use_sparse
     npar = 2 * Nc * Nfreq * D1
     pc = rng.uniform(-0.2, 0.2, (3, npar))
     wa = jq.Working_Arrays(p, npar)
-    r = wa.evaluate(pc)
-    assert wa.last_kernel == 1
     o = oracle_traceobjgrad(p, pc)
-    for b in range(3):
-        assert abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12 and abs(r["leak"][b, 0] - o["leak"][b, 0]) < 1e-12
-        assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL
+    for want in (0, 1, 6):                # automatic (n < 8: generic), generic, dense tensor-core kernel
+        wa.set_kernel(want)
+        r = wa.evaluate(pc)
+        assert wa.last_kernel == (want or 1)
+        for b in range(3):
+            assert abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12 and abs(r["leak"][b, 0] - o["leak"][b, 0]) < 1e-12
+            assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL
     wa.close()
 
 
