@@ -52,6 +52,7 @@ class Working_Arrays:
             device = int(os.environ.get("LOCAL_RANK", "0")) if "JUQBOX_B200_USE_LOCAL_RANK" in os.environ else 0
         self.device = device
         self._keep = []
+        self.comm_size = 1
         self._handle = C.c_void_p()
         pb = self._describe(params)
         _lib.check(lib.jq_create(C.byref(pb), C.c_int(device), C.byref(self._handle)))
@@ -161,9 +162,11 @@ class Working_Arrays:
             unique_id = bytes(t.cpu().tolist())
         assert len(unique_id) == 128
         _lib.check(self._lib.jq_comm_init(self._handle, int(rank), int(nranks), C.c_char_p(unique_id)))
+        self.comm_size = int(nranks)        # weighted evaluations now end with the library's own all-reduce
 
     def comm_destroy(self):
         _lib.check(self._lib.jq_comm_destroy(self._handle))
+        self.comm_size = 1
 
     def set_kernel(self, kernel: int):
         """0 = automatic, 1 = generic kernel, 2 = slot layout, 3 = fibre layout, 4 = tile layout, 5 = latency layout (pipelined roles),

@@ -32,9 +32,16 @@ def pack_partial(r, npar: int, obj_func_type: int) -> np.ndarray:
 
 def risk_neutral_eval(pcof, params, nodes, weights, evaluate, group=None):
     """eval_f_g_grad! over ranks: `evaluate(pcof[None], shifts, weights)` is the per-rank batched evaluation
-    (Working_Arrays.evaluate on a GPU).  Returns (infid, leak, infidgrad, leakgrad) identical on every rank."""
+    (Working_Arrays.evaluate on a GPU).  Returns (infid, leak, infidgrad, leakgrad) identical on every rank.
+
+    The two reduction mechanisms are mutually exclusive: a handle with an attached NCCL communicator (Working_Arrays.comm_init)
+    already all-reduces its weighted sums inside the C ABI, so handing its `evaluate` to this function would reduce twice."""
     import torch
     import torch.distributed as dist
+    owner = getattr(evaluate, "__self__", None)
+    if getattr(owner, "comm_size", 1) > 1:
+        raise ValueError("risk_neutral_eval: this Working_Arrays has its own NCCL communicator (comm_init) and reduces inside "
+                         "evaluate(); call evaluate() with the rank's shard directly, or comm_destroy() first")
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     nodes, weights = np.atleast_1d(np.asarray(nodes, float)), np.atleast_1d(np.asarray(weights, float))
