@@ -37,7 +37,7 @@ struct DCtx {
     __device__ __forceinline__ double *K(int l) const { return KS + (size_t)(2 * l) * sz; }
     __device__ __forceinline__ double *S(int l) const { return KS + (size_t)(2 * l + 1) * sz; }
     double *vr, *vi, *vi05, *vr0, *lr, *li, *lr05, *li0, *rhs, *scr, *k1, *k2, *l1, *l2;
-    double *pcof, *gsm, *ctrl, *shift, *red;
+    double *pcof, *gsm, *ctrl, *shift, *red;      // shift: block-shaped (n x ncols, ldx): diagonal of Hconst's noise shift of the column's sample
     double dtknot, tinv;
 };
 
@@ -88,58 +88,79 @@ __device__ __forceinline__ void dn_assemble(const DCtx &c, double t, double dt) 
     }
     __syncthreads();
     const int sz = c.G.n8 * c.G.ldk;
-    for (int e = threadIdx.x; e < 3 * sz; e += blockDim.x) {
-        const int level = e / sz, r = e % sz;
-        const double *ct = c.ctrl + level * nf;
-        double kk = c.H0[r], ss = 0.0;
-        for (int q = 0; q < c.Nc; ++q) { kk += ct[2 * q] * c.Hs[q * sz + r]; ss += ct[2 * q + 1] * c.Ha[q * sz + r]; }
-        c.K(level)[r] = kk;
-        c.S(level)[r] = ss;
+    for (int r = threadIdx.x; r < sz; r += blockDim.x) {           // every operator entry is read once for the three levels
+        double kk[3], ss[3];
+        const double h0 = c.H0[r];
+        for (int l = 0; l < 3; ++l) { kk[l] = h0; ss[l] = 0.0; }
+        for (int q = 0; q < c.Nc; ++q) {
+            const double hs = c.Hs[q * sz + r], ha = c.Ha[q * sz + r];
+            for (int l = 0; l < 3; ++l) { kk[l] = fma(c.ctrl[l * nf + 2 * q], hs, kk[l]); ss[l] = fma(c.ctrl[l * nf + 2 * q + 1], ha, ss[l]); }
+        }
+        for (int l = 0; l < 3; ++l) { c.K(l)[r] = kk[l]; c.S(l)[r] = ss[l]; }
     }
     __syncthreads();
 }
 
-// Y = alpha * A * X + beta * Y  (+ alpha * diag(shift_s) X for the columns of sample s when SHIFT).  A: n8 x n4 row-major (ldk),
-// X, Y: column-major (ldx).  One 8 x 8 output tile per warp and turn, n4 / 4 DMMA each.  Ends with a CTA barrier.
-template <bool SHIFT>
-__device__ __forceinline__ void dn_gemm(const DCtx &c, double *Y, const double *A, const double *X, double alpha, double beta) {
+// One operator product of a sum: a * A X, A an n8 x n4 row-major matrix (ldk); shift: A is a K(t), i.e. + a * diag(shift_s) X for the
+// columns of sample s (the per-sample diagonal of Hconst).  A == nullptr: term absent.
+struct DTerm { const double *A; const double *X; double a; bool shift; };
+
+// value(row, col) = sum of up to three products (one accumulator pair, n4 / 4 DMMA per product and 8 x 8 tile, one tile per warp and
+// turn), handed to ep(idx, row, col, value) for every live element; ep stores (and may update other blocks at the same position: a tile
+// is always owned by the same warp, so consecutive products into one block need no barrier in between).  Ends with a CTA barrier.
+template <class EP>
+__device__ __forceinline__ void dn_gemm(const DCtx &c, DTerm t0, DTerm t1, DTerm t2, EP ep) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int RT = c.G.n8 >> 3, CT = c.G.N8 >> 3, ldk = c.G.ldk, ldx = c.G.ldx;
     for (int t = warp; t < RT * CT; t += (blockDim.x >> 5)) {
         const int rt = t % RT, ct = t / RT;
-        double c0 = 0.0, c1 = 0.0;
-        const double *ap = A + (8 * rt + (lane >> 2)) * ldk + (lane & 3);
-        const double *bp = X + (8 * ct + (lane >> 2)) * ldx + (lane & 3);
-        for (int kk = 0; kk < c.G.n4; kk += 4) {
-            const double a = ap[kk], b = bp[kk];
-            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-        }
         const int row = 8 * rt + (lane >> 2), col = 8 * ct + 2 * (lane & 3);
-        double *y0 = Y + col * ldx + row, *y1 = y0 + ldx;
-        if (SHIFT && row < c.n) {
-            if (col < c.ncols) c0 = fma(c.shift[(col / c.m) * c.n + row], X[col * ldx + row], c0);
-            if (col + 1 < c.ncols) c1 = fma(c.shift[((col + 1) / c.m) * c.n + row], X[(col + 1) * ldx + row], c1);
+        const int aoff = (8 * rt + (lane >> 2)) * ldk + (lane & 3), boff = (8 * ct + (lane >> 2)) * ldx + (lane & 3);
+        double v0 = 0.0, v1 = 0.0;
+        const DTerm terms[3] = {t0, t1, t2};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (!terms[q].A) continue;
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;       // two accumulator chains: a DMMA waits 26 cycles for its predecessor
+            const double *ap = terms[q].A + aoff, *bp = terms[q].X + boff;
+            int kk = 0;
+            for (; kk + 4 < c.G.n4; kk += 8) {
+                const double a = ap[kk], b = bp[kk], a2 = ap[kk + 4], b2 = bp[kk + 4];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a2), "d"(b2));
+            }
+            if (kk < c.G.n4) {
+                const double a = ap[kk], b = bp[kk];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+            }
+            c0 += d0; c1 += d1;
+            if (terms[q].shift) {            // padding rows / columns of the shift block and of X are zero
+                c0 = fma(c.shift[col * ldx + row], terms[q].X[col * ldx + row], c0);
+                c1 = fma(c.shift[(col + 1) * ldx + row], terms[q].X[(col + 1) * ldx + row], c1);
+            }
+            v0 = fma(terms[q].a, c0, v0);
+            v1 = fma(terms[q].a, c1, v1);
         }
-        *y0 = beta == 0.0 ? alpha * c0 : fma(alpha, c0, beta * *y0);
-        *y1 = beta == 0.0 ? alpha * c1 : fma(alpha, c1, beta * *y1);
+        if (row < c.n) {
+            if (col < c.ncols) ep(col * ldx + row, row, col, v0);
+            if (col + 1 < c.ncols) ep((col + 1) * ldx + row, row, col + 1, v1);
+        }
     }
     __syncthreads();
 }
+#define DT_NONE DTerm{nullptr, nullptr, 0.0, false}
 
-// elementwise loop over the live n x ncols part of the blocks: e -> (i, col, idx)
-#define DN_FOR for (int e = threadIdx.x, i = e % c.n, col = e / c.n, idx = col * c.G.ldx + i; e < c.n * c.ncols; \
-                    e += blockDim.x, i = e % c.n, col = e / c.n, idx = col * c.G.ldx + i)
+// elementwise loop over the live n x ncols part of the blocks (no divisions: a warp per column, lanes over the rows): (i, col, idx)
+#define DN_FOR for (int col = threadIdx.x >> 5; col < c.ncols; col += (blockDim.x >> 5)) \
+                   for (int i = threadIdx.x & 31, idx = col * c.G.ldx + i; i < c.n; i += 32, idx += 32)
 
-// X = sum_{j<=J} (h/2)^j S^j B ; B destroyed, T scratch (src/linear_solvers.jl:94-106)
+// X = sum_{j<=J} (h/2)^j S^j B ; B destroyed, T scratch (src/linear_solvers.jl:94-106).  X must already hold B (the caller's product
+// epilogue writes both); the update X += coeff T rides on the epilogue of the product that makes T.
 __device__ __forceinline__ void dn_neumann(const DCtx &c, const double *Smat, double h, double *B, double *T, double *X) {
-    DN_FOR X[idx] = B[idx];
-    __syncthreads();
     double coeff = 1.0;
     for (int it = 0; it < c.J; ++it) {
         coeff *= 0.5 * h;
-        dn_gemm<false>(c, T, Smat, B, 1.0, 0.0);
-        DN_FOR X[idx] += coeff * T[idx];
-        __syncthreads();
+        dn_gemm(c, DTerm{Smat, B, 1.0, false}, DT_NONE, DT_NONE, [&](int idx, int, int, double v) { T[idx] = v; X[idx] += coeff * v; });
         double *sw = B; B = T; T = sw;
     }
 }
@@ -147,53 +168,50 @@ __device__ __forceinline__ void dn_neumann(const DCtx &c, const double *Smat, do
 // src/StormerVerlet.jl:461-504
 __device__ __forceinline__ void dn_state_step(const DCtx &c, double h) {
     double *u = c.vr, *v = c.vi, *v05 = c.vi05;
-    dn_gemm<true>(c, c.rhs, c.K(1), u, 1.0, 0.0);
-    dn_gemm<false>(c, c.rhs, c.S(1), v, 1.0, 1.0);
+    // rhs = K05 u + S05 v ; l1 = neumann(S05, rhs) ; v05 = v + h/2 l1
+    dn_gemm(c, DTerm{c.K(1), u, 1.0, true}, DTerm{c.S(1), v, 1.0, false}, DT_NONE, [&](int idx, int, int, double val) { c.rhs[idx] = val; c.l1[idx] = val; });
     dn_neumann(c, c.S(1), h, c.rhs, c.scr, c.l1);
     DN_FOR v05[idx] = v[idx] + 0.5 * h * c.l1[idx];
     __syncthreads();
-    dn_gemm<false>(c, c.k1, c.S(0), u, 1.0, 0.0);
-    dn_gemm<true>(c, c.k1, c.K(0), v05, -1.0, 1.0);
-    dn_gemm<false>(c, c.rhs, c.S(2), u, 1.0, 0.0);
-    dn_gemm<false>(c, c.rhs, c.S(2), c.k1, 0.5 * h, 1.0);
-    dn_gemm<true>(c, c.rhs, c.K(2), v05, -1.0, 1.0);
+    // k1 = S0 u - K0 v05
+    dn_gemm(c, DTerm{c.S(0), u, 1.0, false}, DTerm{c.K(0), v05, -1.0, true}, DT_NONE, [&](int idx, int, int, double val) { c.k1[idx] = val; });
+    // rhs = S1 u + h/2 S1 k1 - K1 v05 ; k2 = neumann(S1, rhs) ; u += h/2 k1 (after the products have read u: next barrier)
+    dn_gemm(c, DTerm{c.S(2), u, 1.0, false}, DTerm{c.S(2), c.k1, 0.5 * h, false}, DTerm{c.K(2), v05, -1.0, true},
+            [&](int idx, int, int, double val) { c.rhs[idx] = val; c.k2[idx] = val; });
     DN_FOR u[idx] += 0.5 * h * c.k1[idx];
     __syncthreads();
     dn_neumann(c, c.S(2), h, c.rhs, c.scr, c.k2);
     DN_FOR u[idx] += 0.5 * h * c.k2[idx];
     __syncthreads();
-    dn_gemm<true>(c, c.l2, c.K(1), u, 1.0, 0.0);
-    dn_gemm<false>(c, c.l2, c.S(1), v05, 1.0, 1.0);
-    DN_FOR v[idx] += 0.5 * h * (c.l1[idx] + c.l2[idx]);
-    __syncthreads();
+    // l2 = K05 u + S05 v05 ; v += h/2 (l1 + l2)
+    dn_gemm(c, DTerm{c.K(1), u, 1.0, true}, DTerm{c.S(1), v05, 1.0, false}, DT_NONE, [&](int idx, int, int, double val) { v[idx] += 0.5 * h * (c.l1[idx] + val); });
 }
 
 // src/StormerVerlet.jl:255-303; forcing with the diagonal weights: hr0 = W vr0 / T, hi0 = hi1 = W vi05 / T, hr1 = W vr / T
 __device__ __forceinline__ void dn_adjoint_step(const DCtx &c, double *mu, double *nu, double *X, double h) {
     const double *w = c.P->wdiag;
-    dn_gemm<false>(c, c.rhs, c.S(0), mu, 1.0, 0.0);
-    dn_gemm<true>(c, c.rhs, c.K(1), nu, -1.0, 1.0);
-    DN_FOR c.rhs[idx] += c.tinv * w[i] * c.vr0[idx];
-    __syncthreads();
+    // rhs = S0 mu - K05 nu + hr0 ; k2 = neumann(S0, rhs) ; mu += h/2 k2 ; X = mu
+    dn_gemm(c, DTerm{c.S(0), mu, 1.0, false}, DTerm{c.K(1), nu, -1.0, true}, DT_NONE, [&](int idx, int row, int, double val) {
+        val += c.tinv * w[row] * c.vr0[idx];
+        c.rhs[idx] = val; c.k2[idx] = val;
+    });
     dn_neumann(c, c.S(0), h, c.rhs, c.scr, c.k2);
     DN_FOR { mu[idx] += 0.5 * h * c.k2[idx]; X[idx] = mu[idx]; }
     __syncthreads();
-    dn_gemm<true>(c, c.l2, c.K(0), X, 1.0, 0.0);
-    dn_gemm<false>(c, c.l2, c.S(1), nu, 1.0, 1.0);
-    DN_FOR c.l2[idx] += c.tinv * w[i] * c.vi05[idx];
-    __syncthreads();
-    dn_gemm<false>(c, c.rhs, c.S(1), nu, 1.0, 0.0);
-    dn_gemm<false>(c, c.rhs, c.S(1), c.l2, 0.5 * h, 1.0);
-    dn_gemm<true>(c, c.rhs, c.K(2), X, 1.0, 1.0);
-    DN_FOR c.rhs[idx] += c.tinv * w[i] * c.vi05[idx];
-    __syncthreads();
+    // l2 = K0 X + S05 nu + hi0
+    dn_gemm(c, DTerm{c.K(0), X, 1.0, true}, DTerm{c.S(1), nu, 1.0, false}, DT_NONE,
+            [&](int idx, int row, int, double val) { c.l2[idx] = val + c.tinv * w[row] * c.vi05[idx]; });
+    // rhs = S05 nu + h/2 S05 l2 + K1 X + hi1 ; l1 = neumann(S05, rhs) ; nu += h/2 (l2 + l1)
+    dn_gemm(c, DTerm{c.S(1), nu, 1.0, false}, DTerm{c.S(1), c.l2, 0.5 * h, false}, DTerm{c.K(2), X, 1.0, true}, [&](int idx, int row, int, double val) {
+        val += c.tinv * w[row] * c.vi05[idx];
+        c.rhs[idx] = val; c.l1[idx] = val;
+    });
     dn_neumann(c, c.S(1), h, c.rhs, c.scr, c.l1);
     DN_FOR nu[idx] += 0.5 * h * (c.l2[idx] + c.l1[idx]);
     __syncthreads();
-    dn_gemm<false>(c, c.k1, c.S(2), X, 1.0, 0.0);
-    dn_gemm<true>(c, c.k1, c.K(1), nu, -1.0, 1.0);
-    DN_FOR mu[idx] += 0.5 * h * (c.k1[idx] + c.tinv * w[i] * c.vr[idx]);
-    __syncthreads();
+    // kappa1 = S1 X - K05 nu + hr1 ; mu += h/2 kappa1
+    dn_gemm(c, DTerm{c.S(2), X, 1.0, false}, DTerm{c.K(1), nu, -1.0, true}, DT_NONE,
+            [&](int idx, int row, int, double val) { mu[idx] += 0.5 * h * (val + c.tinv * w[row] * c.vr[idx]); });
 }
 
 // per-sample sums of `cnt` values: warp w takes samples w, w + 8, ...; f(s, e_in_sample, idx, acc)
@@ -203,10 +221,8 @@ __device__ __forceinline__ void dn_sample_sums(const DCtx &c, double *out /* [ST
     for (int s = warp; s < c.ns; s += (blockDim.x >> 5)) {
         double acc[CNT];
         for (int k = 0; k < CNT; ++k) acc[k] = 0.0;
-        for (int e = lane; e < c.n * c.m; e += 32) {
-            const int i = e % c.n, j = e / c.n;
-            f(s, i, j, (s * c.m + j) * c.G.ldx + i, acc);
-        }
+        for (int j = 0; j < c.m; ++j)
+            for (int i = lane; i < c.n; i += 32) f(s, i, j, (s * c.m + j) * c.G.ldx + i, acc);
         for (int k = 0; k < CNT; ++k) {
             double x = acc[k];
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -221,19 +237,19 @@ __device__ __forceinline__ void dn_grad_step(const DCtx &c, double t0, double dt
     const int sz = c.G.n8 * c.G.ldk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int q = 0; q < c.Nc; ++q) {
-        double *aX = c.rhs, *sX = c.scr, *sLi = c.k1, *sLi0 = c.k2, *aLi = c.l1, *aLi0 = c.l2;
-        dn_gemm<false>(c, aX, c.Ha + q * sz, c.lr05, 1.0, 0.0);
-        dn_gemm<false>(c, sX, c.Hs + q * sz, c.lr05, 1.0, 0.0);
-        dn_gemm<false>(c, sLi, c.Hs + q * sz, c.li, 1.0, 0.0);
-        dn_gemm<false>(c, sLi0, c.Hs + q * sz, c.li0, 1.0, 0.0);
-        dn_gemm<false>(c, aLi, c.Ha + q * sz, c.li, 1.0, 0.0);
-        dn_gemm<false>(c, aLi0, c.Ha + q * sz, c.li0, 1.0, 0.0);
+        double *aX = c.rhs, *sX = c.scr, *sLi = c.k1, *sLi0 = c.k2, *aLi = c.l1;
+        auto put = [&](double *dst) { return [dst](int idx, int, int, double val) { dst[idx] = val; }; };
+        dn_gemm(c, DTerm{c.Ha + q * sz, c.lr05, 1.0, false}, DT_NONE, DT_NONE, put(aX));
+        dn_gemm(c, DTerm{c.Hs + q * sz, c.lr05, 1.0, false}, DT_NONE, DT_NONE, put(sX));
+        dn_gemm(c, DTerm{c.Hs + q * sz, c.li, 1.0, false}, DT_NONE, DT_NONE, put(sLi));
+        dn_gemm(c, DTerm{c.Hs + q * sz, c.li0, 1.0, false}, DT_NONE, DT_NONE, put(sLi0));
+        dn_gemm(c, DTerm{c.Ha + q * sz, c.li, 1.0, false}, DTerm{c.Ha + q * sz, c.li0, 1.0, false}, DT_NONE, put(aLi));      // Ha (li + li0)
         dn_sample_sums<5>(c, c.red, [&](int, int, int, int idx, double *T) {
             T[0] += c.vr0[idx] * aX[idx];                               // tr(vr0, Ha, lr05)
             T[1] += c.vi05[idx] * sX[idx];                              // tr(vi05, Hs, lr05)
             T[2] += c.vr[idx] * aX[idx];                                // tr(vr, Ha, lr05)
             T[3] += c.vr[idx] * sLi[idx] + c.vr0[idx] * sLi0[idx];      // tr(vr,Hs,li) + tr(vr0,Hs,li0)
-            T[4] += c.vi05[idx] * (aLi[idx] + aLi0[idx]);               // tr(vi05,Ha,li) + tr(vi05,Ha,li0)
+            T[4] += c.vi05[idx] * aLi[idx];                             // tr(vi05,Ha,li) + tr(vi05,Ha,li0)
         });
         const int kind = c.P->ctrl_kind[q];
         for (int s = warp; s < c.ns; s += (blockDim.x >> 5)) {
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(DN_THREADS) jq_dense_kernel(DevProblem P, Laun
     c.pcof = p; p += c.Npar;
     c.gsm = p; p += G.ST * c.Npar;
     c.ctrl = p; p += 6 * c.Nc;
-    c.shift = p; p += G.ST * c.n;
+    c.shift = p; p += bsz;
     c.red = p;                                          // [ST][5]
     // dense operators: padded global copy (row-major n8 x ldk per operator) -> shared memory, once per CTA
     if (G.ops_smem)
@@ -307,11 +323,13 @@ __global__ void __launch_bounds__(DN_THREADS) jq_dense_kernel(DevProblem P, Laun
         c.ncols = c.m * c.ns;
         for (int k = threadIdx.x; k < c.Npar; k += blockDim.x) c.pcof[k] = A.pcof[(size_t)b * A.pstride + k];
         for (int k = threadIdx.x; k < G.ST * c.Npar; k += blockDim.x) c.gsm[k] = 0.0;
-        for (int k = threadIdx.x; k < G.ST * c.n; k += blockDim.x)
-            c.shift[k] = (A.shift && k / c.n < c.ns) ? A.shift[(size_t)(s0 + k / c.n) * c.n + k % c.n] : 0.0;
         for (int e = threadIdx.x; e < 14 * bsz; e += blockDim.x) c.vr[e] = 0.0;
+        for (int e = threadIdx.x; e < bsz; e += blockDim.x) c.shift[e] = 0.0;
         __syncthreads();
-        DN_FOR c.vr[idx] = P.uinit[i + (size_t)c.n * (col % c.m)];
+        DN_FOR {
+            c.vr[idx] = P.uinit[i + (size_t)c.n * (col % c.m)];
+            if (A.shift) c.shift[idx] = A.shift[(size_t)(s0 + col / c.m) * c.n + i];
+        }
         __syncthreads();
         const double phase = P.pFidType == 3 ? A.pcof[(size_t)b * A.pstride + c.Npar] : P.globalPhase;
 
@@ -393,7 +411,7 @@ int pad_ld(int x) {            // smallest ld >= x with ld % 16 in {4, 12}: 8 ro
 }
 size_t dense_bytes(const DevProblem &P, const LaunchArgs &A, const DenseGeom &G) {
     const size_t d = (size_t)(6 + (G.ops_smem ? 1 + 2 * P.Nc : 0)) * G.n8 * G.ldk + (size_t)14 * G.N8 * G.ldx + A.Npar + (size_t)G.ST * A.Npar +
-                     6 * P.Nc + (size_t)G.ST * P.n + (size_t)G.ST * 5 + 8;
+                     6 * P.Nc + (size_t)G.N8 * G.ldx + (size_t)G.ST * 5 + 8;
     return d * sizeof(double);
 }
 
