@@ -55,6 +55,7 @@ def main():
         wa.evaluate(big)
         wa.evaluate(big)
         rate = big.shape[0] / (wa.last_kernel_ms * 1e-3)
+        k = f"{wa.last_kernel} ({k} for 2 candidates)" if wa.last_kernel != k else k
         print(f"| {Ne} / {Ng} | {kw or ''} | {p.Ntot} x {p.N} | {p.nsteps} | {p.linear_solver.max_iter} | {k} | {why} | "
               f"{err:.1e} (infid {errf:.0e}) | {rate:.3g} |", flush=True)
         wa.close()
