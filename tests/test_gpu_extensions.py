@@ -203,3 +203,35 @@ def test_dense_tensor_core_kernel_vs_oracle_and_generic(n, m, nsamples, pfid):
         rw = wa.evaluate(pcs, shifts, w)
         assert _rel(rw["grad"], (o["grad"] * w[None, :, None]).sum(1)) < TOL
     wa.close()
+
+
+def test_handle_guards_against_silent_misuse():
+    """ADVICE (round 1): params edited after the handle was created must not be silently ignored; device-entry arguments are
+    validated before raw pointers reach the library; host-path and device-path calls may be mixed (shared scratch, two streams)."""
+    import torch
+    import juqbox_b200 as jq
+    from juqbox_b200 import configs
+    cfg = configs.example("risk_neutral")
+    cfg.params.T, cfg.params.nsteps = 30.0, 800
+    p = cfg.params
+    wa = jq.Working_Arrays(p, cfg.nCoeff)
+    pc = configs.synthetic_pcof(cfg, 4) * 20
+    sh = configs.noise_shift(p.Ntot, cfg.nodes)
+    host = wa.evaluate(pc, sh)
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(dev)
+    pcd, shd = torch.from_numpy(pc).to(dev), torch.from_numpy(sh).to(dev)
+    with torch.cuda.stream(side):
+        d = wa.evaluate_device(pcd, shd, None, True, stream=side)       # caller's stream right after the handle's own stream
+    again = wa.evaluate(pc * 1.5, sh)                                     # and back, while `side` may still be running
+    side.synchronize()
+    assert np.array_equal(d["grad"].cpu().numpy(), host["grad"])
+    assert not np.array_equal(again["grad"], host["grad"])
+    with pytest.raises(ValueError):
+        wa.evaluate_device(pcd.float(), shd)                              # wrong dtype
+    with pytest.raises(ValueError):
+        wa.evaluate_device(pcd, shd[:, :-1].contiguous())                 # wrong shape
+    p.nsteps = 900                                                        # the reference would re-read this on the next call
+    with pytest.raises(RuntimeError):
+        wa.evaluate(pc, sh)
+    wa.close()
