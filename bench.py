@@ -37,7 +37,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = ["rabi", "cnot1", "cnot2", "cnot3", "risk_neutral"]
 # candidates per GPU per step: multiples of the resident-CTA wave of the kernel that serves the shape
 DEFAULT_BATCH = {"rabi": 262144, "cnot1": 37888, "cnot2": 16384, "cnot3": 2368, "risk_neutral": 3946}
-KERNEL_NAMES = {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>", 4: "jq_traj_kernel<TileLane>", 5: "jq_traj_kernel<latency layout, pipelined roles>", 6: "jq_dense_kernel (FP64 MMA)"}
+KERNEL_NAMES = {1: "jq_generic_kernel", 2: "jq_traj_kernel<SlotLane>", 3: "jq_traj_kernel<FiberLane>", 4: "jq_traj_kernel<TileLane>", 5: "jq_traj_kernel<latency layout, pipelined roles>", 6: "jq_dense_kernel (FP64 MMA)",
+                7: "time-parallel: jq_traj_kernel<segment sweeps> + jq_seg_chain joins"}
 
 
 def alg_flops_per_eval(p, npar, dense=False):

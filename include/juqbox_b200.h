@@ -173,11 +173,18 @@ int jq_comm_destroy(jq_handle *h);
  * 6 = dense-operator kernel on the FP64 tensor-core path (mma.sync f64; unstructured operators, the noise samples of a candidate
  * batched as columns of one contraction); automatic mode takes it when no register-resident layout applies, n >= 8 and the
  * operators are at least 20% filled.
- * 2 ... 6 fail with JQ_ERR_ARG if the problem has no instantiation. */
+ * 7 = time-parallel evaluation for launches of very few trajectories (the reference's own call pattern: one pcof per Ipopt
+ * callback): the time axis is cut into segments that are swept concurrently by the layout-3/4 steppers and joined through the
+ * segments' discrete propagators (every step of the scheme is linear in the state and affine in the adjoint); same results to
+ * rounding (~1e-13 relative), critical path ~ 3 nsteps / nseg steps.  objFuncType 1, Neumann solver, tile / fibre layouts.
+ * 2 ... 7 fail with JQ_ERR_ARG if the problem has no instantiation. */
 int jq_set_kernel(jq_handle *h, int32_t kernel);
-/* what: 0 = kernel actually used by the last evaluation (1 ... 6), 1 = CUDA-event time of the last evaluation's
- * trajectory kernel in ms (synchronises), 2 = number of kernels launched by the last evaluation,
- * 3 = trajectories resident per CTA, 4 = CTAs launched, 5 = registers per thread, 6 = dynamic smem bytes per CTA. */
+/* Number of time segments of kernel 7; 0 = automatic (about two sub-trajectory CTAs per SM in the propagator launch). */
+int jq_set_time_segments(jq_handle *h, int32_t nseg);
+/* what: 0 = kernel actually used by the last evaluation (1 ... 7), 1 = CUDA-event time of the last evaluation's
+ * trajectory kernel(s) in ms (synchronises), 2 = number of kernels launched by the last evaluation,
+ * 3 = trajectories resident per CTA, 4 = CTAs launched, 5 = registers per thread, 6 = dynamic smem bytes per CTA,
+ * 7 = time segments of the last evaluation (kernel 7; else 0). */
 int jq_query(jq_handle *h, int32_t what, double *value);
 
 /* Measured FP64 FMA throughput of `device` in TFLOP/s (8 independent DFMA chains per thread on every SM, best of

@@ -170,8 +170,12 @@ class Working_Arrays:
 
     def set_kernel(self, kernel: int):
         """0 = automatic, 1 = generic kernel, 2 = slot layout, 3 = fibre layout, 4 = tile layout, 5 = latency layout (pipelined roles),
-        6 = dense-operator kernel on FP64 tensor cores."""
+        6 = dense-operator kernel on FP64 tensor cores, 7 = time-parallel evaluation (segments of the time axis swept concurrently)."""
         _lib.check(self._lib.jq_set_kernel(self._handle, int(kernel)))
+
+    def set_time_segments(self, nseg: int) -> None:
+        """Number of time segments of kernel 7 (0 = automatic)."""
+        _lib.check(self._lib.jq_set_time_segments(self._handle, int(nseg)))
 
     def query(self, what: int) -> float:
         v = C.c_double()

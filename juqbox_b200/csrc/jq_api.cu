@@ -66,6 +66,12 @@ struct jq_handle {
     bool dense_auto = false;            // ... and the operators are dense enough for it to beat the row-wise generic kernel
     char dense_reason[128] = "";
     int lat_ntraj = 0;                  // automatic mode: launches with at most this many trajectories use the latency layout
+    // time-parallel evaluation (jq_seg.cu, kernel id 7): plan whose instantiations have segment sweeps (the non-pipelined latency
+    // tile layout, else the fibre plan -- then shared with `fiber`), workspace, segments (0 = automatic)
+    TrajPlan *seg_plan = nullptr, *seg_prop = nullptr;      // seg_prop: plan of the propagator launch (nullptr: seg_plan)
+    double *d_seg = nullptr; size_t cap_seg = 0;
+    double *d_segt = nullptr; size_t cap_segt = 0; int segt_nseg = 0; std::vector<double> segt;
+    int seg_nseg = 0, seg_ntraj = 0, sms = 148, last_nseg = 0;
     char slot_reason[256] = "", fiber_reason[256] = "", tile_reason[256] = "";
     int kernel_pref = 0;
     bool prefer_tile = true;            // automatic mode: tile layout before the fibre layout
@@ -79,7 +85,7 @@ struct jq_handle {
     std::vector<double> c_pcof, c_shift, c_w, c_igrad, c_lgrad;
     double c_infid = 0.0, c_leak = 0.0;
     // last-evaluation facts
-    int last_kernel = 0, last_launches = 0, last_ctas = 0, last_regs = 0, last_tpc = 1;
+    int last_kernel = 0, last_launches = 0, last_ctas = 0, last_regs = 0, last_tpc = 1, last_traj_launches = 1;
     size_t last_smem = 0;
     bool timed = false;
 };
@@ -347,6 +353,24 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
         for (double v : h->val) nnz += v != 0.0;
         h->dense_auto = h->dense_ok && n >= 8 && (double)nnz >= 0.2 * (double)(1 + 2 * Nc) * n * n;
         h->lat_ntraj = lt ? atoi(lt) : sms * (h->tile_lat ? jq_traj_plan_tpc(h->tile_lat) : 1);
+        // Time-parallel evaluation for launches of very few trajectories (one pcof per Ipopt callback): segments of the time axis
+        // swept concurrently and joined through their propagators
+        h->sms = sms;
+        h->seg_plan = jq_tile_plan_create(P, H, pb->wdiag, Nc == 2 ? 0 : 1, why, sizeof(why), 0);
+        if (!h->seg_plan) h->seg_plan = h->fiber;
+        if (h->seg_plan && !jq_seg_supported(h->seg_plan, P)) { if (h->seg_plan != h->fiber) jq_traj_plan_destroy(h->seg_plan); h->seg_plan = nullptr; }
+        // propagator launch (many independent unit-vector sweeps): the throughput tile layout when the problem has one
+        const char *pe = getenv("JQ_SEG_PROP_TILE");
+        if (h->seg_plan && h->tile && jq_seg_supported(h->tile, P) && (pe ? atoi(pe) != 0 : true)) h->seg_prop = h->tile;
+        // automatic mode: time-parallel while the propagator launch (2 x 2n/m unit-vector sweeps per trajectory and segment) stays within
+        // about four warps per SM -- measured cross-overs against the other kernels: cnot2 ~60 candidates, cnot3 ~30, risk-neutral ~1100
+        // samples (profiles/r02_timeparallel.md)
+        const char *sn = getenv("JQ_SEG_NTRAJ");
+        if (h->seg_plan) {
+            const int lanes = std::max(1, jq_traj_plan_lanes(h->seg_prop ? h->seg_prop : h->seg_plan)), nblk = (2 * n + m - 1) / m;
+            h->seg_ntraj = std::max(1, (4 * sms * 32) / (2 * nblk * lanes));
+        }
+        if (sn) h->seg_ntraj = atoi(sn);
     }
     *out = h;
     return 0;
@@ -360,9 +384,12 @@ extern "C" int jq_destroy(jq_handle *h) {
     for (void *p : h->owned) cudaFree(p);
     for (double *p : {h->d_scal, h->d_grad, h->d_igrad, h->d_in, h->d_out}) if (p) cudaFree(p);
     if (h->slot) jq_traj_plan_destroy(h->slot);
-    if (h->fiber) jq_traj_plan_destroy(h->fiber);
     if (h->tile) jq_traj_plan_destroy(h->tile);
     if (h->tile_lat) jq_traj_plan_destroy(h->tile_lat);
+    if (h->seg_plan && h->seg_plan != h->fiber) jq_traj_plan_destroy(h->seg_plan);
+    if (h->fiber) jq_traj_plan_destroy(h->fiber);
+    if (h->d_seg) cudaFree(h->d_seg);
+    if (h->d_segt) cudaFree(h->d_segt);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -405,13 +432,20 @@ extern "C" int64_t jq_abi_info(int32_t what) {
 }
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
-    if (!h || kernel < 0 || kernel > 6) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0 ... 6");
+    if (!h || kernel < 0 || kernel > 7) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0 ... 7");
+    if (kernel == 7 && !h->seg_plan) return fail(JQ_ERR_ARG, "jq_set_kernel: no time-parallel evaluation for this problem (needs a tile / fibre layout, objFuncType 1, Neumann solver)");
     if (kernel == 6 && !h->dense_ok) return fail(JQ_ERR_ARG, "jq_set_kernel: the dense (tensor-core) kernel cannot serve this problem (%s)", h->dense_reason);
     if (kernel == 5 && !h->tile_lat) return fail(JQ_ERR_ARG, "jq_set_kernel: no latency layout for this problem");
     if (kernel == 4 && !h->tile) return fail(JQ_ERR_ARG, "jq_set_kernel: no tile-layout instantiation for this problem (%s)", h->tile_reason);
     if (kernel == 2 && !h->slot) return fail(JQ_ERR_ARG, "jq_set_kernel: no slot-layout instantiation for this problem (%s)", h->slot_reason);
     if (kernel == 3 && !h->fiber) return fail(JQ_ERR_ARG, "jq_set_kernel: no fibre-layout instantiation for this problem (%s)", h->fiber_reason);
     h->kernel_pref = kernel;
+    return 0;
+}
+
+extern "C" int jq_set_time_segments(jq_handle *h, int32_t nseg) {
+    if (!h || nseg < 0) return fail(JQ_ERR_ARG, "jq_set_time_segments: need a handle and nseg >= 0 (0 = automatic)");
+    h->seg_nseg = nseg;
     return 0;
 }
 
@@ -432,6 +466,7 @@ extern "C" int jq_query(jq_handle *h, int32_t what, double *value) {
     case 4: *value = h->last_ctas; break;
     case 5: *value = h->last_regs; break;
     case 6: *value = (double)h->last_smem; break;
+    case 7: *value = h->last_kernel == 7 ? h->last_nseg : 0; break;
     default: return fail(JQ_ERR_ARG, "jq_query: unknown item %d", what);
     }
     return 0;
@@ -533,6 +568,36 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
     int ctas = 0, regs = 0, tpc = 1;
     size_t smem = 0;
     CU(cudaEventRecord(h->ev0, st));
+    // very few trajectories: time-parallel evaluation (segments of the time axis swept concurrently)
+    const bool seg_able = h->seg_plan && h->P.objFuncType == 1 && h->P.solver == 1 && !A.hist_r;
+    if (pref == 7 || (pref == 0 && seg_able && A.ntraj <= h->seg_ntraj && h->P.nsteps >= 256)) {
+        if (!seg_able) return fail(JQ_ERR_ARG, "time-parallel evaluation: objFuncType 1, Neumann solver, no state history");
+        TrajPlan *prop = h->seg_prop ? h->seg_prop : h->seg_plan;
+        int nseg = h->seg_nseg > 0 ? h->seg_nseg : jq_seg_auto_segments(h->P, A.ntraj, A.evaladjoint, jq_traj_plan_tpc(prop), h->sms);
+        if (nseg > h->P.nsteps) nseg = (int)h->P.nsteps;
+        int rc = grow(&h->d_seg, &h->cap_seg, jq_seg_workspace_doubles(h->P, A.ntraj, A.Npar, nseg, A.evaladjoint));
+        if (rc) return rc;
+        if (h->segt_nseg != nseg) {           // segment start / end times: host recurrence, once per segment count
+            h->segt.resize(2 * (size_t)nseg);
+            jq_seg_times(h->P, nseg, h->segt.data());
+            if ((rc = grow(&h->d_segt, &h->cap_segt, 2 * (size_t)nseg)) != 0) return rc;
+            CU(cudaMemcpyAsync(h->d_segt, h->segt.data(), 2 * (size_t)nseg * sizeof(double), cudaMemcpyHostToDevice, st));
+            h->segt_nseg = nseg;
+        }
+        int nl = 0;
+        cudaError_t e = jq_seg_launch(h->seg_prop, h->seg_plan, h->P, A, nseg, h->d_segt, h->d_seg, st, &ctas, &regs, &smem, &tpc, &nl);
+        if (e == cudaSuccess) {
+            CU(cudaEventRecord(h->ev1, st));
+            h->timed = true;
+            h->last_kernel = 7; h->last_nseg = nseg; h->last_traj_launches = nl;
+            h->last_ctas = ctas; h->last_regs = regs; h->last_smem = smem; h->last_tpc = tpc;
+            return 0;
+        }
+        cudaGetLastError();
+        const bool soft = e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources;
+        if (!soft || pref != 0) return fail(JQ_ERR_CUDA, "time-parallel evaluation failed: %s", cudaGetErrorString(e));
+    }
+    h->last_traj_launches = 1;
     for (int i = 0; i < ncand && !plan; ++i) {
         cudaError_t e = jq_traj_launch(cands[i], h->P, A, st, &ctas, &regs, &smem, &tpc);
         if (e == cudaSuccess) { plan = cands[i]; break; }
@@ -616,7 +681,7 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
         jq_finalize_kernel<<<fg, fb, 0, st>>>(nbatch, nsamples, npar, h->P.objFuncType, A.evaladjoint, weights, h->d_scal, h->d_grad,
                                               h->d_igrad, infid, leak, trace_infid, grad, infidgrad, leakgrad);
     CU(cudaGetLastError());
-    h->last_launches = 2;
+    h->last_launches = 1 + h->last_traj_launches;
     if (h->comm && weights && h->comm_size > 1) {
         // the path's one exchange step: weighted sums over the sample shards of all ranks (sum, FP64), one grouped call
         const size_t nb = (size_t)nbatch, ng = (size_t)nbatch * npar;
@@ -632,7 +697,7 @@ extern "C" int jq_traceobjgrad_batch_device(jq_handle *h, int32_t nbatch, const 
         const int erc = g_nccl.GroupEnd();
         if (nrc == 0) nrc = erc;
         if (nrc != 0) return fail(JQ_ERR_CUDA, "ncclAllReduce of the weighted sample sums: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "nccl error");
-        h->last_launches = 3;
+        h->last_launches += 1;
     }
     CU(cudaEventRecord(h->ev_done, st));
     h->last_stream = st; h->have_last = true;

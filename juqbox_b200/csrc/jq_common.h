@@ -38,6 +38,28 @@ struct DevProblem {
     int any_unc;
 };
 
+// Time-parallel evaluation (jq_seg.cu): the time axis is cut into nseg segments, every segment is swept by its own sub-trajectories
+// and the segments are joined through the discrete propagators (the one-step maps are linear in the state / the adjoint).
+// What the CTAs of one trajectory-kernel launch do: CTAs [0, ctas0) run mode[0], the others mode[1] (0 = none)
+//   1 forward sweep of a block of m unit vectors of R^2n           -> Phi   (state propagator of the segment, column by column)
+//   2 forward sweep of the true state from X[seg]                  -> penpart (the segment's share of the guard-level penalty)
+//   3 adjoint sweep without forcing from a block of unit vectors   -> Adj   (homogeneous adjoint propagator)
+//   4 backward sweep (state from Xb[seg+1], zero terminal adjoint) -> cpart (particular adjoint solution at the segment start)
+//   5 backward sweep (state from Xb[seg+1], adjoint from Lam[seg+1]) -> gpart (the segment's share of the gradient)
+//   6 backward state sweep of the true state from X[seg+1]         -> dpart = J (state reached - X[seg]), J (u; v) = (v; -u): the
+//     defect of the backward recomputation, from which the join builds Xb = X + J' Eta, the states the reference's backward sweep
+//     sees (its time recurrence from T is shifted against the forward one by the rounding of nsteps additions, ~1e-10)
+// Layouts: Phi, Adj [seg][traj][ld (unit vector j)][ld (u rows, then v rows)]; X, Lam, Eta, cpart, dpart [seg][traj][m (column)][2n
+// (u rows, then v rows)] (X, Lam, Eta have nseg + 1 boundary entries); gpart [seg][traj][Npar]; penpart [seg][traj].
+struct SegArgs {
+    int nseg;              // 0: whole trajectories (the plain evaluation)
+    int mode[2], ctas0;
+    int ld;                // leading dimension of Phi / Adj: [seg][traj][ld][ld], zero padded past 2n (jq_seg_ld)
+    double *Phi, *Adj, *X, *Lam, *Eta, *cpart, *dpart, *gpart, *penpart;
+    const double *times;   // [2][nseg]: time at the first step of segment p in the reference's forward recurrence t = t + dt from 0, and at
+                           // its last step in the backward recurrence t = t - dt from T (jq_seg_times): the sweeps see bit-identical times
+};
+
 // Per-launch arguments common to both kernels.
 struct LaunchArgs {
     int ntraj, nsamples, Npar, D1, evaladjoint;
@@ -51,6 +73,7 @@ struct LaunchArgs {
     double *hist_r, *hist_i;   // Re(psi) = vr, Im(psi) = -vi  (src/evalobjgrad.jl:679-680,750-751)
     int save_every;
     long long nsave;
+    SegArgs seg;           // register-resident kernels only
 };
 
 // ---- generic kernel (jq_generic.cu): one CTA per trajectory, blocks in shared memory ----
@@ -80,5 +103,16 @@ TrajPlan *jq_tile_plan_create(const DevProblem &Pdev, const HostOps &H, const do
 void jq_traj_plan_destroy(TrajPlan *);
 int jq_traj_plan_kind(const TrajPlan *);
 int jq_traj_plan_tpc(const TrajPlan *);      // trajectories per CTA
+int jq_traj_plan_lanes(const TrajPlan *);    // lanes per trajectory
 cudaError_t jq_traj_launch(TrajPlan *plan, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta);
+
+// ---- time-parallel evaluation (jq_seg.cu): segment sweeps on a trajectory plan, joined through the segment propagators ----
+bool jq_seg_supported(const TrajPlan *plan, const DevProblem &P);      // the plan has segment-sweep instantiations
+int jq_seg_ld(const DevProblem &P);
+int jq_seg_auto_segments(const DevProblem &P, int ntraj, int evaladjoint, int tpc, int sms);
+size_t jq_seg_workspace_doubles(const DevProblem &P, int ntraj, int Npar, int nseg, int evaladjoint);
+void jq_seg_times(const DevProblem &P, int nseg, double *times /* [2][nseg], host */);
+// plan_prop: plan of the propagator launch (many independent sweeps: a throughput layout pays), plan: the boundary-to-boundary sweeps
+cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem &P, const LaunchArgs &A, int nseg, const double *times, double *work, cudaStream_t st,
+                          int *nctas, int *regs, size_t *smem, int *traj_per_cta, int *nlaunch);

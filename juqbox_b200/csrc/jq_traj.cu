@@ -11,14 +11,14 @@ const Inst kInst[] = {
 };
 
 // jt = 0: the run-time-J instantiation; jt > 0: the one with exactly jt Neumann terms compiled in (if any).
-const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0, int jt = 0, int nw = 0, int pipe = 0) {
-    const Inst *parts[4] = {kInst, kInstB, kInstC, kInstD};
-    const int counts[4] = {(int)(sizeof(kInst) / sizeof(kInst[0])), kInstBCount, kInstCCount, kInstDCount};
-    for (int p = 0; p < 4; ++p)
+const Inst *find_inst(int kind, int R, int C, int NC, int WQ, int LMASK, int UPL, int variant = 0, int GL = 0, int jt = 0, int nw = 0, int pipe = 0, int seg = 0) {
+    const Inst *parts[6] = {kInst, kInstB, kInstC, kInstD, kInstE, kInstF};
+    const int counts[6] = {(int)(sizeof(kInst) / sizeof(kInst[0])), kInstBCount, kInstCCount, kInstDCount, kInstECount, kInstFCount};
+    for (int p = 0; p < 6; ++p)
         for (int j = 0; j < counts[p]; ++j) {
             const Inst &i = parts[p][j];
             if (i.kind == kind && i.R == R && i.C == C && i.NC == NC && i.WQ == WQ && i.LMASK == LMASK && i.UPL == UPL && i.variant == variant &&
-                i.jt == jt && (i.glt == 0 || i.glt == GL) && (nw == 0 || i.nw == nw) && (i.pipe != 0) == (pipe != 0)) return &i;
+                i.jt == jt && (i.glt == 0 || i.glt == GL) && (nw == 0 || i.nw == nw) && (i.pipe != 0) == (pipe != 0) && i.seg == seg) return &i;
         }
     return nullptr;
 }
@@ -371,8 +371,15 @@ void jq_traj_plan_destroy(TrajPlan *pl) {
     delete pl;
 }
 
+bool jq_seg_supported(const TrajPlan *pl, const DevProblem &P) {
+    if (!pl || pl->pipe || pl->nw || !pl->AS || pl->HX || P.objFuncType != 1 || P.solver != 1 || 2 * P.n > 512) return false;
+    return find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J, 0, 0, 1) ||
+           find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, 0, 0, 0, 1);
+}
+
 int jq_traj_plan_kind(const TrajPlan *pl) { return pl ? pl->kind : 0; }
 int jq_traj_plan_tpc(const TrajPlan *pl) { return pl ? pl->TPC : 0; }
+int jq_traj_plan_lanes(const TrajPlan *pl) { return pl ? pl->GPT * pl->GL : 0; }
 
 cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &A, cudaStream_t st, int *nctas, int *regs,
                            size_t *smem, int *traj_per_cta) {
@@ -384,7 +391,13 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     else if (!pl->AS) want = 16;
     if ((want == 64 || want == 128 || want == 8) && !pl->AS) return cudaErrorNotSupported;
     const Inst *inst = nullptr;
-    if (pl->pipe) {
+    const bool seg = A.seg.nseg > 0;
+    if (seg) {                  // segment sweeps of the time-parallel evaluation: plain Neumann problems on a non-pipelined plan
+        if (want != 0 || pl->pipe || pl->nw || A.hist_r) return cudaErrorNotSupported;
+        inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J, 0, 0, 1);
+        if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, 0, 0, 0, 1);
+        if (!inst) return cudaErrorNotSupported;
+    } else if (pl->pipe) {
         if (want != 0 || P.nsteps > 0x7ffffff0LL) return cudaErrorNotSupported;      // the hand-over counters are ints
         inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J, pl->nw, 1);
         if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, 0, pl->nw, 1);
@@ -449,7 +462,19 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     cudaFuncAttributes fa;
     e = cudaFuncGetAttributes(&fa, inst->fn);
     if (e != cudaSuccess) return e;
-    const int grid = (A.ntraj + TPC - 1) / TPC;
+    int grid = (A.ntraj + TPC - 1) / TPC;
+    if (seg) {                  // CTAs per (mode, segment): sub-trajectories = blocks of m unit vectors x trajectories, or the trajectories
+        const int nblk = (2 * P.n + P.m - 1) / P.m;
+        auto ctas = [&](int mode) {
+            if (mode == 0) return 0LL;
+            const long long per = (mode == 1 || mode == 3) ? (long long)nblk * A.ntraj : (long long)A.ntraj;
+            return (long long)A.seg.nseg * ((per + TPC - 1) / TPC);
+        };
+        const long long c0 = ctas(A.seg.mode[0]), c1 = ctas(A.seg.mode[1]);
+        if (c0 + c1 > 0x7fffffffLL || c0 + c1 < 1) return cudaErrorInvalidConfiguration;
+        S.A.seg.ctas0 = (int)c0;
+        grid = (int)(c0 + c1);
+    }
     inst->fn<<<grid, (pipe == 1 ? 3 * nw + 1 : pipe == 2 ? 2 * nw : nw) * 32, bytes, st>>>(S);
     if (nctas) *nctas = grid;
     if (regs) *regs = fa.numRegs;

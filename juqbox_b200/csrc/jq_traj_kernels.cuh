@@ -76,11 +76,13 @@ typedef void (*traj_kernel_t)(const TrajParams);
 // 128 Jacobi solver; 1 (warp-shuffle exchange) and 512 (shared-memory twin of the cnot2 instantiation) are exchange-mode
 // twins selectable for comparisons with the env variable JQ_TRAJ_XMODE.  jt: number of Neumann terms fixed at compile time
 // (0 = run-time J) -- its own field, never folded into `variant`.  glt: compile-time group size (0 = run-time).
-struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; int jt = 0; int nw = TRAJ_WARPS; int pipe = 0; };
+struct Inst { int kind, R, C, NC, WQ, LMASK, UPL, variant; traj_kernel_t fn; int glt = 0; int jt = 0; int nw = TRAJ_WARPS; int pipe = 0; int seg = 0; };
 // The instantiation table is split over jq_traj.cu / jq_traj_inst_b.cu / jq_traj_inst_c.cu so that they compile in parallel.
 extern const Inst kInstB[]; extern const int kInstBCount;
 extern const Inst kInstC[]; extern const int kInstCCount;
 extern const Inst kInstD[]; extern const int kInstDCount;
+extern const Inst kInstE[]; extern const int kInstECount;
+extern const Inst kInstF[]; extern const int kInstFCount;
 
 namespace {
 
@@ -901,10 +903,15 @@ __device__ __forceinline__ void grad_scatter(Updater (&U)[UPL], double *gsm, con
 // reductions and the B-spline scatter.  A single trajectory has no other parallelism beyond its n x m elements: the recomputed
 // state does not depend on the adjoint, and the gradient accumulation feeds nothing back, so the backward sweep costs the
 // longest of the three per-step chains instead of their sum.  Same arithmetic on the same values as PIPE = 0.
-template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0, int NW = TRAJ_WARPS, int PIPE_ = 0>
+//
+// SEG = true (time-parallel evaluation, jq_seg.cu): every CTA sweeps ONE segment of the time axis in one of the modes of SegArgs --
+// forward from a block of unit vectors or from the true boundary state, adjoint without forcing from unit vectors, or the backward
+// sweep between two known boundaries -- with the same steppers on the same lane layout.
+template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT = 0, int NW = TRAJ_WARPS, int PIPE_ = 0, bool SEG = false>
 __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW : NW) * 32, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     constexpr bool PIPE = PIPE_ != 0;
+    static_assert(!SEG || (PIPE_ == 0 && OBJ == 0), "segment sweeps: plain layout, one adjoint set");
     // PIPE_ = 1: roles state | adjoint | gradient + one table warp; PIPE_ = 2 (shapes whose register budget allows 8 warps only):
     // state and adjoint in one role, and the gradient role also produces the control tables in the slack of its own steps
     constexpr int NR = PIPE_ == 1 ? 3 : PIPE_ == 2 ? 2 : 1, R_ADJ = PIPE_ == 1 ? 1 : 0, R_GRAD = NR - 1;
@@ -924,8 +931,25 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     g.group = g.warp * S.GPW + (lane_on ? gw : 0);
     g.tloc = g.group / S.GPT; g.gi = g.group % S.GPT;
     const int gbase_lane = (lane_on ? gw : 0) * GL;          // first lane of this group
-    const int traj = blockIdx.x * S.TPC + g.tloc;
-    const bool live_t = lane_on && g.tloc < S.TPC && traj < A.ntraj;    // dead groups compute on zeros and write nothing
+    // SEG: the CTA's mode and segment, its first sub-trajectory; sub-trajectory = (block of unit vectors, trajectory)
+    int smode = 0, seg = 0, sq0 = 0, sper = 0;
+    if constexpr (SEG) {
+        int b = blockIdx.x;
+        const int part = b >= A.seg.ctas0 ? 1 : 0;
+        if (part) b -= A.seg.ctas0;
+        smode = A.seg.mode[part];
+        sper = (smode == 1 || smode == 3) ? ((2 * P.n + P.m - 1) / P.m) * A.ntraj : A.ntraj;
+        const int cps = (sper + S.TPC - 1) / S.TPC;
+        seg = b / cps; sq0 = (b % cps) * S.TPC;
+    }
+    auto cta_traj = [&](int tloc) -> int {       // trajectory (candidate x sample) of the CTA's tloc-th resident one, -1 if none
+        if constexpr (SEG) { const int q = sq0 + tloc; return q < sper ? q % A.ntraj : -1; }
+        else { const int tg = blockIdx.x * S.TPC + tloc; return tg < A.ntraj ? tg : -1; }
+    };
+    const int traj_ = g.tloc < S.TPC ? cta_traj(g.tloc) : -1;
+    const int traj = traj_ < 0 ? 0 : traj_;
+    const int sblk = SEG && traj_ >= 0 ? (sq0 + g.tloc) / A.ntraj : 0;       // SEG: which block of m unit vectors
+    const bool live_t = lane_on && traj_ >= 0;                          // dead groups compute on zeros and write nothing
     const int s = live_t ? traj % A.nsamples : 0;
     const int n = P.n, m = P.m, Npar = A.Npar, D1 = A.D1, Nfreq = P.Nfreq, J = P.J;
     const double tinv = 1.0 / P.T, dtknot = P.T / (D1 - 2);
@@ -943,8 +967,8 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     }
     // stage this CTA's pcof vectors and zero the per-group gradient accumulators
     for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += blockDim.x) {
-        const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
-        sm[S.o_pcof + tr * S.NparS + k] = tg < A.ntraj ? A.pcof[(size_t)(tg / A.nsamples) * A.pstride + k] : 0.0;
+        const int tr = idx / Npar, k = idx % Npar, tg = cta_traj(tr);
+        sm[S.o_pcof + tr * S.NparS + k] = tg >= 0 ? A.pcof[(size_t)(tg / A.nsamples) * A.pstride + k] : 0.0;
     }
     for (int idx = threadIdx.x; idx < S.ngroups * Npar; idx += blockDim.x) { sm[S.o_gsm + idx] = 0.0; if (OBJ) sm[S.o_gsm2 + idx] = 0.0; }
     volatile int *pcnt = reinterpret_cast<volatile int *>(sm + S.o_cnt);     // [warp][states produced, consumed, traces produced, consumed]
@@ -990,10 +1014,27 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
         else __syncthreads();
     };
 
+    // SEG: steps [k0, k1) of the time axis
+    long long k0 = 0, k1 = P.nsteps;
+    if constexpr (SEG) { k0 = (long long)seg * P.nsteps / A.seg.nseg; k1 = (long long)(seg + 1) * P.nsteps / A.seg.nseg; }
+    const long long nstl = k1 - k0;
+    const size_t nm = (size_t)n * m, sbt = SEG ? ((size_t)seg * A.ntraj + traj) : 0;     // SEG: (segment, trajectory) index of the outputs
     double vr[E], vi[E], vi05[E];
     UNROLL for (int e = 0; e < E; ++e) {
-        vr[e] = ok[e] ? P.uinit[L.row(e) + (size_t)n * L.col(e)] : 0.0;
-        vi[e] = 0.0;
+        const size_t ix = L.row(e) + (size_t)n * L.col(e);
+        const size_t bx = L.row(e) + (size_t)2 * n * L.col(e);           // SEG boundary vectors: [column][u rows, then v rows]
+        if constexpr (!SEG) { vr[e] = ok[e] ? P.uinit[ix] : 0.0; vi[e] = 0.0; }
+        else {
+            const int j = sblk * m + L.col(e);                           // unit vector of this column: u_j (j < n) or v_{j-n}
+            if (smode == 1) { vr[e] = ok[e] && L.row(e) == j ? 1.0 : 0.0; vi[e] = ok[e] && L.row(e) + n == j ? 1.0 : 0.0; }
+            else if (smode == 2) { vr[e] = ok[e] ? A.seg.X[sbt * 2 * nm + bx] : 0.0; vi[e] = ok[e] ? A.seg.X[sbt * 2 * nm + bx + n] : 0.0; }
+            else if (smode >= 4) {                                       // backward sweeps: Xb = X + J' Eta at the segment end (6: X itself)
+                const size_t b1 = (sbt + A.ntraj) * 2 * nm + bx;
+                vr[e] = ok[e] ? A.seg.X[b1] - (smode == 6 ? 0.0 : A.seg.Eta[b1 + n]) : 0.0;
+                vi[e] = ok[e] ? A.seg.X[b1 + n] + (smode == 6 ? 0.0 : A.seg.Eta[b1]) : 0.0;
+            }
+            else { vr[e] = 0.0; vi[e] = 0.0; }
+        }
         vi05[e] = 0.0;
     }
     const double *tabpq = sm + S.o_tabpq;                     // PIPE: re-pointed at the chunk's table buffer
@@ -1014,6 +1055,7 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
 
     // ------------------------------------------------------------ forward sweep (src/evalobjgrad.jl:698-753)
     double dt = P.T / (double)P.nsteps, t = 0.0, pen = 0.0;
+    if constexpr (SEG) t = A.seg.times[seg];
     // forward history (jq_eval_forward; src/evalobjgrad.jl:2847-2849): Re = vr, Im = -vi after every save_every-th step
     const bool hist = A.hist_r != nullptr;
     size_t hpos = hist ? (size_t)(live_t ? traj : 0) * A.nsave * ((size_t)n * m) : 0;      // start of the next saved block
@@ -1029,8 +1071,8 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     if (hist) save_state();
     // two copies of the loop (generic lambda, both inlined): the evaluation path carries no per-step history test
     auto forward_sweep = [&](auto with_hist) {
-        for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
-            const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+        for (long long s0 = 0; s0 < nstl; s0 += TRAJ_CH) {
+            const int nst = (int)((nstl - s0) < TRAJ_CH ? (nstl - s0) : TRAJ_CH);
             if constexpr (PIPE) {
                 const int gk = (int)(s0 / TRAJ_CH);
                 pipe_wait(tabs_ready, gk + 1);
@@ -1048,11 +1090,45 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
             if constexpr (PIPE) pipe_post(cdone + pwarp, (int)(s0 / TRAJ_CH) + 1, g.lane);
         }
     };
+    double *red = sm + S.o_red;
+    double lr[E], li[E], vr0[E];
+    if constexpr (SEG) {
+        if (smode <= 2) {
+            forward_sweep(std::false_type{});
+            if (smode == 1) {                                // column j of the segment's propagator
+                UNROLL for (int e = 0; e < E; ++e) {
+                    const int j = sblk * m + L.col(e);
+                    if (ok[e] && j < 2 * n) {
+                        double *o = A.seg.Phi + (sbt * A.seg.ld + j) * A.seg.ld + L.row(e);
+                        o[0] = vr[e]; o[n] = vi[e];
+                    }
+                }
+                return;
+            }
+            double pv[1] = {pen};
+            group_sum_n(pv, GL, gbase_lane);
+            if (lane_on && g.lg == 0) red[g.group * 4 + 2] = pv[0];
+            __syncthreads();
+            if (live_t && g.gi == 0 && g.lg == 0) {
+                double pens = 0.0;
+                for (int j = 0; j < S.GPT; ++j) pens += red[(tl * S.GPT + j) * 4 + 2];
+                A.seg.penpart[sbt] = 0.5 * dt * pens;
+            }
+            return;
+        }
+        // backward modes: terminal adjoint = unit vectors (3), zero (4) or the boundary value Lam[seg + 1] (5)
+        UNROLL for (int e = 0; e < E; ++e) {
+            const size_t bx = L.row(e) + (size_t)2 * n * L.col(e);
+            const int j = sblk * m + L.col(e);
+            if (smode == 3) { lr[e] = ok[e] && L.row(e) == j ? 1.0 : 0.0; li[e] = ok[e] && L.row(e) + n == j ? 1.0 : 0.0; }
+            else if (smode == 5) { lr[e] = ok[e] ? A.seg.Lam[(sbt + A.ntraj) * 2 * nm + bx] : 0.0; li[e] = ok[e] ? A.seg.Lam[(sbt + A.ntraj) * 2 * nm + bx + n] : 0.0; }
+            else { lr[e] = 0.0; li[e] = 0.0; }
+        }
+    } else {
     if (PIPE && role != 0) {}                                // the adjoint and gradient roles wait at the barrier below
     else if (hist) forward_sweep(std::true_type{});
     else forward_sweep(std::false_type{});
     // infidelity (pFidType 2) and leak: group partials -> shared -> per-trajectory sums in group order
-    double *red = sm + S.o_red;
     {
         double re = 0.0, im = 0.0;
         UNROLL for (int e = 0; e < E; ++e) {
@@ -1097,7 +1173,6 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     // terminal condition (init_adjoint!, :2026-2059): types 1 and 2 share the formula, type 1 on scomplex0 = e^{i phase} - s (:825-826);
     // types 3, 4: lambda_r = Re(rot) / 2N, lambda_i = -Im(rot) / 2N, rot = e^{i phase} (Vtr + i Vti)
     const double rs_ = pfid == 1 ? cph - rs : rs, is_ = pfid == 1 ? sph - is : is;
-    double lr[E], li[E], vr0[E];
     UNROLL for (int e = 0; e < E; ++e) {
         const size_t ix = L.row(e) + (size_t)n * L.col(e);
         const double tr_ = ok[e] ? P.vtr[ix] : 0.0, ti_ = ok[e] ? P.vti[ix] : 0.0;
@@ -1109,6 +1184,7 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
             li[e] = -0.5 * (sph * tr_ + cph * ti_) / m;
         }
     }
+    }   // !SEG
     double lrn[OBJ ? E : 1], lin[OBJ ? E : 1];
     if constexpr (OBJ != 0) { UNROLL for (int e = 0; e < E; ++e) { lrn[e] = lr[e]; lin[e] = li[e]; } }
     // gradient scatter roles: role u = lg + j*GL < NU owns (control, frequency, alpha)
@@ -1131,14 +1207,29 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     const int *tabk = reinterpret_cast<const int *>(sm + S.o_tabk);
 
     t = P.T;
+    if constexpr (SEG) t = A.seg.times[A.seg.nseg + seg];
     dt = -dt;
     if constexpr (!PIPE) {
-        for (long long s0 = 0; s0 < P.nsteps; s0 += TRAJ_CH) {
-            const int nst = (int)((P.nsteps - s0) < TRAJ_CH ? (P.nsteps - s0) : TRAJ_CH);
+        for (long long s0 = 0; s0 < nstl; s0 += TRAJ_CH) {
+            const int nst = (int)((nstl - s0) < TRAJ_CH ? (nstl - s0) : TRAJ_CH);
             fill_table<NC>(S, sm, t, dt, nst, dtknot);
             LOAD_LEVEL0();
             for (int ls = 0; ls < nst; ++ls) {
                 LOAD_LEVELS(ls);
+                if constexpr (SEG) {
+                    if (smode != 5) {        // no gradient: the traces are dead code (DEFER leaves them in registers nobody reads)
+                        double tp[NC * 5];
+                        if (smode == 3) adjoint_step<JT, false, LaneT, true>(L, J, dt, lr, li, vr, vi05, vr, nullptr, GL, gbase_lane, false, tp);
+                        else if (smode == 6) state_step<JT>(L, J, dt, vr, vi, vi05);
+                        else {
+                            UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
+                            state_step<JT>(L, J, dt, vr, vi, vi05);
+                            adjoint_step<JT, true, LaneT, true>(L, J, dt, lr, li, vr0, vi05, vr, nullptr, GL, gbase_lane, false, tp);
+                        }
+                        t = t + dt;
+                        continue;
+                    }
+                }
                 UNROLL for (int e = 0; e < E; ++e) vr0[e] = vr[e];
                 state_step<JT>(L, J, dt, vr, vi, vi05);
                 adjoint_step<JT, true>(L, J, dt, lr, li, vr0, vi05, vr, tred, GL, gbase_lane, lane_on && g.lg == 0);   // traces -> tred
@@ -1214,13 +1305,29 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
         if (U[j].on) { gsm[U[j].gbase + U[j].kw] += U[j].acc0; gsm[U[j].gbase + U[j].kw - 1] += U[j].acc1; gsm[U[j].gbase + U[j].kw - 2] += U[j].acc2; }
         if constexpr (OBJ != 0) if (U2[j].on) { gsm2[U2[j].gbase + U2[j].kw] += U2[j].acc0; gsm2[U2[j].gbase + U2[j].kw - 1] += U2[j].acc1; gsm2[U2[j].gbase + U2[j].kw - 2] += U2[j].acc2; }
     }
+    if constexpr (SEG) {
+        if (smode != 5) {                    // adjoint at the segment start: column j of Adj, or the particular solution
+            UNROLL for (int e = 0; e < E; ++e) {
+                const int j = sblk * m + L.col(e);
+                if (smode == 3) {
+                    if (ok[e] && j < 2 * n) { double *o = A.seg.Adj + (sbt * A.seg.ld + j) * A.seg.ld + L.row(e); o[0] = lr[e]; o[n] = li[e]; }
+                } else if (ok[e]) {
+                    const size_t b0 = sbt * 2 * nm + L.row(e) + (size_t)2 * n * L.col(e);
+                    if (smode == 4) { A.seg.cpart[b0] = lr[e]; A.seg.cpart[b0 + n] = li[e]; }
+                    else { A.seg.dpart[b0] = vi[e] - A.seg.X[b0 + n]; A.seg.dpart[b0 + n] = -(vr[e] - A.seg.X[b0]); }
+                }
+            }
+            return;
+        }
+    }
     consumer_sync();
     // total gradient of each resident trajectory = dt * sum of its groups' partial gradients, in group order
     for (int idx = threadIdx.x; idx < S.TPC * Npar; idx += (PIPE ? NR * NW * 32 : (int)blockDim.x)) {
-        const int tr = idx / Npar, k = idx % Npar, tg = blockIdx.x * S.TPC + tr;
-        if (tg >= A.ntraj) continue;
+        const int tr = idx / Npar, k = idx % Npar, tg = cta_traj(tr);
+        if (tg < 0) continue;
         double gs = 0.0;
         for (int j = 0; j < S.GPT; ++j) gs += sm[S.o_gsm + (tr * S.GPT + j) * Npar + k];
+        if constexpr (SEG) { A.seg.gpart[((size_t)seg * A.ntraj + tg) * Npar + k] = dt * gs; continue; }
         A.grad[(size_t)tg * A.gstride + k] = dt * gs;
         if (OBJ) {
             double g2 = 0.0;
@@ -1250,3 +1357,7 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
 #define FIBERW(R, NC, LMASK, UPL, NW) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 0, 0, NW>, 0, 0, NW}   /* NW warps per CTA: trajectories wider than 4 warps */
 #define FIBERV(R, NC, LMASK, UPL, XM) {3, R, 1, NC, 2, LMASK, UPL, XM, jq_traj_kernel<FiberLane<R, NC, LMASK, 1, XM>, UPL>}   /* exchange mode XM (1 = warp shuffle) */
 }  // namespace
+/* time-parallel evaluation: segment sweeps (SEG) on the tile / fibre layouts */
+#define TILES(NC, NT, UPL, JT, GLT) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT, TRAJ_WARPS, 0, true>, GLT, JT, TRAJ_WARPS, 0, 1}
+#define FIBERS(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT, TRAJ_WARPS, 0, true>, GLT, JT, TRAJ_WARPS, 0, 1}
+#define TILESW(NC, NT, UPL, JT, GLT, NW) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT, NW, 0, true>, GLT, JT, NW, 0, 1}

@@ -290,12 +290,15 @@ def test_long_pcof_falls_back_when_shared_memory_does_not_fit():
     wa = jq.Working_Arrays(p, npar)
     o = oracle_traceobjgrad(p, pc)
     r = wa.evaluate(pc)
-    assert wa.last_kernel == 5        # two candidates: the latency layout (one warp per role), which fits
+    assert wa.last_kernel == 7        # two candidates: the time-parallel evaluation (its sweeps shrink their CTAs like kernel 3)
+    wa.set_kernel(5)
+    r5 = wa.evaluate(pc)
+    assert wa.last_kernel == 5        # the latency layout (one warp per role), which fits
     wa.set_kernel(3)
     r3 = wa.evaluate(pc)
     assert wa.last_kernel == 3        # the 4-warp fibre kernel shrinks its CTAs (fewer warps) instead of falling back
     wa.close()
-    for res in (r, r3):
+    for res in (r, r5, r3):
         for b in range(2):
             assert _rel(res["grad"][b, 0], o["grad"][b, 0]) < TOL and abs(res["infid"][b, 0] - o["infid"][b, 0]) < 1e-12
 
