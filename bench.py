@@ -366,27 +366,41 @@ def main():
             w2.close()
         extra["per_config"] = per
 
-        # ---- one pcof per call: the reference's own call pattern (eval_f_g_grad! from an Ipopt callback)
+        # ---- one pcof per call: the reference's own call pattern (eval_f_g_grad! from an Ipopt callback).  Automatic mode takes the
+        # time-parallel evaluation (kernel 7); the single-sweep latency kernel (5) is timed beside it and must agree to 1e-12
         lat = {}
-        for name in ("cnot2", "cnot3", "risk_neutral"):
+        from oracle import oracle_traceobjgrad
+        for name in ("cnot1", "cnot2", "cnot3", "risk_neutral"):
             c = configs.example(name)
             sh = configs.noise_shift(c.params.Ntot, c.nodes) if name == "risk_neutral" else None
             wts = c.weights if name == "risk_neutral" else None
             w2 = jq.Working_Arrays(c.params, c.nCoeff, device=local_rank)
             p1 = configs.synthetic_pcof(c, 1)
-            w2.evaluate(p1, sh, wts)
-            ts = []
-            for _ in range(3):
-                t0 = time.perf_counter()
-                w2.evaluate(p1, sh, wts)
-                ts.append((time.perf_counter() - t0) * 1e3)
-            launches += 6
-            from oracle import oracle_traceobjgrad
+            row, results = {}, {}
+            for kern in (0, 5):
+                try:
+                    w2.set_kernel(kern)
+                except Exception:
+                    continue
+                results[kern] = w2.evaluate(p1, sh, wts)
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    w2.evaluate(p1, sh, wts)
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                launches += 4 * int(w2.query(2))
+                key = "automatic" if kern == 0 else "single_sweep"
+                row[key] = {"kernel": KERNEL_NAMES[w2.last_kernel], "kernel_ms": w2.last_kernel_ms, "host_call_ms": min(ts),
+                            "launches": int(w2.query(2)), "time_segments": int(w2.query(7))}
+            if 0 in results and 5 in results:
+                g0, g5 = results[0]["grad"].ravel(), results[5]["grad"].ravel()
+                row["rel_grad_diff"] = float(np.linalg.norm(g0 - g5) / np.linalg.norm(g5))
+                row["abs_infid_diff"] = float(np.abs(results[0]["infid"] - results[5]["infid"]).max())
             t0 = time.perf_counter()
             oracle_traceobjgrad(c.params, p1, sh, nthreads=min(nthr, 1 if sh is None else len(sh)))
-            cpu_ms = (time.perf_counter() - t0) * 1e3
-            lat[name] = {"trajectories": 1 if sh is None else len(sh), "kernel": KERNEL_NAMES[w2.last_kernel], "kernel_ms": w2.last_kernel_ms,
-                         "host_call_ms": min(ts), "cpu_ms": cpu_ms, "cpu_threads": min(nthr, 1 if sh is None else len(sh))}
+            row.update({"trajectories": 1 if sh is None else len(sh), "cpu_ms": (time.perf_counter() - t0) * 1e3,
+                        "cpu_threads": min(nthr, 1 if sh is None else len(sh))})
+            lat[name] = row
             w2.close()
         extra["single_eval_latency"] = lat
 

@@ -254,7 +254,10 @@ int jq_seg_auto_segments(const DevProblem &P, int ntraj, int evaladjoint, int tp
     const int nblk = (2 * P.n + P.m - 1) / P.m;
     const double kappa = 2 * P.n <= 32 ? 1.6 : 0.5;
     double nseg = sqrt((double)P.nsteps * kappa);
-    const long long cps = (evaladjoint ? 2 : 1) * (((long long)nblk * ntraj + tpc - 1) / tpc);      // CTAs per segment in the propagator launch
+    // CTAs per segment in the propagator launch -- counted as for an evaluation with gradient also for objective-only calls, so that both
+    // cut the time axis the same way and return bit-identical objectives (a line search mixes the two)
+    (void)evaladjoint;
+    const long long cps = 2 * (((long long)nblk * ntraj + tpc - 1) / tpc);
     const double waves = nseg * (double)cps / sms;
     if (waves >= 0.75 && cps <= sms) nseg = floor(floor(waves + 0.5) * sms / (double)cps);
     nseg = std::min<double>(nseg, (double)(P.nsteps / 16));

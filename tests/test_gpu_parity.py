@@ -344,7 +344,8 @@ def test_jacobi_solver_tolerance_exit_vs_oracle():
 ])
 def test_other_shapes_auto_kernel_vs_oracle(Ne, Ng, kw, kernel):
     """Shapes beyond the named configs (tools/kernel_coverage.py): the auto-selected kernel is the expected one and
-    matches the oracle.  All-4-level qudits go to the tile layout (kernel 4; its latency variant, kernel 5, for a 3-candidate batch).  Exchange couplings a_0' a_q + a_0 a_q' in the drift ride on the fibre kernel's neighbour fetches; a
+    matches the oracle.  All-4-level qudits go to the tile layout (kernel 4; its latency variant, kernel 5, for a 3-candidate batch;
+    the time-parallel evaluation, kernel 7, before either when the problem is long enough).  Exchange couplings a_0' a_q + a_0 a_q' in the drift ride on the fibre kernel's neighbour fetches; a
     coupling between two remote subsystems (three qudits) must fall back to the generic kernel, not be mis-planned."""
     import juqbox_b200 as jq
     from juqbox_b200 import configs
@@ -352,12 +353,28 @@ def test_other_shapes_auto_kernel_vs_oracle(Ne, Ng, kw, kernel):
     cfg = configs.qudit_system(Ne, Ng, **kw)
     wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
     pc = np.random.default_rng(5).uniform(-1, 1, (3, cfg.nCoeff)) * cfg.maxpar[0] * 0.5
-    r = wa.evaluate(pc)
-    assert wa.last_kernel == kernel
     o = oracle_traceobjgrad(cfg.params, pc)
-    for b in range(3):
-        assert abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12 and abs(r["leak"][b, 0] - o["leak"][b, 0]) < 1e-12
-        assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL
+    wa.set_kernel(0)
+    r = wa.evaluate(pc)
+    auto = wa.last_kernel
+    # a 3-candidate launch of a long enough problem with a tile / fibre layout goes to the time-parallel evaluation (kernel 7);
+    # JQ_SEG_NTRAJ=0 style selection (no time-parallel path) must give the listed kernel
+    assert auto in (kernel, 7), auto
+    results = [r]
+    if auto == 7:
+        import os
+        os.environ["JQ_SEG_NTRAJ"] = "0"
+        try:
+            wb = jq.Working_Arrays(cfg.params, cfg.nCoeff)
+            results.append(wb.evaluate(pc))
+            assert wb.last_kernel == kernel
+            wb.close()
+        finally:
+            del os.environ["JQ_SEG_NTRAJ"]
+    for r in results:
+        for b in range(3):
+            assert abs(r["infid"][b, 0] - o["infid"][b, 0]) < 1e-12 and abs(r["leak"][b, 0] - o["leak"][b, 0]) < 1e-12
+            assert _rel(r["grad"][b, 0], o["grad"][b, 0]) < TOL
     wa.close()
 
 

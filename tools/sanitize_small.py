@@ -18,9 +18,11 @@ for name, T, nsteps in (("risk_neutral", 3.0, 40), ("cnot2", 2.0, 40), ("cnot3",
     for obj in (1, 3):
         cfg.params.objFuncType = obj
         wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
-        for k in (1, 2, 3, 4, 5):
+        for k in (1, 2, 3, 4, 5, 7):
             try:
                 wa.set_kernel(k)
+                if k == 7:
+                    wa.set_time_segments(3)      # ragged segments: 40 = 13 + 13 + 14 steps
                 r = wa.evaluate(pc, sh)
             except Exception:      # no instantiation of this layout for the shape / objFuncType
                 continue
