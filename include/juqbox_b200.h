@@ -168,8 +168,8 @@ int jq_comm_destroy(jq_handle *h);
  * 2 = register-resident kernel, slot layout (sparse rows with <= 2 entries per row and control), 3 = fibre layout (Kronecker
  * ladder structure), 4 = tile layout (all subsystems with 4 levels: mirrored half-tiles, shuffle-only exchange), 5 = the tile
  * layout with the fewest elements per lane and pipelined state / adjoint / gradient roles (latency layout; also the single-qudit
- * shapes).  Automatic: launches that fit one latency CTA per SM take 5 (then
- * 3 for three subsystems); otherwise 4, 3, 2, 1 in that order, each handing over when it has no instantiation for the problem.
+ * shapes).  Automatic: launches of very few trajectories of at least 256 steps take 7 (below); launches that fit one latency CTA per SM
+ * take 5 (then 3 for three subsystems); otherwise 4, 3, 2, 1 in that order, each handing over when it has no instantiation for the problem.
  * 6 = dense-operator kernel on the FP64 tensor-core path (mma.sync f64; unstructured operators, the noise samples of a candidate
  * batched as columns of one contraction); automatic mode takes it when no register-resident layout applies, n >= 8 and the
  * operators are at least 20% filled.

@@ -580,12 +580,12 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
         if (h->segt_nseg != nseg) {           // segment start / end times: host recurrence, once per segment count
             h->segt.resize(2 * (size_t)nseg);
             jq_seg_times(h->P, nseg, h->segt.data());
-            if ((rc = grow(&h->d_segt, &h->cap_segt, 2 * (size_t)nseg)) != 0) return rc;
+            if ((rc = grow(&h->d_segt, &h->cap_segt, 2 * (size_t)nseg + 2)) != 0) return rc;      // times, then the four refinement flags
             CU(cudaMemcpyAsync(h->d_segt, h->segt.data(), 2 * (size_t)nseg * sizeof(double), cudaMemcpyHostToDevice, st));
             h->segt_nseg = nseg;
         }
         int nl = 0;
-        cudaError_t e = jq_seg_launch(h->seg_prop, h->seg_plan, h->P, A, nseg, h->d_segt, h->d_seg, st, &ctas, &regs, &smem, &tpc, &nl);
+        cudaError_t e = jq_seg_launch(h->seg_prop, h->seg_plan, h->P, A, nseg, h->d_segt, reinterpret_cast<int *>(h->d_segt + 2 * (size_t)nseg), h->d_seg, st, &ctas, &regs, &smem, &tpc, &nl);
         if (e == cudaSuccess) {
             CU(cudaEventRecord(h->ev1, st));
             h->timed = true;

@@ -56,6 +56,9 @@ struct SegArgs {
     int mode[2], ctas0;
     int ld;                // leading dimension of Phi / Adj: [seg][traj][ld][ld], zero padded past 2n (jq_seg_ld)
     double *Phi, *Adj, *X, *Lam, *Eta, *cpart, *dpart, *gpart, *penpart;
+    int pass;              // mode 6: 0 = defect against the forward boundary states; r > 0 = refinement against X + J' Eta (runs only if flags[r - 1])
+    int *flags;            // [4]: flags[r] = 1 when pass r left a defect entry above refine_tol
+    double refine_tol;
     const double *times;   // [2][nseg]: time at the first step of segment p in the reference's forward recurrence t = t + dt from 0, and at
                            // its last step in the backward recurrence t = t - dt from T (jq_seg_times): the sweeps see bit-identical times
 };
@@ -114,5 +117,5 @@ int jq_seg_auto_segments(const DevProblem &P, int ntraj, int evaladjoint, int tp
 size_t jq_seg_workspace_doubles(const DevProblem &P, int ntraj, int Npar, int nseg, int evaladjoint);
 void jq_seg_times(const DevProblem &P, int nseg, double *times /* [2][nseg], host */);
 // plan_prop: plan of the propagator launch (many independent sweeps: a throughput layout pays), plan: the boundary-to-boundary sweeps
-cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem &P, const LaunchArgs &A, int nseg, const double *times, double *work, cudaStream_t st,
+cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem &P, const LaunchArgs &A, int nseg, const double *times, int *flags /* 4 ints, device */, double *work, cudaStream_t st,
                           int *nctas, int *regs, size_t *smem, int *traj_per_cta, int *nlaunch);

@@ -37,6 +37,10 @@ namespace {
 //         eps_p = Psi_p eps_{p+1} + d_p, Psi_p the backward propagator ~ Phi_p^-1 = J' Phi_p^T J (symplectic up to the Neumann truncation,
 //         ~1e-4 relative, acting on eps ~ 1e-10: exact to rounding); Eta = J eps, and Phi_p^T is the adjoint propagator Adj_p (the adjoint
 //         scheme is the exact discrete adjoint of the state scheme: |Adj_p - Phi_p^T| ~ 1e-14 measured).
+// kind 3: refinement of Eta.  With coarse time steps the Neumann truncation breaks the symplectic identity at more than rounding (a
+//         12-step Rabi problem: 1e-3), and the Eta of kind 2 is off by that factor times eps.  The defect sweep is then repeated from
+//         X + J' Eta (SegArgs::pass), its new defect d' chained the same way and added: each pass gains the same factor.  The passes
+//         are launched unconditionally and return at once unless the previous defect exceeded refine_tol (SegArgs::flags).
 // The columns of a boundary vector are independent chains of nseg dependent matrix-vector products: ONE WARP per (trajectory, column),
 // no block barrier, no shared memory in the small case -- a first version with one CTA per trajectory paid 1.5-2.5 us per segment in
 // __syncthreads round trips and generic-to-shared address arithmetic for a 0.1 us product.  M[j][i] (unit vector j, row i) is contiguous
@@ -47,6 +51,7 @@ struct ChainArgs {
     double *V;             // [nseg + 1][traj][m][2n]
     const double *C;       // [seg][traj][m][2n] or nullptr
     int kind;
+    bool accumulate;       // kind 3: the chain runs on the correction Delta_p = Adj_p Delta_{p+1} + d'_p from 0, and Eta_p += Delta_p
 };
 
 __device__ __forceinline__ ChainArgs chain_args(const LaunchArgs &A, int kind) {
@@ -55,6 +60,7 @@ __device__ __forceinline__ ChainArgs chain_args(const LaunchArgs &A, int kind) {
     c.M = kind == 0 ? A.seg.Phi : A.seg.Adj;
     c.V = kind == 0 ? A.seg.X : kind == 1 ? A.seg.Lam : A.seg.Eta;
     c.C = kind == 0 ? nullptr : kind == 1 ? A.seg.cpart : A.seg.dpart;
+    c.accumulate = kind == 3;
     return c;
 }
 
@@ -70,6 +76,7 @@ __global__ void __launch_bounds__(256) jq_seg_chain_small_kernel(const DevProble
     const int n = P.n, m = P.m, n2 = 2 * n, nseg = A.seg.nseg, nt = A.ntraj, lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);          // warp = (trajectory, column)
     if (w >= nt * m) return;
+    if (kind == 3 && A.seg.flags[A.seg.pass - 1] == 0) return;
     double *xs = strip[threadIdx.x >> 5];
     const int tr = w / m, col = w % m;
     const size_t nv = (size_t)n2 * m;
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(256) jq_seg_chain_small_kernel(const DevProble
         x = on && lane < n ? P.uinit[lane + (size_t)n * col] : 0.0;
         if (on) c.V[(size_t)tr * nv + (size_t)col * n2 + lane] = x;
     } else if (kind == 1) x = on ? c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] : 0.0;
-    else if (on) c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] = 0.0;
+    else if (kind == 2 && on) c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] = 0.0;
     double a[NB][NV], cpv[NB];
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(256) jq_seg_chain_small_kernel(const DevProble
                 for (int k = 8; k < NV; k += 2) { const double2 v = xv[k >> 1]; acc[k & 7] = fma(a[u][k], v.x, acc[k & 7]); acc[(k + 1) & 7] = fma(a[u][k + 1], v.y, acc[(k + 1) & 7]); }
                 x = (((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]))) + cpv[u];
                 __syncwarp();                              // the strip has been read by every lane
-                if (on) Vbase[(long long)s * Vstep] = x;
+                if (on) { if (c.accumulate) Vbase[(long long)s * Vstep] += x; else Vbase[(long long)s * Vstep] = x; }
                 if (s + NB < nstep) fetch(s + NB, a[u], cpv[u]);
             }
         }
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(1024) jq_seg_chain_block_kernel(const DevProbl
     extern __shared__ double sh[];
     const ChainArgs c = chain_args(A, kind);
     const int n = P.n, m = P.m, n2 = 2 * n, nseg = A.seg.nseg, nt = A.ntraj, tid = threadIdx.x;
+    if (kind == 3 && A.seg.flags[A.seg.pass - 1] == 0) return;
     const int tr = blockIdx.x / m, col = blockIdx.x % m;
     const size_t nv = (size_t)n2 * m;
     const int jq = tid / W, i = tid % W, PART = W;
@@ -150,7 +158,7 @@ __global__ void __launch_bounds__(1024) jq_seg_chain_block_kernel(const DevProbl
         if (tid < n2) {
             if (kind == 0) { x0 = tid < n ? P.uinit[tid + (size_t)n * col] : 0.0; c.V[(size_t)tr * nv + (size_t)col * n2 + tid] = x0; }
             else if (kind == 1) x0 = c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + tid];
-            else c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + tid] = 0.0;
+            else if (kind == 2) c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + tid] = 0.0;
         }
         sh[tid] = x0;
     }
@@ -182,7 +190,10 @@ __global__ void __launch_bounds__(1024) jq_seg_chain_block_kernel(const DevProbl
         }
         __syncthreads();                                   // every share and every xs entry has been read
         if (tid < W) sh[tid] = v;
-        if (tid < n2) c.V[((size_t)(kind == 0 ? p + 1 : p) * nt + tr) * nv + (size_t)col * n2 + tid] = v;
+        if (tid < n2) {
+            double *o = c.V + ((size_t)(kind == 0 ? p + 1 : p) * nt + tr) * nv + (size_t)col * n2 + tid;
+            if (c.accumulate) *o += v; else *o = v;
+        }
     }
 }
 
@@ -296,7 +307,7 @@ void jq_seg_times(const DevProblem &P, int nseg, double *times) {
     }
 }
 
-cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem &P, const LaunchArgs &A0, int nseg, const double *times, double *work, cudaStream_t st,
+cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem &P, const LaunchArgs &A0, int nseg, const double *times, int *flags, double *work, cudaStream_t st,
                           int *nctas, int *regs, size_t *smem, int *traj_per_cta, int *nlaunch) {
     if (nseg < 1 || nseg > P.nsteps) return cudaErrorInvalidValue;
     if (P.objFuncType != 1 || P.solver != 1 || A0.hist_r) return cudaErrorNotSupported;
@@ -307,6 +318,9 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem 
     A.seg.times = times;
     const size_t ld = (size_t)jq_seg_ld(P);
     A.seg.ld = (int)ld;
+    A.seg.pass = 0;
+    A.seg.flags = flags;
+    A.seg.refine_tol = 1.0e-9 / (double)nseg;              // |eps| <~ nseg |d|: below 1e-9 the first-order join is exact to 1e-12 and better
     double *w = work;
     auto take = [&](size_t cnt) { double *p = w; w += (cnt + 1) & ~(size_t)1; return p; };
     A.seg.Phi = take(ns * nt * ld * ld);
@@ -340,6 +354,7 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem 
         }
     };
     int launches = 0;
+    cudaMemsetAsync(flags, 0, 4 * sizeof(int), st);
     if (ld != n2) {            // the padding of the propagators must read as zero
         cudaMemsetAsync(A.seg.Phi, 0, ns * nt * ld * ld * sizeof(double), st);
         if (A.evaladjoint) cudaMemsetAsync(A.seg.Adj, 0, ns * nt * ld * ld * sizeof(double), st);
@@ -367,6 +382,15 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem 
     mark();
     if (A.evaladjoint) {
         run_join(2);
+        // refinement passes of the boundary states of the backward sweep: no-ops unless the defects are large (coarse time steps)
+        for (int r = 1; r <= 2; ++r) {
+            A.seg.pass = r; A.seg.mode[0] = 6; A.seg.mode[1] = 0;
+            e = jq_traj_launch(plan, P, A, st, nullptr, nullptr, nullptr, nullptr);
+            if (e != cudaSuccess) return e;
+            run_join(3);
+            launches += 2;
+        }
+        A.seg.pass = 0;
         mark();
         // launch 3: particular adjoint solutions
         A.seg.mode[0] = 4; A.seg.mode[1] = 0;

@@ -941,6 +941,8 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
         sper = (smode == 1 || smode == 3) ? ((2 * P.n + P.m - 1) / P.m) * A.ntraj : A.ntraj;
         const int cps = (sper + S.TPC - 1) / S.TPC;
         seg = b / cps; sq0 = (b % cps) * S.TPC;
+        // refinement pass of the defect sweep: nothing to do when the previous pass left no defect above the tolerance
+        if (smode == 6 && A.seg.pass > 0 && A.seg.flags[A.seg.pass - 1] == 0) return;
     }
     auto cta_traj = [&](int tloc) -> int {       // trajectory (candidate x sample) of the CTA's tloc-th resident one, -1 if none
         if constexpr (SEG) { const int q = sq0 + tloc; return q < sper ? q % A.ntraj : -1; }
@@ -1030,8 +1032,9 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
             else if (smode == 2) { vr[e] = ok[e] ? A.seg.X[sbt * 2 * nm + bx] : 0.0; vi[e] = ok[e] ? A.seg.X[sbt * 2 * nm + bx + n] : 0.0; }
             else if (smode >= 4) {                                       // backward sweeps: Xb = X + J' Eta at the segment end (6: X itself)
                 const size_t b1 = (sbt + A.ntraj) * 2 * nm + bx;
-                vr[e] = ok[e] ? A.seg.X[b1] - (smode == 6 ? 0.0 : A.seg.Eta[b1 + n]) : 0.0;
-                vi[e] = ok[e] ? A.seg.X[b1 + n] + (smode == 6 ? 0.0 : A.seg.Eta[b1]) : 0.0;
+                const bool plain = smode == 6 && A.seg.pass == 0;       // first defect sweep: from the forward boundary state
+                vr[e] = ok[e] ? A.seg.X[b1] - (plain ? 0.0 : A.seg.Eta[b1 + n]) : 0.0;
+                vi[e] = ok[e] ? A.seg.X[b1 + n] + (plain ? 0.0 : A.seg.Eta[b1]) : 0.0;
             }
             else { vr[e] = 0.0; vi[e] = 0.0; }
         }
@@ -1314,7 +1317,14 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
                 } else if (ok[e]) {
                     const size_t b0 = sbt * 2 * nm + L.row(e) + (size_t)2 * n * L.col(e);
                     if (smode == 4) { A.seg.cpart[b0] = lr[e]; A.seg.cpart[b0 + n] = li[e]; }
-                    else { A.seg.dpart[b0] = vi[e] - A.seg.X[b0 + n]; A.seg.dpart[b0 + n] = -(vr[e] - A.seg.X[b0]); }
+                    else {
+                        // defect of the backward recomputation against the current boundary state X_p (+ J' Eta_p in a refinement pass)
+                        const bool plain = A.seg.pass == 0;
+                        const double du = vr[e] - (A.seg.X[b0] - (plain ? 0.0 : A.seg.Eta[b0 + n]));
+                        const double dv = vi[e] - (A.seg.X[b0 + n] + (plain ? 0.0 : A.seg.Eta[b0]));
+                        A.seg.dpart[b0] = dv; A.seg.dpart[b0 + n] = -du;
+                        if (fabs(du) > A.seg.refine_tol || fabs(dv) > A.seg.refine_tol) A.seg.flags[A.seg.pass] = 1;      // benign race: every writer stores 1
+                    }
                 }
             }
             return;

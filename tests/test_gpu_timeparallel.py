@@ -88,6 +88,24 @@ def test_any_number_of_segments(nseg):
     assert _rel(r["grad"], q["grad"]) < TIGHT
 
 
+@pytest.mark.parametrize("name,T,nsteps,scale", [("rabi", 10.0, 12, 20.0), ("risk_neutral", 30.0, 160, 40.0), ("cnot2", 6.0, 90, 60.0)])
+def test_coarse_time_steps_refine_the_backward_boundary_states(name, T, nsteps, scale):
+    """With a few large steps the truncated Neumann solves make the backward recomputation of the states visibly irreversible (the
+    reference recomputes them like that) and break the symplectic identity the first-order join of the boundary states rests on:
+    the refinement passes must bring the time-parallel result back to the plain kernels' (1e-7 without them on the first case)."""
+    from juqbox_b200 import configs
+    cfg = configs.example(name)
+    cfg.params.T, cfg.params.nsteps = T, nsteps
+    pc = configs.synthetic_pcof(cfg, 2) * scale
+    wa = _wa7(cfg.params, cfg.nCoeff, 3)
+    r = wa.evaluate(pc)
+    wa.set_kernel(3)
+    q = wa.evaluate(pc)
+    wa.close()
+    assert np.allclose(r["infid"], q["infid"], rtol=TIGHT, atol=1e-15) and np.allclose(r["leak"], q["leak"], rtol=TIGHT, atol=1e-18)
+    assert _rel(r["grad"], q["grad"]) < TIGHT, _rel(r["grad"], q["grad"])
+
+
 @pytest.mark.parametrize("pfid", [1, 3, 4])
 def test_pfidtype_and_global_phase(pfid):
     from oracle import oracle_traceobjgrad

@@ -23,7 +23,7 @@ for name in configs.EXAMPLES:
     t0 = time.perf_counter()
     oracle_traceobjgrad(cfg.params, pc, shifts, nthreads=1)
     cpu_ms = (time.perf_counter() - t0) * 1e3
-    for k in (3, 4, 5):
+    for k in (3, 4, 5, 7):
         wa = jq.Working_Arrays(cfg.params, cfg.nCoeff)
         try:
             wa.set_kernel(k)
