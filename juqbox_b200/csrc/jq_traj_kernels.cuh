@@ -1074,8 +1074,8 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     if (hist) save_state();
     // two copies of the loop (generic lambda, both inlined): the evaluation path carries no per-step history test
     auto forward_sweep = [&](auto with_hist) {
-        for (long long s0 = 0; s0 < nstl; s0 += TRAJ_CH) {
-            const int nst = (int)((nstl - s0) < TRAJ_CH ? (nstl - s0) : TRAJ_CH);
+        for (long long s0 = 0; s0 < (SEG ? nstl : P.nsteps); s0 += TRAJ_CH) {
+            const int nst = (int)(((SEG ? nstl : P.nsteps) - s0) < TRAJ_CH ? ((SEG ? nstl : P.nsteps) - s0) : TRAJ_CH);
             if constexpr (PIPE) {
                 const int gk = (int)(s0 / TRAJ_CH);
                 pipe_wait(tabs_ready, gk + 1);
@@ -1213,8 +1213,8 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     if constexpr (SEG) t = A.seg.times[A.seg.nseg + seg];
     dt = -dt;
     if constexpr (!PIPE) {
-        for (long long s0 = 0; s0 < nstl; s0 += TRAJ_CH) {
-            const int nst = (int)((nstl - s0) < TRAJ_CH ? (nstl - s0) : TRAJ_CH);
+        for (long long s0 = 0; s0 < (SEG ? nstl : P.nsteps); s0 += TRAJ_CH) {
+            const int nst = (int)(((SEG ? nstl : P.nsteps) - s0) < TRAJ_CH ? ((SEG ? nstl : P.nsteps) - s0) : TRAJ_CH);
             fill_table<NC>(S, sm, t, dt, nst, dtknot);
             LOAD_LEVEL0();
             for (int ls = 0; ls < nst; ++ls) {
