@@ -68,7 +68,7 @@ struct jq_handle {
     int lat_ntraj = 0;                  // automatic mode: launches with at most this many trajectories use the latency layout
     // time-parallel evaluation (jq_seg.cu, kernel id 7): plan whose instantiations have segment sweeps (the non-pipelined latency
     // tile layout, else the fibre plan -- then shared with `fiber`), workspace, segments (0 = automatic)
-    TrajPlan *seg_plan = nullptr, *seg_prop = nullptr;      // seg_prop: plan of the propagator launch (nullptr: seg_plan)
+    TrajPlan *seg_plan = nullptr, *seg_prop = nullptr, *seg_obj = nullptr;      // seg_prop: plan of the propagator launch (nullptr: seg_plan); seg_obj: of the gradient sweep for objFuncType 2/3
     double *d_seg = nullptr; size_t cap_seg = 0;
     double *d_segt = nullptr; size_t cap_segt = 0; int segt_nseg = 0; std::vector<double> segt;
     int seg_nseg = 0, seg_ntraj = 0, sms = 148, last_nseg = 0;
@@ -359,6 +359,11 @@ extern "C" int jq_create(const jq_problem *pb, int device, jq_handle **out) {
         h->seg_plan = jq_tile_plan_create(P, H, pb->wdiag, Nc == 2 ? 0 : 1, why, sizeof(why), 0);
         if (!h->seg_plan) h->seg_plan = h->fiber;
         if (h->seg_plan && !jq_seg_supported(h->seg_plan, P)) { if (h->seg_plan != h->fiber) jq_traj_plan_destroy(h->seg_plan); h->seg_plan = nullptr; }
+        // objFuncType 2/3: the gradient sweep needs the second adjoint set, which the fibre layout has
+        if (h->seg_plan && P.objFuncType != 1) {
+            if (h->fiber && jq_seg_supported(h->fiber, P, true)) h->seg_obj = h->fiber;
+            else { if (h->seg_plan != h->fiber) jq_traj_plan_destroy(h->seg_plan); h->seg_plan = nullptr; }
+        }
         // propagator launch (many independent unit-vector sweeps): the throughput tile layout when the problem has one
         const char *pe = getenv("JQ_SEG_PROP_TILE");
         if (h->seg_plan && h->tile && jq_seg_supported(h->tile, P) && (pe ? atoi(pe) != 0 : true)) h->seg_prop = h->tile;
@@ -433,7 +438,7 @@ extern "C" int64_t jq_abi_info(int32_t what) {
 
 extern "C" int jq_set_kernel(jq_handle *h, int32_t kernel) {
     if (!h || kernel < 0 || kernel > 7) return fail(JQ_ERR_ARG, "jq_set_kernel: kernel must be 0 ... 7");
-    if (kernel == 7 && !h->seg_plan) return fail(JQ_ERR_ARG, "jq_set_kernel: no time-parallel evaluation for this problem (needs a tile / fibre layout, objFuncType 1, Neumann solver)");
+    if (kernel == 7 && !h->seg_plan) return fail(JQ_ERR_ARG, "jq_set_kernel: no time-parallel evaluation for this problem (needs a tile / fibre layout, the Neumann solver, diagonal weights)");
     if (kernel == 6 && !h->dense_ok) return fail(JQ_ERR_ARG, "jq_set_kernel: the dense (tensor-core) kernel cannot serve this problem (%s)", h->dense_reason);
     if (kernel == 5 && !h->tile_lat) return fail(JQ_ERR_ARG, "jq_set_kernel: no latency layout for this problem");
     if (kernel == 4 && !h->tile) return fail(JQ_ERR_ARG, "jq_set_kernel: no tile-layout instantiation for this problem (%s)", h->tile_reason);
@@ -569,9 +574,9 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
     size_t smem = 0;
     CU(cudaEventRecord(h->ev0, st));
     // very few trajectories: time-parallel evaluation (segments of the time axis swept concurrently)
-    const bool seg_able = h->seg_plan && h->P.objFuncType == 1 && h->P.solver == 1 && !A.hist_r;
+    const bool seg_able = h->seg_plan && h->P.solver == 1 && !A.hist_r;
     if (pref == 7 || (pref == 0 && seg_able && A.ntraj <= h->seg_ntraj && h->P.nsteps >= 256)) {
-        if (!seg_able) return fail(JQ_ERR_ARG, "time-parallel evaluation: objFuncType 1, Neumann solver, no state history");
+        if (!seg_able) return fail(JQ_ERR_ARG, "time-parallel evaluation: Neumann solver, no state history");
         TrajPlan *prop = h->seg_prop ? h->seg_prop : h->seg_plan;
         int nseg = h->seg_nseg > 0 ? h->seg_nseg : jq_seg_auto_segments(h->P, A.ntraj, A.evaladjoint, jq_traj_plan_tpc(prop), h->sms);
         if (nseg > h->P.nsteps) nseg = (int)h->P.nsteps;
@@ -585,7 +590,7 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
             h->segt_nseg = nseg;
         }
         int nl = 0;
-        cudaError_t e = jq_seg_launch(h->seg_prop, h->seg_plan, h->P, A, nseg, h->d_segt, reinterpret_cast<int *>(h->d_segt + 2 * (size_t)nseg), h->d_seg, st, &ctas, &regs, &smem, &tpc, &nl);
+        cudaError_t e = jq_seg_launch(h->seg_prop, h->seg_plan, h->seg_obj, h->P, A, nseg, h->d_segt, reinterpret_cast<int *>(h->d_segt + 2 * (size_t)nseg), h->d_seg, st, &ctas, &regs, &smem, &tpc, &nl);
         if (e == cudaSuccess) {
             CU(cudaEventRecord(h->ev1, st));
             h->timed = true;

@@ -56,6 +56,7 @@ struct SegArgs {
     int mode[2], ctas0;
     int ld;                // leading dimension of Phi / Adj: [seg][traj][ld][ld], zero padded past 2n (jq_seg_ld)
     double *Phi, *Adj, *X, *Lam, *Eta, *cpart, *dpart, *gpart, *penpart;
+    double *Lam2, *gpart2; // objFuncType 2/3: boundary values of the second adjoint set (no forcing: Lam2_p = Adj_p Lam2_{p+1}), its gradient shares
     int pass;              // mode 6: 0 = defect against the forward boundary states; r > 0 = refinement against X + J' Eta (runs only if flags[r - 1])
     int *flags;            // [4]: flags[r] = 1 when pass r left a defect entry above refine_tol
     double refine_tol;
@@ -111,11 +112,12 @@ cudaError_t jq_traj_launch(TrajPlan *plan, const DevProblem &P, const LaunchArgs
                            size_t *smem, int *traj_per_cta);
 
 // ---- time-parallel evaluation (jq_seg.cu): segment sweeps on a trajectory plan, joined through the segment propagators ----
-bool jq_seg_supported(const TrajPlan *plan, const DevProblem &P);      // the plan has segment-sweep instantiations
+bool jq_seg_supported(const TrajPlan *plan, const DevProblem &P, bool second_adjoint = false);      // the plan has segment-sweep instantiations
 int jq_seg_ld(const DevProblem &P);
 int jq_seg_auto_segments(const DevProblem &P, int ntraj, int evaladjoint, int tpc, int sms);
 size_t jq_seg_workspace_doubles(const DevProblem &P, int ntraj, int Npar, int nseg, int evaladjoint);
 void jq_seg_times(const DevProblem &P, int nseg, double *times /* [2][nseg], host */);
 // plan_prop: plan of the propagator launch (many independent sweeps: a throughput layout pays), plan: the boundary-to-boundary sweeps
-cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem &P, const LaunchArgs &A, int nseg, const double *times, int *flags /* 4 ints, device */, double *work, cudaStream_t st,
+// plan_obj: plan of the gradient sweep when objFuncType != 1 (second adjoint set; nullptr otherwise)
+cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_obj, const DevProblem &P, const LaunchArgs &A, int nseg, const double *times, int *flags /* 4 ints, device */, double *work, cudaStream_t st,
                           int *nctas, int *regs, size_t *smem, int *traj_per_cta, int *nlaunch);

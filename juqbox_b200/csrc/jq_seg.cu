@@ -37,6 +37,8 @@ namespace {
 //         eps_p = Psi_p eps_{p+1} + d_p, Psi_p the backward propagator ~ Phi_p^-1 = J' Phi_p^T J (symplectic up to the Neumann truncation,
 //         ~1e-4 relative, acting on eps ~ 1e-10: exact to rounding); Eta = J eps, and Phi_p^T is the adjoint propagator Adj_p (the adjoint
 //         scheme is the exact discrete adjoint of the state scheme: |Adj_p - Phi_p^T| ~ 1e-14 measured).
+// kind 4: Lam2_p = Adj_p Lam2_{p+1} from the same terminal value: the second adjoint set of objFuncType 2/3 (no forcing,
+//         src/evalobjgrad.jl:848-855), whose gradient is the infidelity-only one.
 // kind 3: refinement of Eta.  With coarse time steps the Neumann truncation breaks the symplectic identity at more than rounding (a
 //         12-step Rabi problem: 1e-3), and the Eta of kind 2 is off by that factor times eps.  The defect sweep is then repeated from
 //         X + J' Eta (SegArgs::pass), its new defect d' chained the same way and added: each pass gains the same factor.  The passes
@@ -58,8 +60,8 @@ __device__ __forceinline__ ChainArgs chain_args(const LaunchArgs &A, int kind) {
     ChainArgs c;
     c.kind = kind;
     c.M = kind == 0 ? A.seg.Phi : A.seg.Adj;
-    c.V = kind == 0 ? A.seg.X : kind == 1 ? A.seg.Lam : A.seg.Eta;
-    c.C = kind == 0 ? nullptr : kind == 1 ? A.seg.cpart : A.seg.dpart;
+    c.V = kind == 0 ? A.seg.X : kind == 1 ? A.seg.Lam : kind == 4 ? A.seg.Lam2 : A.seg.Eta;
+    c.C = kind == 0 || kind == 4 ? nullptr : kind == 1 ? A.seg.cpart : A.seg.dpart;
     c.accumulate = kind == 3;
     return c;
 }
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(256) jq_seg_chain_small_kernel(const DevProble
     if (kind == 0) {
         x = on && lane < n ? P.uinit[lane + (size_t)n * col] : 0.0;
         if (on) c.V[(size_t)tr * nv + (size_t)col * n2 + lane] = x;
-    } else if (kind == 1) x = on ? c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] : 0.0;
+    } else if (kind == 1 || kind == 4) x = on ? c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] : 0.0;
     else if (kind == 2 && on) c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] = 0.0;
     double a[NB][NV], cpv[NB];
 #pragma unroll
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(256) jq_seg_chain_small_kernel(const DevProble
 // 2n > 32: one CTA per (trajectory, column), NJ groups of W = roundup32(2n) threads: thread (jq, i) forms the share
 // sum_k M[jq + NJ k][i] x[jq + NJ k] of entry i in four independent chains; the NJ shares meet in shared memory.  CNT > 0: the thread's
 // CNT matrix entries of the current segment sit in registers, the next segment's are requested as soon as the products are formed and
-// fly during the reduction; CNT = 0 (2n > 128): plain loads.  sh: xs[W] | part[NJ * W]
+// fly during the reduction (1024 threads, 16 entries each for 2n = 128: measured faster than 512 threads with 32 entries in 128
+// registers, 390 vs 470 us per join of 129 segments); CNT = 0 (2n > 128): plain loads.  sh: xs[W] | part[NJ * W]
 template <int CNT>
 __global__ void __launch_bounds__(1024) jq_seg_chain_block_kernel(const DevProblem P, const LaunchArgs A, int kind, int W, int NJ) {
     extern __shared__ double sh[];
@@ -145,19 +148,22 @@ __global__ void __launch_bounds__(1024) jq_seg_chain_block_kernel(const DevProbl
     const int nstep = kind == 0 ? nseg : nseg - 1;
     const int cnt = (n2 + NJ - 1) / NJ;
     auto seg_of = [&](int s) { return kind == 0 ? s : nseg - 1 - s; };
-    double a[CNT > 0 ? CNT : 1];
+    constexpr int HALF = CNT > 0 ? (CNT + 1) / 2 : 1;       // two arrays of CNT / 2, one per pair of partial sums
+    double a0[HALF], a1[HALF];
     auto fetch = [&](int s) {
         if constexpr (CNT > 0) {
-            const double *M = c.M + ((size_t)seg_of(s) * nt + tr) * n2 * n2;       // leading dimension 2n here (jq_seg_ld)
+            const double *M = c.M + ((size_t)seg_of(s) * nt + tr) * n2 * n2 + i;   // leading dimension 2n here (jq_seg_ld)
 #pragma unroll
-            for (int k = 0; k < CNT; ++k) { const int j = jq + NJ * k; a[k] = on && j < n2 ? M[(size_t)j * n2 + i] : 0.0; }
+            for (int k = 0; k < HALF; ++k) { const int j = jq + NJ * k; a0[k] = on && j < n2 ? M[(size_t)j * n2] : 0.0; }
+#pragma unroll
+            for (int k = 0; k < HALF; ++k) { const int j = jq + NJ * (k + HALF); a1[k] = on && j < n2 ? M[(size_t)j * n2] : 0.0; }
         }
     };
     if (tid < W) {
         double x0 = 0.0;
         if (tid < n2) {
             if (kind == 0) { x0 = tid < n ? P.uinit[tid + (size_t)n * col] : 0.0; c.V[(size_t)tr * nv + (size_t)col * n2 + tid] = x0; }
-            else if (kind == 1) x0 = c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + tid];
+            else if (kind == 1 || kind == 4) x0 = c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + tid];
             else if (kind == 2) c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + tid] = 0.0;
         }
         sh[tid] = x0;
@@ -171,7 +177,9 @@ __global__ void __launch_bounds__(1024) jq_seg_chain_block_kernel(const DevProbl
         double t[4] = {0.0, 0.0, 0.0, 0.0};
         if constexpr (CNT > 0) {
 #pragma unroll
-            for (int k = 0; k < CNT; ++k) { const int j = jq + NJ * k; t[k & 3] = fma(a[k], sh[j < n2 ? j : 0], t[k & 3]); }
+            for (int k = 0; k < HALF; ++k) { const int j = jq + NJ * k; t[k & 1] = fma(a0[k], sh[j < n2 ? j : 0], t[k & 1]); }
+#pragma unroll
+            for (int k = 0; k < HALF; ++k) { const int j = jq + NJ * (k + HALF); t[2 + (k & 1)] = fma(a1[k], sh[j < n2 ? j : 0], t[2 + (k & 1)]); }
             if (s + 1 < nstep) fetch(s + 1);
         } else {
             const double *M = c.M + ((size_t)p * nt + tr) * n2 * n2;
@@ -225,7 +233,10 @@ __global__ void __launch_bounds__(256) jq_seg_objective_kernel(const DevProblem 
     if (tid == 0) {
         double *o = A.scal + (size_t)tr * 4;
         o[0] = infid; o[2] = 1.0 - abs2; o[3] = 0.0;          // o[1] (leak) is the sum of the penalty shares (jq_seg_sum_kernel)
-        if (pfid == 3 && A.evaladjoint) A.grad[(size_t)tr * A.gstride + A.Npar] = rs * sph + is * cph;
+        if (pfid == 3 && A.evaladjoint) {
+            A.grad[(size_t)tr * A.gstride + A.Npar] = rs * sph + is * cph;
+            if (A.infidgrad) A.infidgrad[(size_t)tr * A.gstride + A.Npar] = rs * sph + is * cph;
+        }
     }
     if (!A.evaladjoint) return;
     const double rs_ = pfid == 1 ? cph - rs : rs, is_ = pfid == 1 ? sph - is : is;
@@ -235,22 +246,31 @@ __global__ void __launch_bounds__(256) jq_seg_objective_kernel(const DevProblem 
         const int bx = (idx / n) * n2 + idx % n;             // boundary vectors: [column][u rows, then v rows]
         if (pfid <= 2) { LT[bx] = (rs_ * tr_ + is_ * ti_) / m; LT[bx + n] = (is_ * tr_ - rs_ * ti_) / m; }
         else { LT[bx] = 0.5 * (cph * tr_ - sph * ti_) / m; LT[bx + n] = -0.5 * (sph * tr_ + cph * ti_) / m; }
+        if (A.seg.Lam2) { double *L2 = A.seg.Lam2 + ((size_t)nseg * nt + tr) * nv; L2[bx] = LT[bx]; L2[bx + n] = LT[bx + n]; }
     }
 }
 
-// grad[tr][k] = sum_p gpart[p][tr][k], leak[tr] = sum_p penpart[p][tr], in segment order
+// grad[tr][k] = sum_p gpart[p][tr][k], leak[tr] = sum_p penpart[p][tr]: one warp per output, lane l sums the segments l, l + 32, ... in
+// order, then a butterfly -- a fixed order, independent of the launch geometry
 __global__ void __launch_bounds__(256) jq_seg_sum_kernel(const LaunchArgs A) {
-    const int nseg = A.seg.nseg, nt = A.ntraj, Npar = A.Npar;
-    const long long total = (long long)nt * (Npar + 1);
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int nseg = A.seg.nseg, nt = A.ntraj, Npar = A.Npar, lane = threadIdx.x & 31;
+    const long long total = (long long)nt * (Npar + 1), nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long idx = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); idx < total; idx += nwarps) {
         const int tr = (int)(idx / (Npar + 1)), k = (int)(idx % (Npar + 1));
+        if (k < Npar && !A.evaladjoint) continue;
         double s = 0.0;
-        if (k == Npar) {
-            for (int p = 0; p < nseg; ++p) s += A.seg.penpart[(size_t)p * nt + tr];
-            A.scal[(size_t)tr * 4 + 1] = s;
-        } else if (A.evaladjoint) {
-            for (int p = 0; p < nseg; ++p) s += A.seg.gpart[((size_t)p * nt + tr) * Npar + k];
-            A.grad[(size_t)tr * A.gstride + k] = s;
+        if (k == Npar) { for (int p = lane; p < nseg; p += 32) s += A.seg.penpart[(size_t)p * nt + tr]; }
+        else { for (int p = lane; p < nseg; p += 32) s += A.seg.gpart[((size_t)p * nt + tr) * Npar + k]; }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            if (k == Npar) A.scal[(size_t)tr * 4 + 1] = s;
+            else A.grad[(size_t)tr * A.gstride + k] = s;
+        }
+        if (k < Npar && A.seg.gpart2) {                      // objFuncType 2/3: the infidelity-only gradient
+            double s2 = 0.0;
+            for (int p = lane; p < nseg; p += 32) s2 += A.seg.gpart2[((size_t)p * nt + tr) * Npar + k];
+            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (lane == 0) A.infidgrad[(size_t)tr * A.gstride + k] = s2;
         }
     }
 }
@@ -283,7 +303,8 @@ size_t jq_seg_workspace_doubles(const DevProblem &P, int ntraj, int Npar, int ns
     const size_t n2 = (size_t)jq_seg_ld(P), nm2 = 2 * (size_t)P.n * P.m, nt = (size_t)ntraj, ns = (size_t)nseg;
     size_t tot = ns * nt * n2 * n2 + (ns + 1) * nt * nm2 + ns * nt;                      // Phi, X, penpart
     if (evaladjoint) tot += ns * nt * n2 * n2 + 2 * (ns + 1) * nt * nm2 + 2 * ns * nt * nm2 + ns * nt * (size_t)Npar;     // Adj, Lam, Eta, cpart, dpart, gpart
-    tot += 16;                                                                                                          // even-count padding of every array
+    if (evaladjoint && P.objFuncType != 1) tot += (ns + 1) * nt * nm2 + ns * nt * (size_t)Npar;                      // Lam2, gpart2
+    tot += 20;                                                                                                          // even-count padding of every array
     return tot;
 }
 
@@ -307,10 +328,10 @@ void jq_seg_times(const DevProblem &P, int nseg, double *times) {
     }
 }
 
-cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem &P, const LaunchArgs &A0, int nseg, const double *times, int *flags, double *work, cudaStream_t st,
+cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_obj, const DevProblem &P, const LaunchArgs &A0, int nseg, const double *times, int *flags, double *work, cudaStream_t st,
                           int *nctas, int *regs, size_t *smem, int *traj_per_cta, int *nlaunch) {
     if (nseg < 1 || nseg > P.nsteps) return cudaErrorInvalidValue;
-    if (P.objFuncType != 1 || P.solver != 1 || A0.hist_r) return cudaErrorNotSupported;
+    if (P.solver != 1 || A0.hist_r || (P.objFuncType != 1 && (!plan_obj || (A0.evaladjoint && !A0.infidgrad)))) return cudaErrorNotSupported;
     const size_t n2 = 2 * (size_t)P.n, nm2 = 2 * (size_t)P.n * P.m, nt = (size_t)A0.ntraj, ns = (size_t)nseg;
     if (n2 > 512) return cudaErrorNotSupported;
     LaunchArgs A = A0;
@@ -333,6 +354,10 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem 
         A.seg.cpart = take(ns * nt * nm2);
         A.seg.dpart = take(ns * nt * nm2);
         A.seg.gpart = take(ns * nt * (size_t)A.Npar);
+        if (P.objFuncType != 1) {
+            A.seg.Lam2 = take((ns + 1) * nt * nm2);
+            A.seg.gpart2 = take(ns * nt * (size_t)A.Npar);
+        }
     }
     // joins: one warp per (trajectory, column); small matrices: the columns of a trajectory share a CTA, large ones: a CTA (an SM) each
     const long long nwarps = (long long)nt * P.m;
@@ -347,8 +372,7 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem 
             const int W = (int)((n2 + 31) / 32 * 32), NJ = std::max(1, 1024 / W), cnt = (int)((n2 + NJ - 1) / NJ);
             const unsigned grid = (unsigned)nwarps, thr = (unsigned)(W * NJ);
             const size_t sm = (size_t)(W + NJ * W) * sizeof(double);
-            if (cnt <= 4) jq_seg_chain_block_kernel<4><<<grid, thr, sm, st>>>(P, A, kind, W, NJ);
-            else if (cnt <= 8) jq_seg_chain_block_kernel<8><<<grid, thr, sm, st>>>(P, A, kind, W, NJ);
+            if (cnt <= 8) jq_seg_chain_block_kernel<8><<<grid, thr, sm, st>>>(P, A, kind, W, NJ);
             else if (cnt <= 16) jq_seg_chain_block_kernel<16><<<grid, thr, sm, st>>>(P, A, kind, W, NJ);
             else jq_seg_chain_block_kernel<0><<<grid, thr, sm, st>>>(P, A, kind, W, NJ);
         }
@@ -398,16 +422,17 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, const DevProblem 
         if (e != cudaSuccess) return e;
         mark();
         run_join(1);
+        if (P.objFuncType != 1) { run_join(4); ++launches; }
         mark();
-        // launch 4: gradient shares
+        // launch 4: gradient shares (objFuncType 2/3: with the second adjoint set, on the plan that has it)
         A.seg.mode[0] = 5; A.seg.mode[1] = 0;
-        e = jq_traj_launch(plan, P, A, st, nullptr, nullptr, nullptr, nullptr);
+        e = jq_traj_launch(P.objFuncType != 1 ? plan_obj : plan, P, A, st, nullptr, nullptr, nullptr, nullptr);
         if (e != cudaSuccess) return e;
         launches += 4;
         mark();
     }
     const long long total = (long long)nt * (A.Npar + 1);
-    jq_seg_sum_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 4), 256, 0, st>>>(A);
+    jq_seg_sum_kernel<<<(unsigned)std::min<long long>((total + 7) / 8, 148 * 8), 256, 0, st>>>(A);
     ++launches;
     mark();
     if (timing) {

@@ -371,8 +371,9 @@ void jq_traj_plan_destroy(TrajPlan *pl) {
     delete pl;
 }
 
-bool jq_seg_supported(const TrajPlan *pl, const DevProblem &P) {
-    if (!pl || pl->pipe || pl->nw || !pl->AS || pl->HX || P.objFuncType != 1 || P.solver != 1 || 2 * P.n > 512) return false;
+bool jq_seg_supported(const TrajPlan *pl, const DevProblem &P, bool second_adjoint) {
+    if (!pl || pl->pipe || pl->nw || !pl->AS || pl->HX || P.solver != 1 || 2 * P.n > 512) return false;
+    if (second_adjoint) return find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 64, pl->GL, 0, 0, 0, 1) != nullptr;
     return find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J, 0, 0, 1) ||
            find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, 0, 0, 0, 1);
 }
@@ -392,10 +393,12 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
     if ((want == 64 || want == 128 || want == 8) && !pl->AS) return cudaErrorNotSupported;
     const Inst *inst = nullptr;
     const bool seg = A.seg.nseg > 0;
-    if (seg) {                  // segment sweeps of the time-parallel evaluation: plain Neumann problems on a non-pipelined plan
-        if (want != 0 || pl->pipe || pl->nw || A.hist_r) return cudaErrorNotSupported;
-        inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J, 0, 0, 1);
-        if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, 0, 0, 0, 1);
+    if (seg) {                  // segment sweeps of the time-parallel evaluation: Neumann problems on a non-pipelined plan
+        // objFuncType 2/3: only the gradient sweep (mode 5) carries the second adjoint set; every other mode is the plain one
+        const int segwant = A.seg.mode[0] == 5 ? want : (want == 64 ? 0 : want);
+        if ((segwant != 0 && segwant != 64) || pl->pipe || pl->nw || A.hist_r) return cudaErrorNotSupported;
+        if (segwant == 0) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, 0, pl->GL, P.J, 0, 0, 1);
+        if (!inst) inst = find_inst(pl->kind, pl->R, pl->C, pl->NC, pl->WQ, pl->LMASK, pl->UPL, segwant, pl->GL, 0, 0, 0, 1);
         if (!inst) return cudaErrorNotSupported;
     } else if (pl->pipe) {
         if (want != 0 || P.nsteps > 0x7ffffff0LL) return cudaErrorNotSupported;      // the hand-over counters are ints

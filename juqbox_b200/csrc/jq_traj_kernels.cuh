@@ -911,7 +911,7 @@ template <class LaneT, int UPL, int MINB = 1, int JT = 0, int OBJ = 0, int GLT =
 __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW : NW) * 32, MINB) jq_traj_kernel(const __grid_constant__ TrajParams S) {
     constexpr int E = LaneT::E, NC = LaneT::NC;
     constexpr bool PIPE = PIPE_ != 0;
-    static_assert(!SEG || (PIPE_ == 0 && OBJ == 0), "segment sweeps: plain layout, one adjoint set");
+    static_assert(!SEG || PIPE_ == 0, "segment sweeps: plain layout");
     // PIPE_ = 1: roles state | adjoint | gradient + one table warp; PIPE_ = 2 (shapes whose register budget allows 8 warps only):
     // state and adjoint in one role, and the gradient role also produces the control tables in the slack of its own steps
     constexpr int NR = PIPE_ == 1 ? 3 : PIPE_ == 2 ? 2 : 1, R_ADJ = PIPE_ == 1 ? 1 : 0, R_GRAD = NR - 1;
@@ -1189,7 +1189,17 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
     }
     }   // !SEG
     double lrn[OBJ ? E : 1], lin[OBJ ? E : 1];
-    if constexpr (OBJ != 0) { UNROLL for (int e = 0; e < E; ++e) { lrn[e] = lr[e]; lin[e] = li[e]; } }
+    if constexpr (OBJ != 0) {
+        UNROLL for (int e = 0; e < E; ++e) { lrn[e] = lr[e]; lin[e] = li[e]; }
+        if constexpr (SEG) {                 // second adjoint set (no forcing): its own boundary values Lam2[seg + 1]
+            if (smode == 5) {
+                UNROLL for (int e = 0; e < E; ++e) {
+                    const size_t b1 = (sbt + A.ntraj) * 2 * nm + L.row(e) + (size_t)2 * n * L.col(e);
+                    lrn[e] = ok[e] ? A.seg.Lam2[b1] : 0.0; lin[e] = ok[e] ? A.seg.Lam2[b1 + n] : 0.0;
+                }
+            }
+        }
+    }
     // gradient scatter roles: role u = lg + j*GL < NU owns (control, frequency, alpha)
     const int NU = NC * Nfreq * 2;
     Updater U[UPL], U2[OBJ ? UPL : 1];
@@ -1337,7 +1347,15 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
         if (tg < 0) continue;
         double gs = 0.0;
         for (int j = 0; j < S.GPT; ++j) gs += sm[S.o_gsm + (tr * S.GPT + j) * Npar + k];
-        if constexpr (SEG) { A.seg.gpart[((size_t)seg * A.ntraj + tg) * Npar + k] = dt * gs; continue; }
+        if constexpr (SEG) {
+            A.seg.gpart[((size_t)seg * A.ntraj + tg) * Npar + k] = dt * gs;
+            if constexpr (OBJ != 0) {
+                double g2 = 0.0;
+                for (int j = 0; j < S.GPT; ++j) g2 += sm[S.o_gsm2 + (tr * S.GPT + j) * Npar + k];
+                A.seg.gpart2[((size_t)seg * A.ntraj + tg) * Npar + k] = dt * g2;
+            }
+            continue;
+        }
         A.grad[(size_t)tg * A.gstride + k] = dt * gs;
         if (OBJ) {
             double g2 = 0.0;
@@ -1371,3 +1389,4 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
 #define TILES(NC, NT, UPL, JT, GLT) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT, TRAJ_WARPS, 0, true>, GLT, JT, TRAJ_WARPS, 0, 1}
 #define FIBERS(R, NC, LMASK, UPL, JT, GLT) {3, R, 1, NC, 2, LMASK, UPL, 0, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, JT, 0, GLT, TRAJ_WARPS, 0, true>, GLT, JT, TRAJ_WARPS, 0, 1}
 #define TILESW(NC, NT, UPL, JT, GLT, NW) {4, NT, 1, NC, 0, 0, UPL, 0, jq_traj_kernel<TileLane<NC, NT>, UPL, 1, JT, 0, GLT, NW, 0, true>, GLT, JT, NW, 0, 1}
+#define FIBERSO(R, NC, LMASK, UPL) {3, R, 1, NC, 2, LMASK, UPL, 64, jq_traj_kernel<FiberLane<R, NC, LMASK, 1>, UPL, 1, 0, 1, 0, TRAJ_WARPS, 0, true>, 0, 0, TRAJ_WARPS, 0, 1}   /* objFuncType 2/3 */

@@ -30,7 +30,7 @@ def _wa7(params, ncoeff, nseg=0):
 
 
 @pytest.mark.parametrize("nseg", [0, 3])
-@pytest.mark.parametrize("case", ["swap02", "cnot2", "flux", "cnot3", "rabi"])
+@pytest.mark.parametrize("case", ["swap02", "cnot2", "flux", "cnot3", "rabi", "cnot2-leakieq"])
 def test_time_parallel_matches_reference_golden(case, nseg):
     cfg, g = golden_config(case)
     wa = _wa7(cfg.params, len(cfg.pcof0), nseg)
@@ -150,10 +150,39 @@ def test_risk_neutral_weighted_sums_fused_entry_and_automatic_choice():
     assert _rel(fa["grad_f"], b["grad"][0] + 2 * 0.01 * pc[0] / len(pc[0])) < TIGHT
 
 
+@pytest.mark.parametrize("objFuncType", [2, 3])
+def test_second_adjoint_set_vs_oracle(objFuncType):
+    """objFuncType 2/3 (leakage as a constraint): the infidelity-only gradient comes from a second, unforced adjoint set
+    (src/evalobjgrad.jl:848-855) whose boundary values are joined with the adjoint propagators alone."""
+    from juqbox_b200 import configs
+    from oracle import oracle_traceobjgrad
+    cfg = configs.example("cnot2")
+    cfg.params.objFuncType = objFuncType
+    pc = configs.synthetic_pcof(cfg, 2) * np.array([[1.0], [40.0]])
+    o = oracle_traceobjgrad(cfg.params, pc, None, nthreads=2)
+    wa = _wa7(cfg.params, cfg.nCoeff)
+    r = wa.evaluate(pc)
+    assert wa.last_kernel == 7
+    wa.set_kernel(3)
+    q = wa.evaluate(pc)
+    wa.close()
+    for k in ("infid", "leak"):
+        assert np.all(np.abs(r[k] - o[k]) <= TOL * np.maximum(np.abs(o[k]), 1e-6)), k
+    for gk in ("grad", "infidgrad"):
+        for b in range(2):
+            assert _rel(r[gk][b], o[gk][b]) < TOL, (gk, b, _rel(r[gk][b], o[gk][b]))
+            assert _rel(r[gk][b], q[gk][b]) < 1e-11, (gk, b, _rel(r[gk][b], q[gk][b]))
+    # leakgrad = totalgrad - infidelgrad (src/evalobjgrad.jl:951), a difference of nearly equal vectors when the leakage is tiny
+    # (first candidate: |leakgrad| = 1e-6 |grad|): accurate to the rounding of the two gradients, not of itself
+    for b in range(2):
+        err = np.linalg.norm(r["leakgrad"][b] - o["leakgrad"][b])
+        assert err < TOL * np.linalg.norm(o["leakgrad"][b]) or err < 1e-12 * np.linalg.norm(o["grad"][b]), (b, err)
+
+
 def test_unsupported_problems_say_so_or_fall_back():
-    """objFuncType 2/3 has no time-parallel path (set_kernel refuses, automatic mode uses the other kernels); state histories too."""
+    """The Jacobi solver has no time-parallel path (set_kernel refuses, automatic mode uses the other kernels); state histories too."""
     import juqbox_b200 as jq
-    cfg, _ = golden_config("cnot2-leakieq")
+    cfg, _ = golden_config("cnot2-jacobi")
     wa = jq.Working_Arrays(cfg.params, len(cfg.pcof0))
     with pytest.raises(Exception):
         wa.set_kernel(7)
