@@ -176,7 +176,7 @@ int jq_comm_destroy(jq_handle *h);
  * 7 = time-parallel evaluation for launches of very few trajectories (the reference's own call pattern: one pcof per Ipopt
  * callback): the time axis is cut into segments that are swept concurrently by the layout-3/4 steppers and joined through the
  * segments' discrete propagators (every step of the scheme is linear in the state and affine in the adjoint); same results to
- * rounding (~1e-13 relative), critical path ~ 3 nsteps / nseg steps.  objFuncType 1, Neumann solver, tile / fibre layouts.
+ * rounding (~1e-14 relative), critical path ~ 4 nsteps / nseg steps.  Neumann solver, diagonal weights, tile / fibre layouts.
  * 2 ... 7 fail with JQ_ERR_ARG if the problem has no instantiation. */
 int jq_set_kernel(jq_handle *h, int32_t kernel);
 /* Number of time segments of kernel 7; 0 = automatic (about two sub-trajectory CTAs per SM in the propagator launch). */
