@@ -81,6 +81,8 @@ def test_any_number_of_segments(nseg):
     wa = _wa7(cfg.params, pc.shape[1], nseg)
     r = wa.evaluate(pc)
     assert int(wa.query(7)) == nseg
+    again = wa.evaluate(pc)                                   # bit-reproducible: fixed summation orders, no atomics
+    assert all(np.array_equal(r[k], again[k]) for k in ("infid", "leak", "grad"))
     wa.set_kernel(3)
     q = wa.evaluate(pc)
     wa.close()
