@@ -66,36 +66,46 @@ __device__ __forceinline__ ChainArgs chain_args(const LaunchArgs &A, int kind) {
     return c;
 }
 
-// 2n <= 32: lane i owns entry i of the vector and the matrix entries it multiplies (row i of M^T).  The
-// matrices are stored with leading dimension NV (8, 16 or 32; rows and columns past 2n are zero), so every load is base + immediate and
-// unconditional; NB register buffers rotate through the unrolled step loop (the one just consumed is refilled for step s + NB: no moves).
-// The vector is broadcast through a warp-private strip of shared memory.  Measured on one warp (tools/microbench_chain.cu): 32 shuffle
-// broadcasts of a double cost ~550 cycles, the 32 FMAs in 8 chains + tree ~100 -- so no shuffles.
-template <int NV, int NB>
+// 2n <= 32: lane i owns entry i of the vector.  The matrices are stored with leading dimension NV (8, 16 or 32; rows and columns past
+// 2n are zero) and, with the segment's c_p / d_p, stream through a warp-private ring of D shared-memory slots by cp.async (16-byte
+// copies, one commit group per segment): the loads of segment s + D are in flight while segment s is multiplied, so the chain of nseg
+// dependent products does not wait for L2 (register prefetch two segments ahead left ~0.4 us of a 0.65 us step exposed).  The vector is
+// broadcast through a warp-private strip of shared memory: on one warp (tools/microbench_chain.cu) 32 shuffle broadcasts of a double
+// cost ~550 cycles, the 32 FMAs in 8 chains + tree ~100 -- so no shuffles.  sh: per warp [D][NV * NV + 32] | strip[32]
+template <int NV, int D>
 __global__ void __launch_bounds__(256) jq_seg_chain_small_kernel(const DevProblem P, const LaunchArgs A, int kind) {
-    __shared__ __align__(16) double strip[8][32];
+    extern __shared__ __align__(16) double sh[];
+    constexpr int SLOT = NV * NV + 32;                       // matrix, then the segment's c_p / d_p (32 entries, 2n used)
     const ChainArgs c = chain_args(A, kind);
     const int n = P.n, m = P.m, n2 = 2 * n, nseg = A.seg.nseg, nt = A.ntraj, lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);          // warp = (trajectory, column)
     if (w >= nt * m) return;
     if (kind == 3 && A.seg.flags[A.seg.pass - 1] == 0) return;
-    double *xs = strip[threadIdx.x >> 5];
+    double *ring = sh + (size_t)(threadIdx.x >> 5) * (D * SLOT + 32), *xs = ring + D * SLOT;
     const int tr = w / m, col = w % m;
     const size_t nv = (size_t)n2 * m;
     const bool on = lane < n2;
     const int lc = lane & (NV - 1);                          // lanes past NV repeat work, write nothing
     const int nstep = kind == 0 ? nseg : nseg - 1;
     const int sgn = kind == 0 ? 1 : -1, p0 = kind == 0 ? 0 : nseg - 1;      // segment of step s: p0 + sgn s
-    const double *Mbase = c.M + ((size_t)p0 * nt + tr) * (NV * NV) + lc;
+    const double *Mbase = c.M + ((size_t)p0 * nt + tr) * (NV * NV);
     const long long Mstep = (long long)sgn * nt * (NV * NV);
-    const double *Cbase = c.C ? c.C + ((size_t)p0 * nt + tr) * nv + (size_t)col * n2 + (on ? lane : 0) : nullptr;
+    const double *Cbase = c.C ? c.C + ((size_t)p0 * nt + tr) * nv + (size_t)col * n2 : nullptr;       // 16-byte aligned: 2n is even
     double *Vbase = c.V + ((size_t)(kind == 0 ? 1 : nseg - 1) * nt + tr) * nv + (size_t)col * n2 + (on ? lane : 0);
     const long long Vstep = (long long)sgn * nt * (long long)nv;
-    auto fetch = [&](int s, double (&a)[NV], double &cp) {
-        const double *M = Mbase + (long long)s * Mstep;
+    auto issue = [&](int s) {                                // one commit group per step, empty past the last one
+        if (s < nstep) {
+            const double *M = Mbase + (long long)s * Mstep;
+            double *dst = ring + (s % D) * SLOT;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) a[k] = M[k * NV];
-        cp = Cbase ? Cbase[(long long)s * Vstep] : 0.0;
+            for (int q = 0; q < NV * NV / 64; ++q) {         // NV * NV / 2 chunks of 16 bytes over 32 lanes
+                const int ch = lane + 32 * q;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + 2 * ch)), "l"(M + 2 * ch) : "memory");
+            }
+            if (Cbase && 2 * lane < n2)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + NV * NV + 2 * lane)), "l"(Cbase + (long long)s * Vstep + 2 * lane) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     double x = 0.0;
     if (kind == 0) {
@@ -103,30 +113,27 @@ __global__ void __launch_bounds__(256) jq_seg_chain_small_kernel(const DevProble
         if (on) c.V[(size_t)tr * nv + (size_t)col * n2 + lane] = x;
     } else if (kind == 1 || kind == 4) x = on ? c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] : 0.0;
     else if (kind == 2 && on) c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + lane] = 0.0;
-    double a[NB][NV], cpv[NB];
-#pragma unroll
-    for (int u = 0; u < NB; ++u) {
-        if (u < nstep) fetch(u, a[u], cpv[u]);
-    }
+    for (int s = 0; s < D; ++s) issue(s);
     const double2 *xv = reinterpret_cast<const double2 *>(xs);
-    for (int s0 = 0; s0 < nstep; s0 += NB) {
+    for (int s = 0; s < nstep; ++s) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");        // this lane's copies of step s have landed ...
+        xs[lane] = x;
+        __syncwarp();                                        // ... and so have the other lanes'
+        const double *Ms = ring + (s % D) * SLOT;
+        double acc[8];
 #pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const int s = s0 + u;
-            if (s < nstep) {
-                xs[lane] = x;
-                __syncwarp();
-                double acc[8];
+        for (int k = 0; k < 8; k += 2) { const double2 v = xv[k >> 1]; acc[k] = Ms[k * NV + lc] * v.x; acc[k + 1] = Ms[(k + 1) * NV + lc] * v.y; }
 #pragma unroll
-                for (int k = 0; k < 8; k += 2) { const double2 v = xv[k >> 1]; acc[k] = a[u][k] * v.x; acc[k + 1] = a[u][k + 1] * v.y; }
-#pragma unroll
-                for (int k = 8; k < NV; k += 2) { const double2 v = xv[k >> 1]; acc[k & 7] = fma(a[u][k], v.x, acc[k & 7]); acc[(k + 1) & 7] = fma(a[u][k + 1], v.y, acc[(k + 1) & 7]); }
-                x = (((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]))) + cpv[u];
-                __syncwarp();                              // the strip has been read by every lane
-                if (on) { if (c.accumulate) Vbase[(long long)s * Vstep] += x; else Vbase[(long long)s * Vstep] = x; }
-                if (s + NB < nstep) fetch(s + NB, a[u], cpv[u]);
-            }
+        for (int k = 8; k < NV; k += 2) {
+            const double2 v = xv[k >> 1];
+            acc[k & 7] = fma(Ms[k * NV + lc], v.x, acc[k & 7]);
+            acc[(k + 1) & 7] = fma(Ms[(k + 1) * NV + lc], v.y, acc[(k + 1) & 7]);
         }
+        const double cp = Cbase && on ? Ms[NV * NV + lane] : 0.0;
+        x = (((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]))) + cp;
+        __syncwarp();                                        // the strip and the slot have been read by every lane
+        if (on) { if (c.accumulate) Vbase[(long long)s * Vstep] += x; else Vbase[(long long)s * Vstep] = x; }
+        issue(s + D);
     }
 }
 
@@ -363,11 +370,16 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_ob
     const long long nwarps = (long long)nt * P.m;
     auto run_join = [&](int kind) {
         if (n2 <= 32) {
-            const int wpb = (int)std::min<long long>(8, nwarps);
+            // ring of 8 segments per warp: 8 (NV^2 + 32) + 32 doubles -- one warp per CTA for 2n > 16 (68 KB), up to four otherwise
+            constexpr int D = 8;
+            const int NV = n2 <= 8 ? 8 : n2 <= 16 ? 16 : 32;
+            const int wpb = (int)std::min<long long>(NV == 32 ? 1 : 4, nwarps);
             const unsigned grid = (unsigned)((nwarps + wpb - 1) / wpb);
-            if (n2 <= 8) jq_seg_chain_small_kernel<8, 4><<<grid, wpb * 32, 0, st>>>(P, A, kind);
-            else if (n2 <= 16) jq_seg_chain_small_kernel<16, 4><<<grid, wpb * 32, 0, st>>>(P, A, kind);
-            else jq_seg_chain_small_kernel<32, 2><<<grid, wpb * 32, 0, st>>>(P, A, kind);
+            const size_t sm = (size_t)wpb * (D * (NV * NV + 32) + 32) * sizeof(double);
+            void (*k)(const DevProblem, const LaunchArgs, int) =
+                NV == 8 ? jq_seg_chain_small_kernel<8, D> : NV == 16 ? jq_seg_chain_small_kernel<16, D> : jq_seg_chain_small_kernel<32, D>;
+            if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            k<<<grid, wpb * 32, sm, st>>>(P, A, kind);
         } else {
             const int W = (int)((n2 + 31) / 32 * 32), NJ = std::max(1, 1024 / W), cnt = (int)((n2 + NJ - 1) / NJ);
             const unsigned grid = (unsigned)nwarps, thr = (unsigned)(W * NJ);
