@@ -14,14 +14,16 @@
 //             the times of ITS backward recurrence t = t - dt from T, :810-919, which the rounding of nsteps additions shifts against
 //             the forward ones by ~1e-10: its backward states are not the forward ones, and its gradient sees that at ~5e-11 relative)
 //   join Eta  Xb_p = X_p + eps_p, eps_p = Psi_p eps_{p+1} + d_p: the boundary states the reference's backward sweep passes through
+//             (+ two refinement passes, defect sweep and join, that return at once unless the time steps are coarse)
 //   launch 3  per segment: backward sweep from Xb_{p+1} with zero terminal adjoint -> particular adjoint solution c_p
-//   join Lam  Lam_p = Adj_p Lam_{p+1} + c_p
+//   join Lam  Lam_p = Adj_p Lam_{p+1} + c_p   (objFuncType 2/3: and Lam2_p = Adj_p Lam2_{p+1} for the second, unforced adjoint set)
 //   launch 4  per segment: the reference's backward sweep (state recomputed backwards, adjoint with forcing, gradient traces and
 //             B-spline scatter) between the known boundaries -> gradient share
-//   sum       grad = sum_p gradient shares, leak = sum_p penalty shares, both in segment order
+//   sum       grad = sum_p gradient shares, leak = sum_p penalty shares, in a fixed order
 //
-// The critical path is ~3 nsteps / nseg steps instead of 3 nsteps; the extra work (4n/m forward-equivalents) runs on SMs that a lone
-// trajectory leaves idle.  Results agree with the plain kernels to rounding (tests/test_gpu_timeparallel.py: 1e-12 relative).
+// The critical path is ~4 nsteps / nseg steps + 3 nseg small products instead of 3 nsteps steps; the extra work (4n/m forward-
+// equivalents) runs on SMs that a lone trajectory leaves idle.  Results agree with the plain kernels to rounding
+// (tests/test_gpu_timeparallel.py: 1e-12 relative asserted, 5e-15 ... 3e-14 measured) and are bit-reproducible.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -43,10 +45,10 @@ namespace {
 //         12-step Rabi problem: 1e-3), and the Eta of kind 2 is off by that factor times eps.  The defect sweep is then repeated from
 //         X + J' Eta (SegArgs::pass), its new defect d' chained the same way and added: each pass gains the same factor.  The passes
 //         are launched unconditionally and return at once unless the previous defect exceeded refine_tol (SegArgs::flags).
-// The columns of a boundary vector are independent chains of nseg dependent matrix-vector products: ONE WARP per (trajectory, column),
-// no block barrier, no shared memory in the small case -- a first version with one CTA per trajectory paid 1.5-2.5 us per segment in
-// __syncthreads round trips and generic-to-shared address arithmetic for a 0.1 us product.  M[j][i] (unit vector j, row i) is contiguous
-// in i and was just written (L2 resident).
+// The columns of a boundary vector are independent chains of nseg dependent matrix-vector products: ONE WARP per (trajectory, column)
+// and no block barrier in the small case -- a first version with one CTA per trajectory paid 1.5-2.5 us per segment in __syncthreads
+// round trips and generic-to-shared address arithmetic for a 0.1 us product.  M[j][i] (unit vector j, row i) is contiguous in i and
+// was just written (L2 resident).
 
 struct ChainArgs {
     const double *M;       // [seg][traj][2n][2n]
