@@ -179,8 +179,13 @@ int jq_comm_destroy(jq_handle *h);
  * rounding (~1e-14 relative), critical path ~ 4 nsteps / nseg steps.  Neumann solver, diagonal weights, tile / fibre layouts.
  * 2 ... 7 fail with JQ_ERR_ARG if the problem has no instantiation. */
 int jq_set_kernel(jq_handle *h, int32_t kernel);
-/* Number of time segments of kernel 7; 0 = automatic (about two sub-trajectory CTAs per SM in the propagator launch). */
+/* Number of time segments of kernel 7; 0 = automatic (about sqrt(1.6 nsteps), whole waves of the propagator launch). */
 int jq_set_time_segments(jq_handle *h, int32_t nseg);
+/* Host-only helper (no device needed): the times at which kernel 7 starts the sweeps of its nseg segments.  Segment p covers the steps
+ * [p nsteps / nseg, (p + 1) nsteps / nseg); t_first[p] is the value the reference's forward recurrence t = t + dt from 0
+ * (src/evalobjgrad.jl:745) has at the segment's first step, t_last[p] the value its backward recurrence t = t - dt from T (:810, :919)
+ * has at the segment's last step -- bit-identical to what a single sweep sees, not k dt.  Returns the steps of the longest segment. */
+int64_t jq_time_segments(double T, int64_t nsteps, int32_t nseg, double *t_first, double *t_last);
 /* what: 0 = kernel actually used by the last evaluation (1 ... 7), 1 = CUDA-event time of the last evaluation's
  * trajectory kernel(s) in ms (synchronises), 2 = number of kernels launched by the last evaluation,
  * 3 = trajectories resident per CTA, 4 = CTAs launched, 5 = registers per thread, 6 = dynamic smem bytes per CTA,

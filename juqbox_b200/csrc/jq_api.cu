@@ -454,6 +454,20 @@ extern "C" int jq_set_time_segments(jq_handle *h, int32_t nseg) {
     return 0;
 }
 
+extern "C" int64_t jq_time_segments(double T, int64_t nsteps, int32_t nseg, double *t_first, double *t_last) {
+    if (nseg < 1 || nsteps < nseg || !t_first || !t_last) { fail(JQ_ERR_ARG, "jq_time_segments: need 1 <= nseg <= nsteps and two output arrays"); return -1; }
+    DevProblem P{};
+    P.T = T; P.nsteps = nsteps;
+    std::vector<double> t(2 * (size_t)nseg);
+    jq_seg_times(P, nseg, t.data());
+    int64_t longest = 0;
+    for (int p = 0; p < nseg; ++p) {
+        t_first[p] = t[p]; t_last[p] = t[(size_t)nseg + p];
+        longest = std::max<int64_t>(longest, (int64_t)(p + 1) * nsteps / nseg - (int64_t)p * nsteps / nseg);
+    }
+    return longest;
+}
+
 extern "C" int jq_query(jq_handle *h, int32_t what, double *value) {
     if (!h || !value) return fail(JQ_ERR_ARG, "jq_query: null argument");
     switch (what) {

@@ -74,3 +74,32 @@ def test_harness_reproduces_reference_golden(tmp_path, case, sparse):
         ok, dobj, dgrad = ref_pass(float(fval), gf, g["obj0"], g["grad0"])
         assert ok, (k, dobj, dgrad)
     assert out[6].startswith("badlen -2 ")
+
+
+@pytest.mark.parametrize("T,nsteps,nseg", [(50.0, 4472, 74), (550.0, 31325, 129), (300.0, 7937, 148), (10.0, 12, 3), (1.0, 5, 5), (3.0, 7, 1)])
+def test_time_segments_follow_the_reference_time_recurrences(T, nsteps, nseg):
+    """Host side of the time-parallel evaluation (no device): segment p covers steps [p nsteps / nseg, (p + 1) nsteps / nseg) and starts
+    from the value the reference's own recurrences reach -- t = t + dt from 0 (src/evalobjgrad.jl:745), t = t - dt from T (:810, :919)
+    -- bit for bit, which is not k dt: the backward recurrence is shifted against the forward one by the rounding of nsteps additions."""
+    from juqbox_b200 import _lib
+    lib = _lib.load()
+    first, last = np.zeros(nseg), np.zeros(nseg)
+    dptr = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    longest = lib.jq_time_segments(T, nsteps, nseg, dptr(first), dptr(last))
+    dt = T / nsteps
+    tf, t = [0.0], 0.0
+    for _ in range(nsteps):
+        t = t + dt
+        tf.append(t)
+    tb, t = [T], T
+    for _ in range(nsteps):
+        t = t + (-dt)
+        tb.append(t)                                  # tb[j]: time after j backward steps = step index nsteps - j
+    k0 = [p * nsteps // nseg for p in range(nseg)]
+    k1 = [(p + 1) * nsteps // nseg for p in range(nseg)]
+    assert k0[0] == 0 and k1[-1] == nsteps and all(a == b for a, b in zip(k1[:-1], k0[1:]))
+    assert longest == max(b - a for a, b in zip(k0, k1))
+    assert all(first[p] == tf[k0[p]] for p in range(nseg))
+    assert all(last[p] == tb[nsteps - k1[p]] for p in range(nseg))
+    assert last[-1] == T and first[0] == 0.0
+    assert lib.jq_time_segments(T, nsteps, nsteps + 1, dptr(first), dptr(last)) == -1      # more segments than steps
