@@ -28,7 +28,11 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "jq_common.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -214,6 +218,84 @@ __global__ void __launch_bounds__(1024) jq_seg_chain_block_kernel(const DevProbl
     }
 }
 
+// 2n > 32, spread over a thread-block cluster: one SM streams a freshly written 131 KB matrix (2n = 128) at ~45 GB/s only -- 3 us per
+// segment in the kernel above -- so the chain of one (trajectory, column) runs on a CLUSTER of CS CTAs (CS SMs).  Each CTA owns EPC =
+// 2n / CS entries of the vector: it reads only its EPC columns of every matrix (EPC * 8 bytes of each row), thread (jq, i) forms the
+// share sum_k M[jq + NG k][i] x[jq + NG k] of its entry in registers that were filled NB segments ahead, the NG shares meet in shared
+// memory, and the new entries are written into the vector copy of EVERY CTA of the cluster through distributed shared memory (an
+// all-gather); one cluster.sync per segment (~380 cycles), double-buffered vector.  sh: xs[2][2n] | part[NG * EPC]
+template <int KPT, int NB>
+__global__ void __launch_bounds__(256) jq_seg_chain_cluster_kernel(const DevProblem P, const LaunchArgs A, int kind, int EPC, int NG) {
+    extern __shared__ double sh[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const ChainArgs c = chain_args(A, kind);
+    const int n = P.n, m = P.m, n2 = 2 * n, nseg = A.seg.nseg, nt = A.ntraj, tid = threadIdx.x;
+    if (kind == 3 && A.seg.flags[A.seg.pass - 1] == 0) return;          // uniform over the cluster
+    const int chain = blockIdx.x / CS, tr = chain / m, col = chain % m;
+    const size_t nv = (size_t)n2 * m;
+    const int jq = tid / EPC, i = tid % EPC, gi = rank * EPC + i;       // this thread's entry of the vector
+    const bool worker = jq < NG && gi < n2;
+    double *xs = sh, *part = sh + 2 * n2;
+    const int nstep = kind == 0 ? nseg : nseg - 1;
+    const int sgn = kind == 0 ? 1 : -1, p0 = kind == 0 ? 0 : nseg - 1;
+    const double *Mbase = c.M + ((size_t)p0 * nt + tr) * n2 * n2 + (size_t)jq * n2 + (worker ? gi : 0);     // leading dimension 2n (jq_seg_ld)
+    const long long Mstep = (long long)sgn * nt * n2 * n2;
+    auto fetch = [&](int s, double (&a)[KPT]) {
+        const double *M = Mbase + (long long)s * Mstep;
+#pragma unroll
+        for (int k = 0; k < KPT; ++k) a[k] = worker && jq + NG * k < n2 ? M[(size_t)NG * k * n2] : 0.0;
+    };
+    for (int idx = tid; idx < n2; idx += blockDim.x) {       // every CTA starts from its own copy of the whole vector
+        double x0 = 0.0;
+        if (kind == 0) x0 = idx < n ? P.uinit[idx + (size_t)n * col] : 0.0;
+        else if (kind == 1 || kind == 4) x0 = c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + idx];
+        xs[idx] = x0;
+        if (rank == 0 && kind == 0) c.V[(size_t)tr * nv + (size_t)col * n2 + idx] = x0;
+        if (rank == 0 && kind == 2) c.V[((size_t)nseg * nt + tr) * nv + (size_t)col * n2 + idx] = 0.0;
+    }
+    double a[NB][KPT];
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        if (u < nstep) fetch(u, a[u]);
+    }
+    cluster.sync();
+    int cur = 0;
+    for (int s0 = 0; s0 < nstep; s0 += NB) {
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int s = s0 + u;
+            if (s < nstep) {                                 // uniform over the cluster
+                const int p = p0 + sgn * s;
+                const double *x = xs + cur * n2;
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < KPT; k += 2) {
+                    const int j0 = jq + NG * k, j1 = jq + NG * (k + 1);
+                    t0 = fma(a[u][k], x[j0 < n2 ? j0 : 0], t0);
+                    if (k + 1 < KPT) t1 = fma(a[u][k + 1], x[j1 < n2 ? j1 : 0], t1);
+                }
+                if (jq < NG) part[jq * EPC + i] = t0 + t1;
+                if (s + NB < nstep) fetch(s + NB, a[u]);
+                __syncthreads();
+                if (tid < EPC && rank * EPC + tid < n2) {
+                    const int ge = rank * EPC + tid;
+                    double w[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int q = 0; q < NG; ++q) w[q & 3] += part[q * EPC + tid];
+                    double v = (w[0] + w[1]) + (w[2] + w[3]);
+                    if (c.C) v += c.C[((size_t)p * nt + tr) * nv + (size_t)col * n2 + ge];
+                    double *xn = xs + (cur ^ 1) * n2 + ge;
+                    for (int r = 0; r < CS; ++r) *cluster.map_shared_rank(xn, r) = v;          // all-gather through distributed shared memory
+                    double *o = c.V + ((size_t)(kind == 0 ? p + 1 : p) * nt + tr) * nv + (size_t)col * n2 + ge;
+                    if (c.accumulate) *o += v; else *o = v;
+                }
+                cluster.sync();                              // the new vector is complete in every CTA; part and the old vector are free
+                cur ^= 1;
+            }
+        }
+    }
+}
+
 // Objective terms of the final state X_nseg (src/evalobjgrad.jl:755-792) and the terminal adjoint (init_adjoint!, :2026-2059): the same
 // formulas as the trajectory kernels (jq_traj_kernels.cuh).  One CTA per trajectory, one warp-ordered reduction.
 __global__ void __launch_bounds__(256) jq_seg_objective_kernel(const DevProblem P, const LaunchArgs A) {
@@ -383,6 +465,24 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_ob
             if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             k<<<grid, wpb * 32, sm, st>>>(P, A, kind);
         } else {
+            // cluster version: CS = 8 CTAs per chain, EPC entries each, NG = 256 / EPC row groups, at most 8 matrix entries per thread
+            {
+                const int CS = 8, EPC = (int)((n2 + CS - 1) / CS), NG = EPC <= 256 ? 256 / EPC : 0, kpt = NG ? (int)((n2 + NG - 1) / NG) : 99;
+                const char *cenv = getenv("JQ_SEG_CLUSTER");
+                if ((cenv ? atoi(cenv) != 0 : true) && kpt <= 8) {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)(nwarps * CS)); cfg.blockDim = dim3(256);
+                    cfg.dynamicSmemBytes = (size_t)(2 * n2 + NG * EPC) * sizeof(double); cfg.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    cudaError_t ce = kpt <= 4 ? cudaLaunchKernelEx(&cfg, jq_seg_chain_cluster_kernel<4, 4>, P, A, kind, EPC, NG)
+                                              : cudaLaunchKernelEx(&cfg, jq_seg_chain_cluster_kernel<8, 4>, P, A, kind, EPC, NG);
+                    if (ce == cudaSuccess) return;
+                    cudaGetLastError();                     // fall through to the one-CTA kernel
+                }
+            }
             const int W = (int)((n2 + 31) / 32 * 32), NJ = std::max(1, 1024 / W), cnt = (int)((n2 + NJ - 1) / NJ);
             const unsigned grid = (unsigned)nwarps, thr = (unsigned)(W * NJ);
             const size_t sm = (size_t)(W + NJ * W) * sizeof(double);
