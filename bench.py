@@ -475,6 +475,35 @@ def main():
         extra["risk_neutral_sample_sharded"] = rnleg
         wr.close()
 
+    # ---- extra (N > 1): ONE cnot3 evaluation shared out over the GPUs (jq_comm_set_cooperative): the time segments of the time-parallel
+    # path are split over the ranks, the propagators all-gathered, every rank returns the single-GPU bits
+    if not args.no_extra and world > 1:
+        c3 = configs.example("cnot3")
+        w3 = jq.Working_Arrays(c3.params, c3.nCoeff, device=local_rank)
+        w3.comm_init(rank, world)
+        p3 = configs.synthetic_pcof(c3, 1)
+        coop = {}
+        res3 = {}
+        for mode in ("replicated", "cooperative"):
+            w3.comm_set_cooperative(mode == "cooperative")
+            res3[mode] = w3.evaluate(p3)
+            ts, ks = [], []
+            for _ in range(3):
+                dist.barrier()
+                t0 = time.perf_counter()
+                w3.evaluate(p3)
+                ts.append((time.perf_counter() - t0) * 1e3)
+                ks.append(w3.last_kernel_ms)
+            launches += 4 * int(w3.query(2))
+            coop[mode] = {"kernel": KERNEL_NAMES[w3.last_kernel], "time_segments": int(w3.query(7)), "kernels_ms": max_over_ranks(min(ks)),
+                          "host_call_ms": max_over_ranks(min(ts))}
+        g0, g1 = res3["replicated"]["grad"].ravel(), res3["cooperative"]["grad"].ravel()
+        coop["rel_grad_diff"] = max_over_ranks(float(np.linalg.norm(g0 - g1) / np.linalg.norm(g0)))
+        coop["note"] = "one pcof, every rank the same arguments; cooperative: segments of the propagator launch sharded, one in-place ncclAllGather per propagator array"
+        extra["cooperative_single_eval_cnot3"] = coop
+        w3.comm_destroy()
+        w3.close()
+
     if rank == 0:
         line = {"metric": "objective+gradient evals/sec (traceobjgrad)", "value": value, "unit": "evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,

@@ -163,6 +163,12 @@ int jq_eval_controls(jq_handle *h, const double *pcof, int32_t npar, int32_t nti
 int jq_comm_unique_id(void *id128);
 int jq_comm_init(jq_handle *h, int32_t rank, int32_t nranks, const void *id128);
 int jq_comm_destroy(jq_handle *h);
+/* Cooperative evaluation (on = 1; needs a communicator): every rank passes IDENTICAL arguments and the ranks share out ONE evaluation --
+ * the time segments of the time-parallel path (kernel 7): rank r sweeps the propagators of its nseg / nranks segments, one in-place
+ * ncclAllGather per propagator array completes them everywhere, the rest is replicated, and every rank returns the same bits as a
+ * single GPU would.  Pays when the propagator launch dominates (cnot3: 4.1 of 5.9 ms on one GPU); launches that do not take kernel 7
+ * are simply evaluated by every rank.  Sample-sharded calls (weights given) are not affected. */
+int jq_comm_set_cooperative(jq_handle *h, int32_t on);
 
 /* Kernel selection, for tests and profiling: 0 = automatic, 1 = generic (any operators, dense weights, uncoupled controls),
  * 2 = register-resident kernel, slot layout (sparse rows with <= 2 entries per row and control), 3 = fibre layout (Kronecker

@@ -164,6 +164,11 @@ class Working_Arrays:
         _lib.check(self._lib.jq_comm_init(self._handle, int(rank), int(nranks), C.c_char_p(unique_id)))
         self.comm_size = int(nranks)        # weighted evaluations now end with the library's own all-reduce
 
+    def comm_set_cooperative(self, on: bool = True):
+        """All ranks of the communicator evaluate the SAME arguments together: the time segments of kernel 7 are shared out and the
+        propagators all-gathered; every rank returns the single-GPU bits (jq_comm_set_cooperative)."""
+        _lib.check(self._lib.jq_comm_set_cooperative(self._handle, int(bool(on))))
+
     def comm_destroy(self):
         _lib.check(self._lib.jq_comm_destroy(self._handle))
         self.comm_size = 1

@@ -37,6 +37,7 @@ struct NcclApi {
     int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -48,6 +49,7 @@ static int load_nccl();
 struct jq_handle {
     nccl_comm_t comm = nullptr;
     int comm_rank = 0, comm_size = 1;
+    bool cooperative = false;           // jq_comm_set_cooperative: every rank passes the same arguments, the time segments of kernel 7 are shared out
     int device = 0;
     DevProblem P{};
     int n = 0, m = 0, Nc = 0, Nfreq = 0, pfid = 2;       // Nc: coupled + uncoupled controls
@@ -166,6 +168,7 @@ static int load_nccl() {
     SYM(CommInitRank, "ncclCommInitRank");
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -200,10 +203,23 @@ extern "C" int jq_comm_init(jq_handle *h, int32_t rank, int32_t nranks, const vo
     return 0;
 }
 
+// In-place all-gather of `count` doubles per rank (rank r's share already sits at buf + r * count).
+static int seg_allgather(void *ctx, double *buf, size_t count, cudaStream_t st) {
+    jq_handle *h = static_cast<jq_handle *>(ctx);
+    return g_nccl.AllGather(buf + (size_t)h->comm_rank * count, buf, count, 8 /*ncclDouble*/, h->comm, st);
+}
+
+extern "C" int jq_comm_set_cooperative(jq_handle *h, int32_t on) {
+    if (!h) return fail(JQ_ERR_ARG, "jq_comm_set_cooperative: null handle");
+    if (on && !h->comm) return fail(JQ_ERR_ARG, "jq_comm_set_cooperative: attach a communicator first (jq_comm_init)");
+    h->cooperative = on != 0;
+    return 0;
+}
+
 extern "C" int jq_comm_destroy(jq_handle *h) {
     if (!h) return fail(JQ_ERR_ARG, "jq_comm_destroy: null handle");
     if (h->comm) { CU(cudaSetDevice(h->device)); cudaStreamSynchronize(h->stream); g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
-    h->comm_size = 1; h->comm_rank = 0;
+    h->comm_size = 1; h->comm_rank = 0; h->cooperative = false;
     return 0;
 }
 
@@ -594,6 +610,14 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
         TrajPlan *prop = h->seg_prop ? h->seg_prop : h->seg_plan;
         int nseg = h->seg_nseg > 0 ? h->seg_nseg : jq_seg_auto_segments(h->P, A.ntraj, A.evaladjoint, jq_traj_plan_tpc(prop), h->sms);
         if (nseg > h->P.nsteps) nseg = (int)h->P.nsteps;
+        // cooperative evaluation: the segments are shared out evenly over the ranks (every rank computes the same nseg)
+        // ... when the propagator launch is at least two waves of CTAs: below that its collective costs more than it saves
+        const long long l1_ctas = 2LL * nseg * (((long long)((2 * h->n + h->m - 1) / h->m) * A.ntraj + jq_traj_plan_tpc(prop) - 1) / jq_traj_plan_tpc(prop));
+        const char *cf = getenv("JQ_SEG_COOP_FORCE");     // tests: share out small problems too
+        const bool coop_on = h->cooperative && h->comm && h->comm_size > 1 && (l1_ctas >= 2LL * h->sms || (cf && atoi(cf)));
+        if (coop_on) nseg = std::max(h->comm_size, (nseg + h->comm_size - 1) / h->comm_size * h->comm_size);
+        if (nseg > h->P.nsteps) nseg = (int)(h->P.nsteps / h->comm_size) * h->comm_size;
+        SegCoop coop{h->comm_rank, h->comm_size, seg_allgather, h};
         int rc = grow(&h->d_seg, &h->cap_seg, jq_seg_workspace_doubles(h->P, A.ntraj, A.Npar, nseg, A.evaladjoint));
         if (rc) return rc;
         if (h->segt_nseg != nseg) {           // segment start / end times: host recurrence, once per segment count
@@ -604,7 +628,7 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
             h->segt_nseg = nseg;
         }
         int nl = 0;
-        cudaError_t e = jq_seg_launch(h->seg_prop, h->seg_plan, h->seg_obj, h->P, A, nseg, h->d_segt, reinterpret_cast<int *>(h->d_segt + 2 * (size_t)nseg), h->d_seg, st, &ctas, &regs, &smem, &tpc, &nl);
+        cudaError_t e = jq_seg_launch(h->seg_prop, h->seg_plan, h->seg_obj, h->P, A, nseg, h->d_segt, reinterpret_cast<int *>(h->d_segt + 2 * (size_t)nseg), h->d_seg, st, coop_on && nseg >= h->comm_size ? &coop : nullptr, &ctas, &regs, &smem, &tpc, &nl);
         if (e == cudaSuccess) {
             CU(cudaEventRecord(h->ev1, st));
             h->timed = true;

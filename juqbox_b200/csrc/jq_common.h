@@ -54,6 +54,7 @@ struct DevProblem {
 struct SegArgs {
     int nseg;              // 0: whole trajectories (the plain evaluation)
     int mode[2], ctas0;
+    int seg_lo, seg_cnt;   // this launch sweeps the segments [seg_lo, seg_lo + seg_cnt) only (seg_cnt = 0: all) -- segments sharded over GPUs
     int ld;                // leading dimension of Phi / Adj: [seg][traj][ld][ld], zero padded past 2n (jq_seg_ld)
     double *Phi, *Adj, *X, *Lam, *Eta, *cpart, *dpart, *gpart, *penpart;
     double *Lam2, *gpart2; // objFuncType 2/3: boundary values of the second adjoint set (no forcing: Lam2_p = Adj_p Lam2_{p+1}), its gradient shares
@@ -119,5 +120,13 @@ size_t jq_seg_workspace_doubles(const DevProblem &P, int ntraj, int Npar, int ns
 void jq_seg_times(const DevProblem &P, int nseg, double *times /* [2][nseg], host */);
 // plan_prop: plan of the propagator launch (many independent sweeps: a throughput layout pays), plan: the boundary-to-boundary sweeps
 // plan_obj: plan of the gradient sweep when objFuncType != 1 (second adjoint set; nullptr otherwise)
-cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_obj, const DevProblem &P, const LaunchArgs &A, int nseg, const double *times, int *flags /* 4 ints, device */, double *work, cudaStream_t st,
+// coop: several GPUs evaluate the SAME trajectories together (nullptr: one GPU).  The propagator launch is independent per segment and
+// dominates large problems: rank r sweeps its nseg / nranks segments, then `allgather` (in place, count doubles per rank, on the stream)
+// completes Phi and Adj on every rank; everything after that is replicated, so all ranks return bit-identical results.
+struct SegCoop {
+    int rank, nranks;
+    int (*allgather)(void *ctx, double *buf, size_t count_per_rank, cudaStream_t st);
+    void *ctx;
+};
+cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_obj, const DevProblem &P, const LaunchArgs &A, int nseg, const double *times, int *flags /* 4 ints, device */, double *work, cudaStream_t st, const SegCoop *coop,
                           int *nctas, int *regs, size_t *smem, int *traj_per_cta, int *nlaunch);

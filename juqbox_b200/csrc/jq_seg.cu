@@ -419,7 +419,7 @@ void jq_seg_times(const DevProblem &P, int nseg, double *times) {
     }
 }
 
-cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_obj, const DevProblem &P, const LaunchArgs &A0, int nseg, const double *times, int *flags, double *work, cudaStream_t st,
+cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_obj, const DevProblem &P, const LaunchArgs &A0, int nseg, const double *times, int *flags, double *work, cudaStream_t st, const SegCoop *coop,
                           int *nctas, int *regs, size_t *smem, int *traj_per_cta, int *nlaunch) {
     if (nseg < 1 || nseg > P.nsteps) return cudaErrorInvalidValue;
     if (P.solver != 1 || A0.hist_r || (P.objFuncType != 1 && (!plan_obj || (A0.evaladjoint && !A0.infidgrad)))) return cudaErrorNotSupported;
@@ -505,8 +505,17 @@ cudaError_t jq_seg_launch(TrajPlan *plan_prop, TrajPlan *plan, TrajPlan *plan_ob
     mark();
     // launch 1: propagators
     A.seg.mode[0] = 1; A.seg.mode[1] = A.evaladjoint ? 3 : 0;
+    const bool shared = coop && coop->nranks > 1 && nseg % coop->nranks == 0;
+    if (shared) { A.seg.seg_cnt = nseg / coop->nranks; A.seg.seg_lo = coop->rank * A.seg.seg_cnt; }
     cudaError_t e = jq_traj_launch(plan_prop ? plan_prop : plan, P, A, st, nctas, regs, smem, traj_per_cta);
     if (e != cudaSuccess) return e;
+    if (shared) {               // every rank swept its share of the segments: complete Phi and Adj everywhere
+        const size_t per_rank = (size_t)A.seg.seg_cnt * nt * ld * ld;
+        if (coop->allgather(coop->ctx, A.seg.Phi, per_rank, st) != 0) return cudaErrorUnknown;
+        if (A.evaladjoint && coop->allgather(coop->ctx, A.seg.Adj, per_rank, st) != 0) return cudaErrorUnknown;
+        A.seg.seg_lo = 0; A.seg.seg_cnt = 0;
+        launches += A.evaladjoint ? 2 : 1;
+    }
     mark();
     run_join(0);
     mark();

@@ -471,7 +471,7 @@ cudaError_t jq_traj_launch(TrajPlan *pl, const DevProblem &P, const LaunchArgs &
         auto ctas = [&](int mode) {
             if (mode == 0) return 0LL;
             const long long per = (mode == 1 || mode == 3) ? (long long)nblk * A.ntraj : (long long)A.ntraj;
-            return (long long)A.seg.nseg * ((per + TPC - 1) / TPC);
+            return (long long)(A.seg.seg_cnt > 0 ? A.seg.seg_cnt : A.seg.nseg) * ((per + TPC - 1) / TPC);
         };
         const long long c0 = ctas(A.seg.mode[0]), c1 = ctas(A.seg.mode[1]);
         if (c0 + c1 > 0x7fffffffLL || c0 + c1 < 1) return cudaErrorInvalidConfiguration;

@@ -940,7 +940,7 @@ __global__ void __launch_bounds__((PIPE_ == 1 ? 3 * NW + 1 : PIPE_ == 2 ? 2 * NW
         smode = A.seg.mode[part];
         sper = (smode == 1 || smode == 3) ? ((2 * P.n + P.m - 1) / P.m) * A.ntraj : A.ntraj;
         const int cps = (sper + S.TPC - 1) / S.TPC;
-        seg = b / cps; sq0 = (b % cps) * S.TPC;
+        seg = A.seg.seg_lo + b / cps; sq0 = (b % cps) * S.TPC;
         // refinement pass of the defect sweep: nothing to do when the previous pass left no defect above the tolerance
         if (smode == 6 && A.seg.pass > 0 && A.seg.flags[A.seg.pass - 1] == 0) return;
     }
