@@ -250,3 +250,15 @@ function eval_jac_g_par(pcof::Vector{Float64}, rows::Vector{Int32}, cols::Vector
     jac_g .= lgrad
     return
 end
+
+# ---- kernel selection and multi-GPU switches (optional: automatic mode serves one pcof per callback with the time-parallel path) ----
+# kernel: 0 automatic … 7 time-parallel evaluation; nseg: number of time segments of kernel 7 (0 = automatic)
+set_kernel!(wa::Working_Arrays_B200, kernel::Integer) = jq_check(ccall((:jq_set_kernel, libjq), Cint, (Ptr{Cvoid}, Int32), wa.handle, kernel))
+set_time_segments!(wa::Working_Arrays_B200, nseg::Integer) = jq_check(ccall((:jq_set_time_segments, libjq), Cint, (Ptr{Cvoid}, Int32), wa.handle, nseg))
+# one Julia process per GPU: rank 0 creates the id, every rank attaches (section 5 of INTEGRATION.md)
+comm_unique_id() = (id = zeros(UInt8, 128); jq_check(ccall((:jq_comm_unique_id, libjq), Cint, (Ptr{UInt8},), id)); id)
+comm_init!(wa::Working_Arrays_B200, rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    jq_check(ccall((:jq_comm_init, libjq), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), wa.handle, rank, nranks, id))
+# every rank passes the same pcof: the ranks share out ONE evaluation (time segments of kernel 7), bit-identical result everywhere
+comm_set_cooperative!(wa::Working_Arrays_B200, on::Bool = true) =
+    jq_check(ccall((:jq_comm_set_cooperative, libjq), Cint, (Ptr{Cvoid}, Int32), wa.handle, on ? 1 : 0))
