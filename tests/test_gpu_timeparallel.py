@@ -199,3 +199,8 @@ def test_unsupported_problems_say_so_or_fall_back():
     assert wa.last_kernel != 7
     wa.close()
     assert k_eval in (5, 7)
+    wa = jq.Working_Arrays(cfg.params, len(cfg.pcof0))
+    with pytest.raises(Exception):           # sharing one evaluation over several GPUs needs a communicator first
+        wa.comm_set_cooperative(True)
+    wa.comm_set_cooperative(False)
+    wa.close()
