@@ -614,9 +614,12 @@ static int launch_trajectories(jq_handle *h, const LaunchArgs &A, cudaStream_t s
         // ... when the propagator launch is at least two waves of CTAs: below that its collective costs more than it saves
         const long long l1_ctas = 2LL * nseg * (((long long)((2 * h->n + h->m - 1) / h->m) * A.ntraj + jq_traj_plan_tpc(prop) - 1) / jq_traj_plan_tpc(prop));
         const char *cf = getenv("JQ_SEG_COOP_FORCE");     // tests: share out small problems too
-        const bool coop_on = h->cooperative && h->comm && h->comm_size > 1 && (l1_ctas >= 2LL * h->sms || (cf && atoi(cf)));
-        if (coop_on) nseg = std::max(h->comm_size, (nseg + h->comm_size - 1) / h->comm_size * h->comm_size);
-        if (nseg > h->P.nsteps) nseg = (int)(h->P.nsteps / h->comm_size) * h->comm_size;
+        const bool coop_on = h->cooperative && h->comm && h->comm_size > 1 && h->P.nsteps >= h->comm_size &&
+                             (l1_ctas >= 2LL * h->sms || (cf && atoi(cf)));
+        if (coop_on) {
+            nseg = std::max(h->comm_size, (nseg + h->comm_size - 1) / h->comm_size * h->comm_size);
+            if (nseg > h->P.nsteps) nseg = (int)(h->P.nsteps / h->comm_size) * h->comm_size;       // >= comm_size by the test above
+        }
         SegCoop coop{h->comm_rank, h->comm_size, seg_allgather, h};
         int rc = grow(&h->d_seg, &h->cap_seg, jq_seg_workspace_doubles(h->P, A.ntraj, A.Npar, nseg, A.evaladjoint));
         if (rc) return rc;
